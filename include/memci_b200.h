@@ -1,0 +1,180 @@
+/*
+ * memci_b200.h -- C ABI of the B200-native MEMCI hot path (libmemci_b200.so).
+ *
+ * Drop-in boundary for lhl2617/Interpolatory's MEMCI interpolators.  Every entry
+ * point names the reference interface it replaces; paths are relative to
+ *   Simulator/python/src/Interpolators/MEMCI/   of the reference.
+ *
+ * Conventions
+ *   - plain C: opaque context pointer, raw pointers and sizes, no torch / C++ types;
+ *   - every function returns 0 on success or a negative memci_status; the message of
+ *     the last failure is available from memci_last_error();
+ *   - frames are C-contiguous uint8 [H][W][3] RGB, exactly what
+ *     VideoStream.get_frame() delivers in the reference (src/VideoStream.py:61);
+ *   - the caller owns all host buffers; the library owns the device "slots" inside
+ *     a context.  Nothing allocated by the library is ever returned to the caller;
+ *   - all work is enqueued on the context's CUDA stream; host<->device copies are
+ *     asynchronous when the host buffer is pinned.  memci_sync() waits for the stream.
+ *     A context is not thread-safe; contexts are independent (one per GPU / stream).
+ *   - there is NO CPU fallback: without a CUDA device every call fails with
+ *     MEMCI_ERR_CUDA.
+ */
+#ifndef MEMCI_B200_H
+#define MEMCI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MEMCI_API __attribute__((visibility("default")))
+#else
+#define MEMCI_API
+#endif
+
+typedef struct memci_ctx memci_ctx;
+
+typedef enum memci_status {
+    MEMCI_OK = 0,
+    MEMCI_ERR_ARG = -1,      /* bad argument (slot index, sizes, modes)          */
+    MEMCI_ERR_CUDA = -2,     /* CUDA runtime / driver error (sticky per context)  */
+    MEMCI_ERR_STATE = -3,    /* slot empty / shape mismatch                       */
+    MEMCI_ERR_NOMEM = -4
+} memci_status;
+
+/* smoothing modes: smoothing/threeXthree_mv_smoothing.py:14 `filter_func`,
+ * MCI/MEMCIBaseInterpolator.py:23-29 smoothing_dict */
+enum { MEMCI_FILTER_NONE = 0, MEMCI_FILTER_MEAN = 1, MEMCI_FILTER_MEDIAN = 2, MEMCI_FILTER_WEIGHTED = 3 };
+/* ME/hbma.py:10-13 cost_key_map */
+enum { MEMCI_COST_SAD = 0, MEMCI_COST_SSD = 1 };
+
+#define MEMCI_NUM_FRAME_SLOTS 8
+#define MEMCI_NUM_MV_SLOTS 8
+
+/* ---- library / context ------------------------------------------------------ */
+
+MEMCI_API int memci_version(void);
+/* Number of CUDA devices visible; <0 on error (no driver / no device). */
+MEMCI_API int memci_device_count(void);
+
+/* One context = one GPU + one stream + device slots for frames of height H, width W.
+ * `stream` is an existing cudaStream_t (as void*) to enqueue on, or NULL to let the
+ * library create its own non-blocking stream.
+ * Replaces: the implicit per-interpolator state of MEMCIBaseInterpolator
+ * (MCI/MEMCIBaseInterpolator.py:30-44: MV_field_idx, fwr/bwr_MV_field). */
+MEMCI_API int memci_ctx_create(int device, int H, int W, void *stream, memci_ctx **out);
+MEMCI_API int memci_ctx_destroy(memci_ctx *ctx);
+/* ctx may be NULL: returns the last error of a failed memci_ctx_create. */
+MEMCI_API const char *memci_last_error(memci_ctx *ctx);
+MEMCI_API int memci_sync(memci_ctx *ctx);
+/* The cudaStream_t the context enqueues on (for CUDA-event timing by the caller). */
+MEMCI_API void *memci_stream(memci_ctx *ctx);
+
+/* Page-locked host staging buffers (the decode-to-device staging seam:
+ * src/Interpolators/base.py:46-64 load_input_video / src/VideoStream.py:61 get_frame). */
+MEMCI_API int memci_host_alloc(size_t bytes, void **out);
+MEMCI_API int memci_host_free(void *p);
+
+/* ---- frames ----------------------------------------------------------------- */
+
+/* Host uint8[H][W][3] -> frame slot (async H2D on the context stream). */
+MEMCI_API int memci_upload_frame(memci_ctx *ctx, int slot, const uint8_t *host_hwc);
+/* Device uint8[H][W][3] -> frame slot (D2D; for inputs already resident in HBM). */
+MEMCI_API int memci_set_frame_device(memci_ctx *ctx, int slot, const void *dev_hwc);
+/* Frame slot -> host uint8[H][W][3] (async D2H; memci_sync() before reading). */
+MEMCI_API int memci_download_frame(memci_ctx *ctx, int slot, uint8_t *host_hwc);
+/* Device pointer of a frame slot's uint8[H][W][3] buffer (NULL on bad slot). */
+MEMCI_API void *memci_frame_device_ptr(memci_ctx *ctx, int slot);
+
+/* ---- motion estimation ------------------------------------------------------ */
+
+/* Replaces ME/full_search.py:61 get_motion_vectors(block_size, target_region, im1, im2)
+ * (helper :19-55, get_sad :10-17).  Result (block level) goes to MV slot `mv_slot`. */
+MEMCI_API int memci_me_fs(memci_ctx *ctx, int slot_src, int slot_tgt, int block_size,
+                          int target_region, int mv_slot);
+
+/* Replaces ME/hbma.py:161 get_motion_vectors(block_size, win_size, sub_win_size, steps,
+ * min_block_size, im1, im2, cost_str) (pyramid :171-177, full_search :77-98,
+ * increase_vec_density :100-149).  Result at the final block size goes to `mv_slot`. */
+MEMCI_API int memci_me_hbma(memci_ctx *ctx, int slot_src, int slot_tgt, int block_size,
+                            int win_size, int sub_win_size, int steps, int min_block_size,
+                            int cost_key, int mv_slot);
+
+/* One pyramid level of ME/hbma.py:172-176 on frame slot `slot`, level >= 1, copied to
+ * host uint8[ceil(H/2^l)][ceil(W/2^l)][3] (test / inspection hook). */
+MEMCI_API int memci_download_pyramid_level(memci_ctx *ctx, int slot, int level, uint8_t *host);
+
+/* Replaces smoothing/threeXthree_mv_smoothing.py:14 smooth(filter_func, mv_field, block_size)
+ * with mean_filter.py:2, median_filter.py:3-15, weighted_mean_filter.py:4-19.
+ * mv_in and mv_out may be the same slot. */
+MEMCI_API int memci_smooth(memci_ctx *ctx, int mv_in, int filter_mode, int filter_size, int mv_out);
+
+/* Geometry of an MV slot: the (dy,dx) grid and the SAD grid (they differ after
+ * smoothing: vectors live on filter_size cells, SAD stays on ME blocks). */
+MEMCI_API int memci_mv_info(memci_ctx *ctx, int mv_slot, int *mv_cell, int *mv_rows, int *mv_cols,
+                            int *sad_cell, int *sad_rows, int *sad_cols);
+/* Block-level download: vec[mv_rows][mv_cols][2] (dy,dx) and sad[sad_rows][sad_cols].
+ * Either pointer may be NULL. */
+MEMCI_API int memci_download_mv_blocks(memci_ctx *ctx, int mv_slot, float *vec, float *sad);
+/* Dense float32[H][W][3] (dy,dx,sad): the array the reference's ME functions return
+ * (full_search.py:51-53, hbma.py:151-159 upscale_mvs). */
+MEMCI_API int memci_download_mv_dense(memci_ctx *ctx, int mv_slot, float *host_hw3);
+/* Arbitrary dense float32[H][W][3] field -> MV slot (for callers of the reference's
+ * function-level helper(source, target, MV_field, dist)). */
+MEMCI_API int memci_upload_mv_dense(memci_ctx *ctx, int mv_slot, const float *host_hw3);
+/* Block-level upload: vec[rows][cols][2] on `cell`-sized cells and sad on its own grid. */
+MEMCI_API int memci_upload_mv_blocks(memci_ctx *ctx, int mv_slot, int mv_cell, const float *vec,
+                                     int sad_cell, const float *sad);
+
+/* ---- motion-compensated interpolation --------------------------------------- */
+
+/* Replaces MCI/Unidirectional.py:36 helper(source_frame, target_frame, MV_field, dist). */
+MEMCI_API int memci_mci_unidir(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_slot,
+                               float dist, int out_slot);
+/* Replaces MCI/Bidirectional.py:27 helper(source, target, fwr_MV_field, bwr_MV_field, dist). */
+MEMCI_API int memci_mci_bidir(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd,
+                              int mv_bwd, float dist, int out_slot);
+
+/* ---- fused convenience (one call per output frame of the class API) --------- */
+
+typedef struct memci_pair_params {
+    int me_mode;        /* 0 = fs, 1 = hbma                                   */
+    int block_size;     /* MEMCIBaseInterpolator.py:34                        */
+    int region;         /* target_region / win_size  :35                      */
+    int sub_region;     /* :40                                                */
+    int steps;          /* hbma pyramid depth (caller applies the auto rule)  */
+    int min_block_size; /* :42                                                */
+    int filter_mode;    /* MEMCI_FILTER_*                                     */
+    int filter_size;    /* :39                                                */
+    int bidir;          /* 0 = unidir, 1 = bidir                              */
+} memci_pair_params;
+
+/* ME (+smoothing) for the pair in frame slots (slot_src, slot_tgt) into MV slots
+ * mv_fwd (and mv_bwd when p->bidir).  Mirrors the cache-miss branch of
+ * get_interpolated_frame (Unidirectional.py:109-125, Bidirectional.py:138-155). */
+MEMCI_API int memci_estimate_pair(memci_ctx *ctx, const memci_pair_params *p, int slot_src,
+                                  int slot_tgt, int mv_fwd, int mv_bwd);
+
+/* ---- instrumentation ---------------------------------------------------------- */
+
+/* Kernels launched by this context since creation (or since the last reset). */
+MEMCI_API long long memci_launch_count(memci_ctx *ctx);
+MEMCI_API int memci_reset_launch_count(memci_ctx *ctx);
+/* Statistics of the last memci_me_fs call: candidates evaluated, SAD pixel-ops
+ * (candidates * block_size^2) and blocks re-resolved by the exact float64 path. */
+MEMCI_API int memci_fs_stats(memci_ctx *ctx, long long *n_candidates, long long *px_ops,
+                             int *n_redo_blocks);
+/* Number of holes filled by the last MCI call (synchronises the stream). */
+MEMCI_API int memci_mci_stats(memci_ctx *ctx, int *n_holes);
+/* Device-side time of the last memci_me_fs main kernel / MCI splat kernel, measured
+ * with CUDA events on the context stream when timing is enabled (ms, <0 if none). */
+MEMCI_API int memci_enable_kernel_timing(memci_ctx *ctx, int on);
+MEMCI_API int memci_last_kernel_ms(memci_ctx *ctx, float *fs_ms, float *mci_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEMCI_B200_H */

@@ -1,0 +1,130 @@
+"""Settings, dispatch tables and device plumbing shared by the MEMCI interpolators
+(reference: MCI/MEMCIBaseInterpolator.py:14-98).  Settings arrive as strings, exactly as the
+CLI's `MEMCI:key=val.key=val` syntax delivers them."""
+import math
+
+import numpy as np
+
+from ..base import BaseInterpolator
+from ..device import DeviceContext, FILTER_MODES
+from .._native import PairParams
+from ..ME.full_search import get_motion_vectors as fs
+from ..ME.hbma import get_motion_vectors as hbma
+from ..smoothing import mean_filter, median_filter, weighted_mean_filter, filter_mode_of
+from ..util import hbma_auto_steps
+
+# device slot plan of one interpolator instance
+_FRAME_SLOTS = (0, 1, 2)      # resident source frames (LRU)
+_OUT_SLOT = 7
+_MV_FWD, _MV_BWD = 0, 1
+
+
+def tss(*a, **k):
+    raise NotImplementedError("three-step search is outside this build's hot-path scope (SURVEY 8f #2)")
+
+
+class MEMCIBaseInterpolator(BaseInterpolator):
+    def __init__(self, target_fps, video_in_path=None, video_out_path=None, max_out_frames=math.inf,
+                 max_cache_size=2, **args):
+        super().__init__(target_fps, video_in_path, video_out_path, max_out_frames, max_cache_size, **args)
+        ME_dict = {"fs": fs, "tss": tss, "hbma": hbma}
+        smoothing_dict = {"mean": mean_filter, "median": median_filter, "weighted": weighted_mean_filter, "none": None}
+        self.MV_field_idx = -1
+        self.fwr_MV_field = []
+        self.bwr_MV_field = []
+        self.MV_field = []
+        self.block_size = 8
+        self.region = 7
+        self.me_mode = ME_dict["hbma"]
+        self.filter_mode = smoothing_dict["none"]
+        self.filter_size = 4
+        self.sub_region = 1
+        self.steps = 3
+        self.min_block_size = 4
+        self.upscale_MV = True
+
+        if 'block_size' in args:
+            self.block_size = int(args['block_size'])
+        if 'target_region' in args:
+            self.region = int(args['target_region'])
+        if 'me_mode' in args:
+            self.me_mode = ME_dict[args['me_mode']]             # KeyError on unknown modes, like the reference
+            if self.me_mode is tss:
+                self.region = self.steps
+        if 'filter_mode' in args:
+            self.filter_mode = smoothing_dict[args['filter_mode']]
+        if 'filter_size' in args:
+            self.filter_size = int(args['filter_size'])
+
+        self.pad_size = 4 * self.min_block_size
+        if self.me_mode is fs:
+            self.ME_args = {"block_size": self.block_size, "target_region": self.region}
+        elif self.me_mode is tss:
+            self.ME_args = {"block_size": self.block_size, "steps": self.steps}
+        elif self.me_mode is hbma:
+            self.upscale_MV = False
+            self.ME_args = {"block_size": self.block_size, "win_size": self.region,
+                            "sub_win_size": self.sub_region, "steps": self.steps,
+                            "min_block_size": self.min_block_size, "cost_str": "sad",
+                            "upscale": self.upscale_MV}
+        if self.me_mode is tss:
+            tss()
+        self.device_index = int(args.get('device', 0))
+        self._dev = None
+        self._resident = {}
+        self._resident_stream = None
+
+    # ---- device plumbing ------------------------------------------------------------------
+    def _device(self, shape):
+        H, W = int(shape[0]), int(shape[1])
+        if self._dev is None or (self._dev.H, self._dev.W) != (H, W):
+            if self._dev is not None:
+                self._dev.close()
+            self._dev = DeviceContext(H, W, self.device_index)
+            self._resident = {}
+        return self._dev
+
+    def _frame_slot(self, dev, frame_idx, frame):
+        """Device slot holding source frame `frame_idx` (uploaded once per stream position)."""
+        if self._resident_stream is not self.video_stream:
+            self._resident = {}
+            self._resident_stream = self.video_stream
+        if frame_idx in self._resident:
+            return self._resident[frame_idx]
+        used = set(self._resident.values())
+        free = [s for s in _FRAME_SLOTS if s not in used]
+        if free:
+            slot = free[0]
+        else:
+            victim = min(self._resident)                         # oldest source index
+            slot = self._resident.pop(victim)
+        dev.upload_frame(slot, frame)
+        dev.sync()                                               # pageable host memory: copy is done
+        self._resident[frame_idx] = slot
+        return slot
+
+    def _pair_params(self, shape, bidir):
+        p = PairParams()
+        p.me_mode = 0 if self.me_mode is fs else 1
+        p.block_size = self.block_size
+        p.region = self.region
+        p.sub_region = self.sub_region
+        if self.me_mode is hbma:
+            self.steps = hbma_auto_steps(shape)                  # Unidirectional.py:116-121 / Bidirectional.py:144-149
+        p.steps = self.steps
+        p.min_block_size = self.min_block_size
+        p.filter_mode = FILTER_MODES[filter_mode_of(self.filter_mode)]
+        p.filter_size = self.filter_size
+        p.bidir = 1 if bidir else 0
+        return p
+
+    def clear_cache(self):
+        self._resident = {}
+
+    def close(self):
+        if self._dev is not None:
+            self._dev.close()
+            self._dev = None
+
+    def _mv_dense(self, slot):
+        return self._dev.download_mv_dense(slot)

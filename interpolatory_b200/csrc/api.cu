@@ -1,0 +1,383 @@
+// C ABI of libmemci_b200.so (see include/memci_b200.h): context, slots, copies, dispatch.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "memci_internal.cuh"
+
+static char g_err[512] = "";
+
+int memci_fail(memci_ctx *ctx, int code, const char *fmt, ...)
+{
+    char *dst = ctx ? ctx->err : g_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int memci_reserve(memci_ctx *ctx, void **ptr, size_t *cap, size_t need)
+{
+    if (*cap >= need && *ptr) return MEMCI_OK;
+    if (*ptr) { CK(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(*ptr); *ptr = nullptr; *cap = 0; }
+    size_t sz = need < 256 ? 256 : need;
+    CK(ctx, cudaMalloc(ptr, sz));
+    *cap = sz;
+    return MEMCI_OK;
+}
+
+int memci_mv_reserve(memci_ctx *ctx, MVField *f, int mv_cell, int mv_rows, int mv_cols,
+                     int sad_cell, int sad_rows, int sad_cols)
+{
+    size_t nv = (size_t)mv_rows * mv_cols, ns = (size_t)sad_rows * sad_cols;
+    size_t capv = f->vec_cap * sizeof(float2), caps = f->sad_cap * sizeof(float);
+    int rc;
+    if ((rc = memci_reserve(ctx, (void **)&f->vec, &capv, nv * sizeof(float2)))) return rc;
+    if ((rc = memci_reserve(ctx, (void **)&f->sad, &caps, ns * sizeof(float)))) return rc;
+    f->vec_cap = capv / sizeof(float2);
+    f->sad_cap = caps / sizeof(float);
+    f->mv_cell = mv_cell; f->mv_rows = mv_rows; f->mv_cols = mv_cols;
+    f->sad_cell = sad_cell; f->sad_rows = sad_rows; f->sad_cols = sad_cols;
+    return MEMCI_OK;
+}
+
+#define REQ_CTX(ctx) do { if (!(ctx)) return memci_fail(nullptr, MEMCI_ERR_ARG, "null context"); \
+                          if ((ctx)->sticky) return MEMCI_ERR_CUDA; \
+                          cudaSetDevice((ctx)->device); } while (0)
+#define REQ_FRAME(ctx, s, need_valid) do { \
+        if ((s) < 0 || (s) >= MEMCI_NUM_FRAME_SLOTS) return memci_fail(ctx, MEMCI_ERR_ARG, "frame slot %d out of range", (s)); \
+        if ((need_valid) && !(ctx)->frames[s].valid) return memci_fail(ctx, MEMCI_ERR_STATE, "frame slot %d is empty", (s)); } while (0)
+#define REQ_MV(ctx, s, need_valid) do { \
+        if ((s) < 0 || (s) >= MEMCI_NUM_MV_SLOTS) return memci_fail(ctx, MEMCI_ERR_ARG, "mv slot %d out of range", (s)); \
+        if ((need_valid) && !(ctx)->mvs[s].valid) return memci_fail(ctx, MEMCI_ERR_STATE, "mv slot %d is empty", (s)); } while (0)
+
+extern "C" {
+
+int memci_version(void) { return 100; }
+
+int memci_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { memci_fail(nullptr, MEMCI_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); return MEMCI_ERR_CUDA; }
+    return n;
+}
+
+int memci_ctx_create(int device, int H, int W, void *stream, memci_ctx **out)
+{
+    if (!out) return memci_fail(nullptr, MEMCI_ERR_ARG, "null out pointer");
+    *out = nullptr;
+    if (H <= 0 || W <= 0 || H > 8192 || W > 8192) return memci_fail(nullptr, MEMCI_ERR_ARG, "frame size %dx%d out of range", H, W);
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return memci_fail(nullptr, MEMCI_ERR_CUDA, "cudaSetDevice(%d): %s (no CPU fallback exists)", device, cudaGetErrorString(e));
+    memci_ctx *ctx = (memci_ctx *)calloc(1, sizeof(memci_ctx));
+    if (!ctx) return memci_fail(nullptr, MEMCI_ERR_NOMEM, "out of host memory");
+    ctx->device = device; ctx->H = H; ctx->W = W; ctx->Wp = (W + 3) & ~3;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { free(ctx); return memci_fail(nullptr, MEMCI_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    if (prop.major != 10) { free(ctx); return memci_fail(nullptr, MEMCI_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); }
+    ctx->num_sms = prop.multiProcessorCount;
+    if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = 0; }
+    else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { free(ctx); return memci_fail(nullptr, MEMCI_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+        ctx->own_stream = 1;
+    }
+    size_t fb = (size_t)H * W * 3, lb = (size_t)H * ctx->Wp * 4;
+    for (int i = 0; i < MEMCI_NUM_FRAME_SLOTS; ++i) {
+        if (cudaMalloc(&ctx->frames[i].rgb, fb) != cudaSuccess || cudaMalloc(&ctx->frames[i].luma, lb) != cudaSuccess) {
+            memci_fail(nullptr, MEMCI_ERR_NOMEM, "cudaMalloc of frame slots failed");
+            memci_ctx_destroy(ctx);
+            return MEMCI_ERR_NOMEM;
+        }
+    }
+    if (cudaMalloc(&ctx->d_counters, 16 * sizeof(int)) != cudaSuccess ||
+        cudaMemset(ctx->d_counters, 0, 16 * sizeof(int)) != cudaSuccess) {
+        memci_fail(nullptr, MEMCI_ERR_NOMEM, "cudaMalloc of counters failed");
+        memci_ctx_destroy(ctx);
+        return MEMCI_ERR_NOMEM;
+    }
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+    *out = ctx;
+    return MEMCI_OK;
+}
+
+int memci_ctx_destroy(memci_ctx *ctx)
+{
+    if (!ctx) return MEMCI_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < MEMCI_NUM_FRAME_SLOTS; ++i) {
+        FrameSlot &f = ctx->frames[i];
+        if (f.rgb) cudaFree(f.rgb);
+        if (f.luma) cudaFree(f.luma);
+        for (int l = 0; l <= MEMCI_MAX_PYR; ++l) {
+            if (f.pyr_rgb[l]) cudaFree(f.pyr_rgb[l]);
+            if (f.pyr_luma[l]) cudaFree(f.pyr_luma[l]);
+        }
+    }
+    for (int i = 0; i < MEMCI_NUM_MV_SLOTS; ++i) {
+        if (ctx->mvs[i].vec) cudaFree(ctx->mvs[i].vec);
+        if (ctx->mvs[i].sad) cudaFree(ctx->mvs[i].sad);
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->tmp_mv[i].vec) cudaFree(ctx->tmp_mv[i].vec);
+        if (ctx->tmp_mv[i].sad) cudaFree(ctx->tmp_mv[i].sad);
+        if (ctx->d_disp[i]) cudaFree(ctx->d_disp[i]);
+    }
+    for (int i = 0; i < 4; ++i) {
+        if (ctx->fs_plan[i].d_tiles) cudaFree(ctx->fs_plan[i].d_tiles);
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    }
+    if (ctx->d_redo_list) cudaFree(ctx->d_redo_list);
+    if (ctx->d_counters) cudaFree(ctx->d_counters);
+    if (ctx->d_hole_mask) cudaFree(ctx->d_hole_mask);
+    if (ctx->d_hole_list) cudaFree(ctx->d_hole_list);
+    if (ctx->d_dense) cudaFree(ctx->d_dense);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    free(ctx);
+    return MEMCI_OK;
+}
+
+const char *memci_last_error(memci_ctx *ctx) { return ctx ? ctx->err : g_err; }
+
+int memci_sync(memci_ctx *ctx)
+{
+    REQ_CTX(ctx);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return MEMCI_OK;
+}
+
+void *memci_stream(memci_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int memci_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return MEMCI_ERR_ARG;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) return memci_fail(nullptr, MEMCI_ERR_CUDA, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return MEMCI_OK;
+}
+
+int memci_host_free(void *p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) return MEMCI_ERR_CUDA;
+    return MEMCI_OK;
+}
+
+// ---- frames ----------------------------------------------------------------------------
+static void frame_touched(FrameSlot &f) { f.valid = 1; f.luma_ok = 0; f.pyr_levels = 0; }
+
+int memci_upload_frame(memci_ctx *ctx, int slot, const uint8_t *host)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot, 0);
+    if (!host) return memci_fail(ctx, MEMCI_ERR_ARG, "null host frame");
+    CK(ctx, cudaMemcpyAsync(ctx->frames[slot].rgb, host, (size_t)ctx->H * ctx->W * 3, cudaMemcpyHostToDevice, ctx->stream));
+    frame_touched(ctx->frames[slot]);
+    return MEMCI_OK;
+}
+
+int memci_set_frame_device(memci_ctx *ctx, int slot, const void *dev)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot, 0);
+    if (!dev) return memci_fail(ctx, MEMCI_ERR_ARG, "null device frame");
+    CK(ctx, cudaMemcpyAsync(ctx->frames[slot].rgb, dev, (size_t)ctx->H * ctx->W * 3, cudaMemcpyDeviceToDevice, ctx->stream));
+    frame_touched(ctx->frames[slot]);
+    return MEMCI_OK;
+}
+
+int memci_download_frame(memci_ctx *ctx, int slot, uint8_t *host)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot, 1);
+    if (!host) return memci_fail(ctx, MEMCI_ERR_ARG, "null host frame");
+    CK(ctx, cudaMemcpyAsync(host, ctx->frames[slot].rgb, (size_t)ctx->H * ctx->W * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    return MEMCI_OK;
+}
+
+void *memci_frame_device_ptr(memci_ctx *ctx, int slot)
+{
+    if (!ctx || slot < 0 || slot >= MEMCI_NUM_FRAME_SLOTS) return nullptr;
+    return ctx->frames[slot].rgb;
+}
+
+// ---- ME ----------------------------------------------------------------------------------
+int memci_me_fs(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, int mv_slot)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_MV(ctx, mv_slot, 0);
+    return memci_fs_run(ctx, slot_src, slot_tgt, bs, R, &ctx->mvs[mv_slot]);
+}
+
+int memci_me_hbma(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int win, int sub, int steps,
+                  int min_bs, int cost_key, int mv_slot)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_MV(ctx, mv_slot, 0);
+    return memci_hbma_run(ctx, slot_src, slot_tgt, bs, win, sub, steps, min_bs, cost_key, &ctx->mvs[mv_slot]);
+}
+
+int memci_download_pyramid_level(memci_ctx *ctx, int slot, int level, uint8_t *host)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot, 1);
+    if (level < 1 || level > MEMCI_MAX_PYR || !host) return memci_fail(ctx, MEMCI_ERR_ARG, "bad pyramid level %d", level);
+    int rc = memci_ensure_pyramid(ctx, slot, level);
+    if (rc) return rc;
+    int h = ctx->H, w = ctx->W;
+    for (int l = 1; l <= level; ++l) { h = (h + 1) / 2; w = (w + 1) / 2; }
+    CK(ctx, cudaMemcpyAsync(host, ctx->frames[slot].pyr_rgb[level], (size_t)h * w * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    return MEMCI_OK;
+}
+
+int memci_smooth(memci_ctx *ctx, int mv_in, int mode, int fsz, int mv_out)
+{
+    REQ_CTX(ctx); REQ_MV(ctx, mv_in, 1); REQ_MV(ctx, mv_out, 0);
+    if (mode < MEMCI_FILTER_NONE || mode > MEMCI_FILTER_WEIGHTED) return memci_fail(ctx, MEMCI_ERR_ARG, "unknown filter mode %d", mode);
+    MVField *in = &ctx->mvs[mv_in], *out = &ctx->mvs[mv_out];
+    if (mode == MEMCI_FILTER_NONE) {                    // smooth(None, ...) returns the field unchanged (:15-16)
+        if (in == out) return MEMCI_OK;
+        int rc = memci_mv_reserve(ctx, out, in->mv_cell, in->mv_rows, in->mv_cols, in->sad_cell, in->sad_rows, in->sad_cols);
+        if (rc) return rc;
+        CK(ctx, cudaMemcpyAsync(out->vec, in->vec, sizeof(float2) * (size_t)in->mv_rows * in->mv_cols, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(ctx, cudaMemcpyAsync(out->sad, in->sad, sizeof(float) * (size_t)in->sad_rows * in->sad_cols, cudaMemcpyDeviceToDevice, ctx->stream));
+        out->valid = 1;
+        return MEMCI_OK;
+    }
+    MVField *tmp = &ctx->tmp_mv[0];
+    int rc = memci_smooth_run(ctx, in, mode, fsz, tmp);
+    if (rc) return rc;
+    MVField t = *out; *out = *tmp; *tmp = t;            // hand the buffers over (stream-ordered reuse)
+    tmp->valid = 0;
+    return MEMCI_OK;
+}
+
+int memci_mv_info(memci_ctx *ctx, int s, int *mv_cell, int *mv_rows, int *mv_cols, int *sad_cell, int *sad_rows, int *sad_cols)
+{
+    REQ_CTX(ctx); REQ_MV(ctx, s, 1);
+    MVField &f = ctx->mvs[s];
+    if (mv_cell) *mv_cell = f.mv_cell;
+    if (mv_rows) *mv_rows = f.mv_rows;
+    if (mv_cols) *mv_cols = f.mv_cols;
+    if (sad_cell) *sad_cell = f.sad_cell;
+    if (sad_rows) *sad_rows = f.sad_rows;
+    if (sad_cols) *sad_cols = f.sad_cols;
+    return MEMCI_OK;
+}
+
+int memci_download_mv_blocks(memci_ctx *ctx, int s, float *vec, float *sad)
+{
+    REQ_CTX(ctx); REQ_MV(ctx, s, 1);
+    MVField &f = ctx->mvs[s];
+    if (vec) CK(ctx, cudaMemcpyAsync(vec, f.vec, sizeof(float2) * (size_t)f.mv_rows * f.mv_cols, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sad) CK(ctx, cudaMemcpyAsync(sad, f.sad, sizeof(float) * (size_t)f.sad_rows * f.sad_cols, cudaMemcpyDeviceToHost, ctx->stream));
+    return MEMCI_OK;
+}
+
+int memci_download_mv_dense(memci_ctx *ctx, int s, float *host)
+{
+    REQ_CTX(ctx); REQ_MV(ctx, s, 1);
+    if (!host) return memci_fail(ctx, MEMCI_ERR_ARG, "null host buffer");
+    size_t bytes = (size_t)ctx->H * ctx->W * 3 * sizeof(float), cap = ctx->dense_cap;
+    int rc = memci_reserve(ctx, (void **)&ctx->d_dense, &cap, bytes);
+    ctx->dense_cap = cap;
+    if (rc) return rc;
+    if ((rc = memci_mv_to_dense(ctx, &ctx->mvs[s], ctx->d_dense))) return rc;
+    CK(ctx, cudaMemcpyAsync(host, ctx->d_dense, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return MEMCI_OK;
+}
+
+int memci_upload_mv_dense(memci_ctx *ctx, int s, const float *host)
+{
+    REQ_CTX(ctx); REQ_MV(ctx, s, 0);
+    if (!host) return memci_fail(ctx, MEMCI_ERR_ARG, "null host buffer");
+    size_t bytes = (size_t)ctx->H * ctx->W * 3 * sizeof(float), cap = ctx->dense_cap;
+    int rc = memci_reserve(ctx, (void **)&ctx->d_dense, &cap, bytes);
+    ctx->dense_cap = cap;
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(ctx->d_dense, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return memci_dense_to_mv(ctx, ctx->d_dense, &ctx->mvs[s]);
+}
+
+int memci_upload_mv_blocks(memci_ctx *ctx, int s, int mv_cell, const float *vec, int sad_cell, const float *sad)
+{
+    REQ_CTX(ctx); REQ_MV(ctx, s, 0);
+    if (!vec || !sad || mv_cell <= 0 || sad_cell <= 0) return memci_fail(ctx, MEMCI_ERR_ARG, "bad block-level MV upload arguments");
+    MVField &f = ctx->mvs[s];
+    int mr = ceil_div_i(ctx->H, mv_cell), mc = ceil_div_i(ctx->W, mv_cell);
+    int sr = ceil_div_i(ctx->H, sad_cell), sc = ceil_div_i(ctx->W, sad_cell);
+    int rc = memci_mv_reserve(ctx, &f, mv_cell, mr, mc, sad_cell, sr, sc);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(f.vec, vec, sizeof(float2) * (size_t)mr * mc, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(f.sad, sad, sizeof(float) * (size_t)sr * sc, cudaMemcpyHostToDevice, ctx->stream));
+    f.valid = 1;
+    return MEMCI_OK;
+}
+
+// ---- MCI ---------------------------------------------------------------------------------
+int memci_mci_unidir(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_slot, float dist, int out_slot)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_FRAME(ctx, out_slot, 0); REQ_MV(ctx, mv_slot, 1);
+    if (out_slot == slot_src || out_slot == slot_tgt) return memci_fail(ctx, MEMCI_ERR_ARG, "output slot aliases an input slot");
+    return memci_mci_run(ctx, slot_src, slot_tgt, &ctx->mvs[mv_slot], nullptr, dist, out_slot, 0);
+}
+
+int memci_mci_bidir(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd, int mv_bwd, float dist, int out_slot)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_FRAME(ctx, out_slot, 0);
+    REQ_MV(ctx, mv_fwd, 1); REQ_MV(ctx, mv_bwd, 1);
+    if (out_slot == slot_src || out_slot == slot_tgt) return memci_fail(ctx, MEMCI_ERR_ARG, "output slot aliases an input slot");
+    return memci_mci_run(ctx, slot_src, slot_tgt, &ctx->mvs[mv_fwd], &ctx->mvs[mv_bwd], dist, out_slot, 1);
+}
+
+int memci_estimate_pair(memci_ctx *ctx, const memci_pair_params *p, int slot_src, int slot_tgt, int mv_fwd, int mv_bwd)
+{
+    REQ_CTX(ctx);
+    if (!p) return memci_fail(ctx, MEMCI_ERR_ARG, "null params");
+    int rc;
+    for (int d = 0; d < (p->bidir ? 2 : 1); ++d) {
+        int a = d ? slot_tgt : slot_src, b = d ? slot_src : slot_tgt, mv = d ? mv_bwd : mv_fwd;
+        if (p->me_mode == 0) rc = memci_me_fs(ctx, a, b, p->block_size, p->region, mv);
+        else if (p->me_mode == 1) rc = memci_me_hbma(ctx, a, b, p->block_size, p->region, p->sub_region, p->steps,
+                                                     p->min_block_size, MEMCI_COST_SAD, mv);
+        else return memci_fail(ctx, MEMCI_ERR_ARG, "unknown me_mode %d", p->me_mode);
+        if (rc) return rc;
+        if (p->filter_mode != MEMCI_FILTER_NONE && (rc = memci_smooth(ctx, mv, p->filter_mode, p->filter_size, mv))) return rc;
+    }
+    return MEMCI_OK;
+}
+
+// ---- instrumentation ---------------------------------------------------------------------
+long long memci_launch_count(memci_ctx *ctx) { return ctx ? ctx->launches : -1; }
+int memci_reset_launch_count(memci_ctx *ctx) { if (!ctx) return MEMCI_ERR_ARG; ctx->launches = 0; return MEMCI_OK; }
+
+int memci_fs_stats(memci_ctx *ctx, long long *n_cand, long long *px_ops, int *n_redo)
+{
+    REQ_CTX(ctx);
+    if (n_cand) *n_cand = ctx->fs_last_cand;
+    if (px_ops) *px_ops = ctx->fs_last_ops;
+    if (n_redo) {
+        CK(ctx, cudaMemcpyAsync(n_redo, ctx->d_counters, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MEMCI_OK;
+}
+
+int memci_mci_stats(memci_ctx *ctx, int *n_holes)
+{
+    REQ_CTX(ctx);
+    if (n_holes) {
+        CK(ctx, cudaMemcpyAsync(n_holes, ctx->d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return MEMCI_OK;
+}
+
+int memci_enable_kernel_timing(memci_ctx *ctx, int on) { REQ_CTX(ctx); ctx->timing = on ? 1 : 0; return MEMCI_OK; }
+
+int memci_last_kernel_ms(memci_ctx *ctx, float *fs_ms, float *mci_ms)
+{
+    REQ_CTX(ctx);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (fs_ms) { *fs_ms = -1.f; if (ctx->fs_timed) CK(ctx, cudaEventElapsedTime(fs_ms, ctx->ev[0], ctx->ev[1])); }
+    if (mci_ms) { *mci_ms = -1.f; if (ctx->mci_timed) CK(ctx, cudaEventElapsedTime(mci_ms, ctx->ev[2], ctx->ev[3])); }
+    return MEMCI_OK;
+}
+
+}  // extern "C"

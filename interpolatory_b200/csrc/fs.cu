@@ -1,0 +1,553 @@
+// Full-search block matching (ME/full_search.py) on sm_100a.
+//
+//   fs_tiled_kernel   persistent, TMA-staged, register-tiled luma-SAD + argmin (block sizes 8k)
+//   fs_generic_kernel warp-per-block exact kernel: any block size, and the "redo" pass that
+//                     resolves blocks whose winner may hinge on the float64 truncation (N2)
+//
+// Cost model of the reference (get_sad, full_search.py:10-17): SAD = trunc(sum_f64 |L1 - L2|)
+// with L = 0.299R + 0.587G + 0.114B in float64.  With L1000 = 299R + 587G + 114B (exact int)
+// and S = sum |L1000_1 - L1000_2|:  SAD = S / 1000 unless S % 1000 == 0 && S > 0, where the
+// f64 sum may land just below the integer and SAD = S/1000 - 1 ("flagged" candidates).
+#include "memci_internal.cuh"
+
+#define FS_NT 512
+#define FS_BOXW 256
+#define FS_NBMAX 32
+#define KEY_NONE 0xffffffffffffffffull
+
+// ---- candidate window of one block: full_search.py:33-43 incl. the H-for-W bug at :37 ----
+struct FsBounds { int r0, r1, c0, c1; };
+__host__ __device__ inline FsBounds fs_bounds(int H, int W, int bs, int R, int s_row, int s_col)
+{
+    FsBounds b;
+    int tmr = (s_row + bs >= H) ? s_row + 1 : H - bs;
+    int tmc = (s_col + bs >= H) ? s_col + 1 : W - bs;   // sic: compares against H
+    b.r0 = s_row - R > 0 ? s_row - R : 0;
+    b.r1 = tmr < s_row + R + 1 ? tmr : s_row + R + 1;
+    b.c0 = s_col - R > 0 ? s_col - R : 0;
+    b.c1 = tmc < s_col + R + 1 ? tmc : s_col + R + 1;
+    return b;
+}
+
+// total order of candidates = the reference's update rule (:47): lower SAD, then smaller
+// distance, then earlier in (t_row, t_col) scan order.
+__device__ __forceinline__ unsigned long long fs_key(unsigned sad, unsigned d2, unsigned ri, unsigned ci)
+{
+    return ((unsigned long long)sad << 32) | ((unsigned long long)d2 << 16) | (ri << 8) | ci;
+}
+
+// =========================================================================================
+// Generic exact kernel: one warp per block, lanes stride over candidates.
+// =========================================================================================
+__global__ void fs_generic_kernel(const int32_t *__restrict__ Ls, const int32_t *__restrict__ Lt,
+                                  const uint8_t *__restrict__ rgb_s, const uint8_t *__restrict__ rgb_t,
+                                  int H, int W, int Wp, int bs, int R, int nbr, int nbc,
+                                  const int *__restrict__ list, const int *__restrict__ list_count,
+                                  float2 *__restrict__ out_vec, float *__restrict__ out_sad)
+{
+    int lane = threadIdx.x & 31;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    int total = list ? *list_count : nbr * nbc;
+    for (int it = warp; it < total; it += nwarps) {
+        int blk = list ? list[it] : it;
+        int br = blk / nbc, bc = blk - br * nbc;
+        int s_row = br * bs, s_col = bc * bs;
+        FsBounds b = fs_bounds(H, W, bs, R, s_row, s_col);
+        int nr = b.r1 - b.r0, nc = b.c1 - b.c0;
+        unsigned long long best = KEY_NONE;
+        if (nr > 0 && nc > 0) {
+            int ncand = nr * nc;
+            for (int c = lane; c < ncand; c += 32) {
+                int ri = c / nc, ci = c - ri * nc;
+                int t_row = b.r0 + ri, t_col = b.c0 + ci;
+                unsigned S = sad1000_global(Ls, Lt, H, W, Wp, s_row, s_col, t_row, t_col, bs);
+                unsigned sad = S / 1000u;
+                if (S != 0 && sad * 1000u == S)   // flagged: replay in f64, reference op order
+                    sad = (unsigned)exact_cost_f64(rgb_s, rgb_t, H, W, s_row, s_col, t_row, t_col, bs, 0);
+                int dr = s_row - t_row, dc = s_col - t_col;
+                unsigned long long k = fs_key(sad, (unsigned)(dr * dr + dc * dc), ri, ci);
+                best = k < best ? k : best;
+            }
+        }
+        best = shfl_min_u64(best);
+        if (lane == 0) {
+            float dy, dx, sad;
+            if (best == KEY_NONE) {          // empty window: target_index stays (0,0), sad = inf
+                dy = (float)(-s_row); dx = (float)(-s_col); sad = __int_as_float(0x7f800000);
+            } else {
+                int ri = (int)((best >> 8) & 255), ci = (int)(best & 255);
+                dy = (float)(b.r0 + ri - s_row); dx = (float)(b.c0 + ci - s_col);
+                sad = (float)(unsigned)(best >> 32);
+            }
+            out_vec[blk] = make_float2(dy, dx);
+            out_sad[blk] = sad;
+        }
+    }
+}
+
+// =========================================================================================
+// Tiled kernel.
+//
+// A tile = nb horizontally adjacent blocks of one block row.  Thread 0 stages, with two TMA
+// tile loads (cp.async.bulk.tensor.2d, zero fill outside the frame = the reference's np.pad),
+//   win[box_h][256]  luma1000 of the target frame, rows s_row-R .. s_row+bs+R-1, cols x0-R ..
+//   ref[bs][256]     luma1000 of the source frame, the nb blocks themselves
+// into one of two shared-memory stages while the previous tile is being searched.
+//
+// Work item = (block b, column offset dx, group g of G consecutive row offsets).  A thread
+// keeps the 8x8 reference sub-block in 64 registers and G accumulators, walks the G+7 window
+// rows the group touches (8 conflict-free LDS.32 per row: neighbouring lanes = neighbouring dx)
+// and issues one VABSDIFF (|a-b|+acc) per pixel-candidate.  Blocks larger than 8 are searched
+// as (bs/8)^2 sub-blocks accumulating into the same registers.  Items are dense over the
+// *valid* candidates (frame-edge clipping and the :37 bug remove 23 % of them at 1080p), and
+// the host packs tiles to ~3 items per thread so no lane idles.
+//
+// Argmin: per item in registers, then one shared-memory atomicMin per item on the 64-bit key.
+// Flagged candidates are tracked with SAD-1 as a lower bound; a block whose best lower bound
+// beats its best fast key is appended to the redo list and re-resolved by fs_generic_kernel.
+// =========================================================================================
+struct FsParams {
+    int H, W, bs, R, Rp, m, nbr, nbc, n_tiles, box_h, n_stages;   // Rp = R rounded up to 4: TMA x origin stays 16-byte aligned
+    const FsTile *tiles;
+    float2 *out_vec;
+    float *out_sad;
+    int *redo_list;
+    int *counters;
+    int redo_cap;
+};
+
+struct FsTileTab {
+    int by, bx0, nb, s_row;
+    int r0, n_dy, n_groups, total_dx, n_items;
+    int dx_lo[FS_NBMAX];
+    int pre[FS_NBMAX + 1];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int x, int y, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+
+// geometry of one tile, computed by warp 0 (lane = block within tile)
+__device__ inline void fs_fill_tab(FsTileTab *tab, const FsTile t, const FsParams &p, int lane)
+{
+    int s_row = t.by * p.bs;
+    int n_dx = 0, dx_lo = 0;
+    if (lane < t.nb) {
+        int s_col = (t.bx0 + lane) * p.bs;
+        FsBounds b = fs_bounds(p.H, p.W, p.bs, p.R, s_row, s_col);
+        n_dx = b.c1 - b.c0 > 0 ? b.c1 - b.c0 : 0;
+        dx_lo = b.c0 - s_col;
+    }
+    int incl = n_dx;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane < FS_NBMAX) { tab->dx_lo[lane] = dx_lo; tab->pre[lane + 1] = incl; }
+    if (lane == 0) {
+        FsBounds b = fs_bounds(p.H, p.W, p.bs, p.R, s_row, t.bx0 * p.bs);
+        tab->pre[0] = 0;
+        tab->by = t.by; tab->bx0 = t.bx0; tab->nb = t.nb; tab->s_row = s_row;
+        tab->r0 = b.r0;
+        tab->n_dy = b.r1 - b.r0 > 0 ? b.r1 - b.r0 : 0;
+    }
+    int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (lane == 0) tab->total_dx = total;
+}
+
+template <int G>
+__global__ void __launch_bounds__(FS_NT, 1)
+fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_tgt,
+                const FsParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ FsTileTab tabs[2];
+    __shared__ unsigned long long best_fast[2][FS_NBMAX];
+    __shared__ unsigned long long best_flag[2][FS_NBMAX];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int stage_ints = (p.box_h + p.bs) * FS_BOXW;
+    int *const stage0 = reinterpret_cast<int *>(smem_raw);
+    const unsigned stage_bytes = (unsigned)stage_ints * 4u;
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 2 * FS_NBMAX) {
+        (&best_fast[0][0])[tid] = KEY_NONE;
+        (&best_flag[0][0])[tid] = KEY_NONE;
+    }
+    __syncthreads();
+
+    const int first = blockIdx.x, stride = gridDim.x;
+    if (first >= p.n_tiles) return;
+
+    auto issue = [&](int tile_idx, int k) {        // warp 0 only
+        FsTile t = p.tiles[tile_idx];
+        int s = p.n_stages == 2 ? (k & 1) : 0;
+        fs_fill_tab(&tabs[k & 1], t, p, lane);
+        __syncwarp();
+        if (lane == 0) {
+            int *win = stage0 + (size_t)s * stage_ints;
+            int *ref = win + p.box_h * FS_BOXW;
+            mbar_expect_tx(&mbar[s], stage_bytes);
+            tma_load_2d(win, &tm_tgt, t.bx0 * p.bs - p.Rp, t.by * p.bs - p.R, &mbar[s]);
+            tma_load_2d(ref, &tm_src, t.bx0 * p.bs, t.by * p.bs, &mbar[s]);
+        }
+    };
+
+    if (warp == 0) issue(first, 0);
+    __syncthreads();
+
+    int k = 0;
+    unsigned phase[2] = {0u, 0u};
+    for (int tile_idx = first; tile_idx < p.n_tiles; tile_idx += stride, ++k) {
+        const int s = p.n_stages == 2 ? (k & 1) : 0;
+        const int next = tile_idx + stride;
+        // With two stages the next tile streams in while this one is searched.
+        if (p.n_stages == 2 && warp == 0 && next < p.n_tiles) issue(next, k + 1);
+
+        const FsTileTab *tab = &tabs[k & 1];
+        mbar_wait(&mbar[s], phase[s]);
+        phase[s] ^= 1u;
+
+        const int *win = stage0 + (size_t)s * stage_ints;
+        const int *ref = win + p.box_h * FS_BOXW;
+        const int nb = tab->nb, total_dx = tab->total_dx, n_dy = tab->n_dy;
+        const int n_groups = (n_dy + G - 1) / G;
+        const int n_items = total_dx * n_groups;
+        const int s_row = tab->s_row;
+        const int dy_lo = tab->r0 - s_row;               // first valid row offset
+        const int wrow_base = tab->r0 - (s_row - p.R);   // its row inside win[]
+
+        for (int base = warp * 32; base < n_items; base += FS_NT) {
+            const int item = base + lane;
+            const bool active = item < n_items;
+            unsigned long long kbest = KEY_NONE, kflag = KEY_NONE;
+            int b = 0;
+            if (active) {
+                const int g = item / total_dx;
+                const int f = item - g * total_dx;
+                while (b + 1 < nb && tab->pre[b + 1] <= f) ++b;
+                const int dxi = f - tab->pre[b];
+                const int dx = tab->dx_lo[b] + dxi;
+                const int wr0 = wrow_base + g * G;
+                const int wc = b * p.bs + dx + p.Rp;
+                const int rc = b * p.bs;
+                unsigned acc[G];
+#pragma unroll
+                for (int i = 0; i < G; ++i) acc[i] = 0u;
+                for (int si = 0; si < p.m; ++si) {
+                    for (int sj = 0; sj < p.m; ++sj) {
+                        int r[8][8];
+                        const int *rp = ref + (si * 8) * FS_BOXW + rc + sj * 8;
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            int4 a = *reinterpret_cast<const int4 *>(rp + kk * FS_BOXW);
+                            int4 c = *reinterpret_cast<const int4 *>(rp + kk * FS_BOXW + 4);
+                            r[kk][0] = a.x; r[kk][1] = a.y; r[kk][2] = a.z; r[kk][3] = a.w;
+                            r[kk][4] = c.x; r[kk][5] = c.y; r[kk][6] = c.z; r[kk][7] = c.w;
+                        }
+                        const int *wp = win + (wr0 + si * 8) * FS_BOXW + wc + sj * 8;
+#pragma unroll
+                        for (int w = 0; w < G + 7; ++w) {
+                            int px[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) px[j] = wp[w * FS_BOXW + j];
+#pragma unroll
+                            for (int gi = 0; gi < G; ++gi) {
+                                const int kk = w - gi;
+                                if (kk >= 0 && kk < 8) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) acc[gi] = __sad(r[kk][j], px[j], acc[gi]);
+                                }
+                            }
+                        }
+                    }
+                }
+                const int n_valid = n_dy - g * G;       // > 0
+                const unsigned dx2 = (unsigned)(dx * dx);
+#pragma unroll
+                for (int gi = 0; gi < G; ++gi) {
+                    if (gi < n_valid) {
+                        const unsigned S = acc[gi];
+                        const unsigned q = S / 1000u;
+                        const int ri = g * G + gi;
+                        const int dy = dy_lo + ri;
+                        const unsigned d2 = (unsigned)(dy * dy) + dx2;
+                        const unsigned long long key = fs_key(q, d2, (unsigned)ri, (unsigned)dxi);
+                        kbest = key < kbest ? key : kbest;
+                        if (q * 1000u == S && S != 0u) {
+                            const unsigned long long kl = fs_key(q - 1u, d2, (unsigned)ri, (unsigned)dxi);
+                            kflag = kl < kflag ? kl : kflag;
+                        }
+                    }
+                }
+            }
+            // one atomic per warp when the whole warp works on one block (the common case)
+            const int b0 = __shfl_sync(0xffffffffu, b, 0);
+            if (__all_sync(0xffffffffu, !active || b == b0)) {
+                kbest = shfl_min_u64(kbest);
+                kflag = shfl_min_u64(kflag);
+                if (lane == 0) {
+                    if (kbest != KEY_NONE) atomicMin(&best_fast[k & 1][b0], kbest);
+                    if (kflag != KEY_NONE) atomicMin(&best_flag[k & 1][b0], kflag);
+                }
+            } else if (active) {
+                if (kbest != KEY_NONE) atomicMin(&best_fast[k & 1][b], kbest);
+                if (kflag != KEY_NONE) atomicMin(&best_flag[k & 1][b], kflag);
+            }
+        }
+        __syncthreads();
+
+        if (warp == 0) {
+            if (lane < nb) {
+                const unsigned long long kb = best_fast[k & 1][lane], kf = best_flag[k & 1][lane];
+                best_fast[k & 1][lane] = KEY_NONE;
+                best_flag[k & 1][lane] = KEY_NONE;
+                const int bc = tab->bx0 + lane;
+                const int blk = tab->by * p.nbc + bc;
+                const int s_col = bc * p.bs;
+                float dy, dx, sad;
+                if (kb == KEY_NONE) {
+                    dy = (float)(-s_row); dx = (float)(-s_col); sad = __int_as_float(0x7f800000);
+                } else {
+                    const int ri = (int)((kb >> 8) & 255), ci = (int)(kb & 255);
+                    dy = (float)(dy_lo + ri);
+                    dx = (float)(tab->dx_lo[lane] + ci);
+                    sad = (float)(unsigned)(kb >> 32);
+                }
+                p.out_vec[blk] = make_float2(dy, dx);
+                p.out_sad[blk] = sad;
+                if (kf < kb) {                              // a flagged candidate may win: exact redo
+                    int pos = atomicAdd(&p.counters[0], 1);
+                    if (pos < p.redo_cap) p.redo_list[pos] = blk;
+                }
+            }
+            __syncwarp();
+            if (p.n_stages == 1 && next < p.n_tiles) issue(next, k + 1);
+        }
+        if (p.n_stages == 1) __syncthreads();
+    }
+}
+
+// =========================================================================================
+// Host side: plan (tile table), tensor maps, launch.
+// =========================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+static int make_tmap(memci_ctx *ctx, CUtensorMap *tm, const int32_t *plane, int H, int W, int Wp, int box_w, int box_h)
+{
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) return memci_fail(ctx, MEMCI_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};        // true extent: x >= W / y >= H zero-fill
+    cuuint64_t strides[1] = {(cuuint64_t)Wp * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, (void *)plane, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return memci_fail(ctx, MEMCI_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
+    return MEMCI_OK;
+}
+
+static int pick_G(int R)
+{
+    // group size dividing 2R+1 where possible (no half-empty last group)
+    const int n = 2 * R + 1;
+    const int cands[4] = {11, 13, 8, 5};
+    int best = 11, best_waste = 1 << 30;
+    for (int i = 0; i < 4; ++i) {
+        int g = cands[i];
+        int waste = ((n + g - 1) / g) * g - n;
+        // relative waste, prefer larger G on ties (fewer window re-reads)
+        int score = waste * 1000 / n * 16 + (16 - g);
+        if (score < best_waste) { best_waste = score; best = g; }
+    }
+    return best;
+}
+
+static int fs_smem_bytes(int bs, int box_h, int n_stages, int G)
+{
+    return ((box_h + bs) * n_stages + G + 8) * FS_BOXW * 4;
+}
+
+static FsPlan *fs_get_plan(memci_ctx *ctx, int bs, int R)
+{
+    for (int i = 0; i < 4; ++i)
+        if (ctx->fs_plan[i].valid && ctx->fs_plan[i].bs == bs && ctx->fs_plan[i].R == R) return &ctx->fs_plan[i];
+    FsPlan *pl = nullptr;
+    for (int i = 0; i < 4; ++i)
+        if (!ctx->fs_plan[i].valid) { pl = &ctx->fs_plan[i]; break; }
+    if (!pl) {                       // evict slot 0
+        pl = &ctx->fs_plan[0];
+        if (pl->d_tiles) cudaFree(pl->d_tiles);
+        memset(pl, 0, sizeof(*pl));
+    }
+    const int H = ctx->H, W = ctx->W;
+    const int nbr = ceil_div_i(H, bs), nbc = ceil_div_i(W, bs);
+    pl->bs = bs; pl->R = R; pl->G = pick_G(R);
+    pl->box_w = FS_BOXW; pl->box_h = bs + 2 * R;
+    // exact candidate count -- same bounds as the kernels
+    long long n_cand = 0;
+    for (int br = 0; br < nbr; ++br)
+        for (int bc = 0; bc < nbc; ++bc) {
+            FsBounds b = fs_bounds(H, W, bs, R, br * bs, bc * bs);
+            if (b.r1 > b.r0 && b.c1 > b.c0) n_cand += (long long)(b.r1 - b.r0) * (b.c1 - b.c0);
+        }
+    pl->n_cand = n_cand;
+    pl->n_tiles = 0; pl->d_tiles = nullptr;
+    const bool tiled_ok = (bs % 8 == 0) && bs <= 64 && R <= 120 && (bs + 2 * R + 4) <= FS_BOXW &&
+                          fs_smem_bytes(bs, pl->box_h, 1, pl->G) <= 200 * 1024;
+    if (tiled_ok) {
+        const int Rp = (R + 3) & ~3;
+        const int nb_box = (FS_BOXW - R - Rp) / bs < FS_NBMAX ? (FS_BOXW - R - Rp) / bs : FS_NBMAX;
+        const int m2 = (bs / 8) * (bs / 8);
+        // aim for ~3 items of 8x8 work per thread per tile
+        const int budget = 3 * FS_NT / m2 > FS_NT ? 3 * FS_NT / m2 : FS_NT;
+        FsTile *h = (FsTile *)malloc(sizeof(FsTile) * (size_t)nbr * nbc);
+        int nt = 0;
+        for (int br = 0; br < nbr; ++br) {
+            FsBounds rb = fs_bounds(H, W, bs, R, br * bs, 0);
+            int n_dy = rb.r1 - rb.r0 > 0 ? rb.r1 - rb.r0 : 0;
+            int n_groups = (n_dy + pl->G - 1) / pl->G;
+            int bc = 0;
+            while (bc < nbc) {
+                int nb = 0, items = 0;
+                while (bc + nb < nbc && nb < nb_box) {
+                    FsBounds b = fs_bounds(H, W, bs, R, br * bs, (bc + nb) * bs);
+                    int n_dx = b.c1 - b.c0 > 0 ? b.c1 - b.c0 : 0;
+                    int add = n_dx * n_groups;
+                    if (nb > 0 && items + add > budget) break;
+                    items += add; ++nb;
+                }
+                h[nt].by = br; h[nt].bx0 = bc; h[nt].nb = nb; h[nt].pad = items;
+                ++nt; bc += nb;
+            }
+        }
+        if (cudaMalloc(&pl->d_tiles, sizeof(FsTile) * nt) != cudaSuccess ||
+            cudaMemcpyAsync(pl->d_tiles, h, sizeof(FsTile) * nt, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            free(h);
+            memci_fail(ctx, MEMCI_ERR_CUDA, "fs plan upload failed");
+            return nullptr;
+        }
+        free(h);
+        pl->n_tiles = nt;
+    }
+    pl->valid = 1;
+    return pl;
+}
+
+template <int G>
+static int fs_launch_tiled(memci_ctx *ctx, const CUtensorMap &ts, const CUtensorMap &tt, const FsParams &p, int smem)
+{
+    CK(ctx, cudaFuncSetAttribute(fs_tiled_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int grid = ctx->num_sms < p.n_tiles ? ctx->num_sms : p.n_tiles;
+    fs_tiled_kernel<G><<<grid, FS_NT, smem, ctx->stream>>>(ts, tt, p);
+    CKL(ctx);
+    return MEMCI_OK;
+}
+
+int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out)
+{
+    const int H = ctx->H, W = ctx->W, Wp = ctx->Wp;
+    if (bs <= 0 || bs > 64 || R < 0 || R > 127)
+        return memci_fail(ctx, MEMCI_ERR_ARG, "full search: block_size %d / target_region %d out of range (1..64, 0..127)", bs, R);
+    int rc;
+    if ((rc = memci_ensure_luma(ctx, slot_src))) return rc;
+    if ((rc = memci_ensure_luma(ctx, slot_tgt))) return rc;
+    const int nbr = ceil_div_i(H, bs), nbc = ceil_div_i(W, bs);
+    if ((rc = memci_mv_reserve(ctx, out, bs, nbr, nbc, bs, nbr, nbc))) return rc;
+    FsPlan *pl = fs_get_plan(ctx, bs, R);
+    if (!pl) return MEMCI_ERR_CUDA;
+    ctx->fs_last_cand = pl->n_cand;
+    ctx->fs_last_ops = pl->n_cand * bs * bs;
+    FrameSlot &fs = ctx->frames[slot_src], &ft = ctx->frames[slot_tgt];
+    if ((size_t)ctx->redo_cap < (size_t)nbr * nbc) {
+        if (ctx->d_redo_list) cudaFree(ctx->d_redo_list);
+        ctx->d_redo_list = nullptr;
+        CK(ctx, cudaMalloc(&ctx->d_redo_list, sizeof(int) * (size_t)nbr * nbc));
+        ctx->redo_cap = nbr * nbc;
+    }
+    CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));
+    ctx->fs_timed = 0;
+    if (pl->n_tiles > 0) {
+        CUtensorMap ts, tt;
+        if ((rc = make_tmap(ctx, &ts, fs.luma, H, W, Wp, FS_BOXW, bs))) return rc;
+        if ((rc = make_tmap(ctx, &tt, ft.luma, H, W, Wp, FS_BOXW, pl->box_h))) return rc;
+        FsParams p;
+        p.H = H; p.W = W; p.bs = bs; p.R = R; p.Rp = (R + 3) & ~3; p.m = bs / 8; p.nbr = nbr; p.nbc = nbc;
+        p.n_tiles = pl->n_tiles; p.box_h = pl->box_h;
+        p.n_stages = fs_smem_bytes(bs, pl->box_h, 2, pl->G) <= 220 * 1024 ? 2 : 1;
+        p.tiles = pl->d_tiles; p.out_vec = out->vec; p.out_sad = out->sad;
+        p.redo_list = ctx->d_redo_list; p.counters = ctx->d_counters; p.redo_cap = ctx->redo_cap;
+        const int smem = fs_smem_bytes(bs, pl->box_h, p.n_stages, pl->G);
+        if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        switch (pl->G) {
+        case 5: rc = fs_launch_tiled<5>(ctx, ts, tt, p, smem); break;
+        case 8: rc = fs_launch_tiled<8>(ctx, ts, tt, p, smem); break;
+        case 13: rc = fs_launch_tiled<13>(ctx, ts, tt, p, smem); break;
+        default: rc = fs_launch_tiled<11>(ctx, ts, tt, p, smem); break;
+        }
+        if (rc) return rc;
+        if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->fs_timed = 1; }
+        // exact pass over the (normally few) blocks on the redo list
+        fs_generic_kernel<<<ctx->num_sms, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbr, nbc,
+                                                                 ctx->d_redo_list, ctx->d_counters, out->vec, out->sad);
+        CKL(ctx);
+    } else {
+        if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        fs_generic_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbr, nbc,
+                                                                     nullptr, nullptr, out->vec, out->sad);
+        CKL(ctx);
+        if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->fs_timed = 1; }
+    }
+    out->valid = 1;
+    return MEMCI_OK;
+}

@@ -1,0 +1,398 @@
+// Motion-compensated interpolation: MCI/Unidirectional.py:36-84 and MCI/Bidirectional.py:27-77.
+//
+// The reference is a raster-order SCATTER: every source pixel p splats forward (and backward)
+// onto q = p + round(mv * dist), and what lands on q depends on the ORDER of arrival (strict /
+// non-strict SAD priority, SAD-weighted blend with whatever is already there).  We restate it
+// as an order-preserving GATHER, one thread per target pixel q:
+//
+//   * an "event" at q is a (source pixel p, direction) pair whose splat hits q;
+//   * events reach q in raster order of p, forward before backward at the same p;
+//   * with e = q - p the effective displacement (wrap-around of negative targets folded in,
+//     W1), raster order of p is DESCENDING lexicographic order of e -- independent of q.
+//
+// So each 32x8 tile of targets collects the set of distinct (e, direction) values of the MV
+// cells that can reach it (MVs are piecewise constant on cells, so the set is tiny: ~2-6
+// entries for coherent motion), sorts it once, and every pixel walks that sorted list, testing
+// "does the pixel at q - e really carry displacement e?" and replaying the reference's state
+// machine (SAD_interpolated_frame / Interpolated_Frame) in registers.  Holes (pixels no event
+// reached) are recorded and filled by a second kernel with the 21x21 masked median.
+#include "memci_internal.cuh"
+
+#define MCI_TW 32
+#define MCI_TH 8
+#define MCI_NT (MCI_TW * MCI_TH)
+#define MCI_SLOTS 1024
+#define MCI_MAXKEYS 768
+#define MCI_EMPTY 0xffffffffu
+#define MCI_KOFF 8191
+
+struct MciParams {
+    int H, W, bidir, ndir;
+    float dist;
+    const uint8_t *src, *tgt;
+    uint8_t *out, *mask;
+    int *hole_list, *counters;
+    const short2 *disp[2];
+    int cell[2], cols[2];
+    const float *sad[2];
+    int scell[2], scols[2];
+};
+
+// ---- per-cell integer displacement ---------------------------------------------------------
+// forward : int(round(mv * dist))        f32 product, round-half-even  (Unidirectional.py:48-49,
+//                                         Bidirectional.py:34-35; W1)
+// backward: int(round(mv * (1.0 - dist))) f64 product                   (Bidirectional.py:42-44; W2)
+__global__ void mci_disp_kernel(const float2 *__restrict__ vec, int n, float dist, int backward,
+                                short2 *__restrict__ disp, int *__restrict__ dmax)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int m = 0;
+    if (i < n) {
+        float2 v = vec[i];
+        int dr, dc;
+        if (!backward) {
+            dr = (int)rintf(__fmul_rn(v.x, dist));
+            dc = (int)rintf(__fmul_rn(v.y, dist));
+        } else {
+            double bw = __dsub_rn(1.0, (double)dist);
+            dr = (int)rint(__dmul_rn((double)v.x, bw));
+            dc = (int)rint(__dmul_rn((double)v.y, bw));
+        }
+        dr = max(-32767, min(32767, dr));
+        dc = max(-32767, min(32767, dc));
+        disp[i] = make_short2((short)dr, (short)dc);
+        m = max(abs(dr), abs(dc));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(dmax, m);
+}
+
+// ---- per-pixel state machine -----------------------------------------------------------------
+struct PixState {
+    int v0, v1, v2;      // Interpolated_Frame[q] (int32, -1 = hole)
+    float sadi;          // SAD_interpolated_frame[q]
+    bool written;
+};
+
+__device__ __forceinline__ void mci_try_event(const MciParams &P, PixState &st, int q_r, int q_c,
+                                              int eff_r, int eff_c, int dir)
+{
+    const int p_r = q_r - eff_r, p_c = q_c - eff_c;
+    if (p_r < 0 || p_r >= P.H || p_c < 0 || p_c >= P.W) return;
+    const short2 d = P.disp[dir][(size_t)(p_r / P.cell[dir]) * P.cols[dir] + p_c / P.cell[dir]];
+    const int u_i = p_r + d.x, v_i = p_c + d.y;
+    bool self_write = false;
+    if (u_i < P.H && v_i < P.W) {                       // Unidirectional.py:51, Bidirectional.py:36/45
+        const int t_r = u_i < 0 ? u_i + P.H : u_i;      // negative index wraps (W1)
+        const int t_c = v_i < 0 ? v_i + P.W : v_i;
+        if (t_r != q_r || t_c != q_c) return;
+    } else {
+        // unidir only: out-of-frame target writes the pixel onto itself, unconditionally (:56-58)
+        if (P.bidir || eff_r != 0 || eff_c != 0) return;
+        self_write = true;
+    }
+    const float sad = P.sad[dir][(size_t)(p_r / P.scell[dir]) * P.scols[dir] + p_c / P.scell[dir]];
+    const uint8_t *px = (dir == 0 ? P.src : P.tgt) + ((size_t)p_r * P.W + p_c) * 3;
+    if (!P.bidir) {
+        if (self_write || sad <= st.sadi) {             // :52 (non-strict)
+            st.v0 = px[0]; st.v1 = px[1]; st.v2 = px[2];
+            st.sadi = sad; st.written = true;
+        }
+    } else if (dir == 0) {
+        if (sad < st.sadi) {                            // :37 (strict)
+            st.v0 = px[0]; st.v1 = px[1]; st.v2 = px[2];
+            st.sadi = sad; st.written = true;
+        }
+    } else {
+        if (sad < st.sadi) {                            // :46
+            if (st.sadi != __int_as_float(0x7f800000)) {
+                // :48-49.  numba types the fused expression float32:
+                //   f32( f64( f32(u8*SADI) / t ) + f64(IF) * f64(bsad) / f64(t) ), truncated to int32 (W3)
+                const float t = __fadd_rn(sad, st.sadi);
+                const double td = (double)t, bd = (double)sad;
+                int v[3] = {st.v0, st.v1, st.v2};
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    float a = __fdiv_rn(__fmul_rn((float)px[ch], st.sadi), t);
+                    double c = __ddiv_rn(__dmul_rn((double)v[ch], bd), td);
+                    float s = __double2float_rn(__dadd_rn((double)a, c));
+                    v[ch] = __float2int_rz(s);
+                }
+                st.v0 = v[0]; st.v1 = v[1]; st.v2 = v[2];
+            } else {                                    // :51-53
+                st.v0 = px[0]; st.v1 = px[1]; st.v2 = px[2];
+            }
+            st.sadi = sad; st.written = true;
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned mci_key(int eff_r, int eff_c, int dir)
+{
+    return ((unsigned)(MCI_KOFF - eff_r) << 15) | ((unsigned)(MCI_KOFF - eff_c) << 1) | (unsigned)dir;
+}
+
+__global__ void __launch_bounds__(MCI_NT)
+mci_splat_kernel(const MciParams P)
+{
+    __shared__ unsigned table[MCI_SLOTS];
+    __shared__ unsigned list[MCI_MAXKEYS];
+    __shared__ unsigned sorted[MCI_MAXKEYS];
+    __shared__ int n_keys, overflow;
+
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * MCI_TW, ty0 = blockIdx.y * MCI_TH;
+    const int q_c = tx0 + (tid & 31), q_r = ty0 + (tid >> 5);
+    const int H = P.H, W = P.W;
+    const int dmax = P.counters[2];
+    const bool keys_fit = (H + dmax <= MCI_KOFF) && (W + dmax <= MCI_KOFF) && dmax <= MCI_KOFF;
+
+    for (int i = tid; i < MCI_SLOTS; i += MCI_NT) table[i] = MCI_EMPTY;
+    if (tid == 0) { n_keys = 0; overflow = keys_fit ? 0 : 1; }
+    __syncthreads();
+
+    if (keys_fit) {
+        // ---- 1. distinct (effective displacement, direction) values that can reach this tile ----
+        for (int dir = 0; dir < P.ndir; ++dir) {
+            const int g = P.cell[dir];
+            for (int wr = 0; wr < 2; ++wr) {
+                int lo_r = ty0 - wr * H - dmax, hi_r = ty0 + MCI_TH - 1 - wr * H + dmax;
+                if (wr) hi_r = min(hi_r, dmax - 1);       // wrapping needs u + dr < 0
+                lo_r = max(lo_r, 0); hi_r = min(hi_r, H - 1);
+                if (lo_r > hi_r) continue;
+                for (int wc = 0; wc < 2; ++wc) {
+                    int lo_c = tx0 - wc * W - dmax, hi_c = tx0 + MCI_TW - 1 - wc * W + dmax;
+                    if (wc) hi_c = min(hi_c, dmax - 1);
+                    lo_c = max(lo_c, 0); hi_c = min(hi_c, W - 1);
+                    if (lo_c > hi_c) continue;
+                    const int cr_lo = lo_r / g, cr_hi = hi_r / g, cc_lo = lo_c / g, cc_hi = hi_c / g;
+                    const int ncc = cc_hi - cc_lo + 1, ncell = (cr_hi - cr_lo + 1) * ncc;
+                    for (int i = tid; i < ncell; i += MCI_NT) {
+                        const int cr = cr_lo + i / ncc, cc = cc_lo + i % ncc;
+                        const short2 d = P.disp[dir][(size_t)cr * P.cols[dir] + cc];
+                        const int eff_r = d.x + wr * H, eff_c = d.y + wc * W;
+                        const int pr0 = cr * g, pr1 = min(H, pr0 + g) - 1;
+                        const int pc0 = cc * g, pc1 = min(W, pc0 + g) - 1;
+                        // conservative footprint test (the per-pixel test below is exact)
+                        if (pr1 + eff_r < ty0 || pr0 + eff_r > ty0 + MCI_TH - 1) continue;
+                        if (pc1 + eff_c < tx0 || pc0 + eff_c > tx0 + MCI_TW - 1) continue;
+                        if (wr ? (pr0 + d.x >= 0) : (pr1 + d.x < 0)) continue;
+                        if (wc ? (pc0 + d.y >= 0) : (pc1 + d.y < 0)) continue;
+                        const unsigned key = mci_key(eff_r, eff_c, dir);
+                        unsigned h = (key * 2654435761u) >> 22;          // 10 bits
+                        bool done = false;
+                        for (int probe = 0; probe < MCI_SLOTS && !done; ++probe) {
+                            unsigned prev = atomicCAS(&table[h], MCI_EMPTY, key);
+                            if (prev == MCI_EMPTY || prev == key) done = true;
+                            else h = (h + 1) & (MCI_SLOTS - 1);
+                        }
+                        if (!done) overflow = 1;
+                    }
+                }
+            }
+        }
+        // the unidirectional self-write lives at e = (0,0) and has no footprint of its own
+        if (!P.bidir && tid == 0) {
+            const unsigned key = mci_key(0, 0, 0);
+            unsigned h = (key * 2654435761u) >> 22;
+            bool done = false;
+            for (int probe = 0; probe < MCI_SLOTS && !done; ++probe) {
+                unsigned prev = atomicCAS(&table[h], MCI_EMPTY, key);
+                if (prev == MCI_EMPTY || prev == key) done = true;
+                else h = (h + 1) & (MCI_SLOTS - 1);
+            }
+            if (!done) overflow = 1;
+        }
+        __syncthreads();
+        // ---- 2. compact + rank-sort (ascending key = raster order of the source pixel) ----
+        for (int i = tid; i < MCI_SLOTS; i += MCI_NT) {
+            unsigned k = table[i];
+            if (k != MCI_EMPTY) {
+                int pos = atomicAdd(&n_keys, 1);
+                if (pos < MCI_MAXKEYS) list[pos] = k; else overflow = 1;
+            }
+        }
+        __syncthreads();
+        if (!overflow) {
+            const int n = n_keys;
+            for (int i = tid; i < n; i += MCI_NT) {
+                const unsigned k = list[i];
+                int rank = 0;
+                for (int j = 0; j < n; ++j) rank += list[j] < k;
+                sorted[rank] = k;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- 3. replay the splat for this target pixel ----
+    const bool inside = q_r < H && q_c < W;
+    PixState st;
+    st.v0 = st.v1 = st.v2 = -1;
+    st.sadi = __int_as_float(0x7f800000);
+    st.written = false;
+    if (inside) {
+        if (!overflow) {
+            const int n = n_keys;
+            for (int i = 0; i < n; ++i) {
+                const unsigned k = sorted[i];
+                mci_try_event(P, st, q_r, q_c, MCI_KOFF - (int)(k >> 15), MCI_KOFF - (int)((k >> 1) & 16383u), (int)(k & 1u));
+            }
+        } else {
+            // dense fallback: enumerate every possible displacement in source-raster order
+            // (wrapped rows/cols first: they come from the smallest source coordinates)
+            // e in [H-dmax, H-1] (wrapped) then [dmax, -dmax] (direct), each value visited once
+            for (int eff_r = q_r; eff_r >= -dmax; --eff_r) {
+                if (eff_r > dmax && eff_r < H - dmax) { eff_r = dmax + 1; continue; }
+                if (q_r - eff_r >= H) break;
+                for (int eff_c = q_c; eff_c >= -dmax; --eff_c) {
+                    if (eff_c > dmax && eff_c < W - dmax) { eff_c = dmax + 1; continue; }
+                    if (q_c - eff_c >= W) break;
+                    for (int dir = 0; dir < P.ndir; ++dir) mci_try_event(P, st, q_r, q_c, eff_r, eff_c, dir);
+                }
+            }
+        }
+        const size_t q = (size_t)q_r * W + q_c;
+        uint8_t *o = P.out + q * 3;
+        o[0] = (uint8_t)st.v0; o[1] = (uint8_t)st.v1; o[2] = (uint8_t)st.v2;     // New_IF = uint8(IF)  (:65 / :57)
+        P.mask[q] = st.written ? 0 : 1;
+    }
+    // hole list, one atomic per warp
+    const bool hole = inside && !st.written;
+    const unsigned bal = __ballot_sync(0xffffffffu, hole);
+    if (bal) {
+        const int lane = tid & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&P.counters[1], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hole) P.hole_list[base + __popc(bal & ((1u << lane) - 1u))] = q_r * W + q_c;
+    }
+}
+
+// ---- hole filling: Unidirectional.py:62-80 / Bidirectional.py:55-73 -----------------------------
+// Holes are visited in raster order by the reference; each is first overwritten with the target
+// frame's pixel, then gets the per-channel median of the non-hole values in its clipped 21x21
+// window.  Equivalent rule for hole h (W6): a window pixel contributes its splat value if it is
+// not a hole, the TARGET-frame pixel if it is a hole at raster <= h, nothing otherwise.
+// np.median: middle element, or the f64 mean of the two middles truncated on the uint8 store.
+// One warp per hole; the k-th smallest byte is found by bisection on the value.
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void mci_holefill_kernel(const uint8_t *__restrict__ tgt, uint8_t *out, const uint8_t *__restrict__ mask,
+                                    const int *__restrict__ hole_list, const int *__restrict__ counters, int H, int W)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int n_holes = counters[1];
+    for (int hi = warp; hi < n_holes; hi += nwarps) {
+        const int h = hole_list[hi];
+        const int u = h / W, v = h - u * W;
+        const int u0 = max(0, u - 10), u1 = min(H, u + 11), v0 = max(0, v - 10), v1 = min(W, v + 11);
+        const int ww = v1 - v0, total = (u1 - u0) * ww;
+        unsigned vals[14];
+        int cnt = 0;
+#pragma unroll
+        for (int s = 0; s < 14; ++s) {
+            const int e = lane + 32 * s;
+            unsigned pk = 0u;
+            if (e < total) {
+                const int a = u0 + e / ww, b = v0 + e % ww;
+                const int idx = a * W + b;
+                const uint8_t *p = nullptr;
+                if (!mask[idx]) p = out + (size_t)idx * 3;
+                else if (idx <= h) p = tgt + (size_t)idx * 3;
+                if (p) { pk = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | 0x01000000u; ++cnt; }
+            }
+            vals[s] = pk;
+        }
+        const int n = warp_sum(cnt);                 // >= 1: the hole itself contributes
+        const int k_lo = (n - 1) >> 1, k_hi = n >> 1;
+        unsigned res[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const int sh = 8 * ch;
+            int lo = 0, hi2 = 255;
+            while (lo < hi2) {                       // smallest value with count(<= value) >= k_lo + 1
+                const int mid = (lo + hi2) >> 1;
+                int c = 0;
+#pragma unroll
+                for (int s = 0; s < 14; ++s) c += (vals[s] >> 24) && (int)((vals[s] >> sh) & 255u) <= mid;
+                c = warp_sum(c);
+                if (c >= k_lo + 1) hi2 = mid; else lo = mid + 1;
+            }
+            int v_lo = lo, v_hi = lo;
+            if (k_hi != k_lo) {
+                int c = 0, mn = 256;
+#pragma unroll
+                for (int s = 0; s < 14; ++s) {
+                    const int x = (int)((vals[s] >> sh) & 255u);
+                    const bool ok = vals[s] >> 24;
+                    c += ok && x <= v_lo;
+                    if (ok && x > v_lo) mn = min(mn, x);
+                }
+                c = warp_sum(c);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                if (c < k_hi + 1) v_hi = mn;
+            }
+            res[ch] = (unsigned)((v_lo + v_hi) >> 1);   // (a+b)/2.0 truncated; == v_lo when n is odd
+        }
+        if (lane == 0) {
+            uint8_t *o = out + (size_t)h * 3;
+            o[0] = (uint8_t)res[0]; o[1] = (uint8_t)res[1]; o[2] = (uint8_t)res[2];
+        }
+    }
+}
+
+int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd, const MVField *bwd,
+                  float dist, int out_slot, int bidir)
+{
+    const int H = ctx->H, W = ctx->W;
+    const MVField *fl[2] = {fwd, bwd};
+    const int ndir = bidir ? 2 : 1;
+    int rc;
+    CK(ctx, cudaMemsetAsync(ctx->d_counters + 1, 0, 2 * sizeof(int), ctx->stream));
+    MciParams P;
+    memset(&P, 0, sizeof(P));
+    for (int d = 0; d < ndir; ++d) {
+        const MVField *f = fl[d];
+        size_t n = (size_t)f->mv_rows * f->mv_cols;
+        if ((rc = memci_reserve(ctx, (void **)&ctx->d_disp[d], &ctx->disp_cap[d], n * sizeof(short2)))) return rc;
+        mci_disp_kernel<<<ceil_div_i((int)n, 256), 256, 0, ctx->stream>>>(f->vec, (int)n, dist, d, ctx->d_disp[d],
+                                                                          ctx->d_counters + 2);
+        CKL(ctx);
+        P.disp[d] = ctx->d_disp[d]; P.cell[d] = f->mv_cell; P.cols[d] = f->mv_cols;
+        P.sad[d] = f->sad; P.scell[d] = f->sad_cell; P.scols[d] = f->sad_cols;
+    }
+    size_t npx = (size_t)H * W;
+    if (ctx->hole_cap < npx) {
+        if (ctx->d_hole_mask) cudaFree(ctx->d_hole_mask);
+        if (ctx->d_hole_list) cudaFree(ctx->d_hole_list);
+        ctx->d_hole_mask = nullptr; ctx->d_hole_list = nullptr; ctx->hole_cap = 0;
+        CK(ctx, cudaMalloc(&ctx->d_hole_mask, npx));
+        CK(ctx, cudaMalloc(&ctx->d_hole_list, npx * sizeof(int)));
+        ctx->hole_cap = npx;
+    }
+    P.H = H; P.W = W; P.bidir = bidir; P.ndir = ndir; P.dist = dist;
+    P.src = ctx->frames[slot_src].rgb; P.tgt = ctx->frames[slot_tgt].rgb;
+    P.out = ctx->frames[out_slot].rgb; P.mask = ctx->d_hole_mask;
+    P.hole_list = ctx->d_hole_list; P.counters = ctx->d_counters;
+    dim3 grid(ceil_div_i(W, MCI_TW), ceil_div_i(H, MCI_TH));
+    ctx->mci_timed = 0;
+    if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    mci_splat_kernel<<<grid, MCI_NT, 0, ctx->stream>>>(P);
+    CKL(ctx);
+    if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->mci_timed = 1; }
+    mci_holefill_kernel<<<ctx->num_sms * 4, 128, 0, ctx->stream>>>(P.tgt, P.out, P.mask, P.hole_list, P.counters, H, W);
+    CKL(ctx);
+    FrameSlot &o = ctx->frames[out_slot];
+    o.valid = 1; o.luma_ok = 0; o.pyr_levels = 0;
+    return MEMCI_OK;
+}

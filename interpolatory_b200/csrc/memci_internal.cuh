@@ -1,0 +1,168 @@
+// Internal declarations shared by the CUDA translation units of libmemci_b200.so.
+// Not part of the ABI (see include/memci_b200.h for that).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/memci_b200.h"
+
+#define MEMCI_MAX_PYR 12
+
+struct MVField {
+    int valid;
+    int mv_cell, mv_rows, mv_cols;     // (dy,dx) grid: value of pixel (r,c) = vec[(r/mv_cell)*mv_cols + c/mv_cell]
+    int sad_cell, sad_rows, sad_cols;  // SAD grid (stays on ME blocks after smoothing)
+    float2 *vec;  size_t vec_cap;      // elements
+    float *sad;   size_t sad_cap;
+};
+
+struct FrameSlot {
+    int valid;
+    uint8_t *rgb;                      // [H][W][3]
+    int32_t *luma;                     // [H][Wp] luma*1000 = 299R+587G+114B (exact integer)
+    int luma_ok;
+    // HBMA pyramid cache (levels 1..pyr_levels), invalidated on upload
+    int pyr_levels;
+    uint8_t *pyr_rgb[MEMCI_MAX_PYR + 1];
+    int32_t *pyr_luma[MEMCI_MAX_PYR + 1];
+    size_t pyr_cap[MEMCI_MAX_PYR + 1];
+};
+
+struct FsTile { int by, bx0, nb, pad; };
+
+struct FsPlan {                        // cached per (bs, R): tile table + tensor maps
+    int bs, R, G, box_w, box_h, n_tiles, nb_max, valid;
+    FsTile *d_tiles;
+    long long n_cand;
+};
+
+struct memci_ctx {
+    int device, H, W, Wp;
+    cudaStream_t stream;
+    int own_stream;
+    int num_sms;
+    FrameSlot frames[MEMCI_NUM_FRAME_SLOTS];
+    MVField mvs[MEMCI_NUM_MV_SLOTS];
+    MVField tmp_mv[2];                 // HBMA ping-pong
+    // full-search scratch
+    int *d_redo_list; int redo_cap; int *d_counters;   // [0] redo count, [1] hole count, [2] dmax, [3] tile counter
+    FsPlan fs_plan[4];
+    long long fs_last_cand, fs_last_ops;
+    // MCI scratch
+    short2 *d_disp[2]; size_t disp_cap[2];
+    uint8_t *d_hole_mask; int *d_hole_list; size_t hole_cap;
+    float *d_dense; size_t dense_cap;  // dense MV staging for download/upload
+    // timing
+    int timing; cudaEvent_t ev[4]; int fs_timed, mci_timed;
+    long long launches;
+    int sticky;                        // sticky CUDA error
+    char err[512];
+};
+
+// ---- error handling --------------------------------------------------------------
+int memci_fail(memci_ctx *ctx, int code, const char *fmt, ...);
+#define CK(ctx, call)                                                                   \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            if (ctx) (ctx)->sticky = 1;                                                 \
+            return memci_fail(ctx, MEMCI_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__,  \
+                              #call, cudaGetErrorString(e__));                          \
+        }                                                                               \
+    } while (0)
+#define CKL(ctx) do { (ctx)->launches++; CK(ctx, cudaGetLastError()); } while (0)
+
+int memci_reserve(memci_ctx *ctx, void **ptr, size_t *cap, size_t need_bytes);   // grow-only device buffer
+int memci_mv_reserve(memci_ctx *ctx, MVField *f, int mv_cell, int mv_rows, int mv_cols,
+                     int sad_cell, int sad_rows, int sad_cols);
+
+// ---- stage entry points (host side, enqueue on ctx->stream) -------------------------
+int memci_luma_plane(memci_ctx *ctx, const uint8_t *rgb, int H, int W, int Wp, int32_t *luma);
+int memci_ensure_luma(memci_ctx *ctx, int slot);
+int memci_ensure_pyramid(memci_ctx *ctx, int slot, int levels);
+int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out);
+int memci_hbma_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int win, int sub, int steps,
+                   int min_bs, int cost_key, MVField *out);
+int memci_smooth_run(memci_ctx *ctx, const MVField *in, int mode, int fsz, MVField *out);
+int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd, const MVField *bwd,
+                  float dist, int out_slot, int bidir);
+int memci_mv_to_dense(memci_ctx *ctx, const MVField *f, float *d_dense);
+int memci_dense_to_mv(memci_ctx *ctx, const float *d_dense, MVField *f);
+
+static inline int ceil_div_i(int a, int b) { return (a + b - 1) / b; }
+
+// ---- device helpers ----------------------------------------------------------------
+#ifdef __CUDACC__
+
+// luma*1000 as an exact integer (<= 255000, 18 bits).  SAD_ref = trunc(sum|dL|) relates to
+// S1000 = sum |dL1000| by  SAD_ref = S1000 / 1000  unless S1000 % 1000 == 0.
+__device__ __forceinline__ int luma1000(int r, int g, int b) { return 299 * r + 587 * g + 114 * b; }
+
+// Luma exactly as the reference's numba code evaluates it (f64, separate mul/add, N1):
+// ME/full_search.py:15-16, ME/hbma.py:20-21.
+__device__ __forceinline__ double luma_f64(int r, int g, int b)
+{
+    double t0 = __dmul_rn(0.299, (double)r);
+    double t1 = __dmul_rn(0.587, (double)g);
+    double t2 = __dmul_rn(0.114, (double)b);
+    return __dadd_rn(__dadd_rn(t0, t1), t2);
+}
+
+// Exact replay of get_sad / get_cost in the reference's operation order: sequential
+// row-major f64 accumulation from 0.0.  Pixels outside the frame read as 0 (np.pad).
+// cost_key 0 = SAD (full_search.py:17 / hbma.py:22), 1 = SSD (hbma.py:28).
+__device__ inline double exact_cost_f64(const uint8_t *__restrict__ A, const uint8_t *__restrict__ B,
+                                        int H, int W, int ar, int ac, int br, int bc, int bs, int cost_key)
+{
+    double acc = 0.0;
+    for (int i = 0; i < bs; ++i) {
+        for (int j = 0; j < bs; ++j) {
+            int r1 = ar + i, c1 = ac + j, r2 = br + i, c2 = bc + j;
+            double l1 = 0.0, l2 = 0.0;
+            if (r1 < H && c1 < W) {
+                const uint8_t *p = A + ((size_t)r1 * W + c1) * 3;
+                l1 = luma_f64(p[0], p[1], p[2]);
+            }
+            if (r2 < H && c2 < W) {
+                const uint8_t *p = B + ((size_t)r2 * W + c2) * 3;
+                l2 = luma_f64(p[0], p[1], p[2]);
+            }
+            double d = __dsub_rn(l1, l2);
+            acc = cost_key == 0 ? __dadd_rn(acc, fabs(d)) : __dadd_rn(acc, __dmul_rn(d, d));
+        }
+    }
+    return acc;
+}
+
+// Integer SAD of luma1000 planes over a bs x bs block with zero padding outside the frame.
+__device__ inline unsigned int sad1000_global(const int32_t *__restrict__ LA, const int32_t *__restrict__ LB,
+                                              int H, int W, int Wp, int ar, int ac, int br, int bc, int bs)
+{
+    unsigned int s = 0;
+    for (int i = 0; i < bs; ++i) {
+        int r1 = ar + i, r2 = br + i;
+        for (int j = 0; j < bs; ++j) {
+            int c1 = ac + j, c2 = bc + j;
+            int a = (r1 < H && c1 < W) ? LA[(size_t)r1 * Wp + c1] : 0;
+            int b = (r2 < H && c2 < W) ? LB[(size_t)r2 * Wp + c2] : 0;
+            s = __sad(a, b, s);
+        }
+    }
+    return s;
+}
+
+__device__ __forceinline__ unsigned long long shfl_min_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w < v ? w : v;
+    }
+    return v;
+}
+
+#endif  // __CUDACC__

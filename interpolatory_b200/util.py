@@ -1,0 +1,62 @@
+"""Host-side helpers that define `dist` and the settings string (reference: src/util.py)."""
+import math
+import sys
+
+import numpy as np
+
+
+def eprint(s):
+    print(s, file=sys.stderr)
+
+
+def get_first_frame_idx_and_ratio(idx, rate_ratio):
+    """(index of the last source frame at or before output frame `idx`, 1 - fractional position).
+
+    Bit-identical to src/util.py:49-60 under its numba signature (int32, float32) ->
+    (int32, float32): rate_ratio is rounded to float32 on entry, the division and the
+    subtraction run in float64, the ratio is rounded to float32 on return (and comes back to
+    Python as a float).  The caller's `dist = 1. - ratio` therefore reproduces the reference's
+    0x3ecccccc / 0x3f4ccccd / ... cycle.
+    """
+    rr = float(np.float32(rate_ratio))
+    q = float(int(idx)) / rr
+    first = math.floor(q)
+    return first, float(np.float32(1.0 - (q - first)))
+
+
+def deconstruct_settings(s):
+    """'key=val.key=val' -> dict of strings (src/util.py:65-80); malformed pairs are reported and skipped."""
+    out = {}
+    for pair in s.split('.'):
+        kv = pair.split('=')
+        if len(kv) != 2:
+            eprint(f'Ignoring {pair}, malformed input')
+            continue
+        k, v = kv
+        if k and v:
+            out[k] = v
+        else:
+            eprint(f'Ignoring {k} {v}, malformed input')
+    return out
+
+
+def deconstruct_interpolation_mode_and_settings(s):
+    """'<mode>[:<settings>]' -> (mode, settings dict)  (src/util.py:83-92)."""
+    parts = s.split(':')
+    if len(parts) == 1:
+        return parts[0], {}
+    if len(parts) == 2:
+        return parts[0], deconstruct_settings(parts[1])
+    eprint(f'Invalid interpolation-mode and settings config: {s}')
+    raise SystemExit(1)
+
+
+def hbma_auto_steps(shape):
+    """Pyramid depth rule applied by the interpolator classes before calling HBMA
+    (MCI/Unidirectional.py:116-121, MCI/Bidirectional.py:144-149): 1080p -> 4, 360p -> 2."""
+    min_side = min(shape[0], shape[1])
+    steps = 1
+    while min_side > 255:
+        min_side /= 2
+        steps += 1
+    return steps

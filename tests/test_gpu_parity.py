@@ -1,0 +1,253 @@
+"""Parity proper: the CUDA path, called through the C ABI (ctypes) and through the mirrored
+reference interface, against the CPU oracle on seeded inputs and against the committed golden
+fixtures (outputs of the unmodified reference).  Bar: bit-exact (np.array_equal) everywhere."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from interpolatory_b200.synth import make_sequence  # noqa: E402
+
+
+def sha(a):
+    a = np.ascontiguousarray(a)
+    return hashlib.sha256(a.tobytes()).hexdigest() + f":{a.dtype}:{'x'.join(map(str, a.shape))}"
+
+
+def blocks_of(dense, bs):
+    return np.ascontiguousarray(dense[::bs, ::bs])
+
+
+@pytest.fixture(scope="module")
+def gpu(native_lib):
+    import interpolatory_b200 as pkg
+    return pkg
+
+
+SHAPES = [(72, 96), (50, 70), (37, 53)]
+FS_CFGS = [(8, 7), (8, 3), (4, 5), (16, 9), (8, 16)]
+HB_CFGS = [(8, 7, 1, 2, 4), (8, 3, 1, 1, 4), (8, 5, 2, 3, 2), (4, 2, 1, 1, 4), (16, 4, 1, 1, 4)]
+DISTS = [0.5, 0.39999998, 0.8, 0.19999999, 0.6]
+
+
+# ---------------------------------------------------------------- golden fixtures (reference outputs)
+@pytest.mark.parametrize("shape", SHAPES)
+def test_fs_vs_golden(gpu, golden, shape):
+    from interpolatory_b200.ME.full_search import get_motion_vectors as fs
+    g = golden("functions_small.npz")
+    k = f"{shape[0]}x{shape[1]}"
+    a, b = g[f"{k}/a"], g[f"{k}/b"]
+    for bs, R in FS_CFGS:
+        mv = fs(bs, R, a, b)
+        assert mv.dtype == np.float32 and mv.shape == a.shape
+        assert np.array_equal(blocks_of(mv, bs), g[f"{k}/fs/{bs}_{R}"]), (shape, bs, R)
+    assert np.array_equal(fs(8, 7, a, b), g[f"{k}/fs_dense/8_7"])
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_hbma_vs_golden(gpu, golden, shape):
+    from interpolatory_b200.ME.hbma import get_motion_vectors as hbma
+    g = golden("functions_small.npz")
+    k = f"{shape[0]}x{shape[1]}"
+    a, b = g[f"{k}/a"], g[f"{k}/b"]
+    for cfg in HB_CFGS:
+        mv = hbma(*cfg, a, b, 'sad', False)
+        ref = g[f"{k}/hbma/{'_'.join(map(str, cfg))}"]
+        assert mv.shape == ref.shape and np.array_equal(mv, ref), (shape, cfg)
+    assert np.array_equal(hbma(8, 7, 1, 2, 4, a, b), g[f"{k}/hbma_dense/8_7_1_2_4"])
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_pyramid_vs_golden(gpu, golden, shape):
+    from interpolatory_b200.device import get_context
+    g = golden("functions_small.npz")
+    k = f"{shape[0]}x{shape[1]}"
+    ctx = get_context(*shape)
+    ctx.upload_frame(0, g[f"{k}/a"])
+    for lvl in (1, 2):
+        assert np.array_equal(ctx.pyramid_level(0, lvl), g[f"{k}/pyr/{lvl}"]), (shape, lvl)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_smooth_vs_golden(gpu, golden, oracle, shape):
+    from interpolatory_b200.smoothing import smooth, mean_filter, median_filter, weighted_mean_filter
+    g = golden("functions_small.npz")
+    k = f"{shape[0]}x{shape[1]}"
+    a, b = g[f"{k}/a"], g[f"{k}/b"]
+    fields = {"fs": g[f"{k}/fs_dense/8_7"], "hbma": g[f"{k}/hbma_dense/8_7_1_2_4"]}
+    for name, f in (("mean", mean_filter), ("median", median_filter), ("weighted", weighted_mean_filter)):
+        for fsz in (4, 8, 3):
+            for nm, mv in fields.items():
+                out = smooth(f, mv, fsz)
+                assert np.array_equal(out[:, :, :2], g[f"{k}/smooth/{name}_{fsz}/{nm}"]), (shape, name, fsz, nm)
+                assert np.array_equal(out[:, :, 2], mv[:, :, 2])
+    assert smooth(None, fields["fs"], 4) is fields["fs"]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_mci_vs_golden(gpu, golden, oracle, shape):
+    from interpolatory_b200.MCI.Unidirectional import helper as uni
+    from interpolatory_b200.MCI.Bidirectional import helper as bi
+    g = golden("functions_small.npz")
+    k = f"{shape[0]}x{shape[1]}"
+    H, W = shape
+    a, b = g[f"{k}/a"], g[f"{k}/b"]
+    fwd = g[f"{k}/fs_dense/8_7"]
+    bwd = oracle.fs(8, 7, b, a)
+    fwh = g[f"{k}/hbma_dense/8_7_1_2_4"]
+    bwh = oracle.hbma(8, 7, 1, 2, 4, b, a)
+    for dist in DISTS:
+        d = np.float32(dist)
+        assert np.array_equal(uni(a, b, fwd, d), g[f"{k}/unidir/fs/{dist}"]), (shape, dist)
+        assert np.array_equal(bi(a, b, fwd, bwd, d), g[f"{k}/bidir/fs/{dist}"]), (shape, dist)
+        assert np.array_equal(uni(a, b, fwh, d), g[f"{k}/unidir/hbma/{dist}"]), (shape, dist)
+        assert np.array_equal(bi(a, b, fwh, bwh, d), g[f"{k}/bidir/hbma/{dist}"]), (shape, dist)
+    # adversarial block-constant random fields: wraps, out-of-frame targets, fractional vectors
+    for trial in range(3):
+        gsz = int(g[f"{k}/rand/{trial}/g"])
+        f_ = np.kron(g[f"{k}/rand/{trial}/fwd"], np.ones((gsz, gsz, 1), np.float32))[:H, :W].copy()
+        b_ = np.kron(g[f"{k}/rand/{trial}/bwd"], np.ones((gsz, gsz, 1), np.float32))[:H, :W].copy()
+        for dist in (0.5, 0.39999998, 0.8):
+            d = np.float32(dist)
+            assert np.array_equal(uni(a, b, f_, d), g[f"{k}/rand/{trial}/unidir/{dist}"]), (shape, trial, dist)
+            assert np.array_equal(bi(a, b, f_, b_, d), g[f"{k}/rand/{trial}/bidir/{dist}"]), (shape, trial, dist)
+
+
+def test_middlebury_crops_vs_golden(gpu, golden):
+    from interpolatory_b200.ME.full_search import get_motion_vectors as fs
+    from interpolatory_b200.ME.hbma import get_motion_vectors as hbma
+    from interpolatory_b200.MCI.Unidirectional import helper as uni
+    from interpolatory_b200.MCI.Bidirectional import helper as bi
+    g = golden("middlebury_crops.npz")
+    for name in ("RubberWhale", "Dimetrodon"):
+        a, b = g[f"{name}/a"], g[f"{name}/b"]
+        fwd, bwd = fs(8, 7, a, b), fs(8, 7, b, a)
+        assert np.array_equal(blocks_of(fwd, 8), g[f"{name}/fs_fwd"])
+        assert np.array_equal(blocks_of(bwd, 8), g[f"{name}/fs_bwd"])
+        assert np.array_equal(hbma(8, 7, 1, 1, 4, a, b, 'sad', False), g[f"{name}/hbma_fwd"])
+        assert np.array_equal(bi(a, b, fwd, bwd, np.float32(0.5)), g[f"{name}/bidir"])
+        assert np.array_equal(uni(a, b, fwd, np.float32(0.5)), g[f"{name}/unidir"])
+
+
+def test_class_api_vs_golden(gpu, golden):
+    """MEMCI(...) factory + get_interpolated_frame over a whole clip: dist cycle, pass-through
+    frames, MV cache, auto pyramid depth, smoothing -- against the reference classes' output."""
+    import ast
+    from interpolatory_b200 import MEMCI, ArrayVideoStream
+    g = golden("e2e.npz")
+    keys = sorted({k.split("/")[0] for k in g.files})
+    for key in keys:
+        H, W = map(int, key.split("_")[0].split("x"))
+        fps_in, fps_out = int(key.split("_")[1]), int(key.split("_")[2])
+        seed = int(g[f"{key}/seed"])
+        nsrc = {72: 4, 56: 3, 264: 2}[H]
+        frames = make_sequence(H, W, nsrc, seed=seed)
+        assert sha(frames) == str(g[f"{key}/frames_sha"]), "synthetic generator drifted from the fixture"
+        for si in range(7):
+            if f"{key}/set{si}/settings" not in g.files:
+                continue
+            st = dict(ast.literal_eval(str(g[f"{key}/set{si}/settings"])))
+            it = MEMCI(fps_out, **st)
+            it.set_video_stream(ArrayVideoStream(list(frames), fps_in))
+            want = [str(s) for s in g[f"{key}/set{si}/out_sha"]]
+            for i, w in enumerate(want):
+                out = np.asarray(it.get_interpolated_frame(i))
+                assert sha(out) == w, (key, st, i)
+            it.close()
+
+
+def test_cfg1_360p_vs_golden(gpu, golden):
+    from interpolatory_b200.ME.full_search import get_motion_vectors as fs
+    from interpolatory_b200.ME.hbma import get_motion_vectors as hbma
+    from interpolatory_b200.MCI.Unidirectional import helper as uni
+    from interpolatory_b200.MCI.Bidirectional import helper as bi
+    g = golden("cfg1_360p.npz")
+    fr = make_sequence(360, 640, 2, seed=0)
+    assert sha(fr) == str(g["frames_sha"])
+    a, b = fr[0], fr[1]
+    fwd, bwd = fs(8, 7, a, b), fs(8, 7, b, a)
+    assert np.array_equal(blocks_of(fwd, 8), g["fs_fwd"])
+    assert np.array_equal(blocks_of(bwd, 8), g["fs_bwd"])
+    fwh, bwh = hbma(8, 7, 1, 2, 4, a, b), hbma(8, 7, 1, 2, 4, b, a)
+    assert np.array_equal(blocks_of(fwh, 4), g["hbma_fwd"])
+    assert np.array_equal(blocks_of(bwh, 4), g["hbma_bwd"])
+    for dist in (0.5, 0.39999998):
+        d = np.float32(dist)
+        assert sha(bi(a, b, fwd, bwd, d)) == str(g[f"bidir_fs_sha/{dist}"])
+        assert sha(uni(a, b, fwd, d)) == str(g[f"unidir_fs_sha/{dist}"])
+        assert sha(bi(a, b, fwh, bwh, d)) == str(g[f"bidir_hbma_sha/{dist}"])
+
+
+# ---------------------------------------------------------------- oracle on fresh seeded inputs
+@pytest.mark.parametrize("H,W,bs,R", [(120, 200, 8, 16), (97, 131, 8, 7), (64, 256, 16, 12), (136, 80, 8, 5),
+                                      (90, 160, 24, 6), (48, 64, 6, 4), (40, 300, 8, 20)])
+def test_fs_vs_oracle(gpu, oracle, H, W, bs, R):
+    from interpolatory_b200.device import get_context
+    fr = make_sequence(H, W, 2, seed=H * 7 + W)
+    ctx = get_context(H, W)
+    ctx.upload_frame(0, fr[0]); ctx.upload_frame(1, fr[1])
+    for (s, t) in ((0, 1), (1, 0)):
+        ctx.me_fs(s, t, bs, R, 0)
+        _, vec, _, sad = ctx.download_mv_blocks(0)
+        ref = oracle.fs_blocks(bs, R, fr[s], fr[t])
+        assert np.array_equal(vec, ref[:, :, :2]), (H, W, bs, R)
+        assert np.array_equal(sad, ref[:, :, 2])
+        n_cand, px_ops, n_redo = ctx.fs_stats()
+        assert (n_cand, px_ops) == oracle.fs_work(H, W, bs, R)
+
+
+def test_fs_truncation_fixup_exercised(gpu, oracle):
+    """Frames that differ by a pure grey offset make sum|dL| an exact integer for every
+    candidate: the float64 truncation decides K vs K-1 and the redo pass must run."""
+    from interpolatory_b200.device import get_context
+    rng = np.random.default_rng(5)
+    H, W = 64, 96
+    a = rng.integers(0, 200, size=(H, W, 3)).astype(np.uint8)
+    a[:, :] = a[:, :, :1]                      # grey image: dL1000 = 1000 * dGrey for every pixel pair
+    b = (np.roll(a, (1, -2), (0, 1)).astype(np.int32) + 3).astype(np.uint8)
+    ctx = get_context(H, W)
+    ctx.upload_frame(0, a); ctx.upload_frame(1, b)
+    ctx.me_fs(0, 1, 8, 7, 0)
+    _, vec, _, sad = ctx.download_mv_blocks(0)
+    n_redo = ctx.fs_stats()[2]
+    ref = oracle.fs_blocks(8, 7, a, b)
+    assert n_redo > 0
+    assert np.array_equal(vec, ref[:, :, :2]) and np.array_equal(sad, ref[:, :, 2])
+
+
+@pytest.mark.parametrize("H,W,cfg", [(130, 210, (8, 7, 1, 2, 4)), (300, 420, (8, 7, 1, 2, 4)), (75, 99, (8, 4, 2, 1, 2)),
+                                     (128, 128, (16, 5, 1, 2, 4))])
+def test_hbma_vs_oracle(gpu, oracle, H, W, cfg):
+    from interpolatory_b200.ME.hbma import get_motion_vectors as hbma
+    fr = make_sequence(H, W, 2, seed=H + W)
+    assert np.array_equal(hbma(*cfg, fr[0], fr[1], 'sad', False), oracle.hbma(*cfg, fr[0], fr[1], 'sad', False))
+    assert np.array_equal(hbma(*cfg, fr[1], fr[0], 'ssd', False), oracle.hbma(*cfg, fr[1], fr[0], 'ssd', False))
+
+
+@pytest.mark.parametrize("H,W", [(120, 200), (97, 131)])
+@pytest.mark.parametrize("mode", ["none", "mean", "median", "weighted"])
+def test_pipeline_vs_oracle(gpu, oracle, H, W, mode):
+    """Whole pair through the device-resident path (no dense fields on the host) vs the oracle chain."""
+    from interpolatory_b200.device import get_context
+    from interpolatory_b200._native import PairParams
+    fr = make_sequence(H, W, 2, seed=3 * H + W)
+    a, b = fr[0], fr[1]
+    ctx = get_context(H, W)
+    ctx.upload_frame(0, a); ctx.upload_frame(1, b)
+    for me in ("fs", "hbma"):
+        p = PairParams(0 if me == "fs" else 1, 8, 7, 1, 2, 4, {"none": 0, "mean": 1, "median": 2, "weighted": 3}[mode], 4, 1)
+        ctx.estimate_pair(p, 0, 1, 0, 1)
+        if me == "fs":
+            f_, b_ = oracle.fs(8, 7, a, b), oracle.fs(8, 7, b, a)
+        else:
+            f_, b_ = oracle.hbma(8, 7, 1, 2, 4, a, b), oracle.hbma(8, 7, 1, 2, 4, b, a)
+        f_, b_ = oracle.smooth(mode, f_, 4), oracle.smooth(mode, b_, 4)
+        assert np.array_equal(ctx.download_mv_dense(0), f_)
+        assert np.array_equal(ctx.download_mv_dense(1), b_)
+        for dist in (0.5, 0.19999999):
+            ctx.mci_bidir(0, 1, 0, 1, np.float32(dist), 7)
+            assert np.array_equal(ctx.download_frame(7), oracle.bidir_helper(a, b, f_, b_, np.float32(dist)))
+            ctx.mci_unidir(0, 1, 0, np.float32(dist), 7)
+            assert np.array_equal(ctx.download_frame(7), oracle.unidir_helper(a, b, f_, np.float32(dist)))
