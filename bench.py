@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- interpolated frames/s of the MEMCI hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores
+
+Workload (BASELINE.json configs[1], "cfg2"): 1080p, full search 8x8 blocks +-16, 30 -> 60 fps,
+bidirectional MCI.  A step = one pass of the hot path over a batch of P independent frame pairs:
+2 full-search motion fields (forward + backward) and one interpolated frame per pair.  The
+pass-through source frames of the 60 fps output involve no computation and are not counted in
+`value` (interpolated frames/s); `output_frames_per_s` adds them back.
+
+value    : inputs resident in HBM before the timed region, outputs left in HBM; CUDA events.
+e2e      : same work through the public pipeline API with page-locked HOST buffers, the H2D copy
+           of every source frame and the D2H copy of every interpolated frame inside the timed region.
+roofline : dominant kernel (fs_tiled_kernel): SAD pixel-ops per launch (exact candidate count of the
+           reference's own bounds x 64) / mean launch time from CUDA events recorded around every
+           launch inside the timed region, against the VABSDIFF issue rate measured by a microbenchmark
+           in this run.  The kernel is integer-ALU bound, not HBM bound; its HBM view and
+           the HBM-bound MCI splat kernel are reported beside it.
+cpu_baseline / --impl reference: the C restatement of the reference (oracle/, validated bit-exact
+           against the reference) on the host cores, OpenMP over block rows, one full-size pair per sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (H, W, settings, fps_in, fps_out, default pairs per step)
+    "cfg2": (1080, 1920, dict(me_mode='fs', block_size='8', target_region='16', mci_mode='bidir'), 30, 60, 16),
+    "cfg1": (360, 640, dict(me_mode='fs', block_size='8', target_region='7', mci_mode='bidir'), 24, 60, 64),
+    "cfg3": (1080, 1920, dict(me_mode='hbma', block_size='8', target_region='7', mci_mode='bidir',
+                              filter_mode='median', filter_size='4'), 24, 120, 16),
+    "cfg4": (2160, 3840, dict(me_mode='fs', block_size='16', target_region='32', mci_mode='bidir'), 30, 60, 4),
+}
+WORKLOAD_TEXT = {
+    "cfg2": "cfg2: 1080p full-search 8x8 blocks +-16, 30->60 fps, bidir MCI, synthetic frames",
+    "cfg1": "cfg1: 640x360 full-search 8x8 +-7, 24->60 fps, bidir MCI, synthetic frames",
+    "cfg3": "cfg3: 1080p HBMA (auto 4-level pyramid via class rule) + median MV smoothing, 24->120 fps, bidir MCI",
+    "cfg4": "cfg4: 4K full-search 16x16 +-32, 30->60 fps, bidir MCI, synthetic frames",
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace('.', '').isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference_sample(H, W, st, dists, frames, threads=None):
+    """One full-size pair through the CPU restatement of the reference; returns seconds."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    O.build()
+    if threads:
+        O.set_num_threads(threads)
+    a, b = frames[0], frames[1]
+    bs, R = int(st['block_size']), int(st['target_region'])
+    t0 = time.perf_counter()
+    if st['me_mode'] == 'fs':
+        fwd = O.fs(bs, R, a, b)
+        bwd = O.fs(bs, R, b, a)
+    else:
+        steps = O.hbma_auto_steps(H, W)
+        fwd = O.hbma(bs, R, 1, steps, 4, a, b)
+        bwd = O.hbma(bs, R, 1, steps, 4, b, a)
+    mode = st.get('filter_mode', 'none')
+    fwd = O.smooth(mode, fwd, int(st.get('filter_size', 4)))
+    bwd = O.smooth(mode, bwd, int(st.get('filter_size', 4)))
+    for d in dists:
+        O.bidir_helper(a, b, fwd, bwd, np.float32(d))
+    return time.perf_counter() - t0, O.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from interpolatory_b200.synth import make_sequence
+    from interpolatory_b200.pipeline import interpolation_dists
+    H, W, st, fps_in, fps_out, _ = WORKLOADS[args.workload]
+    dists = interpolation_dists(fps_out / fps_in)
+    frames = make_sequence(H, W, 2, seed=0)
+    for _ in range(args.warmup):
+        cpu_reference_sample(H, W, st, dists, frames)
+    t = 0.0
+    cores = 1
+    for _ in range(args.steps):
+        dt, cores = cpu_reference_sample(H, W, st, dists, frames)
+        t += dt
+    value = args.steps * len(dists) / t
+    sample = f"{args.steps} x 1 full-size frame pair (2 motion fields + {len(dists)} interpolated frame(s)) per step"
+    line = {
+        "impl": "reference", "metric": "interpolated_frames_per_s", "value": value, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD_TEXT[args.workload], "pairs_per_step": 1},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is Python/numba (single-threaded); this arm times its C restatement (oracle/, bit-exact vs the "
+                "reference) with OpenMP over block rows on all host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--pairs", type=int, default=0, help="frame pairs per step per GPU (default: per workload)")
+    ap.add_argument("--contexts", type=int, default=3, help="device contexts (streams) of the e2e pipeline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from interpolatory_b200 import build as B
+    from interpolatory_b200._native import lib, MemciError
+    from interpolatory_b200.device import DeviceContext, PinnedBuffer
+    from interpolatory_b200.pipeline import PairPipeline, interpolation_dists, pair_params_from_settings
+    from interpolatory_b200.synth import make_sequence
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the MEMCI path has no CPU fallback")
+    lib()                                         # fail loudly if the CUDA library is missing
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    H, W, st, fps_in, fps_out, P_default = WORKLOADS[args.workload]
+    P = args.pairs or P_default
+    dists = interpolation_dists(fps_out / fps_in)
+    nd = len(dists)
+    params = pair_params_from_settings((H, W), **st)
+    frame_bytes = H * W * 3
+
+    # ---- inputs: every rank owns its own P pairs (weak scaling; pair-index sharding, no collective) ----
+    frames = make_sequence(H, W, P + 1, seed=100 + rank)
+    dev_frames = torch.from_numpy(frames).cuda()
+    stream = torch.cuda.Stream()              # a real (non-null) stream: the library enqueues on it, torch events time it
+    torch.cuda.set_stream(stream)
+    ctx = DeviceContext(H, W, device=local_rank, stream=stream.cuda_stream)
+    base_ptr = dev_frames.data_ptr()
+
+    def step_resident():
+        for k in range(P):
+            a, b = k % 3, (k + 1) % 3
+            if k == 0:
+                ctx.set_frame_device(a, base_ptr)
+            ctx.set_frame_device(b, base_ptr + (k + 1) * frame_bytes)
+            ctx.estimate_pair(params, a, b, 0, 1)
+            for j, d in enumerate(dists):
+                ctx.mci_bidir(a, b, 0, 1, d, 6 + (j & 1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 1)):
+        step_resident()
+    barrier()
+    n_cand, px_ops, _ = ctx.fs_stats()
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ctx.reset_launch_count()
+    ctx.profile_start(args.steps * P * (2 + nd) + 16)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count()
+    fs_ms_sum, fs_n, mci_ms_sum, mci_n = ctx.profile_collect()
+    clk = clocks.stop()
+    n_holes = ctx.mci_stats()
+    resident_last = ctx.download_frame(6 + ((nd - 1) & 1)).copy()
+
+    # ---- e2e: host buffers, H2D + D2H inside the timed region, through the public pipeline API ----
+    pin_in = PinnedBuffer((P + 1, H, W, 3))
+    pin_in.array[...] = frames
+    pin_out = PinnedBuffer((P * nd, H, W, 3))
+    pipe = PairPipeline(H, W, device=local_rank, n_contexts=args.contexts, **st)
+    for _ in range(max(args.warmup, 1)):
+        pipe.run(pin_in.array, dists, pin_out.array)
+    barrier()
+    l0 = pipe.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        pipe.run(pin_in.array, dists, pin_out.array)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_launches = pipe.launch_count() - l0
+    if not np.array_equal(pin_out.array[P * nd - 1], resident_last):
+        raise SystemExit("e2e pipeline output differs from the device-resident path")
+    n_ctx = min(args.contexts, P)
+
+    # ---- roofline denominator: VABSDIFF issue rate measured now, on this GPU ----
+    ub_ms, ub_ops = min((ctx.microbench(0, 8192) for _ in range(3)), key=lambda x: x[0])
+    peak_tops = ub_ops / (ub_ms * 1e-3) / 1e12
+
+    t_max = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    ms_all, e2e_ms_all = float(t_max[0]), float(t_max[1])
+
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        total_interp = world * P * nd * args.steps
+        value = total_interp / (ms_all * 1e-3)
+        e2e_value = total_interp / (e2e_ms_all * 1e-3)
+        out_per_interp = (fps_out / fps_in) / nd            # output frames (incl. pass-through) per interpolated frame
+        fs_avg_s = (fs_ms_sum / max(fs_n, 1)) * 1e-3
+        achieved_tops = px_ops / fs_avg_s / 1e12 if fs_n else None
+        mci_avg_s = (mci_ms_sum / max(mci_n, 1)) * 1e-3
+        mci_bytes = 9.0 * H * W                               # 2 frame reads + 1 frame write
+        luma_bytes = 2.0 * H * ((W + 3) // 4 * 4) * 4 + (-(-H // int(st['block_size']))) * (-(-W // int(st['block_size']))) * 12
+        line = {
+            "metric": "interpolated_frames_per_s", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_TEXT[args.workload], "pairs_per_step_per_gpu": P, "H": H, "W": W,
+                       "settings": st, "interpolated_per_pair": nd,
+                       "sharding": "pair index, independent per rank, no collective",
+                       "l2_policy": f"inputs larger than L2: {((P + 1) * frame_bytes + 3 * H * W * 4) / 1e6:.0f} MB of frames + luma planes "
+                                    "streamed per step vs 126 MB L2"},
+            "output_frames_per_s": value * out_per_interp,
+            "sad_gops": (2 * px_ops * world * P * args.steps) / (ms_all * 1e-3) / 1e9,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": (P + n_ctx) * frame_bytes,
+                    "d2h_bytes_per_step": P * nd * frame_bytes, "contexts": n_ctx,
+                    "output_frames_per_s": e2e_value * out_per_interp},
+            "gpu_launches": int(launches),
+            "gpu_launches_e2e": int(e2e_launches),
+            "clocks": clk,
+            "roofline": {
+                "kernel": "fs_tiled_kernel (full-search luma-SAD + argmin)", "bound": "int_alu",
+                "achieved": achieved_tops, "peak": peak_tops, "unit": "T SAD px-op/s",
+                "frac": (achieved_tops / peak_tops) if achieved_tops else None,
+                "peak_source": "VABSDIFF issue-rate microbenchmark measured in this run (memci_microbench mode 0)",
+                "ops_per_launch": px_ops, "candidates_per_launch": n_cand, "launches_timed": fs_n,
+                "avg_launch_ms": fs_avg_s * 1e3,
+                "traffic": None,
+                "hbm_view": {"algorithmic_bytes_per_launch": luma_bytes, "achieved_gbs": luma_bytes / fs_avg_s / 1e9 if fs_n else None,
+                             "peak_gbs": peaks["hbm_gbs"], "frac": (luma_bytes / fs_avg_s / 1e9) / peaks["hbm_gbs"] if fs_n else None,
+                             "peak_source": peak_src},
+            },
+            "roofline_mci": {
+                "kernel": "mci_splat_kernel (warp/blend, order-preserving gather)", "bound": "hbm",
+                "achieved": mci_bytes / mci_avg_s / 1e9 if mci_n else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": (mci_bytes / mci_avg_s / 1e9) / peaks["hbm_gbs"] if mci_n else None, "peak_source": peak_src,
+                "bytes_per_launch": mci_bytes, "launches_timed": mci_n, "avg_launch_ms": mci_avg_s * 1e3,
+                "holes_last_frame": n_holes, "traffic": None,
+            },
+            "kernel_share_of_step": {"fs_tiled": fs_ms_sum / ms if ms else None, "mci_splat": mci_ms_sum / ms if ms else None},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            dt, cores = cpu_reference_sample(H, W, st, dists, frames)
+            line["cpu_baseline"] = {"value": nd / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+                                    "sample": f"1 full-size frame pair of the same workload ({dt:.2f} s): C restatement of the "
+                                              "reference (oracle/), OpenMP over block rows"}
+        print(json.dumps(line), flush=True)
+
+    pipe.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -174,6 +174,19 @@ MEMCI_API int memci_mci_stats(memci_ctx *ctx, int *n_holes);
 MEMCI_API int memci_enable_kernel_timing(memci_ctx *ctx, int on);
 MEMCI_API int memci_last_kernel_ms(memci_ctx *ctx, float *fs_ms, float *mci_ms);
 
+/* Per-launch device timing of the two hot kernels inside a caller's timed region: after
+ * memci_profile_start(capacity) every full-search main-kernel launch and every MCI splat launch
+ * is bracketed by a CUDA event pair on the context stream (no synchronisation); collect sums
+ * the elapsed times (ms) and counts, then stops recording. */
+MEMCI_API int memci_profile_start(memci_ctx *ctx, int capacity);
+MEMCI_API int memci_profile_collect(memci_ctx *ctx, double *fs_ms_sum, int *fs_launches,
+                                    double *mci_ms_sum, int *mci_launches);
+
+/* Issue-rate microbenchmark for the SAD kernel's roofline denominator:
+ * mode 0 = integer |a-b|+c (VABSDIFF), 1 = the fp32 two-FADD form, 2/3 = both pipes mixed.
+ * Returns the device time of one launch and the SAD pixel-ops it performed. */
+MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, float *ms, double *px_ops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,9 @@ _PROTOS = {
     "memci_mci_stats": ([_P, C.POINTER(_I)], _I),
     "memci_enable_kernel_timing": ([_P, _I], _I),
     "memci_last_kernel_ms": ([_P, C.POINTER(C.c_float), C.POINTER(C.c_float)], _I),
+    "memci_profile_start": ([_P, _I], _I),
+    "memci_profile_collect": ([_P, C.POINTER(C.c_double), C.POINTER(_I), C.POINTER(C.c_double), C.POINTER(_I)], _I),
+    "memci_microbench": ([_P, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_double)], _I),
 }
 EXPORTS = tuple(sorted(_PROTOS))
 

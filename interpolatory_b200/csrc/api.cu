@@ -51,6 +51,20 @@ int memci_mv_reserve(memci_ctx *ctx, MVField *f, int mv_cell, int mv_rows, int m
         if ((s) < 0 || (s) >= MEMCI_NUM_MV_SLOTS) return memci_fail(ctx, MEMCI_ERR_ARG, "mv slot %d out of range", (s)); \
         if ((need_valid) && !(ctx)->mvs[s].valid) return memci_fail(ctx, MEMCI_ERR_STATE, "mv slot %d is empty", (s)); } while (0)
 
+int memci_prof_begin(memci_ctx *ctx, int kind)
+{
+    if (!ctx->pool || ctx->pool_n >= ctx->pool_cap) return -1;
+    int i = ctx->pool_n++;
+    ctx->pool_kind[i] = (unsigned char)kind;
+    cudaEventRecord(ctx->pool[2 * i], ctx->stream);
+    return i;
+}
+
+void memci_prof_end(memci_ctx *ctx, int idx)
+{
+    if (idx >= 0) cudaEventRecord(ctx->pool[2 * idx + 1], ctx->stream);
+}
+
 extern "C" {
 
 int memci_version(void) { return 100; }
@@ -135,6 +149,8 @@ int memci_ctx_destroy(memci_ctx *ctx)
     if (ctx->d_hole_mask) cudaFree(ctx->d_hole_mask);
     if (ctx->d_hole_list) cudaFree(ctx->d_hole_list);
     if (ctx->d_dense) cudaFree(ctx->d_dense);
+    for (int i = 0; i < 2 * ctx->pool_cap; ++i) cudaEventDestroy(ctx->pool[i]);
+    free(ctx->pool); free(ctx->pool_kind);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
     return MEMCI_OK;
@@ -344,6 +360,42 @@ int memci_estimate_pair(memci_ctx *ctx, const memci_pair_params *p, int slot_src
 }
 
 // ---- instrumentation ---------------------------------------------------------------------
+int memci_profile_start(memci_ctx *ctx, int capacity)
+{
+    REQ_CTX(ctx);
+    if (capacity <= 0) return memci_fail(ctx, MEMCI_ERR_ARG, "profile capacity must be positive");
+    if (ctx->pool_cap < capacity) {
+        for (int i = 0; i < 2 * ctx->pool_cap; ++i) cudaEventDestroy(ctx->pool[i]);
+        free(ctx->pool); free(ctx->pool_kind);
+        ctx->pool = (cudaEvent_t *)calloc(2 * (size_t)capacity, sizeof(cudaEvent_t));
+        ctx->pool_kind = (unsigned char *)calloc(capacity, 1);
+        if (!ctx->pool || !ctx->pool_kind) return memci_fail(ctx, MEMCI_ERR_NOMEM, "out of host memory");
+        for (int i = 0; i < 2 * capacity; ++i) CK(ctx, cudaEventCreate(&ctx->pool[i]));
+        ctx->pool_cap = capacity;
+    }
+    ctx->pool_n = 0;
+    return MEMCI_OK;
+}
+
+int memci_profile_collect(memci_ctx *ctx, double *fs_ms_sum, int *fs_n, double *mci_ms_sum, int *mci_n)
+{
+    REQ_CTX(ctx);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    double s[2] = {0.0, 0.0};
+    int n[2] = {0, 0};
+    for (int i = 0; i < ctx->pool_n; ++i) {
+        float ms = 0.f;
+        CK(ctx, cudaEventElapsedTime(&ms, ctx->pool[2 * i], ctx->pool[2 * i + 1]));
+        s[ctx->pool_kind[i] & 1] += ms; n[ctx->pool_kind[i] & 1]++;
+    }
+    if (fs_ms_sum) *fs_ms_sum = s[0];
+    if (fs_n) *fs_n = n[0];
+    if (mci_ms_sum) *mci_ms_sum = s[1];
+    if (mci_n) *mci_n = n[1];
+    ctx->pool_n = ctx->pool_cap;          // stop recording until the next memci_profile_start
+    return MEMCI_OK;
+}
+
 long long memci_launch_count(memci_ctx *ctx) { return ctx ? ctx->launches : -1; }
 int memci_reset_launch_count(memci_ctx *ctx) { if (!ctx) return MEMCI_ERR_ARG; ctx->launches = 0; return MEMCI_OK; }
 

@@ -87,6 +87,67 @@ __global__ void fs_generic_kernel(const int32_t *__restrict__ Ls, const int32_t 
 }
 
 // =========================================================================================
+// Redo pass: one CTA per listed block (same exact arithmetic as fs_generic_kernel, 8 warps wide).
+// =========================================================================================
+__global__ void __launch_bounds__(256)
+fs_redo_kernel(const int32_t *__restrict__ Ls, const int32_t *__restrict__ Lt,
+               const uint8_t *__restrict__ rgb_s, const uint8_t *__restrict__ rgb_t,
+               int H, int W, int Wp, int bs, int R, int nbc,
+               const int *__restrict__ list, const int *__restrict__ list_count,
+               float2 *__restrict__ out_vec, float *__restrict__ out_sad)
+{
+    extern __shared__ int redo_sm[];                 // ref[bs][bs] then win[bs+2R][bs+2R], zero padded like np.pad
+    __shared__ unsigned long long wbest[8];
+    const int ww = bs + 2 * R;
+    int *ref = redo_sm, *win = redo_sm + bs * bs;
+    const int total = *list_count;
+    for (int it = blockIdx.x; it < total; it += gridDim.x) {
+        const int blk = list[it];
+        const int br = blk / nbc, bc = blk - br * nbc;
+        const int s_row = br * bs, s_col = bc * bs;
+        const FsBounds b = fs_bounds(H, W, bs, R, s_row, s_col);
+        const int nr = b.r1 - b.r0, nc = b.c1 - b.c0;
+        for (int i = threadIdx.x; i < bs * bs; i += blockDim.x) {
+            const int r = s_row + i / bs, c = s_col + i % bs;
+            ref[i] = (r < H && c < W) ? Ls[(size_t)r * Wp + c] : 0;
+        }
+        for (int i = threadIdx.x; i < ww * ww; i += blockDim.x) {
+            const int r = s_row - R + i / ww, c = s_col - R + i % ww;
+            win[i] = (r >= 0 && r < H && c >= 0 && c < W) ? Lt[(size_t)r * Wp + c] : 0;
+        }
+        __syncthreads();
+        unsigned long long best = KEY_NONE;
+        const int ncand = nr > 0 && nc > 0 ? nr * nc : 0;
+        for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
+            const int ri = c / nc, ci = c - ri * nc;
+            const int t_row = b.r0 + ri, t_col = b.c0 + ci;
+            const int *wp = win + (t_row - (s_row - R)) * ww + (t_col - (s_col - R));
+            unsigned S = 0;
+            for (int i = 0; i < bs; ++i)
+                for (int j = 0; j < bs; ++j) S = __sad(ref[i * bs + j], wp[i * ww + j], S);
+            unsigned sad = S / 1000u;
+            if (S != 0 && sad * 1000u == S)          // flagged: replay in f64, reference op order
+                sad = (unsigned)exact_cost_f64(rgb_s, rgb_t, H, W, s_row, s_col, t_row, t_col, bs, 0);
+            const int dr = s_row - t_row, dc = s_col - t_col;
+            const unsigned long long k = fs_key(sad, (unsigned)(dr * dr + dc * dc), ri, ci);
+            best = k < best ? k : best;
+        }
+        best = shfl_min_u64(best);
+        if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) best = wbest[w] < best ? wbest[w] : best;
+            if (best != KEY_NONE) {
+                const int ri = (int)((best >> 8) & 255), ci = (int)(best & 255);
+                out_vec[blk] = make_float2((float)(b.r0 + ri - s_row), (float)(b.c0 + ci - s_col));
+                out_sad[blk] = (float)(unsigned)(best >> 32);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =========================================================================================
 // Tiled kernel.
 //
 // A tile = nb horizontally adjacent blocks of one block row.  Thread 0 stages, with two TMA
@@ -108,7 +169,7 @@ __global__ void fs_generic_kernel(const int32_t *__restrict__ Ls, const int32_t 
 // beats its best fast key is appended to the redo list and re-resolved by fs_generic_kernel.
 // =========================================================================================
 struct FsParams {
-    int H, W, bs, R, Rp, m, nbr, nbc, n_tiles, box_h, n_stages;   // Rp = R rounded up to 4: TMA x origin stays 16-byte aligned
+    int H, W, bs, R, Rp, m, nbr, nbc, n_tiles, box_h, n_stages, ks;   // ks = bits reserved for dist^2 in the 32-bit key   // Rp = R rounded up to 4: TMA x origin stays 16-byte aligned
     const FsTile *tiles;
     float2 *out_vec;
     float *out_sad;
@@ -181,6 +242,36 @@ __device__ inline void fs_fill_tab(FsTileTab *tab, const FsTile t, const FsParam
     if (lane == 0) tab->total_dx = total;
 }
 
+// Per-thread argmin over the G row offsets of one item.  dx is fixed and the row offset ascends
+// with gi, so the 32-bit key  ((sad << ks) + d2 + 1) << 4 | gi  under plain unsigned min
+// reproduces the reference's update rule (lower SAD, then smaller distance, then earlier row).
+// kl is the same minimum with every flagged candidate (S % 1000 == 0) lowered to sad-1 and one
+// notch further, so that "kl < best key" also covers a flagged candidate that would TIE the
+// winner on (sad-1, d2) and could beat it on scan order.  S == 0 also has remainder 0; its
+// lowered key wraps to a huge value and is ignored by the min.
+template <int G, bool CHECK>
+__device__ __forceinline__ void fs_finalize(const unsigned (&acc)[G], int n_valid, int dy0, int dx, int ks,
+                                            unsigned &kb, unsigned &kl)
+{
+    const unsigned d20 = (unsigned)(dy0 * dy0 + dx * dx) + 1u;
+    const int two_dy0 = 2 * dy0;
+    const unsigned lower = ((1u << ks) + 1u) << 4;
+    kb = 0xffffffffu; kl = 0xffffffffu;
+#pragma unroll
+    for (int gi = 0; gi < G; ++gi) {
+        const unsigned S = acc[gi];
+        const unsigned q = S / 1000u;
+        const unsigned rem = S - q * 1000u;
+        const unsigned d2 = d20 + (unsigned)(gi * two_dy0 + gi * gi);
+        unsigned key = (((q << ks) + d2) << 4) + (unsigned)gi;
+        if (CHECK) { if (gi >= n_valid) key = 0xffffffffu; }      // rows past the window lose to everything
+        kb = min(kb, key);
+        unsigned lo = key - (rem == 0u ? lower : 0u);
+        if (CHECK) { if (gi >= n_valid) lo = 0xffffffffu; }
+        kl = min(kl, lo);
+    }
+}
+
 template <int G>
 __global__ void __launch_bounds__(FS_NT, 1)
 fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_tgt,
@@ -190,7 +281,7 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ FsTileTab tabs[2];
     __shared__ unsigned long long best_fast[2][FS_NBMAX];
-    __shared__ unsigned long long best_flag[2][FS_NBMAX];
+    __shared__ unsigned best_low[2][FS_NBMAX];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int stage_ints = (p.box_h + p.bs) * FS_BOXW;
@@ -204,7 +295,7 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
     }
     if (tid < 2 * FS_NBMAX) {
         (&best_fast[0][0])[tid] = KEY_NONE;
-        (&best_flag[0][0])[tid] = KEY_NONE;
+        (&best_low[0][0])[tid] = 0xffffffffu;
     }
     __syncthreads();
 
@@ -252,7 +343,8 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
         for (int base = warp * 32; base < n_items; base += FS_NT) {
             const int item = base + lane;
             const bool active = item < n_items;
-            unsigned long long kbest = KEY_NONE, kflag = KEY_NONE;
+            unsigned long long kbest = KEY_NONE;
+            unsigned klow = 0xffffffffu;
             int b = 0;
             if (active) {
                 const int g = item / total_dx;
@@ -295,45 +387,38 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                     }
                 }
                 const int n_valid = n_dy - g * G;       // > 0
-                const unsigned dx2 = (unsigned)(dx * dx);
-#pragma unroll
-                for (int gi = 0; gi < G; ++gi) {
-                    if (gi < n_valid) {
-                        const unsigned S = acc[gi];
-                        const unsigned q = S / 1000u;
-                        const int ri = g * G + gi;
-                        const int dy = dy_lo + ri;
-                        const unsigned d2 = (unsigned)(dy * dy) + dx2;
-                        const unsigned long long key = fs_key(q, d2, (unsigned)ri, (unsigned)dxi);
-                        kbest = key < kbest ? key : kbest;
-                        if (q * 1000u == S && S != 0u) {
-                            const unsigned long long kl = fs_key(q - 1u, d2, (unsigned)ri, (unsigned)dxi);
-                            kflag = kl < kflag ? kl : kflag;
-                        }
-                    }
+                const int dy0 = dy_lo + g * G;
+                unsigned kb32, kl32;
+                if (n_valid >= G) fs_finalize<G, false>(acc, n_valid, dy0, dx, p.ks, kb32, kl32);
+                else fs_finalize<G, true>(acc, n_valid, dy0, dx, p.ks, kb32, kl32);
+                if (kb32 != 0xffffffffu) {
+                    const unsigned k = (kb32 >> 4) - 1u;
+                    kbest = fs_key(k >> p.ks, k & ((1u << p.ks) - 1u), (unsigned)(g * G) + (kb32 & 15u), (unsigned)dxi);
                 }
+                klow = kl32;
             }
             // one atomic per warp when the whole warp works on one block (the common case)
             const int b0 = __shfl_sync(0xffffffffu, b, 0);
             if (__all_sync(0xffffffffu, !active || b == b0)) {
                 kbest = shfl_min_u64(kbest);
-                kflag = shfl_min_u64(kflag);
+                klow = __reduce_min_sync(0xffffffffu, klow);
                 if (lane == 0) {
                     if (kbest != KEY_NONE) atomicMin(&best_fast[k & 1][b0], kbest);
-                    if (kflag != KEY_NONE) atomicMin(&best_flag[k & 1][b0], kflag);
+                    if (klow != 0xffffffffu) atomicMin(&best_low[k & 1][b0], klow >> 4);
                 }
             } else if (active) {
                 if (kbest != KEY_NONE) atomicMin(&best_fast[k & 1][b], kbest);
-                if (kflag != KEY_NONE) atomicMin(&best_flag[k & 1][b], kflag);
+                if (klow != 0xffffffffu) atomicMin(&best_low[k & 1][b], klow >> 4);
             }
         }
         __syncthreads();
 
         if (warp == 0) {
             if (lane < nb) {
-                const unsigned long long kb = best_fast[k & 1][lane], kf = best_flag[k & 1][lane];
+                const unsigned long long kb = best_fast[k & 1][lane];
+                const unsigned kl = best_low[k & 1][lane];
                 best_fast[k & 1][lane] = KEY_NONE;
-                best_flag[k & 1][lane] = KEY_NONE;
+                best_low[k & 1][lane] = 0xffffffffu;
                 const int bc = tab->bx0 + lane;
                 const int blk = tab->by * p.nbc + bc;
                 const int s_col = bc * p.bs;
@@ -348,7 +433,8 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                 }
                 p.out_vec[blk] = make_float2(dy, dx);
                 p.out_sad[blk] = sad;
-                if (kf < kb) {                              // a flagged candidate may win: exact redo
+                // lowered key of some flagged candidate undercuts the winner's (sad, d2): exact redo
+                if (kb != KEY_NONE && kl < ((unsigned)(kb >> 32) << p.ks) + (unsigned)((kb >> 16) & 0xffffu) + 1u) {
                     int pos = atomicAdd(&p.counters[0], 1);
                     if (pos < p.redo_cap) p.redo_list[pos] = blk;
                 }
@@ -442,7 +528,9 @@ static FsPlan *fs_get_plan(memci_ctx *ctx, int bs, int R)
         }
     pl->n_cand = n_cand;
     pl->n_tiles = 0; pl->d_tiles = nullptr;
-    const bool tiled_ok = (bs % 8 == 0) && bs <= 64 && R <= 120 && (bs + 2 * R + 4) <= FS_BOXW &&
+    int key_bits = 0;
+    { int ks = 1; while ((1 << ks) <= 2 * R * R + 1) ++ks; int qb = 1; while ((1ll << qb) <= (long long)bs * bs * 255) ++qb; key_bits = ks + qb + 4; }
+    const bool tiled_ok = (bs % 8 == 0) && bs <= 64 && R <= 120 && key_bits <= 32 && (bs + 2 * R + 4) <= FS_BOXW &&
                           fs_smem_bytes(bs, pl->box_h, 1, pl->G) <= 200 * 1024;
     if (tiled_ok) {
         const int Rp = (R + 3) & ~3;
@@ -524,22 +612,32 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         FsParams p;
         p.H = H; p.W = W; p.bs = bs; p.R = R; p.Rp = (R + 3) & ~3; p.m = bs / 8; p.nbr = nbr; p.nbc = nbc;
         p.n_tiles = pl->n_tiles; p.box_h = pl->box_h;
+        { int ks = 1; while ((1 << ks) <= 2 * R * R + 1) ++ks; p.ks = ks; }
         p.n_stages = fs_smem_bytes(bs, pl->box_h, 2, pl->G) <= 220 * 1024 ? 2 : 1;
         p.tiles = pl->d_tiles; p.out_vec = out->vec; p.out_sad = out->sad;
         p.redo_list = ctx->d_redo_list; p.counters = ctx->d_counters; p.redo_cap = ctx->redo_cap;
         const int smem = fs_smem_bytes(bs, pl->box_h, p.n_stages, pl->G);
         if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        const int prof = memci_prof_begin(ctx, 0);
         switch (pl->G) {
         case 5: rc = fs_launch_tiled<5>(ctx, ts, tt, p, smem); break;
         case 8: rc = fs_launch_tiled<8>(ctx, ts, tt, p, smem); break;
         case 13: rc = fs_launch_tiled<13>(ctx, ts, tt, p, smem); break;
         default: rc = fs_launch_tiled<11>(ctx, ts, tt, p, smem); break;
         }
+        memci_prof_end(ctx, prof);
         if (rc) return rc;
         if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->fs_timed = 1; }
         // exact pass over the (normally few) blocks on the redo list
-        fs_generic_kernel<<<ctx->num_sms, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbr, nbc,
-                                                                 ctx->d_redo_list, ctx->d_counters, out->vec, out->sad);
+        const int redo_smem = (bs * bs + (bs + 2 * R) * (bs + 2 * R)) * (int)sizeof(int);
+        if (redo_smem <= 160 * 1024) {
+            CK(ctx, cudaFuncSetAttribute(fs_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, redo_smem));
+            fs_redo_kernel<<<ctx->num_sms * 2, 256, redo_smem, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbc,
+                                                                              ctx->d_redo_list, ctx->d_counters, out->vec, out->sad);
+        } else {
+            fs_generic_kernel<<<ctx->num_sms, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbr, nbc,
+                                                                     ctx->d_redo_list, ctx->d_counters, out->vec, out->sad);
+        }
         CKL(ctx);
     } else {
         if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));

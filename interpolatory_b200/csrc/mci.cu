@@ -33,9 +33,9 @@ struct MciParams {
     uint8_t *out, *mask;
     int *hole_list, *counters;
     const short2 *disp[2];
-    int cell[2], cols[2];
+    int cell[2], cols[2], cshift[2];     // cshift >= 0: cell == 1 << cshift (no integer division)
     const float *sad[2];
-    int scell[2], scols[2];
+    int scell[2], scols[2], sshift[2];
 };
 
 // ---- per-cell integer displacement ---------------------------------------------------------
@@ -75,12 +75,14 @@ struct PixState {
     bool written;
 };
 
+__device__ __forceinline__ int cell_of(int x, int cell, int shift) { return shift >= 0 ? (x >> shift) : (x / cell); }
+
 __device__ __forceinline__ void mci_try_event(const MciParams &P, PixState &st, int q_r, int q_c,
                                               int eff_r, int eff_c, int dir)
 {
     const int p_r = q_r - eff_r, p_c = q_c - eff_c;
     if (p_r < 0 || p_r >= P.H || p_c < 0 || p_c >= P.W) return;
-    const short2 d = P.disp[dir][(size_t)(p_r / P.cell[dir]) * P.cols[dir] + p_c / P.cell[dir]];
+    const short2 d = P.disp[dir][cell_of(p_r, P.cell[dir], P.cshift[dir]) * P.cols[dir] + cell_of(p_c, P.cell[dir], P.cshift[dir])];
     const int u_i = p_r + d.x, v_i = p_c + d.y;
     bool self_write = false;
     if (u_i < P.H && v_i < P.W) {                       // Unidirectional.py:51, Bidirectional.py:36/45
@@ -92,7 +94,7 @@ __device__ __forceinline__ void mci_try_event(const MciParams &P, PixState &st, 
         if (P.bidir || eff_r != 0 || eff_c != 0) return;
         self_write = true;
     }
-    const float sad = P.sad[dir][(size_t)(p_r / P.scell[dir]) * P.scols[dir] + p_c / P.scell[dir]];
+    const float sad = P.sad[dir][cell_of(p_r, P.scell[dir], P.sshift[dir]) * P.scols[dir] + cell_of(p_c, P.scell[dir], P.sshift[dir])];
     const uint8_t *px = (dir == 0 ? P.src : P.tgt) + ((size_t)p_r * P.W + p_c) * 3;
     if (!P.bidir) {
         if (self_write || sad <= st.sadi) {             // :52 (non-strict)
@@ -312,37 +314,54 @@ __global__ void mci_holefill_kernel(const uint8_t *__restrict__ tgt, uint8_t *ou
             }
             vals[s] = pk;
         }
-        const int n = warp_sum(cnt);                 // >= 1: the hole itself contributes
+        const int n = __reduce_add_sync(0xffffffffu, cnt);   // >= 1: the hole itself contributes
         const int k_lo = (n - 1) >> 1, k_hi = n >> 1;
-        unsigned res[3];
+        // Bisection on the value for all three channels at once: per channel the smallest v with
+        // count(x <= v) >= k_lo + 1.  The three counts (<= 441 < 2^10) travel in one REDUX.
+        int lo[3] = {0, 0, 0}, hi2[3] = {255, 255, 255};
+#pragma unroll 1
+        for (int step = 0; step < 8; ++step) {
+            const int m0 = (lo[0] + hi2[0]) >> 1, m1 = (lo[1] + hi2[1]) >> 1, m2 = (lo[2] + hi2[2]) >> 1;
+            unsigned c = 0;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const int sh = 8 * ch;
-            int lo = 0, hi2 = 255;
-            while (lo < hi2) {                       // smallest value with count(<= value) >= k_lo + 1
-                const int mid = (lo + hi2) >> 1;
-                int c = 0;
-#pragma unroll
-                for (int s = 0; s < 14; ++s) c += (vals[s] >> 24) && (int)((vals[s] >> sh) & 255u) <= mid;
-                c = warp_sum(c);
-                if (c >= k_lo + 1) hi2 = mid; else lo = mid + 1;
-            }
-            int v_lo = lo, v_hi = lo;
-            if (k_hi != k_lo) {
-                int c = 0, mn = 256;
-#pragma unroll
-                for (int s = 0; s < 14; ++s) {
-                    const int x = (int)((vals[s] >> sh) & 255u);
-                    const bool ok = vals[s] >> 24;
-                    c += ok && x <= v_lo;
-                    if (ok && x > v_lo) mn = min(mn, x);
+            for (int s = 0; s < 14; ++s) {
+                const unsigned v = vals[s];
+                if (v >> 24) {
+                    c += ((int)(v & 255u) <= m0) + (((int)((v >> 8) & 255u) <= m1) << 10) + (((int)((v >> 16) & 255u) <= m2) << 20);
                 }
-                c = warp_sum(c);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                if (c < k_hi + 1) v_hi = mn;
             }
-            res[ch] = (unsigned)((v_lo + v_hi) >> 1);   // (a+b)/2.0 truncated; == v_lo when n is odd
+            c = __reduce_add_sync(0xffffffffu, c);
+            const int c0 = c & 1023, c1 = (c >> 10) & 1023, c2 = c >> 20;
+            if (c0 >= k_lo + 1) hi2[0] = m0; else lo[0] = m0 + 1;
+            if (c1 >= k_lo + 1) hi2[1] = m1; else lo[1] = m1 + 1;
+            if (c2 >= k_lo + 1) hi2[2] = m2; else lo[2] = m2 + 1;
+        }
+        unsigned res[3];
+        if (k_hi == k_lo) {
+            res[0] = lo[0]; res[1] = lo[1]; res[2] = lo[2];
+        } else {
+            // even count: upper middle = lower middle if enough copies of it, else the next larger value
+            unsigned c = 0;
+            int mn[3] = {256, 256, 256};
+#pragma unroll
+            for (int s = 0; s < 14; ++s) {
+                const unsigned v = vals[s];
+                if (v >> 24) {
+                    const int x0 = v & 255u, x1 = (v >> 8) & 255u, x2 = (v >> 16) & 255u;
+                    c += (x0 <= lo[0]) + ((x1 <= lo[1]) << 10) + ((x2 <= lo[2]) << 20);
+                    if (x0 > lo[0]) mn[0] = min(mn[0], x0);
+                    if (x1 > lo[1]) mn[1] = min(mn[1], x1);
+                    if (x2 > lo[2]) mn[2] = min(mn[2], x2);
+                }
+            }
+            c = __reduce_add_sync(0xffffffffu, c);
+            const int cc[3] = {(int)(c & 1023), (int)((c >> 10) & 1023), (int)(c >> 20)};
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const int m = __reduce_min_sync(0xffffffffu, mn[ch]);
+                const int v_hi = cc[ch] < k_hi + 1 ? m : lo[ch];
+                res[ch] = (unsigned)((lo[ch] + v_hi) >> 1);      // (a+b)/2.0 truncated on the uint8 store
+            }
         }
         if (lane == 0) {
             uint8_t *o = out + (size_t)h * 3;
@@ -370,6 +389,8 @@ int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd
         CKL(ctx);
         P.disp[d] = ctx->d_disp[d]; P.cell[d] = f->mv_cell; P.cols[d] = f->mv_cols;
         P.sad[d] = f->sad; P.scell[d] = f->sad_cell; P.scols[d] = f->sad_cols;
+        P.cshift[d] = (f->mv_cell & (f->mv_cell - 1)) == 0 ? __builtin_ctz(f->mv_cell) : -1;
+        P.sshift[d] = (f->sad_cell & (f->sad_cell - 1)) == 0 ? __builtin_ctz(f->sad_cell) : -1;
     }
     size_t npx = (size_t)H * W;
     if (ctx->hole_cap < npx) {
@@ -387,10 +408,12 @@ int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd
     dim3 grid(ceil_div_i(W, MCI_TW), ceil_div_i(H, MCI_TH));
     ctx->mci_timed = 0;
     if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    const int prof = memci_prof_begin(ctx, 1);
     mci_splat_kernel<<<grid, MCI_NT, 0, ctx->stream>>>(P);
+    memci_prof_end(ctx, prof);
     CKL(ctx);
     if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->mci_timed = 1; }
-    mci_holefill_kernel<<<ctx->num_sms * 4, 128, 0, ctx->stream>>>(P.tgt, P.out, P.mask, P.hole_list, P.counters, H, W);
+    mci_holefill_kernel<<<ctx->num_sms * 8, 128, 0, ctx->stream>>>(P.tgt, P.out, P.mask, P.hole_list, P.counters, H, W);
     CKL(ctx);
     FrameSlot &o = ctx->frames[out_slot];
     o.valid = 1; o.luma_ok = 0; o.pyr_levels = 0;

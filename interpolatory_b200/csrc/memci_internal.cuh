@@ -58,6 +58,8 @@ struct memci_ctx {
     float *d_dense; size_t dense_cap;  // dense MV staging for download/upload
     // timing
     int timing; cudaEvent_t ev[4]; int fs_timed, mci_timed;
+    // event pool: per-launch device times of the two hot kernels inside a caller's timed region
+    cudaEvent_t *pool; int pool_cap, pool_n; unsigned char *pool_kind;   // pairs (2i, 2i+1); kind 0 = fs, 1 = mci
     long long launches;
     int sticky;                        // sticky CUDA error
     char err[512];
@@ -91,6 +93,9 @@ int memci_smooth_run(memci_ctx *ctx, const MVField *in, int mode, int fsz, MVFie
 int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd, const MVField *bwd,
                   float dist, int out_slot, int bidir);
 int memci_mv_to_dense(memci_ctx *ctx, const MVField *f, float *d_dense);
+// returns an event pair index (>= 0) after recording the start event, or -1 when profiling is off / full
+int memci_prof_begin(memci_ctx *ctx, int kind);
+void memci_prof_end(memci_ctx *ctx, int idx);
 int memci_dense_to_mv(memci_ctx *ctx, const float *d_dense, MVField *f);
 
 static inline int ceil_div_i(int a, int b) { return (a + b - 1) / b; }

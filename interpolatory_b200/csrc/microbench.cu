@@ -1,0 +1,78 @@
+// Issue-rate microbenchmarks that give the SAD kernel its roofline denominator (SURVEY 8d:
+// "measure, don't assume" -- the int32 lanes per SM of sm_100 are not documented here).
+//   mode 0: independent VABSDIFF (|a-b|+c) chains                 -> peak integer SAD px-ops/s
+//   mode 1: FADD pairs (d = a-b; acc += |d|)                      -> the same op on the fp32 pipe
+//   mode 2: 8 VABSDIFF + 4 FADD pairs per step                    -> both pipes co-issued
+//   mode 3: 8 VABSDIFF + 8 FADD pairs per step
+#include "memci_internal.cuh"
+
+template <int MODE>
+__global__ void __launch_bounds__(512) ub_kernel(int iters, const int *__restrict__ seed, unsigned *__restrict__ out)
+{
+    int r[8];
+    unsigned a[8];
+    float fr[8], fa[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        r[j] = seed[(threadIdx.x + j) & 63] + j;
+        a[j] = (unsigned)seed[(threadIdx.x + 8 + j) & 63];
+        fr[j] = (float)r[j];
+        fa[j] = (float)a[j];
+    }
+#pragma unroll 4
+    for (int it = 0; it < iters; ++it) {
+        if (MODE == 0 || MODE >= 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = __sad(r[j], (int)a[(j + 1) & 7], a[j]);
+        }
+        if (MODE == 1 || MODE == 3) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) fa[j] = __fadd_rn(fa[j], fabsf(__fsub_rn(fr[j], fa[(j + 1) & 7])));
+        }
+        if (MODE == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) fa[j] = __fadd_rn(fa[j], fabsf(__fsub_rn(fr[j], fa[(j + 1) & 3])));
+        }
+    }
+    unsigned s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += a[j] + (unsigned)fa[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, float *ms, double *px_ops)
+{
+    if (!ctx || mode < 0 || mode > 3 || iters <= 0) return MEMCI_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const int grid = ctx->num_sms * 4, nt = 512;
+    int *d_seed = nullptr;
+    unsigned *d_out = nullptr;
+    int h_seed[64];
+    for (int i = 0; i < 64; ++i) h_seed[i] = (i * 7919 + 13) % 255000;
+    CK(ctx, cudaMalloc(&d_seed, sizeof(h_seed)));
+    CK(ctx, cudaMalloc(&d_out, sizeof(unsigned) * (size_t)grid * nt));
+    CK(ctx, cudaMemcpyAsync(d_seed, h_seed, sizeof(h_seed), cudaMemcpyHostToDevice, ctx->stream));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int rep = 0; rep < 2; ++rep) {
+        if (rep == 1) cudaEventRecord(e0, ctx->stream);
+        switch (mode) {
+        case 0: ub_kernel<0><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        case 1: ub_kernel<1><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        case 2: ub_kernel<2><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        default: ub_kernel<3><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        }
+        ctx->launches++;
+    }
+    cudaEventRecord(e1, ctx->stream);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaGetLastError());
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_seed); cudaFree(d_out);
+    const double per_step = mode == 0 ? 8.0 : mode == 1 ? 8.0 : mode == 2 ? 12.0 : 16.0;
+    if (ms) *ms = t;
+    if (px_ops) *px_ops = per_step * (double)iters * (double)grid * nt;
+    return MEMCI_OK;
+}

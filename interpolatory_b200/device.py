@@ -188,6 +188,22 @@ class DeviceContext:
         self._ck(self.L.memci_last_kernel_ms(self._ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def profile_start(self, capacity):
+        self._ck(self.L.memci_profile_start(self._ctx, int(capacity)))
+
+    def profile_collect(self):
+        """(fs_ms_sum, fs_launches, mci_ms_sum, mci_launches) since profile_start()."""
+        a, b = C.c_double(), C.c_double()
+        na, nb = C.c_int(), C.c_int()
+        self._ck(self.L.memci_profile_collect(self._ctx, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
+        return a.value, na.value, b.value, nb.value
+
+    def microbench(self, mode, iters=4096):
+        """(ms, px_ops) of one launch of the issue-rate microbenchmark (roofline denominator)."""
+        ms, ops = C.c_float(), C.c_double()
+        self._ck(self.L.memci_microbench(self._ctx, int(mode), int(iters), C.byref(ms), C.byref(ops)))
+        return ms.value, ops.value
+
 
 _CTX_CACHE = {}
 

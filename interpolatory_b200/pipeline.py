@@ -1,0 +1,104 @@
+"""Throughput path behind the same settings as the MEMCI classes: frame pairs streamed through
+several device contexts (one CUDA stream each) so the host->device copy of the next source frame
+and the device->host copy of the previous output overlap the kernels of the current pair.
+
+Frame pairs are independent: a context takes a contiguous run of pairs, so each source
+frame crosses PCIe once (twice at the run boundaries); nothing is exchanged between contexts.
+"""
+import numpy as np
+
+from ._native import PairParams
+from .device import DeviceContext, FILTER_MODES
+from .util import get_first_frame_idx_and_ratio, hbma_auto_steps
+
+
+def pair_params_from_settings(shape, **st):
+    """String settings of the MEMCI plug-in (MEMCIBaseInterpolator.py:48-78) -> device parameters."""
+    me = st.get('me_mode', 'hbma')
+    if me not in ('fs', 'hbma'):
+        raise NotImplementedError(f"me_mode {me!r} is not part of the B200 hot path")
+    mci = st.get('mci_mode', 'unidir')
+    if mci not in ('unidir', 'bidir'):
+        raise NotImplementedError(f"mci_mode {mci!r} is not part of the B200 hot path")
+    p = PairParams()
+    p.me_mode = 0 if me == 'fs' else 1
+    p.block_size = int(st.get('block_size', 8))
+    p.region = int(st.get('target_region', 7))
+    p.sub_region = 1
+    p.steps = hbma_auto_steps(shape) if me == 'hbma' else 3
+    p.min_block_size = 4
+    p.filter_mode = FILTER_MODES[st.get('filter_mode', 'none')]
+    p.filter_size = int(st.get('filter_size', 4))
+    p.bidir = 1 if mci == 'bidir' else 0
+    return p
+
+
+def interpolation_dists(rate_ratio):
+    """dist values (float32) of the interpolated frames between two source frames, in output
+    order, exactly as the class API derives them (util.get_first_frame_idx_and_ratio, W0)."""
+    out, idx = [], 1
+    while True:
+        first, ratio = get_first_frame_idx_and_ratio(idx, rate_ratio)
+        if first >= 1:
+            break
+        dist = 1. - ratio
+        if dist != 0.:
+            out.append(np.float32(dist))
+        idx += 1
+    return out
+
+
+class PairPipeline:
+    def __init__(self, H, W, device=0, n_contexts=3, **settings):
+        self.H, self.W = int(H), int(W)
+        self.params = pair_params_from_settings((H, W), **settings)
+        self.bidir = bool(self.params.bidir)
+        self.ctxs = [DeviceContext(H, W, device) for _ in range(max(1, int(n_contexts)))]
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+        self.ctxs = []
+
+    def launch_count(self):
+        return sum(c.launch_count() for c in self.ctxs)
+
+    def sync(self):
+        for c in self.ctxs:
+            c.sync()
+
+    def run(self, frames, dists, out):
+        """frames: uint8 [F, H, W, 3] (page-locked for real overlap); dists: float32 dist of each
+        interpolated frame inside a pair; out: uint8 [(F-1)*len(dists), H, W, 3], filled in pair
+        order.  Returns after everything has been enqueued AND completed."""
+        n_pairs = len(frames) - 1
+        nd = len(dists)
+        C = min(len(self.ctxs), n_pairs)
+        bounds = [round(i * n_pairs / C) for i in range(C + 1)]
+        pos = [bounds[i] for i in range(C)]
+        started = [False] * C
+        live = True
+        while live:
+            live = False
+            for c in range(C):
+                k = pos[c]
+                if k >= bounds[c + 1]:
+                    continue
+                live = True
+                ctx = self.ctxs[c]
+                a, b = k % 3, (k + 1) % 3
+                if not started[c]:
+                    ctx.upload_frame(a, frames[k])
+                    started[c] = True
+                ctx.upload_frame(b, frames[k + 1])
+                ctx.estimate_pair(self.params, a, b, 0, 1)
+                for j, d in enumerate(dists):
+                    o = 6 + (j & 1)
+                    if self.bidir:
+                        ctx.mci_bidir(a, b, 0, 1, d, o)
+                    else:
+                        ctx.mci_unidir(a, b, 0, d, o)
+                    ctx.download_frame(o, out[k * nd + j], sync=False)
+                pos[c] += 1
+        self.sync()
+        return out
