@@ -96,10 +96,13 @@ fs_redo_kernel(const int32_t *__restrict__ Ls, const int32_t *__restrict__ Lt,
                const int *__restrict__ list, const int *__restrict__ list_count,
                float2 *__restrict__ out_vec, float *__restrict__ out_sad)
 {
-    extern __shared__ int redo_sm[];                 // ref[bs][bs] then win[bs+2R][bs+2R], zero padded like np.pad
+    // Shared staging, zero padded like np.pad: the block and its search window as luma1000 ints
+    // (fast SAD) and as the reference's float64 luma (exact replay of flagged candidates).
+    extern __shared__ double redo_sm[];
     __shared__ unsigned long long wbest[8];
     const int ww = bs + 2 * R;
-    int *ref = redo_sm, *win = redo_sm + bs * bs;
+    double *dref = redo_sm, *dwin = redo_sm + bs * bs;
+    int *ref = reinterpret_cast<int *>(dwin + ww * ww), *win = ref + bs * bs;
     const int total = *list_count;
     for (int it = blockIdx.x; it < total; it += gridDim.x) {
         const int blk = list[it];
@@ -109,11 +112,23 @@ fs_redo_kernel(const int32_t *__restrict__ Ls, const int32_t *__restrict__ Lt,
         const int nr = b.r1 - b.r0, nc = b.c1 - b.c0;
         for (int i = threadIdx.x; i < bs * bs; i += blockDim.x) {
             const int r = s_row + i / bs, c = s_col + i % bs;
-            ref[i] = (r < H && c < W) ? Ls[(size_t)r * Wp + c] : 0;
+            int v = 0; double d = 0.0;
+            if (r < H && c < W) {
+                const uint8_t *p = rgb_s + ((size_t)r * W + c) * 3;
+                v = Ls[(size_t)r * Wp + c];
+                d = luma_f64(p[0], p[1], p[2]);
+            }
+            ref[i] = v; dref[i] = d;
         }
         for (int i = threadIdx.x; i < ww * ww; i += blockDim.x) {
             const int r = s_row - R + i / ww, c = s_col - R + i % ww;
-            win[i] = (r >= 0 && r < H && c >= 0 && c < W) ? Lt[(size_t)r * Wp + c] : 0;
+            int v = 0; double d = 0.0;
+            if (r >= 0 && r < H && c >= 0 && c < W) {
+                const uint8_t *p = rgb_t + ((size_t)r * W + c) * 3;
+                v = Lt[(size_t)r * Wp + c];
+                d = luma_f64(p[0], p[1], p[2]);
+            }
+            win[i] = v; dwin[i] = d;
         }
         __syncthreads();
         unsigned long long best = KEY_NONE;
@@ -121,13 +136,19 @@ fs_redo_kernel(const int32_t *__restrict__ Ls, const int32_t *__restrict__ Lt,
         for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
             const int ri = c / nc, ci = c - ri * nc;
             const int t_row = b.r0 + ri, t_col = b.c0 + ci;
-            const int *wp = win + (t_row - (s_row - R)) * ww + (t_col - (s_col - R));
+            const int woff = (t_row - (s_row - R)) * ww + (t_col - (s_col - R));
             unsigned S = 0;
             for (int i = 0; i < bs; ++i)
-                for (int j = 0; j < bs; ++j) S = __sad(ref[i * bs + j], wp[i * ww + j], S);
+                for (int j = 0; j < bs; ++j) S = __sad(ref[i * bs + j], win[woff + i * ww + j], S);
             unsigned sad = S / 1000u;
-            if (S != 0 && sad * 1000u == S)          // flagged: replay in f64, reference op order
-                sad = (unsigned)exact_cost_f64(rgb_s, rgb_t, H, W, s_row, s_col, t_row, t_col, bs, 0);
+            if (S != 0 && sad * 1000u == S) {
+                // flagged: sequential f64 accumulation in the reference's order (full_search.py:17)
+                double acc = 0.0;
+                for (int i = 0; i < bs; ++i)
+                    for (int j = 0; j < bs; ++j)
+                        acc = __dadd_rn(acc, fabs(__dsub_rn(dref[i * bs + j], dwin[woff + i * ww + j])));
+                sad = (unsigned)acc;
+            }
             const int dr = s_row - t_row, dc = s_col - t_col;
             const unsigned long long k = fs_key(sad, (unsigned)(dr * dr + dc * dc), ri, ci);
             best = k < best ? k : best;
@@ -180,7 +201,7 @@ struct FsParams {
 
 struct FsTileTab {
     int by, bx0, nb, s_row;
-    int r0, n_dy, n_groups, total_dx, n_items;
+    int r0, n_dy, total_dx, uniform_ndx;   // uniform_ndx > 0: every block has that many valid column offsets
     int dx_lo[FS_NBMAX];
     int pre[FS_NBMAX + 1];
 };
@@ -239,7 +260,9 @@ __device__ inline void fs_fill_tab(FsTileTab *tab, const FsTile t, const FsParam
         tab->n_dy = b.r1 - b.r0 > 0 ? b.r1 - b.r0 : 0;
     }
     int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (lane == 0) tab->total_dx = total;
+    const int n0 = __shfl_sync(0xffffffffu, n_dx, 0);
+    const bool uni = __all_sync(0xffffffffu, lane >= t.nb || n_dx == n0);
+    if (lane == 0) { tab->total_dx = total; tab->uniform_ndx = (uni && n0 > 0) ? n0 : 0; }
 }
 
 // Per-thread argmin over the G row offsets of one item.  dx is fixed and the row offset ascends
@@ -272,13 +295,27 @@ __device__ __forceinline__ void fs_finalize(const unsigned (&acc)[G], int n_vali
     }
 }
 
-template <int G>
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Work item = (block b, column offset dx): one thread walks all row-offset groups of its
+// candidate column, so the per-item bookkeeping (decode, 8x8 reference load when bs == 8,
+// warp reduction, shared-memory atomic) is paid once per 8*8*(2R+1) SAD pixel-ops.
+//
+// Synchronisation is mbarrier-only: full[s] = "tile data landed in stage s" (TMA complete_tx),
+// done[j] = "all 16 warps finished searching the tile using result buffer j".  Only warp 0
+// ever waits on done[] (it writes the tile's motion vectors, re-arms the stage and issues the
+// next TMA), so a warp that finishes early moves straight on to the next tile.
+template <int G, bool SINGLE>
 __global__ void __launch_bounds__(FS_NT, 1)
 fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_tgt,
                 const FsParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ __align__(8) uint64_t full[2];
+    __shared__ __align__(8) uint64_t done[2];
     __shared__ FsTileTab tabs[2];
     __shared__ unsigned long long best_fast[2][FS_NBMAX];
     __shared__ unsigned best_low[2][FS_NBMAX];
@@ -287,10 +324,13 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
     const int stage_ints = (p.box_h + p.bs) * FS_BOXW;
     int *const stage0 = reinterpret_cast<int *>(smem_raw);
     const unsigned stage_bytes = (unsigned)stage_ints * 4u;
+    const int m = SINGLE ? 1 : p.m;
 
     if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        mbar_init(&done[0], FS_NT / 32);
+        mbar_init(&done[1], FS_NT / 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 2 * FS_NBMAX) {
@@ -302,7 +342,7 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
     const int first = blockIdx.x, stride = gridDim.x;
     if (first >= p.n_tiles) return;
 
-    auto issue = [&](int tile_idx, int k) {        // warp 0 only
+    auto issue = [&](int tile_idx, int k) {        // warp 0 only: tile table + two TMA tile loads
         FsTile t = p.tiles[tile_idx];
         int s = p.n_stages == 2 ? (k & 1) : 0;
         fs_fill_tab(&tabs[k & 1], t, p, lane);
@@ -310,32 +350,66 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
         if (lane == 0) {
             int *win = stage0 + (size_t)s * stage_ints;
             int *ref = win + p.box_h * FS_BOXW;
-            mbar_expect_tx(&mbar[s], stage_bytes);
-            tma_load_2d(win, &tm_tgt, t.bx0 * p.bs - p.Rp, t.by * p.bs - p.R, &mbar[s]);
-            tma_load_2d(ref, &tm_src, t.bx0 * p.bs, t.by * p.bs, &mbar[s]);
+            mbar_expect_tx(&full[s], stage_bytes);
+            tma_load_2d(win, &tm_tgt, t.bx0 * p.bs - p.Rp, t.by * p.bs - p.R, &full[s]);
+            tma_load_2d(ref, &tm_src, t.bx0 * p.bs, t.by * p.bs, &full[s]);
         }
     };
 
+    // warp 0, lanes < nb: motion vectors of tile k out, result buffers re-armed, redo list fed
+    auto output = [&](int k) {
+        const FsTileTab *tab = &tabs[k & 1];
+        if (lane < tab->nb) {
+            const unsigned long long kb = best_fast[k & 1][lane];
+            const unsigned kl = best_low[k & 1][lane];
+            best_fast[k & 1][lane] = KEY_NONE;
+            best_low[k & 1][lane] = 0xffffffffu;
+            const int bc = tab->bx0 + lane;
+            const int blk = tab->by * p.nbc + bc;
+            const int s_row = tab->s_row, s_col = bc * p.bs;
+            float dy, dx, sad;
+            if (kb == KEY_NONE) {                       // empty window: target_index stays (0,0), sad = inf
+                dy = (float)(-s_row); dx = (float)(-s_col); sad = __int_as_float(0x7f800000);
+            } else {
+                const int ri = (int)((kb >> 8) & 255), ci = (int)(kb & 255);
+                dy = (float)(tab->r0 - s_row + ri);
+                dx = (float)(tab->dx_lo[lane] + ci);
+                sad = (float)(unsigned)(kb >> 32);
+            }
+            p.out_vec[blk] = make_float2(dy, dx);
+            p.out_sad[blk] = sad;
+            // lowered key of some flagged candidate reaches the winner's (sad, d2): exact redo
+            if (kb != KEY_NONE && kl < ((unsigned)(kb >> 32) << p.ks) + (unsigned)((kb >> 16) & 0xffffu) + 1u) {
+                int pos = atomicAdd(&p.counters[0], 1);
+                if (pos < p.redo_cap) p.redo_list[pos] = blk;
+            }
+        }
+        __syncwarp();
+    };
+
     if (warp == 0) issue(first, 0);
-    __syncthreads();
 
     int k = 0;
-    unsigned phase[2] = {0u, 0u};
+    unsigned full_phase[2] = {0u, 0u}, done_phase[2] = {0u, 0u};
     for (int tile_idx = first; tile_idx < p.n_tiles; tile_idx += stride, ++k) {
         const int s = p.n_stages == 2 ? (k & 1) : 0;
         const int next = tile_idx + stride;
-        // With two stages the next tile streams in while this one is searched.
-        if (p.n_stages == 2 && warp == 0 && next < p.n_tiles) issue(next, k + 1);
+        if (warp == 0 && p.n_stages == 2) {
+            if (k >= 1) {
+                mbar_wait(&done[(k - 1) & 1], done_phase[(k - 1) & 1]);
+                done_phase[(k - 1) & 1] ^= 1u;
+                output(k - 1);
+            }
+            if (next < p.n_tiles) issue(next, k + 1);     // streams in while this tile is searched
+        }
 
+        mbar_wait(&full[s], full_phase[s]);
+        full_phase[s] ^= 1u;
         const FsTileTab *tab = &tabs[k & 1];
-        mbar_wait(&mbar[s], phase[s]);
-        phase[s] ^= 1u;
-
         const int *win = stage0 + (size_t)s * stage_ints;
         const int *ref = win + p.box_h * FS_BOXW;
-        const int nb = tab->nb, total_dx = tab->total_dx, n_dy = tab->n_dy;
+        const int nb = tab->nb, n_items = tab->total_dx, n_dy = tab->n_dy, ndx0 = tab->uniform_ndx;
         const int n_groups = (n_dy + G - 1) / G;
-        const int n_items = total_dx * n_groups;
         const int s_row = tab->s_row;
         const int dy_lo = tab->r0 - s_row;               // first valid row offset
         const int wrow_base = tab->r0 - (s_row - p.R);   // its row inside win[]
@@ -347,27 +421,42 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
             unsigned klow = 0xffffffffu;
             int b = 0;
             if (active) {
-                const int g = item / total_dx;
-                const int f = item - g * total_dx;
-                while (b + 1 < nb && tab->pre[b + 1] <= f) ++b;
-                const int dxi = f - tab->pre[b];
+                if (ndx0 > 0) b = item / ndx0;
+                else while (b + 1 < nb && tab->pre[b + 1] <= item) ++b;
+                const int dxi = item - tab->pre[b];
                 const int dx = tab->dx_lo[b] + dxi;
-                const int wr0 = wrow_base + g * G;
                 const int wc = b * p.bs + dx + p.Rp;
                 const int rc = b * p.bs;
-                unsigned acc[G];
+                int r[8][8];
+                if (SINGLE) {
 #pragma unroll
-                for (int i = 0; i < G; ++i) acc[i] = 0u;
-                for (int si = 0; si < p.m; ++si) {
-                    for (int sj = 0; sj < p.m; ++sj) {
-                        int r[8][8];
-                        const int *rp = ref + (si * 8) * FS_BOXW + rc + sj * 8;
+                    for (int kk = 0; kk < 8; ++kk) {
+                        int4 a = *reinterpret_cast<const int4 *>(ref + kk * FS_BOXW + rc);
+                        int4 c = *reinterpret_cast<const int4 *>(ref + kk * FS_BOXW + rc + 4);
+                        r[kk][0] = a.x; r[kk][1] = a.y; r[kk][2] = a.z; r[kk][3] = a.w;
+                        r[kk][4] = c.x; r[kk][5] = c.y; r[kk][6] = c.z; r[kk][7] = c.w;
+                    }
+                }
+                unsigned kb_run = 0xffffffffu;
+                int g_run = 0;
+#pragma unroll 1
+                for (int g = 0; g < n_groups; ++g) {
+                    const int wr0 = wrow_base + g * G;
+                    unsigned acc[G];
 #pragma unroll
-                        for (int kk = 0; kk < 8; ++kk) {
-                            int4 a = *reinterpret_cast<const int4 *>(rp + kk * FS_BOXW);
-                            int4 c = *reinterpret_cast<const int4 *>(rp + kk * FS_BOXW + 4);
-                            r[kk][0] = a.x; r[kk][1] = a.y; r[kk][2] = a.z; r[kk][3] = a.w;
-                            r[kk][4] = c.x; r[kk][5] = c.y; r[kk][6] = c.z; r[kk][7] = c.w;
+                    for (int i = 0; i < G; ++i) acc[i] = 0u;
+#pragma unroll 1
+                    for (int sub = 0; sub < m * m; ++sub) {
+                        const int si = SINGLE ? 0 : sub / m, sj = SINGLE ? 0 : sub - si * m;
+                        if (!SINGLE) {
+                            const int *rp = ref + (si * 8) * FS_BOXW + rc + sj * 8;
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk) {
+                                int4 a = *reinterpret_cast<const int4 *>(rp + kk * FS_BOXW);
+                                int4 c = *reinterpret_cast<const int4 *>(rp + kk * FS_BOXW + 4);
+                                r[kk][0] = a.x; r[kk][1] = a.y; r[kk][2] = a.z; r[kk][3] = a.w;
+                                r[kk][4] = c.x; r[kk][5] = c.y; r[kk][6] = c.z; r[kk][7] = c.w;
+                            }
                         }
                         const int *wp = win + (wr0 + si * 8) * FS_BOXW + wc + sj * 8;
 #pragma unroll
@@ -385,17 +474,19 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                             }
                         }
                     }
+                    const int n_valid = n_dy - g * G;       // > 0
+                    const int dy0 = dy_lo + g * G;
+                    unsigned kb32, kl32;
+                    if (n_valid >= G) fs_finalize<G, false>(acc, n_valid, dy0, dx, p.ks, kb32, kl32);
+                    else fs_finalize<G, true>(acc, n_valid, dy0, dx, p.ks, kb32, kl32);
+                    // groups ascend in row offset: strict '<' on (sad, d2) keeps the earlier row on ties
+                    if ((kb32 >> 4) < (kb_run >> 4)) { kb_run = kb32; g_run = g; }
+                    klow = min(klow, kl32);
                 }
-                const int n_valid = n_dy - g * G;       // > 0
-                const int dy0 = dy_lo + g * G;
-                unsigned kb32, kl32;
-                if (n_valid >= G) fs_finalize<G, false>(acc, n_valid, dy0, dx, p.ks, kb32, kl32);
-                else fs_finalize<G, true>(acc, n_valid, dy0, dx, p.ks, kb32, kl32);
-                if (kb32 != 0xffffffffu) {
-                    const unsigned k = (kb32 >> 4) - 1u;
-                    kbest = fs_key(k >> p.ks, k & ((1u << p.ks) - 1u), (unsigned)(g * G) + (kb32 & 15u), (unsigned)dxi);
+                if (kb_run != 0xffffffffu) {
+                    const unsigned kq = (kb_run >> 4) - 1u;
+                    kbest = fs_key(kq >> p.ks, kq & ((1u << p.ks) - 1u), (unsigned)(g_run * G) + (kb_run & 15u), (unsigned)dxi);
                 }
-                klow = kl32;
             }
             // one atomic per warp when the whole warp works on one block (the common case)
             const int b0 = __shfl_sync(0xffffffffu, b, 0);
@@ -411,38 +502,19 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                 if (klow != 0xffffffffu) atomicMin(&best_low[k & 1][b], klow >> 4);
             }
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[k & 1]);
 
-        if (warp == 0) {
-            if (lane < nb) {
-                const unsigned long long kb = best_fast[k & 1][lane];
-                const unsigned kl = best_low[k & 1][lane];
-                best_fast[k & 1][lane] = KEY_NONE;
-                best_low[k & 1][lane] = 0xffffffffu;
-                const int bc = tab->bx0 + lane;
-                const int blk = tab->by * p.nbc + bc;
-                const int s_col = bc * p.bs;
-                float dy, dx, sad;
-                if (kb == KEY_NONE) {
-                    dy = (float)(-s_row); dx = (float)(-s_col); sad = __int_as_float(0x7f800000);
-                } else {
-                    const int ri = (int)((kb >> 8) & 255), ci = (int)(kb & 255);
-                    dy = (float)(dy_lo + ri);
-                    dx = (float)(tab->dx_lo[lane] + ci);
-                    sad = (float)(unsigned)(kb >> 32);
-                }
-                p.out_vec[blk] = make_float2(dy, dx);
-                p.out_sad[blk] = sad;
-                // lowered key of some flagged candidate undercuts the winner's (sad, d2): exact redo
-                if (kb != KEY_NONE && kl < ((unsigned)(kb >> 32) << p.ks) + (unsigned)((kb >> 16) & 0xffffu) + 1u) {
-                    int pos = atomicAdd(&p.counters[0], 1);
-                    if (pos < p.redo_cap) p.redo_list[pos] = blk;
-                }
-            }
-            __syncwarp();
-            if (p.n_stages == 1 && next < p.n_tiles) issue(next, k + 1);
+        if (warp == 0 && p.n_stages == 1) {
+            mbar_wait(&done[k & 1], done_phase[k & 1]);
+            done_phase[k & 1] ^= 1u;
+            output(k);
+            if (next < p.n_tiles) issue(next, k + 1);
         }
-        if (p.n_stages == 1) __syncthreads();
+    }
+    if (warp == 0 && p.n_stages == 2 && k >= 1) {
+        mbar_wait(&done[(k - 1) & 1], done_phase[(k - 1) & 1]);
+        output(k - 1);
     }
 }
 
@@ -535,22 +607,18 @@ static FsPlan *fs_get_plan(memci_ctx *ctx, int bs, int R)
     if (tiled_ok) {
         const int Rp = (R + 3) & ~3;
         const int nb_box = (FS_BOXW - R - Rp) / bs < FS_NBMAX ? (FS_BOXW - R - Rp) / bs : FS_NBMAX;
-        const int m2 = (bs / 8) * (bs / 8);
-        // aim for ~3 items of 8x8 work per thread per tile
-        const int budget = 3 * FS_NT / m2 > FS_NT ? 3 * FS_NT / m2 : FS_NT;
+        // one item (candidate column of one block) per thread per tile
+        const int budget = FS_NT;
         FsTile *h = (FsTile *)malloc(sizeof(FsTile) * (size_t)nbr * nbc);
         int nt = 0;
         for (int br = 0; br < nbr; ++br) {
-            FsBounds rb = fs_bounds(H, W, bs, R, br * bs, 0);
-            int n_dy = rb.r1 - rb.r0 > 0 ? rb.r1 - rb.r0 : 0;
-            int n_groups = (n_dy + pl->G - 1) / pl->G;
             int bc = 0;
             while (bc < nbc) {
                 int nb = 0, items = 0;
                 while (bc + nb < nbc && nb < nb_box) {
                     FsBounds b = fs_bounds(H, W, bs, R, br * bs, (bc + nb) * bs);
                     int n_dx = b.c1 - b.c0 > 0 ? b.c1 - b.c0 : 0;
-                    int add = n_dx * n_groups;
+                    int add = n_dx;
                     if (nb > 0 && items + add > budget) break;
                     items += add; ++nb;
                 }
@@ -572,14 +640,20 @@ static FsPlan *fs_get_plan(memci_ctx *ctx, int bs, int R)
     return pl;
 }
 
+template <int G, bool SINGLE>
+static int fs_launch_tiled2(memci_ctx *ctx, const CUtensorMap &ts, const CUtensorMap &tt, const FsParams &p, int smem)
+{
+    CK(ctx, cudaFuncSetAttribute(fs_tiled_kernel<G, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int grid = ctx->num_sms < p.n_tiles ? ctx->num_sms : p.n_tiles;
+    fs_tiled_kernel<G, SINGLE><<<grid, FS_NT, smem, ctx->stream>>>(ts, tt, p);
+    CKL(ctx);
+    return MEMCI_OK;
+}
+
 template <int G>
 static int fs_launch_tiled(memci_ctx *ctx, const CUtensorMap &ts, const CUtensorMap &tt, const FsParams &p, int smem)
 {
-    CK(ctx, cudaFuncSetAttribute(fs_tiled_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int grid = ctx->num_sms < p.n_tiles ? ctx->num_sms : p.n_tiles;
-    fs_tiled_kernel<G><<<grid, FS_NT, smem, ctx->stream>>>(ts, tt, p);
-    CKL(ctx);
-    return MEMCI_OK;
+    return p.m == 1 ? fs_launch_tiled2<G, true>(ctx, ts, tt, p, smem) : fs_launch_tiled2<G, false>(ctx, ts, tt, p, smem);
 }
 
 int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out)
@@ -629,7 +703,7 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         if (rc) return rc;
         if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->fs_timed = 1; }
         // exact pass over the (normally few) blocks on the redo list
-        const int redo_smem = (bs * bs + (bs + 2 * R) * (bs + 2 * R)) * (int)sizeof(int);
+        const int redo_smem = (bs * bs + (bs + 2 * R) * (bs + 2 * R)) * 12;
         if (redo_smem <= 160 * 1024) {
             CK(ctx, cudaFuncSetAttribute(fs_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, redo_smem));
             fs_redo_kernel<<<ctx->num_sms * 2, 256, redo_smem, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbc,

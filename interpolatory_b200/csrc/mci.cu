@@ -279,90 +279,85 @@ mci_splat_kernel(const MciParams P)
 // not a hole, the TARGET-frame pixel if it is a hole at raster <= h, nothing otherwise.
 // np.median: middle element, or the f64 mean of the two middles truncated on the uint8 store.
 // One warp per hole; the k-th smallest byte is found by bisection on the value.
-__device__ __forceinline__ int warp_sum(int v)
+// One warp per hole.  The warp histograms the contributing window pixels per channel in shared
+// memory (3 x 256 counters), then each lane owns 8 bins: a warp prefix scan locates the lane and
+// bin holding rank (n-1)/2 and rank n/2.
+#define HF_WARPS 4
+
+__device__ __forceinline__ int hist_select(const unsigned *__restrict__ hist, int lane, int k_lo, int k_hi, int &v_hi)
 {
+    const uint4 a = *reinterpret_cast<const uint4 *>(hist + lane * 8);
+    const uint4 c = *reinterpret_cast<const uint4 *>(hist + lane * 8 + 4);
+    const unsigned cnt[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    unsigned local = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+    for (int i = 0; i < 8; ++i) local += cnt[i];
+    unsigned incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const unsigned excl = incl - local;
+    int found_lo = -1, found_hi = -1;
+    if ((unsigned)k_lo >= excl && (unsigned)k_lo < incl) {
+        unsigned run = excl;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { run += cnt[i]; if (found_lo < 0 && (unsigned)k_lo < run) found_lo = lane * 8 + i; }
+    }
+    if ((unsigned)k_hi >= excl && (unsigned)k_hi < incl) {
+        unsigned run = excl;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { run += cnt[i]; if (found_hi < 0 && (unsigned)k_hi < run) found_hi = lane * 8 + i; }
+    }
+    v_hi = __reduce_max_sync(0xffffffffu, found_hi);
+    return __reduce_max_sync(0xffffffffu, found_lo);
 }
 
-__global__ void mci_holefill_kernel(const uint8_t *__restrict__ tgt, uint8_t *out, const uint8_t *__restrict__ mask,
-                                    const int *__restrict__ hole_list, const int *__restrict__ counters, int H, int W)
+__global__ void __launch_bounds__(HF_WARPS * 32)
+mci_holefill_kernel(const uint8_t *__restrict__ tgt, uint8_t *out, const uint8_t *__restrict__ mask,
+                    const int *__restrict__ hole_list, const int *__restrict__ counters, int H, int W)
 {
-    const int lane = threadIdx.x & 31;
+    __shared__ __align__(16) unsigned hist_all[HF_WARPS][3][256];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned (*hist)[256] = hist_all[wib];
     const int n_holes = counters[1];
     for (int hi = warp; hi < n_holes; hi += nwarps) {
         const int h = hole_list[hi];
         const int u = h / W, v = h - u * W;
         const int u0 = max(0, u - 10), u1 = min(H, u + 11), v0 = max(0, v - 10), v1 = min(W, v + 11);
         const int ww = v1 - v0, total = (u1 - u0) * ww;
-        unsigned vals[14];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+            *reinterpret_cast<uint4 *>(&hist[0][0] + (i * 32 + lane) * 4) = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
         int cnt = 0;
-#pragma unroll
-        for (int s = 0; s < 14; ++s) {
-            const int e = lane + 32 * s;
-            unsigned pk = 0u;
-            if (e < total) {
-                const int a = u0 + e / ww, b = v0 + e % ww;
-                const int idx = a * W + b;
-                const uint8_t *p = nullptr;
-                if (!mask[idx]) p = out + (size_t)idx * 3;
-                else if (idx <= h) p = tgt + (size_t)idx * 3;
-                if (p) { pk = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | 0x01000000u; ++cnt; }
+        for (int e = lane; e < total; e += 32) {
+            const int a = u0 + e / ww, b = v0 + e % ww;
+            const int idx = a * W + b;
+            const uint8_t *p = nullptr;
+            if (!mask[idx]) p = out + (size_t)idx * 3;            // splat value
+            else if (idx <= h) p = tgt + (size_t)idx * 3;         // earlier hole: already replaced by the target pixel
+            if (p) {
+                atomicAdd(&hist[0][p[0]], 1u);
+                atomicAdd(&hist[1][p[1]], 1u);
+                atomicAdd(&hist[2][p[2]], 1u);
+                ++cnt;
             }
-            vals[s] = pk;
         }
-        const int n = __reduce_add_sync(0xffffffffu, cnt);   // >= 1: the hole itself contributes
+        __syncwarp();
+        const int n = __reduce_add_sync(0xffffffffu, cnt);        // >= 1: the hole itself contributes
         const int k_lo = (n - 1) >> 1, k_hi = n >> 1;
-        // Bisection on the value for all three channels at once: per channel the smallest v with
-        // count(x <= v) >= k_lo + 1.  The three counts (<= 441 < 2^10) travel in one REDUX.
-        int lo[3] = {0, 0, 0}, hi2[3] = {255, 255, 255};
-#pragma unroll 1
-        for (int step = 0; step < 8; ++step) {
-            const int m0 = (lo[0] + hi2[0]) >> 1, m1 = (lo[1] + hi2[1]) >> 1, m2 = (lo[2] + hi2[2]) >> 1;
-            unsigned c = 0;
-#pragma unroll
-            for (int s = 0; s < 14; ++s) {
-                const unsigned v = vals[s];
-                if (v >> 24) {
-                    c += ((int)(v & 255u) <= m0) + (((int)((v >> 8) & 255u) <= m1) << 10) + (((int)((v >> 16) & 255u) <= m2) << 20);
-                }
-            }
-            c = __reduce_add_sync(0xffffffffu, c);
-            const int c0 = c & 1023, c1 = (c >> 10) & 1023, c2 = c >> 20;
-            if (c0 >= k_lo + 1) hi2[0] = m0; else lo[0] = m0 + 1;
-            if (c1 >= k_lo + 1) hi2[1] = m1; else lo[1] = m1 + 1;
-            if (c2 >= k_lo + 1) hi2[2] = m2; else lo[2] = m2 + 1;
-        }
         unsigned res[3];
-        if (k_hi == k_lo) {
-            res[0] = lo[0]; res[1] = lo[1]; res[2] = lo[2];
-        } else {
-            // even count: upper middle = lower middle if enough copies of it, else the next larger value
-            unsigned c = 0;
-            int mn[3] = {256, 256, 256};
 #pragma unroll
-            for (int s = 0; s < 14; ++s) {
-                const unsigned v = vals[s];
-                if (v >> 24) {
-                    const int x0 = v & 255u, x1 = (v >> 8) & 255u, x2 = (v >> 16) & 255u;
-                    c += (x0 <= lo[0]) + ((x1 <= lo[1]) << 10) + ((x2 <= lo[2]) << 20);
-                    if (x0 > lo[0]) mn[0] = min(mn[0], x0);
-                    if (x1 > lo[1]) mn[1] = min(mn[1], x1);
-                    if (x2 > lo[2]) mn[2] = min(mn[2], x2);
-                }
-            }
-            c = __reduce_add_sync(0xffffffffu, c);
-            const int cc[3] = {(int)(c & 1023), (int)((c >> 10) & 1023), (int)(c >> 20)};
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const int m = __reduce_min_sync(0xffffffffu, mn[ch]);
-                const int v_hi = cc[ch] < k_hi + 1 ? m : lo[ch];
-                res[ch] = (unsigned)((lo[ch] + v_hi) >> 1);      // (a+b)/2.0 truncated on the uint8 store
-            }
+        for (int ch = 0; ch < 3; ++ch) {
+            int v_hi;
+            const int v_lo = hist_select(hist[ch], lane, k_lo, k_hi, v_hi);
+            res[ch] = (unsigned)((v_lo + v_hi) >> 1);             // np.median: (a+b)/2.0, truncated on the uint8 store
         }
+        __syncwarp();
         if (lane == 0) {
             uint8_t *o = out + (size_t)h * 3;
             o[0] = (uint8_t)res[0]; o[1] = (uint8_t)res[1]; o[2] = (uint8_t)res[2];
@@ -413,7 +408,7 @@ int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd
     memci_prof_end(ctx, prof);
     CKL(ctx);
     if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->mci_timed = 1; }
-    mci_holefill_kernel<<<ctx->num_sms * 8, 128, 0, ctx->stream>>>(P.tgt, P.out, P.mask, P.hole_list, P.counters, H, W);
+    mci_holefill_kernel<<<ctx->num_sms * 8, HF_WARPS * 32, 0, ctx->stream>>>(P.tgt, P.out, P.mask, P.hole_list, P.counters, H, W);
     CKL(ctx);
     FrameSlot &o = ctx->frames[out_slot];
     o.valid = 1; o.luma_ok = 0; o.pyr_levels = 0;
