@@ -464,12 +464,14 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                             int px[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) px[j] = wp[w * FS_BOXW + j];
+                            // pixel-major order: consecutive VABSDIFFs feed different accumulators
+                            // (independent chains), so one warp alone can keep the pipe busy
 #pragma unroll
-                            for (int gi = 0; gi < G; ++gi) {
-                                const int kk = w - gi;
-                                if (kk >= 0 && kk < 8) {
+                            for (int j = 0; j < 8; ++j) {
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) acc[gi] = __sad(r[kk][j], px[j], acc[gi]);
+                                for (int gi = 0; gi < G; ++gi) {
+                                    const int kk = w - gi;
+                                    if (kk >= 0 && kk < 8) acc[gi] = __sad(r[kk][j], px[j], acc[gi]);
                                 }
                             }
                         }

@@ -1,0 +1,141 @@
+"""CPU suite, part 2: host-side logic of the product (no GPU, no compute calls into the library)."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol(native_lib):
+    """include/memci_b200.h is the ABI: every MEMCI_API function must be exported by the .so
+    and bound by the ctypes layer."""
+    from interpolatory_b200 import _native
+    hdr = open(os.path.join(ROOT, "include", "memci_b200.h")).read()
+    declared = set(re.findall(r"MEMCI_API\s+[\w\s\*]+?\b(memci_\w+)\s*\(", hdr))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(native_lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
+    assert native_lib.memci_version() >= 100
+
+
+def test_no_cpu_fallback(native_lib):
+    """Without a device the product path must fail loudly, never compute on the host."""
+    from interpolatory_b200 import _native
+    from interpolatory_b200.ME.full_search import get_motion_vectors as fs
+    if native_lib.memci_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    z = np.zeros((16, 16, 3), np.uint8)
+    with pytest.raises(_native.MemciError):
+        fs(8, 7, z, z)
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dp, _, files in os.walk(os.path.join(ROOT, "interpolatory_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M) or "memci_oracle" in txt or "oracle/" in txt:
+                    bad.append(f)
+    assert not bad, bad
+
+
+def test_settings_parsing_and_dispatch():
+    from interpolatory_b200.MCI.MEMCIBaseInterpolator import MEMCIBaseInterpolator, fs, hbma
+    from interpolatory_b200.smoothing import median_filter
+    it = MEMCIBaseInterpolator(60)
+    assert (it.block_size, it.region, it.filter_size, it.sub_region, it.min_block_size, it.steps) == (8, 7, 4, 1, 4, 3)
+    assert it.me_mode is hbma and it.filter_mode is None and it.MV_field_idx == -1 and it.pad_size == 16
+    assert it.ME_args["upscale"] is False and it.ME_args["cost_str"] == "sad"
+    it = MEMCIBaseInterpolator(60, me_mode='fs', block_size='16', target_region='32', filter_mode='median', filter_size='8')
+    assert it.me_mode is fs and it.ME_args == {"block_size": 16, "target_region": 32}
+    assert it.filter_mode is median_filter and it.filter_size == 8
+    with pytest.raises(KeyError):
+        MEMCIBaseInterpolator(60, me_mode='nope')
+    with pytest.raises(KeyError):
+        MEMCIBaseInterpolator(60, filter_mode='nope')
+    with pytest.raises(ValueError):
+        MEMCIBaseInterpolator(60, block_size='8.5')
+
+
+def test_factory():
+    from interpolatory_b200 import MEMCI, UniDirInterpolator, BiDirInterpolator, InterpolatorDictionary
+    assert isinstance(MEMCI(60), UniDirInterpolator) and str(MEMCI(60)) == 'uniMEMCI'
+    assert isinstance(MEMCI(60, mci_mode='bidir'), BiDirInterpolator) and str(MEMCI(60, mci_mode='bidir')) == 'bwMEMCI'
+    assert InterpolatorDictionary['MEMCI'] is MEMCI
+    with pytest.raises(Exception, match='Unknown mci_mode'):
+        MEMCI(60, mci_mode='sideways')
+    with pytest.raises(NotImplementedError):
+        MEMCI(60, mci_mode='bidir2')
+    with pytest.raises(NotImplementedError):
+        MEMCI(60, me_mode='tss')
+
+
+def test_cli_settings_string():
+    from interpolatory_b200.util import deconstruct_interpolation_mode_and_settings as dec
+    mode, st = dec("MEMCI:me_mode=fs.mci_mode=bidir.block_size=8.target_region=16")
+    assert mode == "MEMCI" and st == dict(me_mode='fs', mci_mode='bidir', block_size='8', target_region='16')
+    assert dec("MEMCI") == ("MEMCI", {})
+    assert dec("MEMCI:junk.block_size=4")[1] == {"block_size": "4"}
+
+
+def test_auto_pyramid_depth_and_dist_cycle():
+    from interpolatory_b200.util import hbma_auto_steps, get_first_frame_idx_and_ratio
+    from interpolatory_b200.pipeline import interpolation_dists
+    assert hbma_auto_steps((1080, 1920)) == 4 and hbma_auto_steps((360, 640)) == 2 and hbma_auto_steps((2160, 3840)) == 5
+    assert hbma_auto_steps((72, 96)) == 1 and hbma_auto_steps((256, 256)) == 2
+    bits = lambda d: int(np.float32(d).view(np.uint32))
+    assert [bits(d) for d in interpolation_dists(2.0)] == [0x3f000000]
+    assert [bits(1. - get_first_frame_idx_and_ratio(i, 2.5)[1]) for i in (1, 2, 3, 4)] == [0x3ecccccc, 0x3f4ccccd, 0x3e4ccccc, 0x3f19999a]
+    assert [bits(d) for d in interpolation_dists(5.0)] == [0x3e4ccccc, 0x3ecccccc, 0x3f19999a, 0x3f4ccccd]
+    assert math.isclose(1. - get_first_frame_idx_and_ratio(4, 2.0)[1], 0.)
+
+
+def test_smoothing_tokens():
+    from interpolatory_b200.smoothing import filter_mode_of, mean_filter, median_filter, weighted_mean_filter
+
+    def weighted_mean_filter_ref(block):      # a reference-style callable is recognised by name
+        return 0
+    weighted_mean_filter_ref.__name__ = "weighted_mean_filter"
+    assert filter_mode_of(None) == "none" and filter_mode_of(mean_filter) == "mean"
+    assert filter_mode_of(median_filter) == "median" and filter_mode_of(weighted_mean_filter) == "weighted"
+    assert filter_mode_of(weighted_mean_filter_ref) == "weighted" and filter_mode_of("median") == "median"
+    with pytest.raises(ValueError):
+        filter_mode_of(lambda b: b)
+
+
+def test_sharding_plan():
+    from interpolatory_b200.sharding import pairs_of_rank, runs_of_rank, frames_needed, band_split
+    for n, w in ((16, 8), (17, 8), (5, 2), (3, 4)):
+        allp = sorted(p for r in range(w) for p in pairs_of_rank(n, r, w))
+        assert allp == list(range(n))
+        spans = [runs_of_rank(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n and all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+    assert frames_needed([2, 3, 7]) == [2, 3, 4, 7, 8]
+    bands = band_split(270, 8)          # 8K, 16-px blocks
+    assert bands[0][0] == 0 and bands[-1][1] == 270 and max(b - a for a, b in bands) - min(b - a for a, b in bands) <= 1
+
+
+def test_synthetic_sequence_is_deterministic():
+    from interpolatory_b200.synth import make_sequence
+    a = make_sequence(72, 96, 3, seed=5)
+    b = make_sequence(72, 96, 3, seed=5)
+    assert a.dtype == np.uint8 and a.shape == (3, 72, 96, 3) and np.array_equal(a, b)
+    assert not np.array_equal(a[0], a[1])
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """bench.py --impl reference needs no GPU: it times the CPU restatement on the host cores."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "frames/s"

@@ -1,0 +1,175 @@
+"""CPU suite, part 1: the oracle (oracle/memci_oracle.c) against the committed golden fixtures,
+i.e. against outputs of the UNMODIFIED reference (tests/golden/*.npz, made by oracle/gen_golden.py).
+This is what pins the oracle; the GPU tests then compare the CUDA path with the oracle."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from interpolatory_b200.synth import make_sequence
+
+SHAPES = [(72, 96), (50, 70), (37, 53)]
+FS_CFGS = [(8, 7), (8, 3), (4, 5), (16, 9), (8, 16)]
+HB_CFGS = [(8, 7, 1, 2, 4), (8, 3, 1, 1, 4), (8, 5, 2, 3, 2), (4, 2, 1, 1, 4), (16, 4, 1, 1, 4)]
+DISTS = [0.5, 0.39999998, 0.8, 0.19999999, 0.6]
+
+
+def sha(a):
+    a = np.ascontiguousarray(a)
+    return hashlib.sha256(a.tobytes()).hexdigest() + f":{a.dtype}:{'x'.join(map(str, a.shape))}"
+
+
+def test_ratio_table(oracle, golden):
+    """get_first_frame_idx_and_ratio: oracle copy and the product's host copy (src/util.py:49-60)."""
+    from interpolatory_b200.util import get_first_frame_idx_and_ratio as host_fn
+    tab = golden("ratio.npz")["table"]
+    for rr, idx, first, ratio in tab:
+        assert oracle.get_first_frame_idx_and_ratio(int(idx), rr) == (int(first), float(ratio))
+        assert host_fn(int(idx), rr) == (int(first), float(ratio))
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_fs(oracle, golden, shape):
+    g = golden("functions_small.npz")
+    k = f"{shape[0]}x{shape[1]}"
+    a, b = g[f"{k}/a"], g[f"{k}/b"]
+    fr = make_sequence(shape[0], shape[1], 2, seed=shape[0])
+    assert np.array_equal(fr[0], a) and np.array_equal(fr[1], b), "synthetic generator drifted from the fixtures"
+    for bs, R in FS_CFGS:
+        assert np.array_equal(oracle.fs_blocks(bs, R, a, b), g[f"{k}/fs/{bs}_{R}"]), (shape, bs, R)
+    assert np.array_equal(oracle.fs(8, 7, a, b), g[f"{k}/fs_dense/8_7"])
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_hbma_and_pyramid(oracle, golden, shape):
+    g = golden("functions_small.npz")
+    k = f"{shape[0]}x{shape[1]}"
+    a, b = g[f"{k}/a"], g[f"{k}/b"]
+    lvl = a
+    for s in (1, 2):
+        lvl = oracle.pyr_down(lvl)
+        assert np.array_equal(lvl, g[f"{k}/pyr/{s}"])
+    for cfg in HB_CFGS:
+        ref = g[f"{k}/hbma/{'_'.join(map(str, cfg))}"]
+        assert np.array_equal(oracle.hbma(*cfg, a, b, 'sad', False), ref), (shape, cfg)
+    assert np.array_equal(oracle.hbma(8, 7, 1, 2, 4, a, b), g[f"{k}/hbma_dense/8_7_1_2_4"])
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_smooth(oracle, golden, shape):
+    g = golden("functions_small.npz")
+    k = f"{shape[0]}x{shape[1]}"
+    fields = {"fs": g[f"{k}/fs_dense/8_7"], "hbma": g[f"{k}/hbma_dense/8_7_1_2_4"]}
+    for mode in ("mean", "median", "weighted"):
+        for fsz in (4, 8, 3):
+            for nm, mv in fields.items():
+                out = oracle.smooth(mode, mv, fsz)
+                assert np.array_equal(out[:, :, :2], g[f"{k}/smooth/{mode}_{fsz}/{nm}"]), (shape, mode, fsz, nm)
+                assert np.array_equal(out[:, :, 2], mv[:, :, 2])
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_mci(oracle, golden, shape):
+    g = golden("functions_small.npz")
+    k = f"{shape[0]}x{shape[1]}"
+    H, W = shape
+    a, b = g[f"{k}/a"], g[f"{k}/b"]
+    fwd, bwd = g[f"{k}/fs_dense/8_7"], oracle.fs(8, 7, b, a)
+    fwh, bwh = g[f"{k}/hbma_dense/8_7_1_2_4"], oracle.hbma(8, 7, 1, 2, 4, b, a)
+    for dist in DISTS:
+        d = np.float32(dist)
+        assert np.array_equal(oracle.unidir_helper(a, b, fwd, d), g[f"{k}/unidir/fs/{dist}"])
+        assert np.array_equal(oracle.bidir_helper(a, b, fwd, bwd, d), g[f"{k}/bidir/fs/{dist}"])
+        assert np.array_equal(oracle.unidir_helper(a, b, fwh, d), g[f"{k}/unidir/hbma/{dist}"])
+        assert np.array_equal(oracle.bidir_helper(a, b, fwh, bwh, d), g[f"{k}/bidir/hbma/{dist}"])
+    for trial in range(3):
+        gsz = int(g[f"{k}/rand/{trial}/g"])
+        f_ = np.kron(g[f"{k}/rand/{trial}/fwd"], np.ones((gsz, gsz, 1), np.float32))[:H, :W].copy()
+        b_ = np.kron(g[f"{k}/rand/{trial}/bwd"], np.ones((gsz, gsz, 1), np.float32))[:H, :W].copy()
+        for dist in (0.5, 0.39999998, 0.8):
+            d = np.float32(dist)
+            assert np.array_equal(oracle.unidir_helper(a, b, f_, d), g[f"{k}/rand/{trial}/unidir/{dist}"])
+            assert np.array_equal(oracle.bidir_helper(a, b, f_, b_, d), g[f"{k}/rand/{trial}/bidir/{dist}"])
+
+
+def test_middlebury_crops(oracle, golden):
+    g = golden("middlebury_crops.npz")
+    for name in ("RubberWhale", "Dimetrodon"):
+        a, b = g[f"{name}/a"], g[f"{name}/b"]
+        fwd, bwd = oracle.fs(8, 7, a, b), oracle.fs(8, 7, b, a)
+        assert np.array_equal(fwd[::8, ::8], g[f"{name}/fs_fwd"])
+        assert np.array_equal(bwd[::8, ::8], g[f"{name}/fs_bwd"])
+        assert np.array_equal(oracle.hbma(8, 7, 1, 1, 4, a, b, 'sad', False), g[f"{name}/hbma_fwd"])
+        assert np.array_equal(oracle.bidir_helper(a, b, fwd, bwd, np.float32(0.5)), g[f"{name}/bidir"])
+        assert np.array_equal(oracle.unidir_helper(a, b, fwd, np.float32(0.5)), g[f"{name}/unidir"])
+
+
+def test_class_api_small_clip(oracle, golden):
+    """The reference classes' whole-clip output (dist cycle, pass-through, MV cache) rebuilt from
+    oracle calls, for the two small clips of e2e.npz."""
+    import ast
+    from interpolatory_b200.util import get_first_frame_idx_and_ratio, hbma_auto_steps
+    g = golden("e2e.npz")
+    for key in ("72x96_24_60", "56x88_30_60"):
+        frames = g[f"{key}/frames"]
+        H, W = frames.shape[1:3]
+        fps_in, fps_out = int(key.split("_")[1]), int(key.split("_")[2])
+        rr = fps_out / fps_in
+        for si in range(7):
+            st = dict(ast.literal_eval(str(g[f"{key}/set{si}/settings"])))
+            want = g[f"{key}/set{si}/out"]
+            me = st.get('me_mode', 'hbma')
+            bs, R = int(st.get('block_size', 8)), int(st.get('target_region', 7))
+            mode, fsz = st.get('filter_mode', 'none'), int(st.get('filter_size', 4))
+            bidir = st.get('mci_mode', 'unidir') == 'bidir'
+            cache = {}
+            for i in range(len(want)):
+                first, ratio = get_first_frame_idx_and_ratio(i, rr)
+                dist = 1. - ratio
+                if dist == 0.:
+                    assert np.array_equal(frames[first], want[i])
+                    continue
+                a, b = frames[first], frames[first + 1]
+                if first not in cache:
+                    def est(x, y):
+                        mv = oracle.fs(bs, R, x, y) if me == 'fs' else oracle.hbma(bs, R, 1, hbma_auto_steps((H, W)), 4, x, y)
+                        return oracle.smooth(mode, mv, fsz)
+                    cache = {first: (est(a, b), est(b, a) if bidir else None)}
+                f_, b_ = cache[first]
+                out = oracle.bidir_helper(a, b, f_, b_, np.float32(dist)) if bidir else oracle.unidir_helper(a, b, f_, np.float32(dist))
+                assert np.array_equal(out, want[i]), (key, st, i)
+
+
+def test_cfg1_360p_digests(oracle, golden):
+    g = golden("cfg1_360p.npz")
+    fr = make_sequence(360, 640, 2, seed=0)
+    assert sha(fr) == str(g["frames_sha"])
+    a, b = fr[0], fr[1]
+    fwd, bwd = oracle.fs(8, 7, a, b), oracle.fs(8, 7, b, a)
+    assert np.array_equal(fwd[::8, ::8], g["fs_fwd"]) and np.array_equal(bwd[::8, ::8], g["fs_bwd"])
+    assert sha(oracle.bidir_helper(a, b, fwd, bwd, np.float32(0.5))) == str(g["bidir_fs_sha/0.5"])
+    assert sha(oracle.unidir_helper(a, b, fwd, np.float32(0.39999998))) == str(g["unidir_fs_sha/0.39999998"])
+    fwh = oracle.hbma(8, 7, 1, 2, 4, a, b)
+    assert np.array_equal(fwh[::4, ::4], g["hbma_fwd"])
+
+
+def test_fs_work_counts(oracle):
+    """Algorithmic candidate counts quoted in SURVEY.md 8d (incl. the H-for-W bound quirk)."""
+    assert oracle.fs_work(360, 640, 8, 7) == (622001, 39808064)
+    assert oracle.fs_work(1080, 1920, 8, 16) == (27311000, 1747904000)
+    n, ops = oracle.fs_work(2160, 3840, 16, 32)
+    assert ops == n * 256 and abs(ops - 2.701e10) / 2.701e10 < 1e-3
+
+
+def test_edge_cases(oracle):
+    """Frames smaller than a block, single-row/column block grids, flat frames (all-tie search)."""
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)
+    b = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)
+    mv = oracle.fs(8, 3, a, b)
+    assert mv.shape == (5, 7, 3) and np.all(mv[:, :, :2] == 0)
+    flat = np.full((24, 40, 3), 77, np.uint8)
+    mv = oracle.fs(8, 4, flat, flat)
+    assert np.all(mv == 0)          # SAD 0 everywhere: the zero vector wins the distance tie-break
+    out = oracle.bidir_helper(flat, flat, mv, mv, np.float32(0.5))
+    assert np.array_equal(out, flat)
