@@ -59,41 +59,60 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed regions (NVML in a thread, every ~2 ms;
+    falls back to `nvidia-smi -lms` when pynvml is unavailable)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.sm, self.pw, self.mask, self.max_sm = gpu_index, [], [], 0, None
+        self.stop_flag, self.thread, self.proc, self.rows = False, None, None, []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.pw.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                        self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            try:
+                q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                              "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.thread = threading.Thread(target=lambda: [self.rows.append([x.strip() for x in l.split(",")]) for l in self.proc.stdout],
+                                               daemon=True)
+                self.thread.start()
+            except Exception:
+                self.proc = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
-        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace('.', '').isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+            for r in self.rows:
+                if len(r) >= 7 and r[0].replace('.', '').isdigit():
+                    self.sm.append(float(r[0])); self.max_sm = float(r[1]); self.pw.append(float(r[2]))
+                    for i, n in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                        if r[3 + i].lower().startswith("active"):
+                            self.mask |= self.REASONS[n]
+        elif self.thread:
+            self.thread.join(timeout=1)
+        reasons = [n for n, bit in self.REASONS.items() if self.mask & bit]
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "power_w_max": max(self.pw) if self.pw else None, "samples": len(self.sm), "reasons": reasons,
+                "window": "device-resident timed region + e2e timed region"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -238,7 +257,6 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count()
     fs_ms_sum, fs_n, mci_ms_sum, mci_n = ctx.profile_collect()
-    clk = clocks.stop()
     n_holes = ctx.mci_stats()
     resident_last = ctx.download_frame(6 + ((nd - 1) & 1)).copy()
 
@@ -256,6 +274,7 @@ def main():
         pipe.run(pin_in.array, dists, pin_out.array)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
     e2e_launches = pipe.launch_count() - l0
     if not np.array_equal(pin_out.array[P * nd - 1], resident_last):
         raise SystemExit("e2e pipeline output differs from the device-resident path")

@@ -62,6 +62,10 @@ int memci_ensure_luma(memci_ctx *ctx, int slot)
 // ---------------------------------------------------------------------------------------
 __global__ void pyr_down_kernel(const uint8_t *__restrict__ in, int H, int W, uint8_t *__restrict__ out, int Ho, int Wo)
 {
+    // v / 255.0 for the 256 byte values, one correctly rounded f64 divide each (blockDim.x == 256)
+    __shared__ double lut[256];
+    lut[threadIdx.x] = __ddiv_rn((double)threadIdx.x, 255.0);
+    __syncthreads();
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= Ho * Wo) return;
     int oy = idx / Wo, ox = idx - oy * Wo;
@@ -78,8 +82,7 @@ __global__ void pyr_down_kernel(const uint8_t *__restrict__ in, int H, int W, ui
                 const uint8_t *p = in + ((size_t)yy * W + xx) * 3;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    double v = __ddiv_rn((double)p[c], 255.0);
-                    acc[c] = __dadd_rn(acc[c], __dmul_rn(v, w));
+                    acc[c] = __dadd_rn(acc[c], __dmul_rn(lut[p[c]], w));
                 }
             }
             // out-of-frame taps add 0.0 * w = +0.0, which never changes acc

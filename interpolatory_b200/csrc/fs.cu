@@ -8,6 +8,8 @@
 // with L = 0.299R + 0.587G + 0.114B in float64.  With L1000 = 299R + 587G + 114B (exact int)
 // and S = sum |L1000_1 - L1000_2|:  SAD = S / 1000 unless S % 1000 == 0 && S > 0, where the
 // f64 sum may land just below the integer and SAD = S/1000 - 1 ("flagged" candidates).
+#include <stdlib.h>
+
 #include "memci_internal.cuh"
 
 #define FS_NT 512
@@ -265,32 +267,42 @@ __device__ inline void fs_fill_tab(FsTileTab *tab, const FsTile t, const FsParam
     if (lane == 0) { tab->total_dx = total; tab->uniform_ndx = (uni && n0 > 0) ? n0 : 0; }
 }
 
-// Per-thread argmin over the G row offsets of one item.  dx is fixed and the row offset ascends
-// with gi, so the 32-bit key  ((sad << ks) + d2 + 1) << 4 | gi  under plain unsigned min
+// Per-thread argmin over the G row offsets of one group.  dx is fixed and the row offset ascends
+// with gi, so the 32-bit key  ((sad << ks) + d2 + 1) << GB | gi   (GB = 4 bits for G <= 16, else 6)  under plain unsigned min
 // reproduces the reference's update rule (lower SAD, then smaller distance, then earlier row).
 // kl is the same minimum with every flagged candidate (S % 1000 == 0) lowered to sad-1 and one
 // notch further, so that "kl < best key" also covers a flagged candidate that would TIE the
 // winner on (sad-1, d2) and could beat it on scan order.  S == 0 also has remainder 0; its
 // lowered key wraps to a huge value and is ignored by the min.
+//
+// The kernel is bound by the integer-ALU pipe (VABSDIFF), so everything here that can be an IMAD
+// is written as one (multiplies by run-time constants instead of shifts): the FMA pipe is idle.
+// Per candidate: 7 IMAD (fma pipe) + ~4 alu-pipe ops.  mulg = (1 << GB) << ks.
 template <int G, bool CHECK>
-__device__ __forceinline__ void fs_finalize(const unsigned (&acc)[G], int n_valid, int dy0, int dx, int ks,
+__device__ __forceinline__ void fs_finalize(const unsigned (&acc)[G], int n_valid, int dy0, int dx, unsigned mulg,
                                             unsigned &kb, unsigned &kl)
 {
-    const unsigned d20 = (unsigned)(dy0 * dy0 + dx * dx) + 1u;
-    const int two_dy0 = 2 * dy0;
-    const unsigned lower = ((1u << ks) + 1u) << 4;
+    constexpr unsigned GM = G <= 16 ? 16u : 64u;
+    const unsigned base = ((unsigned)(dy0 * dy0 + dx * dx) + 1u) * GM;
+    const unsigned two_dy0 = (unsigned)(2 * dy0);
+    const unsigned lower = mulg + GM;                        // one SAD step + one notch, in key units
+    const unsigned base_lo = base - lower;
     kb = 0xffffffffu; kl = 0xffffffffu;
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
         const unsigned S = acc[gi];
-        const unsigned q = S / 1000u;
-        const unsigned rem = S - q * 1000u;
-        const unsigned d2 = d20 + (unsigned)(gi * two_dy0 + gi * gi);
-        unsigned key = (((q << ks) + d2) << 4) + (unsigned)gi;
-        if (CHECK) { if (gi >= n_valid) key = 0xffffffffu; }      // rows past the window lose to everything
+        const unsigned q = S / 1000u;                         // IMAD.HI + one shift
+        unsigned rem, dk, dkl, key, lo, t;
+        // inline PTX keeps these as IMADs (the compiler would turn them into ALU-pipe shifts/adds/selects)
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(rem) : "r"(q), "r"(0xfffffc18u), "r"(S));                       // S - 1000 q
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(dk) : "r"(two_dy0), "r"(GM * (unsigned)gi), "r"(base + (GM * (unsigned)(gi * gi) + (unsigned)gi)));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(dkl) : "r"(two_dy0), "r"(GM * (unsigned)gi), "r"(base_lo + (GM * (unsigned)(gi * gi) + (unsigned)gi)));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(q), "r"(mulg), "r"(dk));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lo) : "r"(q), "r"(mulg), "r"(dkl));                            // key - lower
+        asm("min.u32 %0, %1, 1;" : "=r"(t) : "r"(rem));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lo) : "r"(t), "r"(lower), "r"(lo));                             // back to key unless rem == 0
+        if (CHECK) { if (gi >= n_valid) { key = 0xffffffffu; lo = 0xffffffffu; } }   // rows past the window lose
         kb = min(kb, key);
-        unsigned lo = key - (rem == 0u ? lower : 0u);
-        if (CHECK) { if (gi >= n_valid) lo = 0xffffffffu; }
         kl = min(kl, lo);
     }
 }
@@ -325,6 +337,8 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
     int *const stage0 = reinterpret_cast<int *>(smem_raw);
     const unsigned stage_bytes = (unsigned)stage_ints * 4u;
     const int m = SINGLE ? 1 : p.m;
+    constexpr int GB = G <= 16 ? 4 : 6;
+    const unsigned mulg = (1u << GB) << p.ks;
 
     if (tid == 0) {
         mbar_init(&full[0], 1);
@@ -479,15 +493,15 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                     const int n_valid = n_dy - g * G;       // > 0
                     const int dy0 = dy_lo + g * G;
                     unsigned kb32, kl32;
-                    if (n_valid >= G) fs_finalize<G, false>(acc, n_valid, dy0, dx, p.ks, kb32, kl32);
-                    else fs_finalize<G, true>(acc, n_valid, dy0, dx, p.ks, kb32, kl32);
+                    if (n_valid >= G) fs_finalize<G, false>(acc, n_valid, dy0, dx, mulg, kb32, kl32);
+                    else fs_finalize<G, true>(acc, n_valid, dy0, dx, mulg, kb32, kl32);
                     // groups ascend in row offset: strict '<' on (sad, d2) keeps the earlier row on ties
-                    if ((kb32 >> 4) < (kb_run >> 4)) { kb_run = kb32; g_run = g; }
+                    if ((kb32 >> GB) < (kb_run >> GB)) { kb_run = kb32; g_run = g; }
                     klow = min(klow, kl32);
                 }
                 if (kb_run != 0xffffffffu) {
-                    const unsigned kq = (kb_run >> 4) - 1u;
-                    kbest = fs_key(kq >> p.ks, kq & ((1u << p.ks) - 1u), (unsigned)(g_run * G) + (kb_run & 15u), (unsigned)dxi);
+                    const unsigned kq = (kb_run >> GB) - 1u;
+                    kbest = fs_key(kq >> p.ks, kq & ((1u << p.ks) - 1u), (unsigned)(g_run * G) + (kb_run & ((1u << GB) - 1u)), (unsigned)dxi);
                 }
             }
             // one atomic per warp when the whole warp works on one block (the common case)
@@ -497,11 +511,11 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                 klow = __reduce_min_sync(0xffffffffu, klow);
                 if (lane == 0) {
                     if (kbest != KEY_NONE) atomicMin(&best_fast[k & 1][b0], kbest);
-                    if (klow != 0xffffffffu) atomicMin(&best_low[k & 1][b0], klow >> 4);
+                    if (klow != 0xffffffffu) atomicMin(&best_low[k & 1][b0], klow >> GB);
                 }
             } else if (active) {
                 if (kbest != KEY_NONE) atomicMin(&best_fast[k & 1][b], kbest);
-                if (klow != 0xffffffffu) atomicMin(&best_low[k & 1][b], klow >> 4);
+                if (klow != 0xffffffffu) atomicMin(&best_low[k & 1][b], klow >> GB);
             }
         }
         __syncwarp();
@@ -558,6 +572,10 @@ static int make_tmap(memci_ctx *ctx, CUtensorMap *tm, const int32_t *plane, int 
 
 static int pick_G(int R)
 {
+    if (const char *e = getenv("MEMCI_FS_G")) {          // tuning override
+        int g = atoi(e);
+        if (g == 5 || g == 8 || g == 11 || g == 13 || g == 17 || g == 33) return g;
+    }
     // group size dividing 2R+1 where possible (no half-empty last group)
     const int n = 2 * R + 1;
     const int cands[4] = {11, 13, 8, 5};
@@ -603,12 +621,11 @@ static FsPlan *fs_get_plan(memci_ctx *ctx, int bs, int R)
     pl->n_cand = n_cand;
     pl->n_tiles = 0; pl->d_tiles = nullptr;
     int key_bits = 0;
-    { int ks = 1; while ((1 << ks) <= 2 * R * R + 1) ++ks; int qb = 1; while ((1ll << qb) <= (long long)bs * bs * 255) ++qb; key_bits = ks + qb + 4; }
+    { int ks = 1; while ((1 << ks) <= 2 * R * R + 1) ++ks; int qb = 1; while ((1ll << qb) <= (long long)bs * bs * 255) ++qb; key_bits = ks + qb + (pl->G <= 16 ? 4 : 6); }
     const bool tiled_ok = (bs % 8 == 0) && bs <= 64 && R <= 120 && key_bits <= 32 && (bs + 2 * R + 4) <= FS_BOXW &&
                           fs_smem_bytes(bs, pl->box_h, 1, pl->G) <= 200 * 1024;
     if (tiled_ok) {
         const int Rp = (R + 3) & ~3;
-        const int nb_box = (FS_BOXW - R - Rp) / bs < FS_NBMAX ? (FS_BOXW - R - Rp) / bs : FS_NBMAX;
         // one item (candidate column of one block) per thread per tile
         const int budget = FS_NT;
         FsTile *h = (FsTile *)malloc(sizeof(FsTile) * (size_t)nbr * nbc);
@@ -617,10 +634,13 @@ static FsPlan *fs_get_plan(memci_ctx *ctx, int bs, int R)
             int bc = 0;
             while (bc < nbc) {
                 int nb = 0, items = 0;
-                while (bc + nb < nbc && nb < nb_box) {
+                while (bc + nb < nbc && nb < FS_NBMAX) {
                     FsBounds b = fs_bounds(H, W, bs, R, br * bs, (bc + nb) * bs);
                     int n_dx = b.c1 - b.c0 > 0 ? b.c1 - b.c0 : 0;
                     int add = n_dx;
+                    // rightmost window column this block reads: origin is x0 - Rp, last offset is c1 - 1
+                    int right = Rp + nb * bs + (n_dx > 0 ? (b.c1 - 1 - (bc + nb) * bs) : 0) + bs;
+                    if (right > FS_BOXW || (nb + 1) * bs > FS_BOXW) break;
                     if (nb > 0 && items + add > budget) break;
                     items += add; ++nb;
                 }
@@ -699,6 +719,8 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         case 5: rc = fs_launch_tiled<5>(ctx, ts, tt, p, smem); break;
         case 8: rc = fs_launch_tiled<8>(ctx, ts, tt, p, smem); break;
         case 13: rc = fs_launch_tiled<13>(ctx, ts, tt, p, smem); break;
+        case 17: rc = fs_launch_tiled<17>(ctx, ts, tt, p, smem); break;
+        case 33: rc = fs_launch_tiled<33>(ctx, ts, tt, p, smem); break;
         default: rc = fs_launch_tiled<11>(ctx, ts, tt, p, smem); break;
         }
         memci_prof_end(ctx, prof);

@@ -2,7 +2,7 @@
 //
 // HBMA evaluates ~27 candidates per block per level (3 candidate vectors x 3x3 refinement),
 // two orders of magnitude less SAD work than full search, so the kernels here are the simple
-// warp-per-block form: lanes = candidates, luma1000 planes read through L1/L2.
+// warp-per-block form: lanes = candidates, block + search region staged per warp in shared memory.
 //
 // Cost model (get_cost, hbma.py:15-31): float32( sum_f64 |L1-L2| ), compared as float32.
 // (float)((double)S1000 / 1000.0) reproduces it unless the value sits within the f64
@@ -63,19 +63,109 @@ __device__ inline BwRes bwfs_warp(const int32_t *__restrict__ L1, const int32_t 
     return res;
 }
 
+
+// float32 cost of a candidate from its integer SAD S (luma*1000 units): get_cost returns
+// float32(f64 sum), and the f64 sum is within eps of S/1000.  fdiv_rn(S, 1000) is the correctly
+// rounded float32 of S/1000; it is also the reference's value unless S/1000 lies within eps of the
+// rounding boundary (half an ulp away from the result), in which case the caller replays in f64.
+__device__ __forceinline__ bool cost_from_S(unsigned S, float eps, float &cost)
+{
+    if (S >= (1u << 24)) return false;
+    const float Sf = (float)S;
+    const float f = __fdiv_rn(Sf, 1000.0f);
+    const float r = fmaf(-f, 1000.0f, Sf);                              // exact remainder S - 1000 f
+    const float half_ulp = __int_as_float(max((__float_as_int(f) & 0x7f800000) - (24 << 23), 0));
+    cost = f;
+    return S == 0u || (half_ulp - fabsf(r) * 0.001f) > eps + half_ulp * 1e-3f;
+}
+
+// block_wise_fs (hbma.py:34-75) with the block and the search region staged in this warp's
+// shared memory (zero filled outside the frame = np.pad).  Lanes = candidates; every lane returns
+// the winner.  `sm` must hold bs*bs + (bs+2*win)^2 ints.
+__device__ inline BwRes bwfs_warp_staged(int *sm, const int32_t *__restrict__ L1, const int32_t *__restrict__ L2,
+                                         const uint8_t *__restrict__ rgb1, const uint8_t *__restrict__ rgb2,
+                                         int H, int W, int Wp, int ar, int ac, int idx_r, int idx_c, int win, int bs,
+                                         int cost_key, float eps, int lane, bool block_staged)
+{
+    BwRes res;
+    if (idx_r >= H || idx_c >= W || idx_r < 0 || idx_c < 0) {           // :36-37
+        res.r = 0.f; res.c = 0.f; res.cost = __int_as_float(0x7f800000);
+        return res;
+    }
+    int max_r = win + 1, min_r = -win, max_c = win + 1, min_c = -win;
+    if (idx_r + win + bs >= H) max_r = max(1, H - idx_r - bs);           // :53-54
+    if (idx_r - win < 0) min_r += win - idx_r;                           // :55-56
+    if (idx_c + win + bs >= W) max_c = max(1, W - idx_c - bs);
+    if (idx_c - win < 0) min_c += win - idx_c;
+    const int nr = max_r - min_r, nc = max_c - min_c, n = nr * nc;
+    int *blk = sm, *reg = sm + bs * bs;
+    const int rh = nr + bs - 1, rw = nc + bs - 1;
+    if (!block_staged) {
+        for (int i = lane; i < bs * bs; i += 32) {
+            const int r = ar + i / bs, c = ac + i % bs;
+            blk[i] = (r < H && c < W) ? L1[(size_t)r * Wp + c] : 0;
+        }
+    }
+    __syncwarp();
+    const int r0 = idx_r + min_r, c0 = idx_c + min_c;                    // >= 0 by construction
+    for (int i = lane; i < rh * rw; i += 32) {
+        const int r = r0 + i / rw, c = c0 + i % rw;
+        reg[i] = (r < H && c < W) ? L2[(size_t)r * Wp + c] : 0;
+    }
+    __syncwarp();
+    unsigned long long best = 0xffffffffffffffffull;
+    for (int cand = lane; cand < n; cand += 32) {
+        const int ri = cand / nc, ci = cand - ri * nc;
+        const int r_off = min_r + ri, c_off = min_c + ci;
+        float cost;
+        bool ok = false;
+        if (cost_key == 0) {
+            unsigned S = 0;
+            const int *rp = reg + ri * rw + ci;
+            for (int i = 0; i < bs; ++i)
+                for (int j = 0; j < bs; ++j) S = __sad(blk[i * bs + j], rp[i * rw + j], S);
+            ok = cost_from_S(S, eps, cost);
+        }
+        if (!ok) cost = (float)exact_cost_f64(rgb1, rgb2, H, W, ar, ac, idx_r + r_off, idx_c + c_off, bs, cost_key);
+        const unsigned d2 = (unsigned)(r_off * r_off + c_off * c_off);
+        const unsigned long long k = ((unsigned long long)__float_as_uint(cost) << 32) |
+                                     ((unsigned long long)d2 << 16) | ((unsigned)ri << 8) | (unsigned)ci;
+        best = k < best ? k : best;
+    }
+    best = shfl_min_u64(best);
+    __syncwarp();
+    res.r = (float)(min_r + (int)((best >> 8) & 255));
+    res.c = (float)(min_c + (int)(best & 255));
+    res.cost = __uint_as_float((unsigned)(best >> 32));
+    return res;
+}
+
+#define HBMA_WARPS 8
+__device__ __forceinline__ BwRes bwfs_any(int *sm, int sm_ints, const int32_t *L1, const int32_t *L2, const uint8_t *rgb1,
+                                          const uint8_t *rgb2, int H, int W, int Wp, int ar, int ac, int idx_r, int idx_c,
+                                          int win, int bs, int cost_key, double eps, int lane, bool block_staged)
+{
+    const int need = bs * bs + (bs + 2 * win) * (bs + 2 * win);
+    if (need <= sm_ints)
+        return bwfs_warp_staged(sm, L1, L2, rgb1, rgb2, H, W, Wp, ar, ac, idx_r, idx_c, win, bs, cost_key, (float)eps, lane, block_staged);
+    return bwfs_warp(L1, L2, rgb1, rgb2, H, W, Wp, ar, ac, idx_r, idx_c, win, bs, cost_key, eps, lane);
+}
+
 // full_search_jit (hbma.py:77-90): block-level field on the coarsest level.
 __global__ void hbma_fs_kernel(const int32_t *__restrict__ L1, const int32_t *__restrict__ L2,
                                const uint8_t *__restrict__ rgb1, const uint8_t *__restrict__ rgb2,
                                int H, int W, int Wp, int bs, int win, int cost_key, double eps,
-                               int rows, int cols, float2 *__restrict__ vec, float *__restrict__ cost)
+                               int rows, int cols, float2 *__restrict__ vec, float *__restrict__ cost, int sm_ints)
 {
+    extern __shared__ int hbma_sm[];
+    int *sm = hbma_sm + (threadIdx.x >> 5) * sm_ints;
     int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int blk = warp; blk < rows * cols; blk += nwarps) {
         int row = blk / cols, col = blk - row * cols;
-        BwRes r = bwfs_warp(L1, L2, rgb1, rgb2, H, W, Wp, row * bs, col * bs, row * bs, col * bs, win, bs,
-                            cost_key, eps, lane);
+        BwRes r = bwfs_any(sm, sm_ints, L1, L2, rgb1, rgb2, H, W, Wp, row * bs, col * bs, row * bs, col * bs, win, bs,
+                           cost_key, eps, lane, false);
         if (lane == 0) { vec[blk] = make_float2(r.r, r.c); cost[blk] = r.cost; }
     }
 }
@@ -86,8 +176,10 @@ __global__ void hbma_densify_kernel(const int32_t *__restrict__ L1, const int32_
                                     int H, int W, int Wp, int bs, int sub_win, int cost_key, double eps, int vec_scale,
                                     const float2 *__restrict__ in_vec, int in_rows, int in_cols, int in_pitch,
                                     float2 *__restrict__ out_vec, float *__restrict__ out_cost,
-                                    int out_rows, int out_cols, int out_pitch)
+                                    int out_rows, int out_cols, int out_pitch, int sm_ints)
 {
+    extern __shared__ int hbma_sm[];
+    int *sm = hbma_sm + (threadIdx.x >> 5) * sm_ints;
     int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -115,15 +207,89 @@ __global__ void hbma_densify_kernel(const int32_t *__restrict__ L1, const int32_
             v[2] = make_float2(__fmul_rn(u.x, sc), __fmul_rn(u.y, sc));
             int im_r = o_r * bs, im_c = o_c * bs;
             float lowest = __int_as_float(0x7f800000);
+            if (sm_ints > 0) {                       // stage the child block once for its three searches
+                for (int i = lane; i < bs * bs; i += 32) {
+                    const int r = im_r + i / bs, c = im_c + i % bs;
+                    sm[i] = (r < H && c < W) ? L1[(size_t)r * Wp + c] : 0;
+                }
+                __syncwarp();
+            }
+            const int rdim = bs + 2 * sub_win;
+            if (sm_ints >= bs * bs + 3 * rdim * rdim) {
+                // ---- fused: the three searches' candidates (<= 3 (2 sub+1)^2) share one pass over the lanes ----
+                int idr[3], idc[3], mnr[3], mnc[3], nr[3], nc[3], off[4];
+                off[0] = 0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    idr[k] = (int)((double)im_r + (double)v[k].x);                // f64 sum, trunc to int32 (:134)
+                    idc[k] = (int)((double)im_c + (double)v[k].y);
+                    const bool inside = !(idr[k] >= H || idc[k] >= W || idr[k] < 0 || idc[k] < 0);   // :36-37
+                    int max_r = sub_win + 1, min_r = -sub_win, max_c = sub_win + 1, min_c = -sub_win;
+                    if (idr[k] + sub_win + bs >= H) max_r = max(1, H - idr[k] - bs);
+                    if (idr[k] - sub_win < 0) min_r += sub_win - idr[k];
+                    if (idc[k] + sub_win + bs >= W) max_c = max(1, W - idc[k] - bs);
+                    if (idc[k] - sub_win < 0) min_c += sub_win - idc[k];
+                    mnr[k] = min_r; mnc[k] = min_c;
+                    nr[k] = inside ? max_r - min_r : 0; nc[k] = inside ? max_c - min_c : 0;
+                    off[k + 1] = off[k] + nr[k] * nc[k];
+                    if (inside) {
+                        int *reg = sm + bs * bs + k * rdim * rdim;
+                        const int rh = nr[k] + bs - 1, rw = nc[k] + bs - 1;
+                        const int r0 = idr[k] + min_r, c0 = idc[k] + min_c;
+                        for (int i = lane; i < rh * rw; i += 32) {
+                            const int r = r0 + i / rw, c = c0 + i % rw;
+                            reg[i] = (r < H && c < W) ? L2[(size_t)r * Wp + c] : 0;
+                        }
+                    }
+                }
+                __syncwarp();
+                unsigned long long best[3] = {~0ull, ~0ull, ~0ull};
+                for (int cand = lane; cand < off[3]; cand += 32) {
+                    const int k = cand >= off[2] ? 2 : (cand >= off[1] ? 1 : 0);
+                    const int loc = cand - off[k];
+                    const int ri = loc / nc[k], ci = loc - ri * nc[k];
+                    const int r_off = mnr[k] + ri, c_off = mnc[k] + ci;
+                    const int rw = nc[k] + bs - 1;
+                    float cost;
+                    bool ok = false;
+                    if (cost_key == 0) {
+                        unsigned S = 0;
+                        const int *rp = sm + bs * bs + k * rdim * rdim + ri * rw + ci;
+                        for (int i = 0; i < bs; ++i)
+                            for (int j = 0; j < bs; ++j) S = __sad(sm[i * bs + j], rp[i * rw + j], S);
+                        ok = cost_from_S(S, (float)eps, cost);
+                    }
+                    if (!ok) cost = (float)exact_cost_f64(rgb1, rgb2, H, W, im_r, im_c, idr[k] + r_off, idc[k] + c_off, bs, cost_key);
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(cost) << 32) |
+                                                   ((unsigned long long)(unsigned)(r_off * r_off + c_off * c_off) << 16) |
+                                                   ((unsigned)ri << 8) | (unsigned)ci;
+#pragma unroll
+                    for (int kk = 0; kk < 3; ++kk) if (kk == k) best[kk] = key < best[kk] ? key : best[kk];
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const unsigned long long bk = shfl_min_u64(best[k]);
+                    // out-of-frame search centre returns [0, 0, inf] and is never selected (:36-37, :135)
+                    const float cost = nr[k] > 0 ? __uint_as_float((unsigned)(bk >> 32)) : __int_as_float(0x7f800000);
+                    if (cost < lowest) {                                          // strict: first vector wins ties (:135)
+                        lowest = cost;
+                        oc = cost;
+                        o = make_float2(__fadd_rn((float)(mnr[k] + (int)((bk >> 8) & 255)), v[k].x),
+                                        __fadd_rn((float)(mnc[k] + (int)(bk & 255)), v[k].y));
+                    }
+                }
+                __syncwarp();
+            } else {
 #pragma unroll 1
-            for (int k = 0; k < 3; ++k) {
-                int ir = (int)((double)im_r + (double)v[k].x);                    // f64 sum, trunc to int32 (:134)
-                int ic = (int)((double)im_c + (double)v[k].y);
-                BwRes r = bwfs_warp(L1, L2, rgb1, rgb2, H, W, Wp, im_r, im_c, ir, ic, sub_win, bs, cost_key, eps, lane);
-                if (r.cost < lowest) {                                            // strict: first vector wins ties (:135)
-                    lowest = r.cost;
-                    oc = r.cost;
-                    o = make_float2(__fadd_rn(r.r, v[k].x), __fadd_rn(r.c, v[k].y));
+                for (int k = 0; k < 3; ++k) {
+                    int ir = (int)((double)im_r + (double)v[k].x);                // f64 sum, trunc to int32 (:134)
+                    int ic = (int)((double)im_c + (double)v[k].y);
+                    BwRes r = bwfs_any(sm, sm_ints, L1, L2, rgb1, rgb2, H, W, Wp, im_r, im_c, ir, ic, sub_win, bs, cost_key, eps, lane, true);
+                    if (r.cost < lowest) {                                        // strict: first vector wins ties (:135)
+                        lowest = r.cost;
+                        oc = r.cost;
+                        o = make_float2(__fadd_rn(r.r, v[k].x), __fadd_rn(r.c, v[k].y));
+                    }
                 }
             }
         }
@@ -195,21 +361,29 @@ int memci_hbma_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int win, 
     for (int i = 0; i < 2; ++i)
         if ((rc = memci_mv_reserve(ctx, &ctx->tmp_mv[i], 1, 1, (int)max_cells, 1, 1, (int)max_cells))) return rc;
 
-    const int grid = ctx->num_sms * 8, nt = 256;
+    const int grid = ctx->num_sms * 8, nt = HBMA_WARPS * 32;
+    auto sm_ints_for = [&](int b, int w) {               // per-warp staging: block + search region, capped at 6 KB
+        int need = b * b + (b + 2 * w) * (b + 2 * w);
+        return need <= 1536 ? need : 0;
+    };
     int cur = 0;
     int rows = ceil_div_i(hs[steps], bs), cols = ceil_div_i(ws[steps], bs), pitch = cols;
-    hbma_fs_kernel<<<grid, nt, 0, ctx->stream>>>(LUMA(f1, steps), LUMA(f2, steps), RGB(f1, steps), RGB(f2, steps),
-                                                 hs[steps], ws[steps], WP(steps), bs, win, cost_key, hbma_eps(bs),
-                                                 rows, cols, ctx->tmp_mv[cur].vec, ctx->tmp_mv[cur].sad);
+    {
+        const int smi = sm_ints_for(bs, win);
+        hbma_fs_kernel<<<grid, nt, smi * HBMA_WARPS * sizeof(int), ctx->stream>>>(
+            LUMA(f1, steps), LUMA(f2, steps), RGB(f1, steps), RGB(f2, steps), hs[steps], ws[steps], WP(steps), bs, win,
+            cost_key, hbma_eps(bs), rows, cols, ctx->tmp_mv[cur].vec, ctx->tmp_mv[cur].sad, smi);
+    }
     CKL(ctx);
     auto densify = [&](int lvl, int b, int vec_scale) -> int {
         int orows = ceil_div_i(hs[lvl], b), ocols = ceil_div_i(ws[lvl], b);   // the slice kept by the reference
         int opitch = cols * 2;
-        hbma_densify_kernel<<<grid, nt, 0, ctx->stream>>>(LUMA(f1, lvl), LUMA(f2, lvl), RGB(f1, lvl), RGB(f2, lvl),
-                                                          hs[lvl], ws[lvl], WP(lvl), b, sub, cost_key, hbma_eps(b), vec_scale,
-                                                          ctx->tmp_mv[cur].vec, rows, cols, pitch,
-                                                          ctx->tmp_mv[cur ^ 1].vec, ctx->tmp_mv[cur ^ 1].sad,
-                                                          orows, ocols, opitch);
+        int smi = b * b + 3 * (b + 2 * sub) * (b + 2 * sub);          // fused three-vector search
+        if (smi > 1536) smi = sm_ints_for(b, sub);
+        hbma_densify_kernel<<<grid, nt, smi * HBMA_WARPS * sizeof(int), ctx->stream>>>(
+            LUMA(f1, lvl), LUMA(f2, lvl), RGB(f1, lvl), RGB(f2, lvl), hs[lvl], ws[lvl], WP(lvl), b, sub, cost_key, hbma_eps(b),
+            vec_scale, ctx->tmp_mv[cur].vec, rows, cols, pitch, ctx->tmp_mv[cur ^ 1].vec, ctx->tmp_mv[cur ^ 1].sad,
+            orows, ocols, opitch, smi);
         CKL(ctx);
         cur ^= 1; rows = orows; cols = ocols; pitch = opitch;
         return MEMCI_OK;

@@ -16,6 +16,8 @@
 // "does the pixel at q - e really carry displacement e?" and replaying the reference's state
 // machine (SAD_interpolated_frame / Interpolated_Frame) in registers.  Holes (pixels no event
 // reached) are recorded and filled by a second kernel with the 21x21 masked median.
+#include <type_traits>
+
 #include "memci_internal.cuh"
 
 #define MCI_TW 32
@@ -77,6 +79,62 @@ struct PixState {
 
 __device__ __forceinline__ int cell_of(int x, int cell, int shift) { return shift >= 0 ? (x >> shift) : (x / cell); }
 
+// Apply the event "source pixel (p_r, p_c) of direction DIR lands on this target pixel".
+template <int DIR>
+__device__ __forceinline__ void mci_apply_t(const MciParams &P, PixState &st, int p_r, int p_c, bool self_write)
+{
+    const float sad = P.sad[DIR][cell_of(p_r, P.scell[DIR], P.sshift[DIR]) * P.scols[DIR] + cell_of(p_c, P.scell[DIR], P.sshift[DIR])];
+    const uint8_t *px = (DIR == 0 ? P.src : P.tgt) + ((size_t)p_r * P.W + p_c) * 3;
+    if (!P.bidir) {
+        if (self_write || sad <= st.sadi) {             // Unidirectional.py:52 (non-strict) / :56-58
+            st.v0 = px[0]; st.v1 = px[1]; st.v2 = px[2];
+            st.sadi = sad; st.written = true;
+        }
+    } else if (DIR == 0) {
+        if (sad < st.sadi) {                            // Bidirectional.py:37 (strict)
+            st.v0 = px[0]; st.v1 = px[1]; st.v2 = px[2];
+            st.sadi = sad; st.written = true;
+        }
+    } else {
+        if (sad < st.sadi) {                            // :46
+            if (st.sadi != __int_as_float(0x7f800000)) {
+                // :48-49.  numba types the fused expression float32:
+                //   f32( f64( f32(u8*SADI) / t ) + f64(IF) * f64(bsad) / f64(t) ), truncated to int32 (W3)
+                const float t = __fadd_rn(sad, st.sadi);
+                const double td = (double)t, bd = (double)sad;
+                int v[3] = {st.v0, st.v1, st.v2};
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    // fast estimate of the blended value; it decides the truncation unless it falls
+                    // within 1e-3 of an integer (its error is < 1e-4), where the exact mixed-precision
+                    // expression of the reference is evaluated instead (f64 divide: ~100 instructions)
+                    const float est = __fdividef(fmaf((float)px[ch], st.sadi, (float)v[ch] * sad), t);
+                    const float fl = floorf(est), fr = est - fl;
+                    if (fr > 1e-3f && fr < 0.999f) {
+                        v[ch] = (int)fl;
+                    } else {
+                        float a = __fdiv_rn(__fmul_rn((float)px[ch], st.sadi), t);
+                        double c = __ddiv_rn(__dmul_rn((double)v[ch], bd), td);
+                        float s = __double2float_rn(__dadd_rn((double)a, c));
+                        v[ch] = __float2int_rz(s);
+                    }
+                }
+                st.v0 = v[0]; st.v1 = v[1]; st.v2 = v[2];
+            } else {                                    // :51-53
+                st.v0 = px[0]; st.v1 = px[1]; st.v2 = px[2];
+            }
+            st.sadi = sad; st.written = true;
+        }
+    }
+}
+
+__device__ __forceinline__ void mci_apply(const MciParams &P, PixState &st, int p_r, int p_c, int dir, bool self_write)
+{
+    if (dir == 0) mci_apply_t<0>(P, st, p_r, p_c, self_write);
+    else mci_apply_t<1>(P, st, p_r, p_c, self_write);
+}
+
+// Generic event test (dense fallback): does the pixel at q - e carry effective displacement e?
 __device__ __forceinline__ void mci_try_event(const MciParams &P, PixState &st, int q_r, int q_c,
                                               int eff_r, int eff_c, int dir)
 {
@@ -94,40 +152,7 @@ __device__ __forceinline__ void mci_try_event(const MciParams &P, PixState &st, 
         if (P.bidir || eff_r != 0 || eff_c != 0) return;
         self_write = true;
     }
-    const float sad = P.sad[dir][cell_of(p_r, P.scell[dir], P.sshift[dir]) * P.scols[dir] + cell_of(p_c, P.scell[dir], P.sshift[dir])];
-    const uint8_t *px = (dir == 0 ? P.src : P.tgt) + ((size_t)p_r * P.W + p_c) * 3;
-    if (!P.bidir) {
-        if (self_write || sad <= st.sadi) {             // :52 (non-strict)
-            st.v0 = px[0]; st.v1 = px[1]; st.v2 = px[2];
-            st.sadi = sad; st.written = true;
-        }
-    } else if (dir == 0) {
-        if (sad < st.sadi) {                            // :37 (strict)
-            st.v0 = px[0]; st.v1 = px[1]; st.v2 = px[2];
-            st.sadi = sad; st.written = true;
-        }
-    } else {
-        if (sad < st.sadi) {                            // :46
-            if (st.sadi != __int_as_float(0x7f800000)) {
-                // :48-49.  numba types the fused expression float32:
-                //   f32( f64( f32(u8*SADI) / t ) + f64(IF) * f64(bsad) / f64(t) ), truncated to int32 (W3)
-                const float t = __fadd_rn(sad, st.sadi);
-                const double td = (double)t, bd = (double)sad;
-                int v[3] = {st.v0, st.v1, st.v2};
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    float a = __fdiv_rn(__fmul_rn((float)px[ch], st.sadi), t);
-                    double c = __ddiv_rn(__dmul_rn((double)v[ch], bd), td);
-                    float s = __double2float_rn(__dadd_rn((double)a, c));
-                    v[ch] = __float2int_rz(s);
-                }
-                st.v0 = v[0]; st.v1 = v[1]; st.v2 = v[2];
-            } else {                                    // :51-53
-                st.v0 = px[0]; st.v1 = px[1]; st.v2 = px[2];
-            }
-            st.sadi = sad; st.written = true;
-        }
-    }
+    mci_apply(P, st, p_r, p_c, dir, self_write);
 }
 
 __device__ __forceinline__ unsigned mci_key(int eff_r, int eff_c, int dir)
@@ -135,12 +160,20 @@ __device__ __forceinline__ unsigned mci_key(int eff_r, int eff_c, int dir)
     return ((unsigned)(MCI_KOFF - eff_r) << 15) | ((unsigned)(MCI_KOFF - eff_c) << 1) | (unsigned)dir;
 }
 
+// sorted list entry: effective displacement, the raw per-cell displacement it stands for, direction.
+// kind 0 = ordinary event; kind 1 = the unidirectional self-write slot at e = (0,0).
+struct __align__(16) MciEntry { int eff_r, eff_c; unsigned dpacked; int dir_kind; };
+
+#define MCI_STAGE_MAX 1536      // staged displacement cells per direction (6 KB)
+
 __global__ void __launch_bounds__(MCI_NT)
 mci_splat_kernel(const MciParams P)
 {
     __shared__ unsigned table[MCI_SLOTS];
     __shared__ unsigned list[MCI_MAXKEYS];
-    __shared__ unsigned sorted[MCI_MAXKEYS];
+    __shared__ unsigned dlist[MCI_MAXKEYS];
+    __shared__ MciEntry sorted[MCI_MAXKEYS];
+    __shared__ unsigned stage[2][MCI_STAGE_MAX];
     __shared__ int n_keys, overflow;
 
     const int tid = threadIdx.x;
@@ -154,10 +187,29 @@ mci_splat_kernel(const MciParams P)
     if (tid == 0) { n_keys = 0; overflow = keys_fit ? 0 : 1; }
     __syncthreads();
 
+    // un-wrapped neighbourhood of the tile, in cells, per direction (also the staging window)
+    int s_r0[2], s_c0[2], s_nc[2];
+    bool staged[2];
+    for (int dir = 0; dir < 2; ++dir) { s_r0[dir] = s_c0[dir] = 0; s_nc[dir] = 1; staged[dir] = false; }
+
     if (keys_fit) {
         // ---- 1. distinct (effective displacement, direction) values that can reach this tile ----
+        auto insert = [&](unsigned key, unsigned dpacked) {
+            unsigned h = (key * 2654435761u) >> 22;          // 10 bits
+            for (int probe = 0; probe < MCI_SLOTS; ++probe) {
+                const unsigned prev = atomicCAS(&table[h], MCI_EMPTY, key);
+                if (prev == key) return;
+                if (prev == MCI_EMPTY) {                      // this thread owns the new entry
+                    const int pos = atomicAdd(&n_keys, 1);
+                    if (pos < MCI_MAXKEYS) { list[pos] = key; dlist[pos] = dpacked; } else overflow = 1;
+                    return;
+                }
+                h = (h + 1) & (MCI_SLOTS - 1);
+            }
+            overflow = 1;
+        };
         for (int dir = 0; dir < P.ndir; ++dir) {
-            const int g = P.cell[dir];
+            const int g = P.cell[dir], sh = P.cshift[dir];
             for (int wr = 0; wr < 2; ++wr) {
                 int lo_r = ty0 - wr * H - dmax, hi_r = ty0 + MCI_TH - 1 - wr * H + dmax;
                 if (wr) hi_r = min(hi_r, dmax - 1);       // wrapping needs u + dr < 0
@@ -168,61 +220,45 @@ mci_splat_kernel(const MciParams P)
                     if (wc) hi_c = min(hi_c, dmax - 1);
                     lo_c = max(lo_c, 0); hi_c = min(hi_c, W - 1);
                     if (lo_c > hi_c) continue;
-                    const int cr_lo = lo_r / g, cr_hi = hi_r / g, cc_lo = lo_c / g, cc_hi = hi_c / g;
+                    const int cr_lo = cell_of(lo_r, g, sh), cr_hi = cell_of(hi_r, g, sh);
+                    const int cc_lo = cell_of(lo_c, g, sh), cc_hi = cell_of(hi_c, g, sh);
                     const int ncc = cc_hi - cc_lo + 1, ncell = (cr_hi - cr_lo + 1) * ncc;
+                    const bool do_stage = !wr && !wc && ncell <= MCI_STAGE_MAX;
+                    if (do_stage) { s_r0[dir] = cr_lo; s_c0[dir] = cc_lo; s_nc[dir] = ncc; staged[dir] = true; }
                     for (int i = tid; i < ncell; i += MCI_NT) {
                         const int cr = cr_lo + i / ncc, cc = cc_lo + i % ncc;
-                        const short2 d = P.disp[dir][(size_t)cr * P.cols[dir] + cc];
-                        const int eff_r = d.x + wr * H, eff_c = d.y + wc * W;
+                        const unsigned dp = reinterpret_cast<const unsigned *>(P.disp[dir])[(size_t)cr * P.cols[dir] + cc];
+                        if (do_stage) stage[dir][i] = dp;
+                        const int dx_ = (short)(dp & 0xffffu), dy_ = (short)(dp >> 16);   // short2: .x low half, .y high half
+                        const int eff_r = dx_ + wr * H, eff_c = dy_ + wc * W;
                         const int pr0 = cr * g, pr1 = min(H, pr0 + g) - 1;
                         const int pc0 = cc * g, pc1 = min(W, pc0 + g) - 1;
                         // conservative footprint test (the per-pixel test below is exact)
                         if (pr1 + eff_r < ty0 || pr0 + eff_r > ty0 + MCI_TH - 1) continue;
                         if (pc1 + eff_c < tx0 || pc0 + eff_c > tx0 + MCI_TW - 1) continue;
-                        if (wr ? (pr0 + d.x >= 0) : (pr1 + d.x < 0)) continue;
-                        if (wc ? (pc0 + d.y >= 0) : (pc1 + d.y < 0)) continue;
-                        const unsigned key = mci_key(eff_r, eff_c, dir);
-                        unsigned h = (key * 2654435761u) >> 22;          // 10 bits
-                        bool done = false;
-                        for (int probe = 0; probe < MCI_SLOTS && !done; ++probe) {
-                            unsigned prev = atomicCAS(&table[h], MCI_EMPTY, key);
-                            if (prev == MCI_EMPTY || prev == key) done = true;
-                            else h = (h + 1) & (MCI_SLOTS - 1);
-                        }
-                        if (!done) overflow = 1;
+                        if (wr ? (pr0 + dx_ >= 0) : (pr1 + dx_ < 0)) continue;
+                        if (wc ? (pc0 + dy_ >= 0) : (pc1 + dy_ < 0)) continue;
+                        insert(mci_key(eff_r, eff_c, dir), dp);
                     }
                 }
             }
         }
         // the unidirectional self-write lives at e = (0,0) and has no footprint of its own
-        if (!P.bidir && tid == 0) {
-            const unsigned key = mci_key(0, 0, 0);
-            unsigned h = (key * 2654435761u) >> 22;
-            bool done = false;
-            for (int probe = 0; probe < MCI_SLOTS && !done; ++probe) {
-                unsigned prev = atomicCAS(&table[h], MCI_EMPTY, key);
-                if (prev == MCI_EMPTY || prev == key) done = true;
-                else h = (h + 1) & (MCI_SLOTS - 1);
-            }
-            if (!done) overflow = 1;
-        }
+        if (!P.bidir && tid == 0) insert(mci_key(0, 0, 0), 0u);
         __syncthreads();
-        // ---- 2. compact + rank-sort (ascending key = raster order of the source pixel) ----
-        for (int i = tid; i < MCI_SLOTS; i += MCI_NT) {
-            unsigned k = table[i];
-            if (k != MCI_EMPTY) {
-                int pos = atomicAdd(&n_keys, 1);
-                if (pos < MCI_MAXKEYS) list[pos] = k; else overflow = 1;
-            }
-        }
-        __syncthreads();
+        // ---- 2. rank-sort (ascending key = raster order of the source pixel) ----
         if (!overflow) {
             const int n = n_keys;
             for (int i = tid; i < n; i += MCI_NT) {
                 const unsigned k = list[i];
                 int rank = 0;
                 for (int j = 0; j < n; ++j) rank += list[j] < k;
-                sorted[rank] = k;
+                MciEntry e;
+                e.eff_r = MCI_KOFF - (int)(k >> 15);
+                e.eff_c = MCI_KOFF - (int)((k >> 1) & 16383u);
+                e.dpacked = dlist[i];
+                e.dir_kind = (int)(k & 1u);
+                sorted[rank] = e;
             }
         }
         __syncthreads();
@@ -237,13 +273,35 @@ mci_splat_kernel(const MciParams P)
     if (inside) {
         if (!overflow) {
             const int n = n_keys;
+            // An entry stands for "displacement d, wrapped or not": e = d (+H / +W).  If the pixel at
+            // p = q - e carries exactly d, its target is q by construction (the reference's bounds test
+            // and negative-index wrap are already folded into e), so the test is one compare.
+            auto test = [&](auto dir_tag, const MciEntry &e, int p_r, int p_c, int sr0, int sc0, int snc, bool stg) {
+                constexpr int D = decltype(dir_tag)::value;
+                const int cr = cell_of(p_r, P.cell[D], P.cshift[D]), cc = cell_of(p_c, P.cell[D], P.cshift[D]);
+                const int lr = cr - sr0, lc = cc - sc0;
+                unsigned dp;
+                if (stg && lr >= 0 && lc >= 0 && lc < snc && lr * snc + lc < MCI_STAGE_MAX && e.eff_r <= dmax && e.eff_c <= dmax)
+                    dp = stage[D][lr * snc + lc];
+                else
+                    dp = reinterpret_cast<const unsigned *>(P.disp[D])[(size_t)cr * P.cols[D] + cc];
+                if (dp == e.dpacked) {
+                    mci_apply_t<D>(P, st, p_r, p_c, false);
+                } else if (D == 0 && !P.bidir && e.eff_r == 0 && e.eff_c == 0) {
+                    // unidir: this pixel's own vector leaves the frame -> it writes itself (:56-58)
+                    const int u_i = p_r + (short)(dp & 0xffffu), v_i = p_c + (short)(dp >> 16);
+                    if (!(u_i < H && v_i < W)) mci_apply_t<0>(P, st, p_r, p_c, true);
+                }
+            };
             for (int i = 0; i < n; ++i) {
-                const unsigned k = sorted[i];
-                mci_try_event(P, st, q_r, q_c, MCI_KOFF - (int)(k >> 15), MCI_KOFF - (int)((k >> 1) & 16383u), (int)(k & 1u));
+                const MciEntry e = sorted[i];                     // one broadcast LDS.128
+                const int p_r = q_r - e.eff_r, p_c = q_c - e.eff_c;
+                if ((unsigned)p_r >= (unsigned)H || (unsigned)p_c >= (unsigned)W) continue;
+                if (e.dir_kind == 0) test(std::integral_constant<int, 0>{}, e, p_r, p_c, s_r0[0], s_c0[0], s_nc[0], staged[0]);
+                else test(std::integral_constant<int, 1>{}, e, p_r, p_c, s_r0[1], s_c0[1], s_nc[1], staged[1]);
             }
         } else {
             // dense fallback: enumerate every possible displacement in source-raster order
-            // (wrapped rows/cols first: they come from the smallest source coordinates)
             // e in [H-dmax, H-1] (wrapped) then [dmax, -dmax] (direct), each value visited once
             for (int eff_r = q_r; eff_r >= -dmax; --eff_r) {
                 if (eff_r > dmax && eff_r < H - dmax) { eff_r = dmax + 1; continue; }
