@@ -138,6 +138,30 @@ MEMCI_API int memci_mci_unidir(memci_ctx *ctx, int slot_src, int slot_tgt, int m
 MEMCI_API int memci_mci_bidir(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd,
                               int mv_bwd, float dist, int out_slot);
 
+/* ---- spatial tiling of one frame pair into horizontal bands (8K mode) -------------
+ * A band = block rows [block_row0, block_row1).  Each GPU holds full-size slots but only fills the
+ * rows it owns plus the halo rows it received; these entry points restrict the work to a band. */
+
+/* Full search for block rows [block_row0, block_row1) only; other rows of the MV slot are left
+ * untouched (they are filled by memci_mv_device_ptrs + a peer copy). */
+MEMCI_API int memci_me_fs_rows(memci_ctx *ctx, int slot_src, int slot_tgt, int block_size, int target_region,
+                               int mv_slot, int block_row0, int block_row1);
+/* MCI (bidir != 0: Bidirectional.helper, else Unidirectional.helper) for output rows [row0, row1):
+ * the splat is evaluated for the rows and 10 rows of hole-fill halo either side; only holes in
+ * [row0, row1) are filled.  mv_bwd is ignored when bidir == 0. */
+MEMCI_API int memci_mci_rows(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd, int mv_bwd, float dist,
+                             int out_slot, int bidir, int row0, int row1);
+/* Rows [row0, row1) of a frame slot <-> the same rows of a full-size host frame. */
+MEMCI_API int memci_upload_frame_rows(memci_ctx *ctx, int slot, const uint8_t *host_hwc, int row0, int row1);
+MEMCI_API int memci_download_frame_rows(memci_ctx *ctx, int slot, uint8_t *host_hwc, int row0, int row1);
+/* Declare a frame slot valid / modified after its device buffer (memci_frame_device_ptr) was written
+ * from outside (peer copy, NCCL recv): cached luma planes and pyramids are dropped. */
+MEMCI_API int memci_frame_mark(memci_ctx *ctx, int slot);
+/* Allocate a full-size MV slot on `cell`-sized blocks without computing it, and expose the device
+ * arrays (float2 vec[rows][cols], float sad[rows][cols]) for halo exchange. */
+MEMCI_API int memci_mv_alloc(memci_ctx *ctx, int mv_slot, int cell);
+MEMCI_API int memci_mv_device_ptrs(memci_ctx *ctx, int mv_slot, void **vec, void **sad);
+
 /* ---- fused convenience (one call per output frame of the class API) --------- */
 
 typedef struct memci_pair_params {

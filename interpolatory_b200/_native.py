@@ -47,6 +47,13 @@ _PROTOS = {
     "memci_upload_mv_blocks": ([_P, _I, _I, _P, _I, _P], _I),
     "memci_mci_unidir": ([_P, _I, _I, _I, C.c_float, _I], _I),
     "memci_mci_bidir": ([_P, _I, _I, _I, _I, C.c_float, _I], _I),
+    "memci_me_fs_rows": ([_P, _I, _I, _I, _I, _I, _I, _I], _I),
+    "memci_mci_rows": ([_P, _I, _I, _I, _I, C.c_float, _I, _I, _I, _I], _I),
+    "memci_upload_frame_rows": ([_P, _I, _P, _I, _I], _I),
+    "memci_download_frame_rows": ([_P, _I, _P, _I, _I], _I),
+    "memci_frame_mark": ([_P, _I], _I),
+    "memci_mv_alloc": ([_P, _I, _I], _I),
+    "memci_mv_device_ptrs": ([_P, _I, C.POINTER(_P), C.POINTER(_P)], _I),
     "memci_estimate_pair": ([_P, C.POINTER(PairParams), _I, _I, _I, _I], _I),
     "memci_launch_count": ([_P], C.c_longlong),
     "memci_reset_launch_count": ([_P], _I),

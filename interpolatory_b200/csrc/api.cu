@@ -142,6 +142,7 @@ int memci_ctx_destroy(memci_ctx *ctx)
     }
     for (int i = 0; i < 4; ++i) {
         if (ctx->fs_plan[i].d_tiles) cudaFree(ctx->fs_plan[i].d_tiles);
+        free(ctx->fs_plan[i].row_tile_start); free(ctx->fs_plan[i].row_cand);
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     }
     if (ctx->d_redo_list) cudaFree(ctx->d_redo_list);
@@ -220,7 +221,13 @@ void *memci_frame_device_ptr(memci_ctx *ctx, int slot)
 int memci_me_fs(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, int mv_slot)
 {
     REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_MV(ctx, mv_slot, 0);
-    return memci_fs_run(ctx, slot_src, slot_tgt, bs, R, &ctx->mvs[mv_slot]);
+    return memci_fs_run(ctx, slot_src, slot_tgt, bs, R, &ctx->mvs[mv_slot], 0, -1);
+}
+
+int memci_me_fs_rows(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, int mv_slot, int block_row0, int block_row1)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_MV(ctx, mv_slot, 0);
+    return memci_fs_run(ctx, slot_src, slot_tgt, bs, R, &ctx->mvs[mv_slot], block_row0, block_row1);
 }
 
 int memci_me_hbma(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int win, int sub, int steps,
@@ -331,7 +338,7 @@ int memci_mci_unidir(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_slot, fl
 {
     REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_FRAME(ctx, out_slot, 0); REQ_MV(ctx, mv_slot, 1);
     if (out_slot == slot_src || out_slot == slot_tgt) return memci_fail(ctx, MEMCI_ERR_ARG, "output slot aliases an input slot");
-    return memci_mci_run(ctx, slot_src, slot_tgt, &ctx->mvs[mv_slot], nullptr, dist, out_slot, 0);
+    return memci_mci_run(ctx, slot_src, slot_tgt, &ctx->mvs[mv_slot], nullptr, dist, out_slot, 0, 0, -1);
 }
 
 int memci_mci_bidir(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd, int mv_bwd, float dist, int out_slot)
@@ -339,7 +346,66 @@ int memci_mci_bidir(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd, int 
     REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_FRAME(ctx, out_slot, 0);
     REQ_MV(ctx, mv_fwd, 1); REQ_MV(ctx, mv_bwd, 1);
     if (out_slot == slot_src || out_slot == slot_tgt) return memci_fail(ctx, MEMCI_ERR_ARG, "output slot aliases an input slot");
-    return memci_mci_run(ctx, slot_src, slot_tgt, &ctx->mvs[mv_fwd], &ctx->mvs[mv_bwd], dist, out_slot, 1);
+    return memci_mci_run(ctx, slot_src, slot_tgt, &ctx->mvs[mv_fwd], &ctx->mvs[mv_bwd], dist, out_slot, 1, 0, -1);
+}
+
+int memci_mci_rows(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd, int mv_bwd, float dist, int out_slot,
+                   int bidir, int row0, int row1)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_FRAME(ctx, out_slot, 0);
+    REQ_MV(ctx, mv_fwd, 1);
+    if (bidir) REQ_MV(ctx, mv_bwd, 1);
+    if (out_slot == slot_src || out_slot == slot_tgt) return memci_fail(ctx, MEMCI_ERR_ARG, "output slot aliases an input slot");
+    return memci_mci_run(ctx, slot_src, slot_tgt, &ctx->mvs[mv_fwd], bidir ? &ctx->mvs[mv_bwd] : nullptr, dist, out_slot,
+                         bidir ? 1 : 0, row0, row1);
+}
+
+// ---- spatial (band) tiling support: rows of frames / MV fields written from outside ------------
+int memci_frame_mark(memci_ctx *ctx, int slot)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot, 0);
+    frame_touched(ctx->frames[slot]);
+    return MEMCI_OK;
+}
+
+int memci_upload_frame_rows(memci_ctx *ctx, int slot, const uint8_t *host_hwc, int row0, int row1)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot, 0);
+    if (!host_hwc || row0 < 0 || row1 > ctx->H || row0 >= row1) return memci_fail(ctx, MEMCI_ERR_ARG, "bad row range [%d, %d)", row0, row1);
+    const size_t pitch = (size_t)ctx->W * 3;
+    CK(ctx, cudaMemcpyAsync(ctx->frames[slot].rgb + row0 * pitch, host_hwc + row0 * pitch, (size_t)(row1 - row0) * pitch,
+                            cudaMemcpyHostToDevice, ctx->stream));
+    frame_touched(ctx->frames[slot]);
+    return MEMCI_OK;
+}
+
+int memci_download_frame_rows(memci_ctx *ctx, int slot, uint8_t *host_hwc, int row0, int row1)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot, 1);
+    if (!host_hwc || row0 < 0 || row1 > ctx->H || row0 >= row1) return memci_fail(ctx, MEMCI_ERR_ARG, "bad row range [%d, %d)", row0, row1);
+    const size_t pitch = (size_t)ctx->W * 3;
+    CK(ctx, cudaMemcpyAsync(host_hwc + row0 * pitch, ctx->frames[slot].rgb + row0 * pitch, (size_t)(row1 - row0) * pitch,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    return MEMCI_OK;
+}
+
+int memci_mv_alloc(memci_ctx *ctx, int mv_slot, int cell)
+{
+    REQ_CTX(ctx); REQ_MV(ctx, mv_slot, 0);
+    if (cell <= 0) return memci_fail(ctx, MEMCI_ERR_ARG, "bad cell size %d", cell);
+    const int r = ceil_div_i(ctx->H, cell), c = ceil_div_i(ctx->W, cell);
+    int rc = memci_mv_reserve(ctx, &ctx->mvs[mv_slot], cell, r, c, cell, r, c);
+    if (rc) return rc;
+    ctx->mvs[mv_slot].valid = 1;
+    return MEMCI_OK;
+}
+
+int memci_mv_device_ptrs(memci_ctx *ctx, int mv_slot, void **vec, void **sad)
+{
+    REQ_CTX(ctx); REQ_MV(ctx, mv_slot, 1);
+    if (vec) *vec = ctx->mvs[mv_slot].vec;
+    if (sad) *sad = ctx->mvs[mv_slot].sad;
+    return MEMCI_OK;
 }
 
 int memci_estimate_pair(memci_ctx *ctx, const memci_pair_params *p, int slot_src, int slot_tgt, int mv_fwd, int mv_bwd)

@@ -43,16 +43,16 @@ __device__ __forceinline__ unsigned long long fs_key(unsigned sad, unsigned d2, 
 // =========================================================================================
 __global__ void fs_generic_kernel(const int32_t *__restrict__ Ls, const int32_t *__restrict__ Lt,
                                   const uint8_t *__restrict__ rgb_s, const uint8_t *__restrict__ rgb_t,
-                                  int H, int W, int Wp, int bs, int R, int nbr, int nbc,
+                                  int H, int W, int Wp, int bs, int R, int blk_begin, int blk_end, int nbc,
                                   const int *__restrict__ list, const int *__restrict__ list_count,
                                   float2 *__restrict__ out_vec, float *__restrict__ out_sad)
 {
     int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int nwarps = (gridDim.x * blockDim.x) >> 5;
-    int total = list ? *list_count : nbr * nbc;
+    int total = list ? *list_count : blk_end - blk_begin;
     for (int it = warp; it < total; it += nwarps) {
-        int blk = list ? list[it] : it;
+        int blk = list ? list[it] : blk_begin + it;
         int br = blk / nbc, bc = blk - br * nbc;
         int s_row = br * bs, s_col = bc * bs;
         FsBounds b = fs_bounds(H, W, bs, R, s_row, s_col);
@@ -605,6 +605,7 @@ static FsPlan *fs_get_plan(memci_ctx *ctx, int bs, int R)
     if (!pl) {                       // evict slot 0
         pl = &ctx->fs_plan[0];
         if (pl->d_tiles) cudaFree(pl->d_tiles);
+        free(pl->row_tile_start); free(pl->row_cand);
         memset(pl, 0, sizeof(*pl));
     }
     const int H = ctx->H, W = ctx->W;
@@ -613,16 +614,20 @@ static FsPlan *fs_get_plan(memci_ctx *ctx, int bs, int R)
     pl->box_w = FS_BOXW; pl->box_h = bs + 2 * R;
     // exact candidate count -- same bounds as the kernels
     long long n_cand = 0;
-    for (int br = 0; br < nbr; ++br)
+    pl->row_cand = (long long *)calloc(nbr, sizeof(long long));
+    pl->row_tile_start = (int *)calloc(nbr + 1, sizeof(int));
+    for (int br = 0; br < nbr; ++br) {
         for (int bc = 0; bc < nbc; ++bc) {
             FsBounds b = fs_bounds(H, W, bs, R, br * bs, bc * bs);
-            if (b.r1 > b.r0 && b.c1 > b.c0) n_cand += (long long)(b.r1 - b.r0) * (b.c1 - b.c0);
+            if (b.r1 > b.r0 && b.c1 > b.c0) pl->row_cand[br] += (long long)(b.r1 - b.r0) * (b.c1 - b.c0);
         }
+        n_cand += pl->row_cand[br];
+    }
     pl->n_cand = n_cand;
     pl->n_tiles = 0; pl->d_tiles = nullptr;
     int key_bits = 0;
     { int ks = 1; while ((1 << ks) <= 2 * R * R + 1) ++ks; int qb = 1; while ((1ll << qb) <= (long long)bs * bs * 255) ++qb; key_bits = ks + qb + (pl->G <= 16 ? 4 : 6); }
-    const bool tiled_ok = (bs % 8 == 0) && bs <= 64 && R <= 120 && key_bits <= 32 && (bs + 2 * R + 4) <= FS_BOXW &&
+    const bool tiled_ok = !getenv("MEMCI_FS_FORCE_GENERIC") && (bs % 8 == 0) && bs <= 64 && R <= 120 && key_bits <= 32 && (bs + 2 * R + 4) <= FS_BOXW &&
                           fs_smem_bytes(bs, pl->box_h, 1, pl->G) <= 200 * 1024;
     if (tiled_ok) {
         const int Rp = (R + 3) & ~3;
@@ -631,6 +636,7 @@ static FsPlan *fs_get_plan(memci_ctx *ctx, int bs, int R)
         FsTile *h = (FsTile *)malloc(sizeof(FsTile) * (size_t)nbr * nbc);
         int nt = 0;
         for (int br = 0; br < nbr; ++br) {
+            pl->row_tile_start[br] = nt;
             int bc = 0;
             while (bc < nbc) {
                 int nb = 0, items = 0;
@@ -656,6 +662,7 @@ static FsPlan *fs_get_plan(memci_ctx *ctx, int bs, int R)
             return nullptr;
         }
         free(h);
+        pl->row_tile_start[nbr] = nt;
         pl->n_tiles = nt;
     }
     pl->valid = 1;
@@ -678,7 +685,7 @@ static int fs_launch_tiled(memci_ctx *ctx, const CUtensorMap &ts, const CUtensor
     return p.m == 1 ? fs_launch_tiled2<G, true>(ctx, ts, tt, p, smem) : fs_launch_tiled2<G, false>(ctx, ts, tt, p, smem);
 }
 
-int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out)
+int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out, int br0, int br1)
 {
     const int H = ctx->H, W = ctx->W, Wp = ctx->Wp;
     if (bs <= 0 || bs > 64 || R < 0 || R > 127)
@@ -690,8 +697,12 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
     if ((rc = memci_mv_reserve(ctx, out, bs, nbr, nbc, bs, nbr, nbc))) return rc;
     FsPlan *pl = fs_get_plan(ctx, bs, R);
     if (!pl) return MEMCI_ERR_CUDA;
-    ctx->fs_last_cand = pl->n_cand;
-    ctx->fs_last_ops = pl->n_cand * bs * bs;
+    if (br1 < 0) { br0 = 0; br1 = nbr; }
+    if (br0 < 0 || br1 > nbr || br0 >= br1) return memci_fail(ctx, MEMCI_ERR_ARG, "block row range [%d, %d) outside [0, %d)", br0, br1, nbr);
+    long long cand = 0;
+    for (int r = br0; r < br1; ++r) cand += pl->row_cand[r];
+    ctx->fs_last_cand = cand;
+    ctx->fs_last_ops = cand * bs * bs;
     FrameSlot &fs = ctx->frames[slot_src], &ft = ctx->frames[slot_tgt];
     if ((size_t)ctx->redo_cap < (size_t)nbr * nbc) {
         if (ctx->d_redo_list) cudaFree(ctx->d_redo_list);
@@ -707,10 +718,10 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         if ((rc = make_tmap(ctx, &tt, ft.luma, H, W, Wp, FS_BOXW, pl->box_h))) return rc;
         FsParams p;
         p.H = H; p.W = W; p.bs = bs; p.R = R; p.Rp = (R + 3) & ~3; p.m = bs / 8; p.nbr = nbr; p.nbc = nbc;
-        p.n_tiles = pl->n_tiles; p.box_h = pl->box_h;
+        p.n_tiles = pl->row_tile_start[br1] - pl->row_tile_start[br0]; p.box_h = pl->box_h;
         { int ks = 1; while ((1 << ks) <= 2 * R * R + 1) ++ks; p.ks = ks; }
         p.n_stages = fs_smem_bytes(bs, pl->box_h, 2, pl->G) <= 220 * 1024 ? 2 : 1;
-        p.tiles = pl->d_tiles; p.out_vec = out->vec; p.out_sad = out->sad;
+        p.tiles = pl->d_tiles + pl->row_tile_start[br0]; p.out_vec = out->vec; p.out_sad = out->sad;
         p.redo_list = ctx->d_redo_list; p.counters = ctx->d_counters; p.redo_cap = ctx->redo_cap;
         const int smem = fs_smem_bytes(bs, pl->box_h, p.n_stages, pl->G);
         if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -733,13 +744,13 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
             fs_redo_kernel<<<ctx->num_sms * 2, 256, redo_smem, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbc,
                                                                               ctx->d_redo_list, ctx->d_counters, out->vec, out->sad);
         } else {
-            fs_generic_kernel<<<ctx->num_sms, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbr, nbc,
+            fs_generic_kernel<<<ctx->num_sms, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, 0, 0, nbc,
                                                                      ctx->d_redo_list, ctx->d_counters, out->vec, out->sad);
         }
         CKL(ctx);
     } else {
         if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-        fs_generic_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbr, nbc,
+        fs_generic_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, br0 * nbc, br1 * nbc, nbc,
                                                                      nullptr, nullptr, out->vec, out->sad);
         CKL(ctx);
         if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->fs_timed = 1; }

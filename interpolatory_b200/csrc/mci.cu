@@ -30,6 +30,8 @@
 
 struct MciParams {
     int H, W, bidir, ndir;
+    int y_begin, y_end;          // target rows splatted by this launch (band + hole-fill halo)
+    int fill_begin, fill_end;    // target rows whose holes this launch fills
     float dist;
     const uint8_t *src, *tgt;
     uint8_t *out, *mask;
@@ -177,7 +179,7 @@ mci_splat_kernel(const MciParams P)
     __shared__ int n_keys, overflow;
 
     const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * MCI_TW, ty0 = blockIdx.y * MCI_TH;
+    const int tx0 = blockIdx.x * MCI_TW, ty0 = P.y_begin + blockIdx.y * MCI_TH;
     const int q_c = tx0 + (tid & 31), q_r = ty0 + (tid >> 5);
     const int H = P.H, W = P.W;
     const int dmax = P.counters[2];
@@ -265,7 +267,7 @@ mci_splat_kernel(const MciParams P)
     }
 
     // ---- 3. replay the splat for this target pixel ----
-    const bool inside = q_r < H && q_c < W;
+    const bool inside = q_r < P.y_end && q_c < W;
     PixState st;
     st.v0 = st.v1 = st.v2 = -1;
     st.sadi = __int_as_float(0x7f800000);
@@ -319,7 +321,7 @@ mci_splat_kernel(const MciParams P)
         P.mask[q] = st.written ? 0 : 1;
     }
     // hole list, one atomic per warp
-    const bool hole = inside && !st.written;
+    const bool hole = inside && !st.written && q_r >= P.fill_begin && q_r < P.fill_end;
     const unsigned bal = __ballot_sync(0xffffffffu, hole);
     if (bal) {
         const int lane = tid & 31;
@@ -424,7 +426,7 @@ mci_holefill_kernel(const uint8_t *__restrict__ tgt, uint8_t *out, const uint8_t
 }
 
 int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd, const MVField *bwd,
-                  float dist, int out_slot, int bidir)
+                  float dist, int out_slot, int bidir, int row0, int row1)
 {
     const int H = ctx->H, W = ctx->W;
     const MVField *fl[2] = {fwd, bwd};
@@ -454,11 +456,16 @@ int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd
         CK(ctx, cudaMalloc(&ctx->d_hole_list, npx * sizeof(int)));
         ctx->hole_cap = npx;
     }
+    if (row1 < 0) { row0 = 0; row1 = H; }
+    if (row0 < 0 || row1 > H || row0 >= row1) return memci_fail(ctx, MEMCI_ERR_ARG, "row range [%d, %d) outside [0, %d)", row0, row1, H);
     P.H = H; P.W = W; P.bidir = bidir; P.ndir = ndir; P.dist = dist;
+    P.fill_begin = row0; P.fill_end = row1;
+    P.y_begin = row0 - 10 > 0 ? row0 - 10 : 0;           // the 21x21 hole-fill window reads 10 rows of splat either side
+    P.y_end = row1 + 10 < H ? row1 + 10 : H;
     P.src = ctx->frames[slot_src].rgb; P.tgt = ctx->frames[slot_tgt].rgb;
     P.out = ctx->frames[out_slot].rgb; P.mask = ctx->d_hole_mask;
     P.hole_list = ctx->d_hole_list; P.counters = ctx->d_counters;
-    dim3 grid(ceil_div_i(W, MCI_TW), ceil_div_i(H, MCI_TH));
+    dim3 grid(ceil_div_i(W, MCI_TW), ceil_div_i(P.y_end - P.y_begin, MCI_TH));
     ctx->mci_timed = 0;
     if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     const int prof = memci_prof_begin(ctx, 1);

@@ -38,6 +38,8 @@ struct FsPlan {                        // cached per (bs, R): tile table + tenso
     int bs, R, G, box_w, box_h, n_tiles, nb_max, valid;
     FsTile *d_tiles;
     long long n_cand;
+    int *row_tile_start;               // host: first tile of each block row (nbr + 1 entries)
+    long long *row_cand;               // host: candidates per block row
 };
 
 struct memci_ctx {
@@ -86,12 +88,12 @@ int memci_mv_reserve(memci_ctx *ctx, MVField *f, int mv_cell, int mv_rows, int m
 int memci_luma_plane(memci_ctx *ctx, const uint8_t *rgb, int H, int W, int Wp, int32_t *luma);
 int memci_ensure_luma(memci_ctx *ctx, int slot);
 int memci_ensure_pyramid(memci_ctx *ctx, int slot, int levels);
-int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out);
+int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out, int br0, int br1);   // block rows [br0, br1); br1 < 0 = all
 int memci_hbma_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int win, int sub, int steps,
                    int min_bs, int cost_key, MVField *out);
 int memci_smooth_run(memci_ctx *ctx, const MVField *in, int mode, int fsz, MVField *out);
 int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd, const MVField *bwd,
-                  float dist, int out_slot, int bidir);
+                  float dist, int out_slot, int bidir, int row0, int row1);   // output rows [row0, row1); row1 < 0 = all
 int memci_mv_to_dense(memci_ctx *ctx, const MVField *f, float *d_dense);
 // returns an event pair index (>= 0) after recording the start event, or -1 when profiling is off / full
 int memci_prof_begin(memci_ctx *ctx, int kind);

@@ -139,3 +139,29 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "frames/s"
+
+
+def test_band_plan_covers_every_needed_row():
+    """8K band split: every frame row / MV block row a band needs is owned or arrives by a transfer."""
+    from interpolatory_b200.tiling import BandPlan, HOLE_K
+    for (H, W, bs, R, n) in ((4320, 7680, 16, 32, 8), (4320, 7680, 16, 32, 2), (360, 640, 8, 7, 4), (200, 320, 8, 16, 8), (1080, 1920, 8, 16, 3)):
+        plan = BandPlan(H, W, bs, R, n)
+        assert plan.block_rows[0][0] == 0 and plan.block_rows[-1][1] == plan.nbr
+        assert plan.rows[-1][1] == H
+        for kind, own, need in (("frame", plan.rows, plan.frame_need), ("mv", plan.block_rows, plan.mv_need)):
+            tr = plan.transfers(kind)
+            for dst in range(n):
+                have = set(range(*own[dst]))
+                for s, d, r0, r1 in tr:
+                    if d == dst:
+                        assert set(range(r0, r1)) <= set(range(*own[s]))       # the sender owns what it sends
+                        have |= set(range(r0, r1))
+                for span in need[dst]:
+                    assert set(range(*span)) <= have, (kind, dst, span)
+            # ME window and splat reach are inside the needed rows
+        for i, (y0, y1) in enumerate(plan.rows):
+            lo, hi = plan.frame_need[i][0]
+            assert lo <= max(0, y0 - R - HOLE_K) and hi >= min(H, y1 + R + HOLE_K)
+        if (H, n) == (4320, 8):
+            f, m = plan.bytes_moved()
+            assert f < 40e6 and m < 2e6                                         # halo traffic is latency-, not bandwidth-bound
