@@ -276,3 +276,88 @@ def test_band_split_matches_single_gpu(gpu, oracle, H, W, bs, R, n_bands):
     assert np.array_equal(want, oracle.bidir_helper(a, b, f_, b_, np.float32(0.8)))
     fbytes, mbytes = plan.bytes_moved()
     assert fbytes > 0 and mbytes > 0
+
+
+# ---------------------------------------------------------------- BASELINE.json's full sizes
+def test_cfg2_1080p_full_size_vs_oracle(gpu, oracle):
+    """cfg2 at full size (1080p, fs 8x8 +-16, bidir): motion fields and the interpolated frame against
+    the oracle (OpenMP on the host cores: a few seconds)."""
+    from interpolatory_b200.device import DeviceContext
+    H, W, bs, R = 1080, 1920, 8, 16
+    fr = make_sequence(H, W, 2, seed=42)
+    a, b = fr[0], fr[1]
+    ctx = DeviceContext(H, W)
+    try:
+        ctx.upload_frame(0, a); ctx.upload_frame(1, b)
+        ctx.me_fs(0, 1, bs, R, 0); ctx.me_fs(1, 0, bs, R, 1)
+        assert ctx.fs_stats()[:2] == (27311000, 1747904000)
+        fwd, bwd = oracle.fs_blocks(bs, R, a, b), oracle.fs_blocks(bs, R, b, a)
+        for slot, ref in ((0, fwd), (1, bwd)):
+            _, vec, _, sad = ctx.download_mv_blocks(slot)
+            assert np.array_equal(vec, ref[:, :, :2]) and np.array_equal(sad, ref[:, :, 2])
+        ctx.mci_bidir(0, 1, 0, 1, np.float32(0.5), 7)
+        got = ctx.download_frame(7)
+        want = oracle.bidir_helper(a, b, oracle.expand_dense(fwd, bs, H, W), oracle.expand_dense(bwd, bs, H, W), np.float32(0.5))
+        assert np.array_equal(got, want)
+        ctx.mci_unidir(0, 1, 0, np.float32(0.5), 7)
+        assert np.array_equal(ctx.download_frame(7), oracle.unidir_helper(a, b, oracle.expand_dense(fwd, bs, H, W), np.float32(0.5)))
+    finally:
+        ctx.close()
+
+
+def test_tiled_kernel_equals_generic_kernel_1080p(gpu):
+    """Two independent code paths (TMA-tiled register kernel vs warp-per-block exact kernel) agree on
+    every block of a 1080p pair."""
+    import os
+    from interpolatory_b200.device import DeviceContext
+    H, W = 1080, 1920
+    fr = make_sequence(H, W, 2, seed=77)
+    res = []
+    for force in (False, True):
+        if force:
+            os.environ["MEMCI_FS_FORCE_GENERIC"] = "1"
+        try:
+            ctx = DeviceContext(H, W)
+            ctx.upload_frame(0, fr[0]); ctx.upload_frame(1, fr[1])
+            ctx.me_fs(0, 1, 8, 16, 0)
+            res.append(ctx.download_mv_blocks(0))
+            ctx.close()
+        finally:
+            os.environ.pop("MEMCI_FS_FORCE_GENERIC", None)
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][3], res[1][3])
+
+
+@pytest.mark.parametrize("H,W,bs,R", [(2160, 3840, 16, 32), (4320, 7680, 16, 32)])
+def test_full_size_properties_4k_8k(gpu, oracle, H, W, bs, R):
+    """Size-independent properties at cfg4 / cfg5 sizes (the oracle would take minutes here):
+    identical frames -> zero field, zero SAD, output == input; a pure translation inside the search
+    range -> that vector with SAD 0 on every interior block, backward field = minus forward field;
+    candidate count == the reference's bounds."""
+    from interpolatory_b200.device import DeviceContext
+    base = make_sequence(H // 4, W // 4, 1, seed=H)[0]
+    rng = np.random.default_rng(H)
+    a = np.ascontiguousarray(np.tile(base, (4, 4, 1)))
+    a = (a.astype(np.int16) + rng.integers(-20, 21, size=(H, W, 1))).clip(0, 255).astype(np.uint8)   # break the 4x4 periodicity
+    dy, dx = 11, -23
+    b = np.roll(a, (dy, dx), axis=(0, 1))
+    ctx = DeviceContext(H, W)
+    try:
+        ctx.upload_frame(0, a); ctx.upload_frame(1, a)
+        ctx.me_fs(0, 1, bs, R, 0); ctx.me_fs(1, 0, bs, R, 1)
+        assert ctx.fs_stats()[:2] == oracle.fs_work(H, W, bs, R)
+        _, vec, _, sad = ctx.download_mv_blocks(0)
+        assert not vec.any() and not sad.any()
+        ctx.mci_bidir(0, 1, 0, 1, np.float32(0.5), 7)
+        assert np.array_equal(ctx.download_frame(7), a) and ctx.mci_stats() == 0
+        ctx.upload_frame(1, b)
+        ctx.me_fs(0, 1, bs, R, 0); ctx.me_fs(1, 0, bs, R, 1)
+        _, vf, _, sf = ctx.download_mv_blocks(0)
+        _, vb, _, sb = ctx.download_mv_blocks(1)
+        m = R // bs + 3                                  # stay clear of the frame edges and of the column-bound quirk
+        nbc_ok = (H - bs) // bs - 1                      # columns where the reference searches dx > 0 (full_search.py:37)
+        inner_f = vf[m:-m, m:min(nbc_ok, vf.shape[1] - m)]
+        assert np.all(inner_f[..., 0] == dy) and np.all(inner_f[..., 1] == dx) and not sf[m:-m, m:min(nbc_ok, vf.shape[1] - m)].any()
+        inner_b = vb[m:-m, m:min(nbc_ok, vb.shape[1] - m)]
+        assert np.all(inner_b[..., 0] == -dy) and np.all(inner_b[..., 1] == -dx)
+    finally:
+        ctx.close()
