@@ -53,6 +53,15 @@ WORKLOAD_TEXT = {
 }
 
 
+def load_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -423,7 +432,7 @@ def main():
                 "peak_source": "VABSDIFF issue-rate microbenchmark measured in this run (memci_microbench mode 0)",
                 "ops_per_launch": px_ops, "candidates_per_launch": n_cand, "launches_timed": fs_n,
                 "avg_launch_ms": fs_avg_s * 1e3,
-                "traffic": None,
+                "traffic": load_traffic("fs_tiled_kernel") if args.workload == "cfg2" else None,
                 "hbm_view": {"algorithmic_bytes_per_launch": luma_bytes, "achieved_gbs": luma_bytes / fs_avg_s / 1e9 if fs_n else None,
                              "peak_gbs": peaks["hbm_gbs"], "frac": (luma_bytes / fs_avg_s / 1e9) / peaks["hbm_gbs"] if fs_n else None,
                              "peak_source": peak_src},
@@ -433,7 +442,7 @@ def main():
                 "achieved": mci_bytes / mci_avg_s / 1e9 if mci_n else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": (mci_bytes / mci_avg_s / 1e9) / peaks["hbm_gbs"] if mci_n else None, "peak_source": peak_src,
                 "bytes_per_launch": mci_bytes, "launches_timed": mci_n, "avg_launch_ms": mci_avg_s * 1e3,
-                "holes_last_frame": n_holes, "traffic": None,
+                "holes_last_frame": n_holes, "traffic": load_traffic("mci_splat_kernel") if args.workload == "cfg2" else None,
             },
             "kernel_share_of_step": {"fs_tiled": fs_ms_sum / ms if ms else None, "mci_splat": mci_ms_sum / ms if ms else None},
         }

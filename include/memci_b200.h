@@ -96,6 +96,9 @@ MEMCI_API void *memci_frame_device_ptr(memci_ctx *ctx, int slot);
 MEMCI_API int memci_me_fs(memci_ctx *ctx, int slot_src, int slot_tgt, int block_size,
                           int target_region, int mv_slot);
 
+/* Replaces ME/tss.py:63 get_motion_vectors(block_size, steps, im1, im2) (helper :18-61). */
+MEMCI_API int memci_me_tss(memci_ctx *ctx, int slot_src, int slot_tgt, int block_size, int steps, int mv_slot);
+
 /* Replaces ME/hbma.py:161 get_motion_vectors(block_size, win_size, sub_win_size, steps,
  * min_block_size, im1, im2, cost_str) (pyramid :171-177, full_search :77-98,
  * increase_vec_density :100-149).  Result at the final block size goes to `mv_slot`. */
@@ -165,7 +168,7 @@ MEMCI_API int memci_mv_device_ptrs(memci_ctx *ctx, int mv_slot, void **vec, void
 /* ---- fused convenience (one call per output frame of the class API) --------- */
 
 typedef struct memci_pair_params {
-    int me_mode;        /* 0 = fs, 1 = hbma                                   */
+    int me_mode;        /* 0 = fs, 1 = hbma, 2 = tss (region = steps)          */
     int block_size;     /* MEMCIBaseInterpolator.py:34                        */
     int region;         /* target_region / win_size  :35                      */
     int sub_region;     /* :40                                                */

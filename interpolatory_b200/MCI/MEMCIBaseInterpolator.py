@@ -10,6 +10,7 @@ from ..device import DeviceContext, FILTER_MODES
 from .._native import PairParams
 from ..ME.full_search import get_motion_vectors as fs
 from ..ME.hbma import get_motion_vectors as hbma
+from ..ME.tss import get_motion_vectors as tss
 from ..smoothing import mean_filter, median_filter, weighted_mean_filter, filter_mode_of
 from ..util import hbma_auto_steps
 
@@ -17,10 +18,6 @@ from ..util import hbma_auto_steps
 _FRAME_SLOTS = (0, 1, 2)      # resident source frames (LRU)
 _OUT_SLOT = 7
 _MV_FWD, _MV_BWD = 0, 1
-
-
-def tss(*a, **k):
-    raise NotImplementedError("three-step search is outside this build's hot-path scope (SURVEY 8f #2)")
 
 
 class MEMCIBaseInterpolator(BaseInterpolator):
@@ -67,8 +64,6 @@ class MEMCIBaseInterpolator(BaseInterpolator):
                             "sub_win_size": self.sub_region, "steps": self.steps,
                             "min_block_size": self.min_block_size, "cost_str": "sad",
                             "upscale": self.upscale_MV}
-        if self.me_mode is tss:
-            tss()
         self.device_index = int(args.get('device', 0))
         self._dev = None
         self._resident = {}
@@ -105,7 +100,7 @@ class MEMCIBaseInterpolator(BaseInterpolator):
 
     def _pair_params(self, shape, bidir):
         p = PairParams()
-        p.me_mode = 0 if self.me_mode is fs else 1
+        p.me_mode = 0 if self.me_mode is fs else (2 if self.me_mode is tss else 1)
         p.block_size = self.block_size
         p.region = self.region
         p.sub_region = self.sub_region

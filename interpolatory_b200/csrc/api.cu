@@ -230,6 +230,12 @@ int memci_me_fs_rows(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, 
     return memci_fs_run(ctx, slot_src, slot_tgt, bs, R, &ctx->mvs[mv_slot], block_row0, block_row1);
 }
 
+int memci_me_tss(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int steps, int mv_slot)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_MV(ctx, mv_slot, 0);
+    return memci_tss_run(ctx, slot_src, slot_tgt, bs, steps, &ctx->mvs[mv_slot]);
+}
+
 int memci_me_hbma(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int win, int sub, int steps,
                   int min_bs, int cost_key, int mv_slot)
 {
@@ -418,6 +424,7 @@ int memci_estimate_pair(memci_ctx *ctx, const memci_pair_params *p, int slot_src
         if (p->me_mode == 0) rc = memci_me_fs(ctx, a, b, p->block_size, p->region, mv);
         else if (p->me_mode == 1) rc = memci_me_hbma(ctx, a, b, p->block_size, p->region, p->sub_region, p->steps,
                                                      p->min_block_size, MEMCI_COST_SAD, mv);
+        else if (p->me_mode == 2) rc = memci_me_tss(ctx, a, b, p->block_size, p->region, mv);
         else return memci_fail(ctx, MEMCI_ERR_ARG, "unknown me_mode %d", p->me_mode);
         if (rc) return rc;
         if (p->filter_mode != MEMCI_FILTER_NONE && (rc = memci_smooth(ctx, mv, p->filter_mode, p->filter_size, mv))) return rc;

@@ -89,6 +89,7 @@ int memci_luma_plane(memci_ctx *ctx, const uint8_t *rgb, int H, int W, int Wp, i
 int memci_ensure_luma(memci_ctx *ctx, int slot);
 int memci_ensure_pyramid(memci_ctx *ctx, int slot, int levels);
 int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out, int br0, int br1);   // block rows [br0, br1); br1 < 0 = all
+int memci_tss_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int steps, MVField *out);
 int memci_hbma_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int win, int sub, int steps,
                    int min_bs, int cost_key, MVField *out);
 int memci_smooth_run(memci_ctx *ctx, const MVField *in, int mode, int fsz, MVField *out);

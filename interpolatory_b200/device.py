@@ -104,6 +104,9 @@ class DeviceContext:
     def me_fs(self, src, tgt, block_size, target_region, mv_slot):
         self._ck(self.L.memci_me_fs(self._ctx, src, tgt, int(block_size), int(target_region), mv_slot))
 
+    def me_tss(self, src, tgt, block_size, steps, mv_slot):
+        self._ck(self.L.memci_me_tss(self._ctx, src, tgt, int(block_size), int(steps), mv_slot))
+
     def me_hbma(self, src, tgt, block_size, win, sub, steps, min_bs, mv_slot, cost_key=0):
         self._ck(self.L.memci_me_hbma(self._ctx, src, tgt, int(block_size), int(win), int(sub), int(steps),
                                       int(min_bs), int(cost_key), mv_slot))

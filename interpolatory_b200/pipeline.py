@@ -15,15 +15,15 @@ from .util import get_first_frame_idx_and_ratio, hbma_auto_steps
 def pair_params_from_settings(shape, **st):
     """String settings of the MEMCI plug-in (MEMCIBaseInterpolator.py:48-78) -> device parameters."""
     me = st.get('me_mode', 'hbma')
-    if me not in ('fs', 'hbma'):
+    if me not in ('fs', 'hbma', 'tss'):
         raise NotImplementedError(f"me_mode {me!r} is not part of the B200 hot path")
     mci = st.get('mci_mode', 'unidir')
     if mci not in ('unidir', 'bidir'):
         raise NotImplementedError(f"mci_mode {mci!r} is not part of the B200 hot path")
     p = PairParams()
-    p.me_mode = 0 if me == 'fs' else 1
+    p.me_mode = {'fs': 0, 'hbma': 1, 'tss': 2}[me]
     p.block_size = int(st.get('block_size', 8))
-    p.region = int(st.get('target_region', 7))
+    p.region = 3 if me == 'tss' else int(st.get('target_region', 7))      # tss: region = steps (MEMCIBaseInterpolator.py:63-64)
     p.sub_region = 1
     p.steps = hbma_auto_steps(shape) if me == 'hbma' else 3
     p.min_block_size = 4

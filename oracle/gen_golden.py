@@ -31,9 +31,39 @@ def blocks_of(dense, bs):
     return np.ascontiguousarray(dense[::bs, ::bs])
 
 
+def gen_tss(ns):
+    """Three-step search (ME/tss.py): function level + the class API with me_mode=tss."""
+    t = {}
+    for (H, W) in [(72, 96), (50, 70), (37, 53), (120, 40)]:
+        fr = make_sequence(H, W, 2, seed=H)
+        k = f"{H}x{W}"
+        for bs, steps in ((8, 3), (8, 1), (4, 2), (16, 4), (8, 5)):
+            t[f"{k}/tss/{bs}_{steps}"] = blocks_of(ns.tss.get_motion_vectors(bs, steps, fr[0], fr[1]), bs)
+
+    class SynthStream(ns.BaseVideoStream):
+        def __init__(self, frames, fps):
+            self.frames, self.nframes, self.fps, self.duration = frames, len(frames), fps, len(frames) / fps
+
+        def get_frame(self, idx):
+            return self.frames[idx]
+
+    frames = make_sequence(72, 96, 3, seed=2072)
+    for si, st in enumerate([dict(me_mode='tss', mci_mode='unidir'),
+                             dict(me_mode='tss', mci_mode='bidir', filter_mode='mean', block_size='8', target_region='9')]):
+        it = ns.MEMCI(60, **dict(st))
+        it.video_stream = SynthStream(list(frames), 24)
+        it.rate_ratio = 60 / 24
+        t[f"e2e/set{si}/settings"] = np.array(repr(sorted(st.items())))
+        t[f"e2e/set{si}/out"] = np.stack([np.asarray(it.get_interpolated_frame(i)) for i in range(5)])
+    np.savez_compressed(os.path.join(OUT, "tss_small.npz"), **t)
+
+
 def main():
     ns = ref_harness.load()
     os.makedirs(OUT, exist_ok=True)
+    if "--only-tss" in sys.argv:
+        return gen_tss(ns)
+    gen_tss(ns)
     rng = np.random.default_rng(7)
 
     # ---- ratio / dist table (src/util.py:49-60) ---------------------------------
@@ -76,8 +106,7 @@ def main():
         bwh = ns.hbma.get_motion_vectors(8, 7, 1, 2, 4, b, a)
         for mode in ("mean", "median", "weighted"):
             for fsz in (4, 8, 3):
-                d[f"{k}/smooth/{mode}_{fsz}/fs"] = blocks_of(np.asarray(ns.smooth(ns.filters[mode], fwd, fsz), np.float32), 1)[::1, ::1] \
-                    if False else np.asarray(ns.smooth(ns.filters[mode], fwd, fsz), np.float32)[:, :, :2].astype(np.float32)
+                d[f"{k}/smooth/{mode}_{fsz}/fs"] = np.asarray(ns.smooth(ns.filters[mode], fwd, fsz), np.float32)[:, :, :2].astype(np.float32)
                 d[f"{k}/smooth/{mode}_{fsz}/hbma"] = np.asarray(ns.smooth(ns.filters[mode], fwh, fsz), np.float32)[:, :, :2].astype(np.float32)
         for dist in dists:
             dd = np.float32(dist)

@@ -159,6 +159,54 @@ ORC_API int orc_fs_blocks(const uint8_t *im1, const uint8_t *im2, int H, int W,
     return 0;
 }
 
+/* ------------------------------------------------------------------------ */
+/* Three-step search  (ME/tss.py:18-61 helper, :63-69 get_motion_vectors)     */
+/* ------------------------------------------------------------------------ */
+ORC_API int orc_tss_blocks(const uint8_t *im1, const uint8_t *im2, int H, int W,
+                           int bs, int steps, float *out)
+{
+    static const int prec[9] = {1, 2, 1, 2, 3, 2, 1, 2, 1};                /* :21 */
+    if (H <= 0 || W <= 0 || bs <= 0 || steps < 0 || steps > 20) return -1;
+    uint8_t *sp = pad_frame(im1, H, W, bs), *tp = pad_frame(im2, H, W, bs);
+    if (!sp || !tp) { free(sp); free(tp); return -2; }
+    int Wp = W + bs;
+    int nbr = ceil_div(H, bs), nbc = ceil_div(W, bs);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int br = 0; br < nbr; ++br)
+        for (int bc = 0; bc < nbc; ++bc) {
+            int s_row = br * bs, s_col = bc * bs;
+            const uint8_t *sb = sp + ((size_t)s_row * Wp + s_col) * 3;
+            int have_center = 0;                                            /* center_sad is None  :26 */
+            double lowest_sad = INFINITY;
+            int li_r = 0, li_c = 0, lowest_i = 0;
+            int curr_row = s_row, curr_col = s_col;
+            int tmr = (s_row + bs >= H) ? s_row + 1 : H - bs;               /* :36-39 */
+            int tmc = (s_col + bs >= H) ? s_col + 1 : W - bs;               /* :40-43, sic: H */
+            for (int step = steps; step > 0; --step) {
+                int S = 1 << (step - 1);
+                int i = -1;
+                for (int t_row = curr_row - S; t_row < curr_row + S + 1; t_row += S)
+                    for (int t_col = curr_col - S; t_col < curr_col + S + 1; t_col += S) {
+                        ++i;
+                        if ((t_row != curr_row || t_col != curr_col || !have_center) &&
+                            (t_row >= 0 && t_row <= tmr && t_col >= 0 && t_col <= tmc)) {       /* :48 inclusive */
+                            const uint8_t *tb = tp + ((size_t)t_row * Wp + t_col) * 3;
+                            double sad = (double)(uint32_t)sad_f64(sb, Wp, tb, Wp, bs);
+                            if (sad < lowest_sad || (sad == lowest_sad && prec[i] > prec[lowest_i])) {   /* :51 */
+                                lowest_sad = sad; li_r = t_row; li_c = t_col; lowest_i = i;
+                            }
+                        }
+                    }
+                curr_row = li_r; curr_col = li_c;                           /* :55-57 */
+                have_center = 1;
+            }
+            float *o = out + ((size_t)br * nbc + bc) * 3;
+            o[0] = (float)(li_r - s_row); o[1] = (float)(li_c - s_col); o[2] = (float)lowest_sad;
+        }
+    free(sp); free(tp);
+    return 0;
+}
+
 /* Exact algorithmic work of one full-search direction: number of candidates and
  * SAD pixel-ops (candidates * bs^2), from the reference's own bounds. */
 ORC_API int orc_fs_work(int H, int W, int bs, int R, long long *n_cand, long long *px_ops)

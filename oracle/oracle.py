@@ -5,6 +5,7 @@ names and argument order mirror the reference so parity tests read like calls
 into the reference:
 
   fs(block_size, target_region, im1, im2)            ME/full_search.py:61
+  tss(block_size, steps, im1, im2)                   ME/tss.py:63
   hbma(block_size, win, sub_win, steps, min_bs, im1, im2, cost_str, upscale)   ME/hbma.py:161
   smooth(mode, mv_field, filter_size)                smoothing/threeXthree_mv_smoothing.py:14
   unidir_helper(src, tgt, mv, dist)                  MCI/Unidirectional.py:36
@@ -39,6 +40,7 @@ def lib():
         build()
         L = C.CDLL(_SO)
         L.orc_fs_blocks.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
+        L.orc_tss_blocks.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
         L.orc_fs_work.argtypes = [C.c_int] * 4 + [C.POINTER(C.c_longlong)] * 2
         L.orc_expand_dense.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
         L.orc_pyr_down.argtypes = [_u8p, C.c_int, C.c_int, _u8p]
@@ -91,6 +93,19 @@ def expand_dense(blocks, bs, H, W):
 def fs(block_size, target_region, im1, im2):
     H, W, _ = im1.shape
     return expand_dense(fs_blocks(block_size, target_region, im1, im2), block_size, H, W)
+
+
+def tss_blocks(block_size, steps, im1, im2):
+    im1, im2 = _frame(im1), _frame(im2)
+    H, W, _ = im1.shape
+    out = np.empty((-(-H // block_size), -(-W // block_size), 3), np.float32)
+    _chk(lib().orc_tss_blocks(im1, im2, H, W, block_size, steps, out), "tss")
+    return out
+
+
+def tss(block_size, steps, im1, im2):
+    H, W, _ = im1.shape
+    return expand_dense(tss_blocks(block_size, steps, im1, im2), block_size, H, W)
 
 
 def fs_work(H, W, block_size, target_region):

@@ -1,0 +1,80 @@
+"""Turn gpurun_out/{launches.csv,prof_*.ncu-rep} into small text summaries under profiles/."""
+import collections, csv, subprocess, sys, os
+tag = sys.argv[1]
+out = open(f"profiles/{tag}_summary.md", "w")
+def w(s=""):
+    out.write(s + "\n")
+w(f"# ncu summaries, {tag}")
+w()
+w("Command profiled: `python bench.py --steps 1 --warmup 1 --pairs 4 --no-cpu-baseline` (cfg2: 1080p, fs 8x8 +-16, bidir),")
+w("each ncu pass run only after the same command exited 0 without ncu (profiles/capture.sh).")
+w()
+w("## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`) -- cold-cache, serialised: compare SHARES")
+w()
+lines = [l for l in open("gpurun_out/launches.csv") if l.startswith('"')]
+agg = collections.defaultdict(lambda: [0, 0.0])
+for row in csv.DictReader(lines):
+    name = row['Kernel Name'].split('(')[0].replace('void ', '')
+    v = float(row['Metric Value'].replace(',', ''))
+    u = row['Metric Unit']
+    v *= {'ns': 1, 'us': 1e3, 'ms': 1e6}.get(u, 1)
+    agg[name][0] += 1; agg[name][1] += v
+step = {k: v for k, v in agg.items() if not k.startswith('ub_kernel')}
+tot = sum(v[1] for v in step.values())
+w("| kernel | launches | total us | avg us | share of hot-path kernels |")
+w("|---|---:|---:|---:|---:|")
+for k, v in sorted(step.items(), key=lambda kv: -kv[1][1]):
+    w(f"| {k} | {v[0]} | {v[1]/1e3:.1f} | {v[1]/v[0]/1e3:.1f} | {v[1]/tot:.3f} |")
+for k, v in agg.items():
+    if k.startswith('ub_kernel'):
+        w(f"| ({k}: roofline microbenchmark, not part of a step) | {v[0]} | {v[1]/1e3:.1f} | {v[1]/v[0]/1e3:.1f} | - |")
+w()
+want = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__inst_executed.sum',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__warps_eligible.avg.per_cycle_active',
+        'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_sector_hit_rate.pct']
+for rep, title in (("prof_fs", "fs_tiled_kernel (dominant kernel)"), ("prof_mci", "mci_splat_kernel")):
+    path = f"gpurun_out/{rep}.ncu-rep"
+    if not os.path.exists(path):
+        continue
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    w(f"## `ncu --set full --clock-control none --import-source on`: {title}")
+    w()
+    w("| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |")
+    w("|---|---|" + "---:|" * len(data))
+    for m in ['Kernel Name'] + want:
+        if m in hdr:
+            i = hdr.index(m)
+            w(f"| {m} | {units[i]} | " + " | ".join(r[i][:70] for r in data) + " |")
+    w()
+import json
+traffic = {}
+for rep, kname in (("prof_fs", "fs_tiled_kernel"), ("prof_mci", "mci_splat_kernel")):
+    path = f"gpurun_out/{rep}.ncu-rep"
+    if not os.path.exists(path):
+        continue
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    def col(m):
+        i = hdr.index(m)
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+        return [float(r[i]) * mult for r in data]
+    rd, wr = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
+    traffic[kname] = {"dram_bytes_per_launch": sum(rd) / len(rd) + sum(wr) / len(wr), "launches_captured": len(rd),
+                      "source": f"profiles/{tag}_summary.md (ncu --set full --clock-control none)"}
+json.dump(traffic, open("profiles/traffic.json", "w"), indent=1)
+out.close()
+print(open(f"profiles/{tag}_summary.md").read()[:6000])

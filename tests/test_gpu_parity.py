@@ -361,3 +361,25 @@ def test_full_size_properties_4k_8k(gpu, oracle, H, W, bs, R):
         assert np.all(inner_b[..., 0] == -dy) and np.all(inner_b[..., 1] == -dx)
     finally:
         ctx.close()
+
+
+# ---------------------------------------------------------------- three-step search
+def test_tss_vs_golden_and_oracle(gpu, golden, oracle):
+    import ast
+    from interpolatory_b200 import MEMCI, ArrayVideoStream
+    from interpolatory_b200.ME.tss import get_motion_vectors as tss
+    g = golden("tss_small.npz")
+    for (H, W) in [(72, 96), (50, 70), (37, 53), (120, 40)]:
+        fr = make_sequence(H, W, 2, seed=H)
+        for bs, steps in ((8, 3), (8, 1), (4, 2), (16, 4), (8, 5)):
+            assert np.array_equal(blocks_of(tss(bs, steps, fr[0], fr[1]), bs), g[f"{H}x{W}/tss/{bs}_{steps}"]), (H, W, bs, steps)
+    fr = make_sequence(300, 500, 2, seed=8)
+    assert np.array_equal(tss(8, 3, fr[0], fr[1]), oracle.tss(8, 3, fr[0], fr[1]))
+    frames = make_sequence(72, 96, 3, seed=2072)
+    for si in range(2):
+        st = dict(ast.literal_eval(str(g[f"e2e/set{si}/settings"])))
+        it = MEMCI(60, **st)
+        it.set_video_stream(ArrayVideoStream(list(frames), 24))
+        for i, want in enumerate(g[f"e2e/set{si}/out"]):
+            assert np.array_equal(np.asarray(it.get_interpolated_frame(i)), want), (st, i)
+        it.close()

@@ -71,8 +71,8 @@ def test_factory():
         MEMCI(60, mci_mode='sideways')
     with pytest.raises(NotImplementedError):
         MEMCI(60, mci_mode='bidir2')
-    with pytest.raises(NotImplementedError):
-        MEMCI(60, me_mode='tss')
+    it = MEMCI(60, me_mode='tss', target_region='9')
+    assert it.region == it.steps == 3 and it.ME_args == {"block_size": 8, "steps": 3}      # tss forces region = steps
 
 
 def test_cli_settings_string():

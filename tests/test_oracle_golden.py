@@ -173,3 +173,11 @@ def test_edge_cases(oracle):
     assert np.all(mv == 0)          # SAD 0 everywhere: the zero vector wins the distance tie-break
     out = oracle.bidir_helper(flat, flat, mv, mv, np.float32(0.5))
     assert np.array_equal(out, flat)
+
+
+def test_tss(oracle, golden):
+    g = golden("tss_small.npz")
+    for (H, W) in [(72, 96), (50, 70), (37, 53), (120, 40)]:
+        fr = make_sequence(H, W, 2, seed=H)
+        for bs, steps in ((8, 3), (8, 1), (4, 2), (16, 4), (8, 5)):
+            assert np.array_equal(oracle.tss_blocks(bs, steps, fr[0], fr[1]), g[f"{H}x{W}/tss/{bs}_{steps}"]), (H, W, bs, steps)
