@@ -96,6 +96,12 @@ MEMCI_API void *memci_frame_device_ptr(memci_ctx *ctx, int slot);
 MEMCI_API int memci_me_fs(memci_ctx *ctx, int slot_src, int slot_tgt, int block_size,
                           int target_region, int mv_slot);
 
+/* Both directions of one frame pair in ONE persistent launch (the two get_motion_vectors calls of
+ * Bidirectional.py:138-143: fwd = fs(bs, R, a, b), bwd = fs(bs, R, b, a)); same results as two
+ * memci_me_fs calls, one kernel start-up / tail and one exact-redo pass instead of two. */
+MEMCI_API int memci_me_fs_pair(memci_ctx *ctx, int slot_a, int slot_b, int block_size, int target_region,
+                               int mv_fwd, int mv_bwd);
+
 /* Replaces ME/tss.py:63 get_motion_vectors(block_size, steps, im1, im2) (helper :18-61). */
 MEMCI_API int memci_me_tss(memci_ctx *ctx, int slot_src, int slot_tgt, int block_size, int steps, int mv_slot);
 

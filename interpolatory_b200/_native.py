@@ -37,6 +37,7 @@ _PROTOS = {
     "memci_download_frame": ([_P, _I, _P], _I),
     "memci_frame_device_ptr": ([_P, _I], _P),
     "memci_me_fs": ([_P, _I, _I, _I, _I, _I], _I),
+    "memci_me_fs_pair": ([_P, _I, _I, _I, _I, _I, _I], _I),
     "memci_me_tss": ([_P, _I, _I, _I, _I, _I], _I),
     "memci_me_hbma": ([_P] + [_I] * 9, _I),
     "memci_download_pyramid_level": ([_P, _I, _I, _P], _I),

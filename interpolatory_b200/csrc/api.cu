@@ -100,7 +100,7 @@ int memci_ctx_create(int device, int H, int W, void *stream, memci_ctx **out)
     }
     size_t fb = (size_t)H * W * 3, lb = (size_t)H * ctx->Wp * 4;
     for (int i = 0; i < MEMCI_NUM_FRAME_SLOTS; ++i) {
-        if (cudaMalloc(&ctx->frames[i].rgb, fb) != cudaSuccess || cudaMalloc(&ctx->frames[i].luma, lb) != cudaSuccess) {
+        if (cudaMalloc(&ctx->frames[i].rgb, fb + 16) != cudaSuccess   /* +16: the splat kernel reads pixels as aligned word pairs */ || cudaMalloc(&ctx->frames[i].luma, lb) != cudaSuccess) {
             memci_fail(nullptr, MEMCI_ERR_NOMEM, "cudaMalloc of frame slots failed");
             memci_ctx_destroy(ctx);
             return MEMCI_ERR_NOMEM;
@@ -147,7 +147,7 @@ int memci_ctx_destroy(memci_ctx *ctx)
     }
     if (ctx->d_redo_list) cudaFree(ctx->d_redo_list);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
-    if (ctx->d_hole_mask) cudaFree(ctx->d_hole_mask);
+    if (ctx->d_fill) cudaFree(ctx->d_fill);
     if (ctx->d_hole_list) cudaFree(ctx->d_hole_list);
     if (ctx->d_dense) cudaFree(ctx->d_dense);
     for (int i = 0; i < 2 * ctx->pool_cap; ++i) cudaEventDestroy(ctx->pool[i]);
@@ -222,6 +222,13 @@ int memci_me_fs(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, int m
 {
     REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_MV(ctx, mv_slot, 0);
     return memci_fs_run(ctx, slot_src, slot_tgt, bs, R, &ctx->mvs[mv_slot], 0, -1);
+}
+
+int memci_me_fs_pair(memci_ctx *ctx, int slot_a, int slot_b, int bs, int R, int mv_fwd, int mv_bwd)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot_a, 1); REQ_FRAME(ctx, slot_b, 1); REQ_MV(ctx, mv_fwd, 0); REQ_MV(ctx, mv_bwd, 0);
+    if (mv_fwd == mv_bwd) return memci_fail(ctx, MEMCI_ERR_ARG, "pair search needs two distinct MV slots");
+    return memci_fs_run(ctx, slot_a, slot_b, bs, R, &ctx->mvs[mv_fwd], 0, -1, &ctx->mvs[mv_bwd]);
 }
 
 int memci_me_fs_rows(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, int mv_slot, int block_row0, int block_row1)
@@ -419,9 +426,12 @@ int memci_estimate_pair(memci_ctx *ctx, const memci_pair_params *p, int slot_src
     REQ_CTX(ctx);
     if (!p) return memci_fail(ctx, MEMCI_ERR_ARG, "null params");
     int rc;
+    const bool fused = p->me_mode == 0 && p->bidir && mv_fwd != mv_bwd;
+    if (fused && (rc = memci_me_fs_pair(ctx, slot_src, slot_tgt, p->block_size, p->region, mv_fwd, mv_bwd))) return rc;
     for (int d = 0; d < (p->bidir ? 2 : 1); ++d) {
         int a = d ? slot_tgt : slot_src, b = d ? slot_src : slot_tgt, mv = d ? mv_bwd : mv_fwd;
-        if (p->me_mode == 0) rc = memci_me_fs(ctx, a, b, p->block_size, p->region, mv);
+        if (fused) rc = MEMCI_OK;
+        else if (p->me_mode == 0) rc = memci_me_fs(ctx, a, b, p->block_size, p->region, mv);
         else if (p->me_mode == 1) rc = memci_me_hbma(ctx, a, b, p->block_size, p->region, p->sub_region, p->steps,
                                                      p->min_block_size, MEMCI_COST_SAD, mv);
         else if (p->me_mode == 2) rc = memci_me_tss(ctx, a, b, p->block_size, p->region, mv);

@@ -41,18 +41,24 @@ __device__ __forceinline__ unsigned long long fs_key(unsigned sad, unsigned d2, 
 // =========================================================================================
 // Generic exact kernel: one warp per block, lanes stride over candidates.
 // =========================================================================================
-__global__ void fs_generic_kernel(const int32_t *__restrict__ Ls, const int32_t *__restrict__ Lt,
-                                  const uint8_t *__restrict__ rgb_s, const uint8_t *__restrict__ rgb_t,
+__global__ void fs_generic_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
+                                  const uint8_t *__restrict__ rgb0, const uint8_t *__restrict__ rgb1,
                                   int H, int W, int Wp, int bs, int R, int blk_begin, int blk_end, int nbc,
                                   const int *__restrict__ list, const int *__restrict__ list_count,
-                                  float2 *__restrict__ out_vec, float *__restrict__ out_sad)
+                                  float2 *__restrict__ out_vec0, float *__restrict__ out_sad0,
+                                  float2 *__restrict__ out_vec1, float *__restrict__ out_sad1)
 {
     int lane = threadIdx.x & 31;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int nwarps = (gridDim.x * blockDim.x) >> 5;
     int total = list ? *list_count : blk_end - blk_begin;
     for (int it = warp; it < total; it += nwarps) {
-        int blk = list ? list[it] : blk_begin + it;
+        const int entry = list ? list[it] : blk_begin + it;
+        const int dir = (entry & 0x40000000) ? 1 : 0, blk = entry & 0x3fffffff;     // FS_DIR_BIT (redo list of a pair launch)
+        const int32_t *Ls = dir ? L1 : L0, *Lt = dir ? L0 : L1;
+        const uint8_t *rgb_s = dir ? rgb1 : rgb0, *rgb_t = dir ? rgb0 : rgb1;
+        float2 *out_vec = dir ? out_vec1 : out_vec0;
+        float *out_sad = dir ? out_sad1 : out_sad0;
         int br = blk / nbc, bc = blk - br * nbc;
         int s_row = br * bs, s_col = bc * bs;
         FsBounds b = fs_bounds(H, W, bs, R, s_row, s_col);
@@ -91,12 +97,15 @@ __global__ void fs_generic_kernel(const int32_t *__restrict__ Ls, const int32_t 
 // =========================================================================================
 // Redo pass: one CTA per listed block (same exact arithmetic as fs_generic_kernel, 8 warps wide).
 // =========================================================================================
+// List entries carry the search direction in bit 30 (pair launches: direction 1 swaps the frames).
+#define FS_DIR_BIT 0x40000000
 __global__ void __launch_bounds__(256)
-fs_redo_kernel(const int32_t *__restrict__ Ls, const int32_t *__restrict__ Lt,
-               const uint8_t *__restrict__ rgb_s, const uint8_t *__restrict__ rgb_t,
+fs_redo_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
+               const uint8_t *__restrict__ rgb0, const uint8_t *__restrict__ rgb1,
                int H, int W, int Wp, int bs, int R, int nbc,
                const int *__restrict__ list, const int *__restrict__ list_count,
-               float2 *__restrict__ out_vec, float *__restrict__ out_sad)
+               float2 *__restrict__ out_vec0, float *__restrict__ out_sad0,
+               float2 *__restrict__ out_vec1, float *__restrict__ out_sad1)
 {
     // Shared staging, zero padded like np.pad: the block and its search window as luma1000 ints
     // (fast SAD) and as the reference's float64 luma (exact replay of flagged candidates).
@@ -107,7 +116,12 @@ fs_redo_kernel(const int32_t *__restrict__ Ls, const int32_t *__restrict__ Lt,
     int *ref = reinterpret_cast<int *>(dwin + ww * ww), *win = ref + bs * bs;
     const int total = *list_count;
     for (int it = blockIdx.x; it < total; it += gridDim.x) {
-        const int blk = list[it];
+        const int entry = list[it];
+        const int dir = (entry & FS_DIR_BIT) ? 1 : 0, blk = entry & (FS_DIR_BIT - 1);
+        const int32_t *Ls = dir ? L1 : L0, *Lt = dir ? L0 : L1;
+        const uint8_t *rgb_s = dir ? rgb1 : rgb0, *rgb_t = dir ? rgb0 : rgb1;
+        float2 *out_vec = dir ? out_vec1 : out_vec0;
+        float *out_sad = dir ? out_sad1 : out_sad0;
         const int br = blk / nbc, bc = blk - br * nbc;
         const int s_row = br * bs, s_col = bc * bs;
         const FsBounds b = fs_bounds(H, W, bs, R, s_row, s_col);
@@ -193,16 +207,17 @@ fs_redo_kernel(const int32_t *__restrict__ Ls, const int32_t *__restrict__ Lt,
 // =========================================================================================
 struct FsParams {
     int H, W, bs, R, Rp, m, nbr, nbc, n_tiles, box_h, n_stages, ks;   // ks = bits reserved for dist^2 in the 32-bit key   // Rp = R rounded up to 4: TMA x origin stays 16-byte aligned
+    int n_tiles_dir;             // tiles of one direction; tile index >= n_tiles_dir = reverse direction (pair launch)
     const FsTile *tiles;
-    float2 *out_vec;
-    float *out_sad;
+    float2 *out_vec[2];
+    float *out_sad[2];
     int *redo_list;
     int *counters;
     int redo_cap;
 };
 
 struct FsTileTab {
-    int by, bx0, nb, s_row;
+    int by, bx0, nb, s_row, dir;
     int r0, n_dy, total_dx, uniform_ndx;   // uniform_ndx > 0: every block has that many valid column offsets
     int dx_lo[FS_NBMAX];
     int pre[FS_NBMAX + 1];
@@ -237,7 +252,7 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, in
 }
 
 // geometry of one tile, computed by warp 0 (lane = block within tile)
-__device__ inline void fs_fill_tab(FsTileTab *tab, const FsTile t, const FsParams &p, int lane)
+__device__ inline void fs_fill_tab(FsTileTab *tab, const FsTile t, const FsParams &p, int lane, int dir)
 {
     int s_row = t.by * p.bs;
     int n_dx = 0, dx_lo = 0;
@@ -257,7 +272,7 @@ __device__ inline void fs_fill_tab(FsTileTab *tab, const FsTile t, const FsParam
     if (lane == 0) {
         FsBounds b = fs_bounds(p.H, p.W, p.bs, p.R, s_row, t.bx0 * p.bs);
         tab->pre[0] = 0;
-        tab->by = t.by; tab->bx0 = t.bx0; tab->nb = t.nb; tab->s_row = s_row;
+        tab->by = t.by; tab->bx0 = t.bx0; tab->nb = t.nb; tab->s_row = s_row; tab->dir = dir;
         tab->r0 = b.r0;
         tab->n_dy = b.r1 - b.r0 > 0 ? b.r1 - b.r0 : 0;
     }
@@ -323,6 +338,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 template <int G, bool SINGLE>
 __global__ void __launch_bounds__(FS_NT, 1)
 fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_tgt,
+                const __grid_constant__ CUtensorMap tm_src1, const __grid_constant__ CUtensorMap tm_tgt1,
                 const FsParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -357,16 +373,17 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
     if (first >= p.n_tiles) return;
 
     auto issue = [&](int tile_idx, int k) {        // warp 0 only: tile table + two TMA tile loads
-        FsTile t = p.tiles[tile_idx];
+        const int dir = tile_idx >= p.n_tiles_dir ? 1 : 0;
+        FsTile t = p.tiles[tile_idx - dir * p.n_tiles_dir];
         int s = p.n_stages == 2 ? (k & 1) : 0;
-        fs_fill_tab(&tabs[k & 1], t, p, lane);
+        fs_fill_tab(&tabs[k & 1], t, p, lane, dir);
         __syncwarp();
         if (lane == 0) {
             int *win = stage0 + (size_t)s * stage_ints;
             int *ref = win + p.box_h * FS_BOXW;
             mbar_expect_tx(&full[s], stage_bytes);
-            tma_load_2d(win, &tm_tgt, t.bx0 * p.bs - p.Rp, t.by * p.bs - p.R, &full[s]);
-            tma_load_2d(ref, &tm_src, t.bx0 * p.bs, t.by * p.bs, &full[s]);
+            tma_load_2d(win, dir ? &tm_tgt1 : &tm_tgt, t.bx0 * p.bs - p.Rp, t.by * p.bs - p.R, &full[s]);
+            tma_load_2d(ref, dir ? &tm_src1 : &tm_src, t.bx0 * p.bs, t.by * p.bs, &full[s]);
         }
     };
 
@@ -390,12 +407,12 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                 dx = (float)(tab->dx_lo[lane] + ci);
                 sad = (float)(unsigned)(kb >> 32);
             }
-            p.out_vec[blk] = make_float2(dy, dx);
-            p.out_sad[blk] = sad;
+            (tab->dir ? p.out_vec[1] : p.out_vec[0])[blk] = make_float2(dy, dx);     // no dynamic index into the param struct
+            (tab->dir ? p.out_sad[1] : p.out_sad[0])[blk] = sad;
             // lowered key of some flagged candidate reaches the winner's (sad, d2): exact redo
             if (kb != KEY_NONE && kl < ((unsigned)(kb >> 32) << p.ks) + (unsigned)((kb >> 16) & 0xffffu) + 1u) {
                 int pos = atomicAdd(&p.counters[0], 1);
-                if (pos < p.redo_cap) p.redo_list[pos] = blk;
+                if (pos < p.redo_cap) p.redo_list[pos] = blk | (tab->dir ? FS_DIR_BIT : 0);
             }
         }
         __syncwarp();
@@ -504,18 +521,25 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                     kbest = fs_key(kq >> p.ks, kq & ((1u << p.ks) - 1u), (unsigned)(g_run * G) + (kb_run & ((1u << GB) - 1u)), (unsigned)dxi);
                 }
             }
-            // one atomic per warp when the whole warp works on one block (the common case)
-            const int b0 = __shfl_sync(0xffffffffu, b, 0);
-            if (__all_sync(0xffffffffu, !active || b == b0)) {
-                kbest = shfl_min_u64(kbest);
-                klow = __reduce_min_sync(0xffffffffu, klow);
-                if (lane == 0) {
-                    if (kbest != KEY_NONE) atomicMin(&best_fast[k & 1][b0], kbest);
-                    if (klow != 0xffffffffu) atomicMin(&best_low[k & 1][b0], klow >> GB);
+            // Segmented warp reduction: the 32 items of a warp belong to a few adjacent blocks (usually
+            // two); one REDUX-based 64-bit min + two shared-memory atomics per (warp, block) instead of
+            // per-lane CAS loops on the same address.
+            unsigned todo = __ballot_sync(0xffffffffu, active);
+            while (todo) {
+                const int leader = __ffs(todo) - 1;
+                const int bb = __shfl_sync(0xffffffffu, b, leader);
+                const bool mine = active && b == bb;
+                const unsigned hi = mine ? (unsigned)(kbest >> 32) : 0xffffffffu;
+                const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+                const unsigned lo = (mine && hi == mh) ? (unsigned)kbest : 0xffffffffu;
+                const unsigned ml = __reduce_min_sync(0xffffffffu, lo);
+                const unsigned kl_b = __reduce_min_sync(0xffffffffu, mine ? klow : 0xffffffffu);
+                if (lane == leader) {
+                    const unsigned long long kw = ((unsigned long long)mh << 32) | ml;
+                    if (kw != KEY_NONE) atomicMin(&best_fast[k & 1][bb], kw);
+                    if (kl_b != 0xffffffffu) atomicMin(&best_low[k & 1][bb], kl_b >> GB);
                 }
-            } else if (active) {
-                if (kbest != KEY_NONE) atomicMin(&best_fast[k & 1][b], kbest);
-                if (klow != 0xffffffffu) atomicMin(&best_low[k & 1][b], klow >> GB);
+                todo &= ~__ballot_sync(0xffffffffu, mine);
             }
         }
         __syncwarp();
@@ -670,22 +694,24 @@ static FsPlan *fs_get_plan(memci_ctx *ctx, int bs, int R)
 }
 
 template <int G, bool SINGLE>
-static int fs_launch_tiled2(memci_ctx *ctx, const CUtensorMap &ts, const CUtensorMap &tt, const FsParams &p, int smem)
+static int fs_launch_tiled2(memci_ctx *ctx, const CUtensorMap *tm, const FsParams &p, int smem)
 {
     CK(ctx, cudaFuncSetAttribute(fs_tiled_kernel<G, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = ctx->num_sms < p.n_tiles ? ctx->num_sms : p.n_tiles;
-    fs_tiled_kernel<G, SINGLE><<<grid, FS_NT, smem, ctx->stream>>>(ts, tt, p);
+    fs_tiled_kernel<G, SINGLE><<<grid, FS_NT, smem, ctx->stream>>>(tm[0], tm[1], tm[2], tm[3], p);
     CKL(ctx);
     return MEMCI_OK;
 }
 
 template <int G>
-static int fs_launch_tiled(memci_ctx *ctx, const CUtensorMap &ts, const CUtensorMap &tt, const FsParams &p, int smem)
+static int fs_launch_tiled(memci_ctx *ctx, const CUtensorMap *tm, const FsParams &p, int smem)
 {
-    return p.m == 1 ? fs_launch_tiled2<G, true>(ctx, ts, tt, p, smem) : fs_launch_tiled2<G, false>(ctx, ts, tt, p, smem);
+    return p.m == 1 ? fs_launch_tiled2<G, true>(ctx, tm, p, smem) : fs_launch_tiled2<G, false>(ctx, tm, p, smem);
 }
 
-int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out, int br0, int br1)
+// out2 != nullptr: pair launch -- the same persistent kernel also searches the reverse direction
+// (slot_tgt -> slot_src) into out2 (one launch, one redo pass for both motion fields).
+int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out, int br0, int br1, MVField *out2)
 {
     const int H = ctx->H, W = ctx->W, Wp = ctx->Wp;
     if (bs <= 0 || bs > 64 || R < 0 || R > 127)
@@ -695,44 +721,52 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
     if ((rc = memci_ensure_luma(ctx, slot_tgt))) return rc;
     const int nbr = ceil_div_i(H, bs), nbc = ceil_div_i(W, bs);
     if ((rc = memci_mv_reserve(ctx, out, bs, nbr, nbc, bs, nbr, nbc))) return rc;
+    if (out2 && (rc = memci_mv_reserve(ctx, out2, bs, nbr, nbc, bs, nbr, nbc))) return rc;
+    const int ndir = out2 ? 2 : 1;
     FsPlan *pl = fs_get_plan(ctx, bs, R);
     if (!pl) return MEMCI_ERR_CUDA;
     if (br1 < 0) { br0 = 0; br1 = nbr; }
     if (br0 < 0 || br1 > nbr || br0 >= br1) return memci_fail(ctx, MEMCI_ERR_ARG, "block row range [%d, %d) outside [0, %d)", br0, br1, nbr);
     long long cand = 0;
     for (int r = br0; r < br1; ++r) cand += pl->row_cand[r];
-    ctx->fs_last_cand = cand;
-    ctx->fs_last_ops = cand * bs * bs;
+    ctx->fs_last_cand = cand * ndir;
+    ctx->fs_last_ops = cand * ndir * bs * bs;
     FrameSlot &fs = ctx->frames[slot_src], &ft = ctx->frames[slot_tgt];
-    if ((size_t)ctx->redo_cap < (size_t)nbr * nbc) {
+    if ((size_t)ctx->redo_cap < 2 * (size_t)nbr * nbc) {
         if (ctx->d_redo_list) cudaFree(ctx->d_redo_list);
         ctx->d_redo_list = nullptr;
-        CK(ctx, cudaMalloc(&ctx->d_redo_list, sizeof(int) * (size_t)nbr * nbc));
-        ctx->redo_cap = nbr * nbc;
+        CK(ctx, cudaMalloc(&ctx->d_redo_list, sizeof(int) * 2 * (size_t)nbr * nbc));
+        ctx->redo_cap = 2 * nbr * nbc;
     }
     CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));
     ctx->fs_timed = 0;
     if (pl->n_tiles > 0) {
-        CUtensorMap ts, tt;
-        if ((rc = make_tmap(ctx, &ts, fs.luma, H, W, Wp, FS_BOXW, bs))) return rc;
-        if ((rc = make_tmap(ctx, &tt, ft.luma, H, W, Wp, FS_BOXW, pl->box_h))) return rc;
+        CUtensorMap tm[4];                     // src/tgt of direction 0, src/tgt of direction 1
+        if ((rc = make_tmap(ctx, &tm[0], fs.luma, H, W, Wp, FS_BOXW, bs))) return rc;
+        if ((rc = make_tmap(ctx, &tm[1], ft.luma, H, W, Wp, FS_BOXW, pl->box_h))) return rc;
+        if (out2) {
+            if ((rc = make_tmap(ctx, &tm[2], ft.luma, H, W, Wp, FS_BOXW, bs))) return rc;
+            if ((rc = make_tmap(ctx, &tm[3], fs.luma, H, W, Wp, FS_BOXW, pl->box_h))) return rc;
+        } else { tm[2] = tm[0]; tm[3] = tm[1]; }
         FsParams p;
         p.H = H; p.W = W; p.bs = bs; p.R = R; p.Rp = (R + 3) & ~3; p.m = bs / 8; p.nbr = nbr; p.nbc = nbc;
-        p.n_tiles = pl->row_tile_start[br1] - pl->row_tile_start[br0]; p.box_h = pl->box_h;
+        p.n_tiles_dir = pl->row_tile_start[br1] - pl->row_tile_start[br0]; p.n_tiles = ndir * p.n_tiles_dir; p.box_h = pl->box_h;
         { int ks = 1; while ((1 << ks) <= 2 * R * R + 1) ++ks; p.ks = ks; }
         p.n_stages = fs_smem_bytes(bs, pl->box_h, 2, pl->G) <= 220 * 1024 ? 2 : 1;
-        p.tiles = pl->d_tiles + pl->row_tile_start[br0]; p.out_vec = out->vec; p.out_sad = out->sad;
+        p.tiles = pl->d_tiles + pl->row_tile_start[br0];
+        p.out_vec[0] = out->vec; p.out_sad[0] = out->sad;
+        p.out_vec[1] = out2 ? out2->vec : out->vec; p.out_sad[1] = out2 ? out2->sad : out->sad;
         p.redo_list = ctx->d_redo_list; p.counters = ctx->d_counters; p.redo_cap = ctx->redo_cap;
         const int smem = fs_smem_bytes(bs, pl->box_h, p.n_stages, pl->G);
         if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
         const int prof = memci_prof_begin(ctx, 0);
         switch (pl->G) {
-        case 5: rc = fs_launch_tiled<5>(ctx, ts, tt, p, smem); break;
-        case 8: rc = fs_launch_tiled<8>(ctx, ts, tt, p, smem); break;
-        case 13: rc = fs_launch_tiled<13>(ctx, ts, tt, p, smem); break;
-        case 17: rc = fs_launch_tiled<17>(ctx, ts, tt, p, smem); break;
-        case 33: rc = fs_launch_tiled<33>(ctx, ts, tt, p, smem); break;
-        default: rc = fs_launch_tiled<11>(ctx, ts, tt, p, smem); break;
+        case 5: rc = fs_launch_tiled<5>(ctx, tm, p, smem); break;
+        case 8: rc = fs_launch_tiled<8>(ctx, tm, p, smem); break;
+        case 13: rc = fs_launch_tiled<13>(ctx, tm, p, smem); break;
+        case 17: rc = fs_launch_tiled<17>(ctx, tm, p, smem); break;
+        case 33: rc = fs_launch_tiled<33>(ctx, tm, p, smem); break;
+        default: rc = fs_launch_tiled<11>(ctx, tm, p, smem); break;
         }
         memci_prof_end(ctx, prof);
         if (rc) return rc;
@@ -742,19 +776,27 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         if (redo_smem <= 160 * 1024) {
             CK(ctx, cudaFuncSetAttribute(fs_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, redo_smem));
             fs_redo_kernel<<<ctx->num_sms * 2, 256, redo_smem, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbc,
-                                                                              ctx->d_redo_list, ctx->d_counters, out->vec, out->sad);
+                                                                              ctx->d_redo_list, ctx->d_counters, out->vec, out->sad,
+                                                                              p.out_vec[1], p.out_sad[1]);
         } else {
             fs_generic_kernel<<<ctx->num_sms, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, 0, 0, nbc,
-                                                                     ctx->d_redo_list, ctx->d_counters, out->vec, out->sad);
+                                                                     ctx->d_redo_list, ctx->d_counters, out->vec, out->sad,
+                                                                     p.out_vec[1], p.out_sad[1]);
         }
         CKL(ctx);
     } else {
         if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
         fs_generic_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, br0 * nbc, br1 * nbc, nbc,
-                                                                     nullptr, nullptr, out->vec, out->sad);
+                                                                     nullptr, nullptr, out->vec, out->sad, nullptr, nullptr);
         CKL(ctx);
+        if (out2) {
+            fs_generic_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ft.luma, fs.luma, ft.rgb, fs.rgb, H, W, Wp, bs, R, br0 * nbc, br1 * nbc, nbc,
+                                                                         nullptr, nullptr, out2->vec, out2->sad, nullptr, nullptr);
+            CKL(ctx);
+        }
         if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->fs_timed = 1; }
     }
     out->valid = 1;
+    if (out2) out2->valid = 1;
     return MEMCI_OK;
 }

@@ -20,13 +20,12 @@
 
 #include "memci_internal.cuh"
 
-#define MCI_TW 32
-#define MCI_TH 8
-#define MCI_NT (MCI_TW * MCI_TH)
-#define MCI_SLOTS 1024
-#define MCI_MAXKEYS 768
 #define MCI_EMPTY 0xffffffffu
 #define MCI_KOFF 8191
+#define HF_WARPS 8
+#define HF_MAXRUN 8                          // holes per run (power of two, <= 32)
+#define HF_TW (21 + HF_MAXRUN - 1)           // staged window width of a run
+#define HF_TWP (HF_TW | 1)                   // odd row stride: conflict-free column reads
 
 struct MciParams {
     int H, W, bidir, ndir;
@@ -34,12 +33,16 @@ struct MciParams {
     int fill_begin, fill_end;    // target rows whose holes this launch fills
     float dist;
     const uint8_t *src, *tgt;
-    uint8_t *out, *mask;
+    uint8_t *out;
+    uint32_t *fill;              // per pixel: v0 | v1<<8 | v2<<16 | hole<<24 (holes carry the TARGET-frame pixel): hole-fill input
     int *hole_list, *counters;
     const short2 *disp[2];
-    int cell[2], cols[2], cshift[2];     // cshift >= 0: cell == 1 << cshift (no integer division)
+    int cell[2], cols[2];
+    unsigned cmul[2];            // ceil(2^32 / cell): x / cell == umulhi(x, cmul) for 0 <= x < 2^16 (0 when cell == 1)
     const float *sad[2];
-    int scell[2], scols[2], sshift[2];
+    int scell[2], scols[2];
+    unsigned smul[2];
+    int sad_nested[2];           // scell % cell == 0: every pixel of an MV cell reads the same SAD cell
 };
 
 // ---- per-cell integer displacement ---------------------------------------------------------
@@ -79,13 +82,49 @@ struct PixState {
     bool written;
 };
 
-__device__ __forceinline__ int cell_of(int x, int cell, int shift) { return shift >= 0 ? (x >> shift) : (x / cell); }
+// x / cell for 0 <= x < 2^16 as one IMAD.HI (exact: x * cell < 2^32); mul == 0 encodes cell == 1
+__device__ __forceinline__ int cell_of(int x, unsigned mul) { return mul ? (int)__umulhi((unsigned)x, mul) : x; }
+
+// Exact mixed-precision blend of Bidirectional.py:48-49 (W3); out of line: it is the rare path of
+// mci_apply_t and the splat kernel instantiates that 16 times.
+__device__ __noinline__ int mci_blend_exact(float pxv, float sadi, float t, int v, double bd, double td)
+{
+    float a = __fdiv_rn(__fmul_rn(pxv, sadi), t);
+    double c = __ddiv_rn(__dmul_rn((double)v, bd), td);
+    float s = __double2float_rn(__dadd_rn((double)a, c));
+    return __float2int_rz(s);
+}
 
 // Apply the event "source pixel (p_r, p_c) of direction DIR lands on this target pixel".
 template <int DIR>
-__device__ __forceinline__ void mci_apply_t(const MciParams &P, PixState &st, int p_r, int p_c, bool self_write)
+__device__ __forceinline__ float mci_sad_at(const MciParams &P, int p_r, int p_c)
 {
-    const float sad = P.sad[DIR][cell_of(p_r, P.scell[DIR], P.sshift[DIR]) * P.scols[DIR] + cell_of(p_c, P.scell[DIR], P.sshift[DIR])];
+    return P.sad[DIR][cell_of(p_r, P.smul[DIR]) * P.scols[DIR] + cell_of(p_c, P.smul[DIR])];
+}
+
+// Bidirectional.py:48-49: IF = tgt*SADI/t + IF*bsad/t with t = bsad + SADI.  numba types the fused
+// expression float32:  f32( f64( f32(u8*SADI) / t ) + f64(IF) * f64(bsad) / f64(t) ), truncated to int32 (W3).
+// A fast estimate decides the truncation unless it falls within 1e-3 of an integer (its error is < 1e-4),
+// where the exact mixed-precision expression is evaluated instead (f64 divide: ~100 instructions).
+__device__ __forceinline__ void mci_blend3(int &v0, int &v1, int &v2, int t0, int t1, int t2, float sad, float sadi)
+{
+    const float t = __fadd_rn(sad, sadi);
+    const double td = (double)t, bd = (double)sad;
+    int v[3] = {v0, v1, v2};
+    const int px[3] = {t0, t1, t2};
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+        const float est = __fdividef(fmaf((float)px[ch], sadi, (float)v[ch] * sad), t);
+        const float fl = floorf(est), fr = est - fl;
+        if (fr > 1e-3f && fr < 0.999f) v[ch] = (int)fl;
+        else v[ch] = mci_blend_exact((float)px[ch], sadi, t, v[ch], bd, td);
+    }
+    v0 = v[0]; v1 = v[1]; v2 = v[2];
+}
+
+template <int DIR>
+__device__ __forceinline__ void mci_apply_t(const MciParams &P, PixState &st, int p_r, int p_c, bool self_write, const float sad)
+{
     const uint8_t *px = (DIR == 0 ? P.src : P.tgt) + ((size_t)p_r * P.W + p_c) * 3;
     if (!P.bidir) {
         if (self_write || sad <= st.sadi) {             // Unidirectional.py:52 (non-strict) / :56-58
@@ -100,28 +139,7 @@ __device__ __forceinline__ void mci_apply_t(const MciParams &P, PixState &st, in
     } else {
         if (sad < st.sadi) {                            // :46
             if (st.sadi != __int_as_float(0x7f800000)) {
-                // :48-49.  numba types the fused expression float32:
-                //   f32( f64( f32(u8*SADI) / t ) + f64(IF) * f64(bsad) / f64(t) ), truncated to int32 (W3)
-                const float t = __fadd_rn(sad, st.sadi);
-                const double td = (double)t, bd = (double)sad;
-                int v[3] = {st.v0, st.v1, st.v2};
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    // fast estimate of the blended value; it decides the truncation unless it falls
-                    // within 1e-3 of an integer (its error is < 1e-4), where the exact mixed-precision
-                    // expression of the reference is evaluated instead (f64 divide: ~100 instructions)
-                    const float est = __fdividef(fmaf((float)px[ch], st.sadi, (float)v[ch] * sad), t);
-                    const float fl = floorf(est), fr = est - fl;
-                    if (fr > 1e-3f && fr < 0.999f) {
-                        v[ch] = (int)fl;
-                    } else {
-                        float a = __fdiv_rn(__fmul_rn((float)px[ch], st.sadi), t);
-                        double c = __ddiv_rn(__dmul_rn((double)v[ch], bd), td);
-                        float s = __double2float_rn(__dadd_rn((double)a, c));
-                        v[ch] = __float2int_rz(s);
-                    }
-                }
-                st.v0 = v[0]; st.v1 = v[1]; st.v2 = v[2];
+                mci_blend3(st.v0, st.v1, st.v2, px[0], px[1], px[2], sad, st.sadi);       // :48-49
             } else {                                    // :51-53
                 st.v0 = px[0]; st.v1 = px[1]; st.v2 = px[2];
             }
@@ -132,8 +150,8 @@ __device__ __forceinline__ void mci_apply_t(const MciParams &P, PixState &st, in
 
 __device__ __forceinline__ void mci_apply(const MciParams &P, PixState &st, int p_r, int p_c, int dir, bool self_write)
 {
-    if (dir == 0) mci_apply_t<0>(P, st, p_r, p_c, self_write);
-    else mci_apply_t<1>(P, st, p_r, p_c, self_write);
+    if (dir == 0) mci_apply_t<0>(P, st, p_r, p_c, self_write, mci_sad_at<0>(P, p_r, p_c));
+    else mci_apply_t<1>(P, st, p_r, p_c, self_write, mci_sad_at<1>(P, p_r, p_c));
 }
 
 // Generic event test (dense fallback): does the pixel at q - e carry effective displacement e?
@@ -142,7 +160,7 @@ __device__ __forceinline__ void mci_try_event(const MciParams &P, PixState &st, 
 {
     const int p_r = q_r - eff_r, p_c = q_c - eff_c;
     if (p_r < 0 || p_r >= P.H || p_c < 0 || p_c >= P.W) return;
-    const short2 d = P.disp[dir][cell_of(p_r, P.cell[dir], P.cshift[dir]) * P.cols[dir] + cell_of(p_c, P.cell[dir], P.cshift[dir])];
+    const short2 d = P.disp[dir][cell_of(p_r, P.cmul[dir]) * P.cols[dir] + cell_of(p_c, P.cmul[dir])];
     const int u_i = p_r + d.x, v_i = p_c + d.y;
     bool self_write = false;
     if (u_i < P.H && v_i < P.W) {                       // Unidirectional.py:51, Bidirectional.py:36/45
@@ -162,173 +180,426 @@ __device__ __forceinline__ unsigned mci_key(int eff_r, int eff_c, int dir)
     return ((unsigned)(MCI_KOFF - eff_r) << 15) | ((unsigned)(MCI_KOFF - eff_c) << 1) | (unsigned)dir;
 }
 
-// sorted list entry: effective displacement, the raw per-cell displacement it stands for, direction.
-// kind 0 = ordinary event; kind 1 = the unidirectional self-write slot at e = (0,0).
-struct __align__(16) MciEntry { int eff_r, eff_c; unsigned dpacked; int dir_kind; };
+// ---- splat kernel: one WARP per 32 x SW_TH tile of target pixels -------------------------------
+// Lane = column, the SW_TH rows of the lane live in registers.  The warp (no CTA barrier anywhere)
+//   1. scans the MV cells whose footprint can reach the tile (un-wrapped and, at the frame's far edges,
+//      wrapped neighbourhoods), de-duplicates their (effective displacement, direction) keys with
+//      match.any inside a 32-cell chunk and a broadcast scan of the short list across chunks, and stages
+//      the un-wrapped neighbourhood's packed displacements in shared memory;
+//   2. rank-sorts the list (ascending key = raster order of the source pixel, forward before backward);
+//   3. walks it: for every entry the lane tests its SW_TH pixels -- "does the cell of q - e carry exactly
+//      this displacement?" is one shared-memory load and one compare -- and replays the reference's state
+//      machine on a match.
+// Output: the uint8 frame, the packed hole-fill image (P.fill) and the list of hole runs.
+#define SW_TH 8
+#define SW_WARPS 4
+#define SW_MAXK 256          // distinct (displacement, direction) keys per tile; more -> dense fallback
+#define SW_STAGE 320         // staged displacement cells per direction
 
-#define MCI_STAGE_MAX 1536      // staged displacement cells per direction (6 KB)
+struct SwShared {
+    unsigned keys[SW_MAXK];
+    unsigned dps[SW_MAXK];
+    uint2 sorted[SW_MAXK];   // .x = key, .y = packed per-cell displacement the entry stands for
+    unsigned stage[2][SW_STAGE];
+    float stage_sad[2][SW_STAGE];
+    unsigned rowbuf[24];     // one output row of the tile (32 px x 3 B) for 4-byte coalesced stores
+    int s_r0[2], s_c0[2], s_nc[2], staged[2];   // staged neighbourhood per direction (first cell row / column, cells per row)
+};
 
-__global__ void __launch_bounds__(MCI_NT)
-mci_splat_kernel(const MciParams P)
+// Dense fallback (key list overflow / huge frames): enumerate every possible displacement in
+// source-raster order, e in [H-dmax, H-1] (wrapped) then [dmax, -dmax] (direct), each value once.
+__device__ __noinline__ void sw_dense_pixel(const MciParams &P, PixState &st, int q_r, int q_c, int dmax)
 {
-    __shared__ unsigned table[MCI_SLOTS];
-    __shared__ unsigned list[MCI_MAXKEYS];
-    __shared__ unsigned dlist[MCI_MAXKEYS];
-    __shared__ MciEntry sorted[MCI_MAXKEYS];
-    __shared__ unsigned stage[2][MCI_STAGE_MAX];
-    __shared__ int n_keys, overflow;
-
-    const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * MCI_TW, ty0 = P.y_begin + blockIdx.y * MCI_TH;
-    const int q_c = tx0 + (tid & 31), q_r = ty0 + (tid >> 5);
     const int H = P.H, W = P.W;
+    for (int eff_r = q_r; eff_r >= -dmax; --eff_r) {
+        if (eff_r > dmax && eff_r < H - dmax) { eff_r = dmax + 1; continue; }
+        if (q_r - eff_r >= H) break;
+        for (int eff_c = q_c; eff_c >= -dmax; --eff_c) {
+            if (eff_c > dmax && eff_c < W - dmax) { eff_c = dmax + 1; continue; }
+            if (q_c - eff_c >= W) break;
+            for (int dir = 0; dir < P.ndir; ++dir) mci_try_event(P, st, q_r, q_c, eff_r, eff_c, dir);
+        }
+    }
+}
+
+// ---- decision state of one target pixel ----------------------------------------------------------
+// The control flow of the reference's state machine depends only on SADs, never on pixel values, so
+// the walk (phase A) records WHICH events fire -- the last overriding copy plus at most one backward
+// blend stacked on it -- in five registers per pixel, without touching the frames; phase B then issues
+// the pixel loads of the whole tile at once and evaluates the blends.
+//   sadi : SAD_interpolated_frame[q]
+//   base : kind << 28 | payload.  kind 0 nothing yet (hole), 1 source-frame pixel (payload = linear index),
+//          2 target-frame pixel, 3 literal packed value (a longer blend chain that was evaluated early)
+//   bp   : target-frame pixel of the pending backward blend (-1: none), bs / bi: its bsad and the SADI it saw
+#define SW_KIND(base) ((unsigned)(base) >> 28)
+#define SW_PAYLOAD(base) ((base) & 0x0fffffff)
+
+// 24-bit RGB of pixel p_lin as two aligned word loads (frame slots carry 16 bytes of slack)
+__device__ __forceinline__ void sw_px_issue(const uint8_t *frame, int p_lin, unsigned &lo, unsigned &hi, unsigned &sh)
+{
+    const size_t a = (size_t)frame + (size_t)p_lin * 3;
+    const unsigned *w = reinterpret_cast<const unsigned *>(a & ~(size_t)3);
+    lo = w[0]; hi = w[1]; sh = (unsigned)(a & 3) * 8u;
+}
+__device__ __forceinline__ unsigned sw_px_finish(unsigned lo, unsigned hi, unsigned sh) { return __funnelshift_r(lo, hi, sh) & 0xffffffu; }
+
+// Bidirectional.py:48-49 on packed values: v = blend(target pixel t, v)
+__device__ __noinline__ unsigned sw_blend_packed(unsigned v, unsigned t, float sad, float sadi)
+{
+    int v0 = (int)(v & 255u), v1 = (int)((v >> 8) & 255u), v2 = (int)((v >> 16) & 255u);
+    mci_blend3(v0, v1, v2, (int)(t & 255u), (int)((t >> 8) & 255u), (int)((t >> 16) & 255u), sad, sadi);
+    return (unsigned)v0 | ((unsigned)v1 << 8) | ((unsigned)v2 << 16);
+}
+
+// value of a pixel whose decision state is (base, bp, bs, bi); only called when base != hole
+__device__ __noinline__ unsigned sw_eval(const MciParams *P, int base, int bp, float bs, float bi)
+{
+    unsigned v;
+    if (SW_KIND(base) == 3u) v = (unsigned)SW_PAYLOAD(base) & 0xffffffu;
+    else {
+        unsigned lo, hi, sh;
+        sw_px_issue(SW_KIND(base) == 1u ? P->src : P->tgt, SW_PAYLOAD(base), lo, hi, sh);
+        v = sw_px_finish(lo, hi, sh);
+    }
+    if (bp >= 0) {
+        unsigned lo, hi, sh;
+        sw_px_issue(P->tgt, bp, lo, hi, sh);
+        v = sw_blend_packed(v, sw_px_finish(lo, hi, sh), bs, bi);
+    }
+    return v;
+}
+
+// The event "pixel p_lin of direction D lands on this target pixel" (Unidirectional.py:52-58,
+// Bidirectional.py:37-53) as a decision only, written with selects (the call sites are unrolled).
+template <int D, bool BIDIR>
+__device__ __forceinline__ void sw_fire(const MciParams &P, float &sadi, int &base, int &bp, float &bs, float &bi,
+                                        int p_lin, float sad, bool self_write)
+{
+    if (!BIDIR) {
+        const bool t = self_write || sad <= sadi;                       // :52 (non-strict) / :56-58
+        base = t ? ((1 << 28) | p_lin) : base;
+        sadi = t ? sad : sadi;
+    } else if (D == 0) {
+        const bool t = sad < sadi;                                      // :37 (strict): plain copy
+        base = t ? ((1 << 28) | p_lin) : base;
+        bp = t ? -1 : bp;
+        sadi = t ? sad : sadi;
+    } else {
+        const bool t = sad < sadi;                                      // :46
+        const bool occ = sadi != __int_as_float(0x7f800000);
+        const bool blend = t && occ;                                    // :48-49 blend with what is there
+        if (blend && bp >= 0) base = (int)((3u << 28) | sw_eval(&P, base, bp, bs, bi));   // second stacked blend (rare): evaluate the first now
+        base = (t && !occ) ? ((2 << 28) | p_lin) : base;                // :51-53 empty: copy
+        bp = t ? (occ ? p_lin : -1) : bp;
+        bs = blend ? sad : bs;
+        bi = blend ? sadi : bi;
+        sadi = t ? sad : sadi;
+    }
+}
+
+// Fast path: one list entry against the lane's SW_TH target pixels, everything staged in shared memory
+// (un-wrapped entry, displacement + SAD of the cell staged).  p_r = ty0 + j - eff_r is the same for every
+// lane, so all row arithmetic is warp-uniform; per lane and row it is one shared-memory load and a compare.
+template <int D, bool BIDIR>
+__device__ __forceinline__ void sw_walk_entry(const MciParams &P, const SwShared &sm, float (&sadi)[SW_TH], int (&base)[SW_TH],
+                                              int (&bp)[SW_TH], float (&bs)[SW_TH], float (&bi)[SW_TH], const uint2 ent,
+                                              int eff_r, int eff_c, int ty0, int q_c, bool col_in, int sr0, int sc0, int snc)
+{
+    const int H = P.H, W = P.W;
+    const int p_c = q_c - eff_c;
+    const bool col_ok = col_in && (unsigned)p_c < (unsigned)W;
+    const int lc = (col_ok ? cell_of(p_c, P.cmul[D]) : sc0) - sc0;
+    const int p_r0 = ty0 - eff_r;
+    const unsigned want = col_ok ? ent.y : 0x80008000u;          // (-32768, -32768) is never a displacement: mci_disp_kernel clamps to +-32767
+#pragma unroll
+    for (int j = 0; j < SW_TH; ++j) {
+        const int p_r = p_r0 + j;
+        if ((unsigned)p_r >= (unsigned)H || ty0 + j >= P.y_end) continue;          // warp-uniform
+        const int si = (cell_of(p_r, P.cmul[D]) - sr0) * snc + lc;
+        if (sm.stage[D][si] == want)
+            sw_fire<D, BIDIR>(P, sadi[j], base[j], bp[j], bs[j], bi[j], p_r * W + p_c, sm.stage_sad[D][si], false);
+    }
+}
+
+// Generic path: one list entry against one target pixel, any geometry (wrapped entries, neighbourhoods too
+// large to stage, SAD cells that do not nest, the unidirectional self-write slot).
+template <int D, bool BIDIR>
+__device__ __forceinline__ void sw_test_entry(const MciParams &P, const SwShared &sm, float &sadi, int &base, int &bp, float &bs, float &bi,
+                                              const uint2 ent, int eff_r, int eff_c, int p_r, int p_c, bool use_stage, int sr0, int sc0, int snc)
+{
+    const int cr = cell_of(p_r, P.cmul[D]), cc = cell_of(p_c, P.cmul[D]);
+    const unsigned dp = use_stage ? sm.stage[D][(cr - sr0) * snc + (cc - sc0)]
+                                  : reinterpret_cast<const unsigned *>(P.disp[D])[(size_t)cr * P.cols[D] + cc];
+    if (dp == ent.y) {
+        sw_fire<D, BIDIR>(P, sadi, base, bp, bs, bi, p_r * P.W + p_c, mci_sad_at<D>(P, p_r, p_c), false);
+    } else if (D == 0 && !BIDIR && eff_r == 0 && eff_c == 0) {
+        // unidir: this pixel's own vector leaves the frame -> it writes itself (:56-58)
+        const int u_i = p_r + (short)(dp & 0xffffu), v_i = p_c + (short)(dp >> 16);
+        if (!(u_i < P.H && v_i < P.W)) sw_fire<0, false>(P, sadi, base, bp, bs, bi, p_r * P.W + p_c, mci_sad_at<0>(P, p_r, p_c), true);
+    }
+}
+
+template <bool BIDIR>
+__global__ void __launch_bounds__(SW_WARPS * 32, 5)
+mci_splat_kernel(const __grid_constant__ MciParams P, int tiles_x, int n_tiles)
+{
+    __shared__ SwShared sm_all[SW_WARPS];
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
+    if (tile >= n_tiles) return;
+    SwShared &sm = sm_all[threadIdx.x >> 5];
+    const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
+    const int tx0 = txi * 32, ty0 = P.y_begin + tyi * SW_TH;
+    const int q_c = tx0 + lane;
+    const int H = P.H, W = P.W;
+    const bool col_in = q_c < W;
     const int dmax = P.counters[2];
     const bool keys_fit = (H + dmax <= MCI_KOFF) && (W + dmax <= MCI_KOFF) && dmax <= MCI_KOFF;
+    const unsigned lt_mask = (1u << lane) - 1u;
 
-    for (int i = tid; i < MCI_SLOTS; i += MCI_NT) table[i] = MCI_EMPTY;
-    if (tid == 0) { n_keys = 0; overflow = keys_fit ? 0 : 1; }
-    __syncthreads();
-
-    // un-wrapped neighbourhood of the tile, in cells, per direction (also the staging window)
-    int s_r0[2], s_c0[2], s_nc[2];
-    bool staged[2];
-    for (int dir = 0; dir < 2; ++dir) { s_r0[dir] = s_c0[dir] = 0; s_nc[dir] = 1; staged[dir] = false; }
+    int n = 0;
+    bool overflow = !keys_fit;
+    bool any_far = false;                                      // a wrapped entry made it into the list
+    if (lane < 2) { sm.s_r0[lane] = 0; sm.s_c0[lane] = 0; sm.s_nc[lane] = 1; sm.staged[lane] = 0; }
+    __syncwarp();
 
     if (keys_fit) {
         // ---- 1. distinct (effective displacement, direction) values that can reach this tile ----
-        auto insert = [&](unsigned key, unsigned dpacked) {
-            unsigned h = (key * 2654435761u) >> 22;          // 10 bits
-            for (int probe = 0; probe < MCI_SLOTS; ++probe) {
-                const unsigned prev = atomicCAS(&table[h], MCI_EMPTY, key);
-                if (prev == key) return;
-                if (prev == MCI_EMPTY) {                      // this thread owns the new entry
-                    const int pos = atomicAdd(&n_keys, 1);
-                    if (pos < MCI_MAXKEYS) { list[pos] = key; dlist[pos] = dpacked; } else overflow = 1;
-                    return;
-                }
-                h = (h + 1) & (MCI_SLOTS - 1);
-            }
-            overflow = 1;
-        };
+#pragma unroll 1
         for (int dir = 0; dir < P.ndir; ++dir) {
-            const int g = P.cell[dir], sh = P.cshift[dir];
+            const int g = P.cell[dir];
+            const unsigned gm = P.cmul[dir];
+            const unsigned *gdisp = reinterpret_cast<const unsigned *>(P.disp[dir]);
+#pragma unroll 1
             for (int wr = 0; wr < 2; ++wr) {
-                int lo_r = ty0 - wr * H - dmax, hi_r = ty0 + MCI_TH - 1 - wr * H + dmax;
+                int lo_r = ty0 - wr * H - dmax, hi_r = ty0 + SW_TH - 1 - wr * H + dmax;
                 if (wr) hi_r = min(hi_r, dmax - 1);       // wrapping needs u + dr < 0
                 lo_r = max(lo_r, 0); hi_r = min(hi_r, H - 1);
                 if (lo_r > hi_r) continue;
+#pragma unroll 1
                 for (int wc = 0; wc < 2; ++wc) {
-                    int lo_c = tx0 - wc * W - dmax, hi_c = tx0 + MCI_TW - 1 - wc * W + dmax;
+                    int lo_c = tx0 - wc * W - dmax, hi_c = tx0 + 31 - wc * W + dmax;
                     if (wc) hi_c = min(hi_c, dmax - 1);
                     lo_c = max(lo_c, 0); hi_c = min(hi_c, W - 1);
                     if (lo_c > hi_c) continue;
-                    const int cr_lo = cell_of(lo_r, g, sh), cr_hi = cell_of(hi_r, g, sh);
-                    const int cc_lo = cell_of(lo_c, g, sh), cc_hi = cell_of(hi_c, g, sh);
+                    const int cr_lo = cell_of(lo_r, gm), cr_hi = cell_of(hi_r, gm);
+                    const int cc_lo = cell_of(lo_c, gm), cc_hi = cell_of(hi_c, gm);
                     const int ncc = cc_hi - cc_lo + 1, ncell = (cr_hi - cr_lo + 1) * ncc;
-                    const bool do_stage = !wr && !wc && ncell <= MCI_STAGE_MAX;
-                    if (do_stage) { s_r0[dir] = cr_lo; s_c0[dir] = cc_lo; s_nc[dir] = ncc; staged[dir] = true; }
-                    for (int i = tid; i < ncell; i += MCI_NT) {
-                        const int cr = cr_lo + i / ncc, cc = cc_lo + i % ncc;
-                        const unsigned dp = reinterpret_cast<const unsigned *>(P.disp[dir])[(size_t)cr * P.cols[dir] + cc];
-                        if (do_stage) stage[dir][i] = dp;
-                        const int dx_ = (short)(dp & 0xffffu), dy_ = (short)(dp >> 16);   // short2: .x low half, .y high half
-                        const int eff_r = dx_ + wr * H, eff_c = dy_ + wc * W;
-                        const int pr0 = cr * g, pr1 = min(H, pr0 + g) - 1;
-                        const int pc0 = cc * g, pc1 = min(W, pc0 + g) - 1;
-                        // conservative footprint test (the per-pixel test below is exact)
-                        if (pr1 + eff_r < ty0 || pr0 + eff_r > ty0 + MCI_TH - 1) continue;
-                        if (pc1 + eff_c < tx0 || pc0 + eff_c > tx0 + MCI_TW - 1) continue;
-                        if (wr ? (pr0 + dx_ >= 0) : (pr1 + dx_ < 0)) continue;
-                        if (wc ? (pc0 + dy_ >= 0) : (pc1 + dy_ < 0)) continue;
-                        insert(mci_key(eff_r, eff_c, dir), dp);
+                    const bool do_stage = !wr && !wc && ncell <= SW_STAGE;
+                    if (do_stage && lane == 0) { sm.s_r0[dir] = cr_lo; sm.s_c0[dir] = cc_lo; sm.s_nc[dir] = ncc; sm.staged[dir] = 1; }
+                    for (int base = 0; base < ncell; base += 32) {
+                        const int i = base + lane;
+                        bool want = false;
+                        unsigned key = MCI_EMPTY, dp = 0u;
+                        if (i < ncell) {
+                            const int ro = (int)__fdividef((float)i + 0.5f, (float)ncc);    // exact for these small integers
+                            const int cr = cr_lo + ro, cc = cc_lo + (i - ro * ncc);
+                            dp = gdisp[(size_t)cr * P.cols[dir] + cc];
+                            if (do_stage) {
+                                sm.stage[dir][i] = dp;
+                                if (P.sad_nested[dir])
+                                    sm.stage_sad[dir][i] = P.sad[dir][cell_of(cr * g, P.smul[dir]) * P.scols[dir] + cell_of(cc * g, P.smul[dir])];
+                            }
+                            const int dx_ = (short)(dp & 0xffffu), dy_ = (short)(dp >> 16);   // short2: .x low half, .y high half
+                            const int eff_r = dx_ + wr * H, eff_c = dy_ + wc * W;
+                            const int pr0 = cr * g, pr1 = min(H, pr0 + g) - 1;
+                            const int pc0 = cc * g, pc1 = min(W, pc0 + g) - 1;
+                            // conservative footprint test (the per-pixel test in the walk is exact)
+                            want = !(pr1 + eff_r < ty0 || pr0 + eff_r > ty0 + SW_TH - 1) &&
+                                   !(pc1 + eff_c < tx0 || pc0 + eff_c > tx0 + 31) &&
+                                   !(wr ? (pr0 + dx_ >= 0) : (pr1 + dx_ < 0)) &&
+                                   !(wc ? (pc0 + dy_ >= 0) : (pc1 + dy_ < 0));
+                            if (want) key = mci_key(eff_r, eff_c, dir);
+                        }
+                        if (!__any_sync(0xffffffffu, want)) continue;
+                        const unsigned peers = __match_any_sync(0xffffffffu, key);
+                        bool isnew = want && (__ffs(peers) - 1 == lane);
+                        const int n_scan = min(n, SW_MAXK);
+                        for (int j = 0; j < n_scan; ++j) isnew = isnew && (sm.keys[j] != key);     // broadcast reads
+                        const unsigned nb = __ballot_sync(0xffffffffu, isnew);
+                        if (isnew) {
+                            const int pos = n + __popc(nb & lt_mask);
+                            if (pos < SW_MAXK) { sm.keys[pos] = key; sm.dps[pos] = dp; }
+                        }
+                        n += __popc(nb);
+                        if (nb && (wr || wc)) any_far = true;
+                        __syncwarp();
                     }
                 }
             }
         }
         // the unidirectional self-write lives at e = (0,0) and has no footprint of its own
-        if (!P.bidir && tid == 0) insert(mci_key(0, 0, 0), 0u);
-        __syncthreads();
+        if (!BIDIR) {
+            const unsigned key = mci_key(0, 0, 0);
+            bool have = false;
+            const int n_scan = min(n, SW_MAXK);
+            for (int j = 0; j < n_scan; ++j) have = have || (sm.keys[j] == key);
+            if (!have) {
+                if (lane == 0 && n < SW_MAXK) { sm.keys[n] = key; sm.dps[n] = 0u; }
+                ++n;
+            }
+            __syncwarp();
+        }
+        if (n > SW_MAXK) overflow = true;
         // ---- 2. rank-sort (ascending key = raster order of the source pixel) ----
         if (!overflow) {
-            const int n = n_keys;
-            for (int i = tid; i < n; i += MCI_NT) {
-                const unsigned k = list[i];
+            for (int i = lane; i < n; i += 32) {
+                const unsigned k = sm.keys[i];
                 int rank = 0;
-                for (int j = 0; j < n; ++j) rank += list[j] < k;
-                MciEntry e;
-                e.eff_r = MCI_KOFF - (int)(k >> 15);
-                e.eff_c = MCI_KOFF - (int)((k >> 1) & 16383u);
-                e.dpacked = dlist[i];
-                e.dir_kind = (int)(k & 1u);
-                sorted[rank] = e;
+                for (int j = 0; j < n; ++j) rank += sm.keys[j] < k;
+                sm.sorted[rank] = make_uint2(k, sm.dps[i]);
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 
-    // ---- 3. replay the splat for this target pixel ----
-    const bool inside = q_r < P.y_end && q_c < W;
-    PixState st;
-    st.v0 = st.v1 = st.v2 = -1;
-    st.sadi = __int_as_float(0x7f800000);
-    st.written = false;
-    if (inside) {
-        if (!overflow) {
-            const int n = n_keys;
-            // An entry stands for "displacement d, wrapped or not": e = d (+H / +W).  If the pixel at
-            // p = q - e carries exactly d, its target is q by construction (the reference's bounds test
-            // and negative-index wrap are already folded into e), so the test is one compare.
-            auto test = [&](auto dir_tag, const MciEntry &e, int p_r, int p_c, int sr0, int sc0, int snc, bool stg) {
-                constexpr int D = decltype(dir_tag)::value;
-                const int cr = cell_of(p_r, P.cell[D], P.cshift[D]), cc = cell_of(p_c, P.cell[D], P.cshift[D]);
-                const int lr = cr - sr0, lc = cc - sc0;
-                unsigned dp;
-                if (stg && lr >= 0 && lc >= 0 && lc < snc && lr * snc + lc < MCI_STAGE_MAX && e.eff_r <= dmax && e.eff_c <= dmax)
-                    dp = stage[D][lr * snc + lc];
-                else
-                    dp = reinterpret_cast<const unsigned *>(P.disp[D])[(size_t)cr * P.cols[D] + cc];
-                if (dp == e.dpacked) {
-                    mci_apply_t<D>(P, st, p_r, p_c, false);
-                } else if (D == 0 && !P.bidir && e.eff_r == 0 && e.eff_c == 0) {
-                    // unidir: this pixel's own vector leaves the frame -> it writes itself (:56-58)
-                    const int u_i = p_r + (short)(dp & 0xffffu), v_i = p_c + (short)(dp >> 16);
-                    if (!(u_i < H && v_i < W)) mci_apply_t<0>(P, st, p_r, p_c, true);
-                }
-            };
-            for (int i = 0; i < n; ++i) {
-                const MciEntry e = sorted[i];                     // one broadcast LDS.128
-                const int p_r = q_r - e.eff_r, p_c = q_c - e.eff_c;
-                if ((unsigned)p_r >= (unsigned)H || (unsigned)p_c >= (unsigned)W) continue;
-                if (e.dir_kind == 0) test(std::integral_constant<int, 0>{}, e, p_r, p_c, s_r0[0], s_c0[0], s_nc[0], staged[0]);
-                else test(std::integral_constant<int, 1>{}, e, p_r, p_c, s_r0[1], s_c0[1], s_nc[1], staged[1]);
+    // ---- 3. phase A: which events fire for the lane's SW_TH pixels (no frame access) ----
+    unsigned val[SW_TH];                                       // packed result, bit 24 = hole
+    const int sr0_0 = sm.s_r0[0], sc0_0 = sm.s_c0[0], snc_0 = sm.s_nc[0], sr0_1 = sm.s_r0[1], sc0_1 = sm.s_c0[1], snc_1 = sm.s_nc[1];
+    const bool st0 = sm.staged[0] != 0, st1 = sm.staged[1] != 0;
+    // fast path: every entry un-wrapped and its cells (displacement + SAD) staged; unidirectional tiles must
+    // also be out of reach of the self-write rule (a vector leaving the frame at the bottom / right, :56-58)
+    const bool fast = !overflow && !any_far && st0 && P.sad_nested[0] &&
+                      (BIDIR ? (st1 && P.sad_nested[1]) : (ty0 + SW_TH - 1 + dmax < H && tx0 + 31 + dmax < W));
+    if (fast) {
+        float sadi[SW_TH], bs[SW_TH], bi[SW_TH];
+        int base[SW_TH], bp[SW_TH];
+#pragma unroll
+        for (int j = 0; j < SW_TH; ++j) { sadi[j] = __int_as_float(0x7f800000); base[j] = 0; bp[j] = -1; bs[j] = 0.f; bi[j] = 0.f; }
+#pragma unroll 1
+        for (int i = 0; i < n; ++i) {
+            const uint2 ent = sm.sorted[i];                    // one broadcast LDS.64
+            const int eff_r = MCI_KOFF - (int)(ent.x >> 15);
+            const int eff_c = MCI_KOFF - (int)((ent.x >> 1) & 16383u);
+            if (!BIDIR || (ent.x & 1u) == 0u) sw_walk_entry<0, BIDIR>(P, sm, sadi, base, bp, bs, bi, ent, eff_r, eff_c, ty0, q_c, col_in, sr0_0, sc0_0, snc_0);
+            else sw_walk_entry<1, BIDIR>(P, sm, sadi, base, bp, bs, bi, ent, eff_r, eff_c, ty0, q_c, col_in, sr0_1, sc0_1, snc_1);
+        }
+        // ---- phase B: the pixel loads of four rows in flight together, then the pending blends ----
+#pragma unroll
+        for (int h = 0; h < SW_TH; h += 4) {
+            unsigned alo[4], ahi[4], ash[4], blo[4], bhi[4], bsh[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = h + k;
+                alo[k] = ahi[k] = ash[k] = blo[k] = bhi[k] = bsh[k] = 0u;
+                const unsigned kind = SW_KIND(base[j]);
+                if (kind == 1u || kind == 2u) sw_px_issue(kind == 1u ? P.src : P.tgt, SW_PAYLOAD(base[j]), alo[k], ahi[k], ash[k]);
+                if (BIDIR && bp[j] >= 0) sw_px_issue(P.tgt, bp[j], blo[k], bhi[k], bsh[k]);
             }
-        } else {
-            // dense fallback: enumerate every possible displacement in source-raster order
-            // e in [H-dmax, H-1] (wrapped) then [dmax, -dmax] (direct), each value visited once
-            for (int eff_r = q_r; eff_r >= -dmax; --eff_r) {
-                if (eff_r > dmax && eff_r < H - dmax) { eff_r = dmax + 1; continue; }
-                if (q_r - eff_r >= H) break;
-                for (int eff_c = q_c; eff_c >= -dmax; --eff_c) {
-                    if (eff_c > dmax && eff_c < W - dmax) { eff_c = dmax + 1; continue; }
-                    if (q_c - eff_c >= W) break;
-                    for (int dir = 0; dir < P.ndir; ++dir) mci_try_event(P, st, q_r, q_c, eff_r, eff_c, dir);
-                }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int j = h + k;
+                const unsigned kind = SW_KIND(base[j]);
+                unsigned v = kind == 3u ? ((unsigned)SW_PAYLOAD(base[j]) & 0xffffffu) : sw_px_finish(alo[k], ahi[k], ash[k]);
+                if (BIDIR && bp[j] >= 0) v = sw_blend_packed(v, sw_px_finish(blo[k], bhi[k], bsh[k]), bs[j], bi[j]);
+                val[j] = kind == 0u ? 0x1ffffffu : v;         // hole: uint8(-1) per channel until the fill kernel runs
             }
         }
-        const size_t q = (size_t)q_r * W + q_c;
-        uint8_t *o = P.out + q * 3;
-        o[0] = (uint8_t)st.v0; o[1] = (uint8_t)st.v1; o[2] = (uint8_t)st.v2;     // New_IF = uint8(IF)  (:65 / :57)
-        P.mask[q] = st.written ? 0 : 1;
+    } else {
+        // generic path, one tile row at a time (rolled loops)
+#pragma unroll 1
+        for (int j = 0; j < SW_TH; ++j) {
+            const int q_r = ty0 + j;
+            unsigned v = 0x1ffffffu;
+            if (q_r < P.y_end && col_in) {
+                if (!overflow) {
+                    float sadi = __int_as_float(0x7f800000), bs = 0.f, bi = 0.f;
+                    int base = 0, bp = -1;
+#pragma unroll 1
+                    for (int i = 0; i < n; ++i) {
+                        const uint2 ent = sm.sorted[i];
+                        const int eff_r = MCI_KOFF - (int)(ent.x >> 15);
+                        const int eff_c = MCI_KOFF - (int)((ent.x >> 1) & 16383u);
+                        const int p_r = q_r - eff_r, p_c = q_c - eff_c;
+                        if ((unsigned)p_r >= (unsigned)H || (unsigned)p_c >= (unsigned)W) continue;
+                        // un-wrapped entries (|e| <= dmax) only ever look at cells of the staged neighbourhood
+                        const bool near = eff_r <= dmax && eff_c <= dmax;
+                        if (!BIDIR || (ent.x & 1u) == 0u) sw_test_entry<0, BIDIR>(P, sm, sadi, base, bp, bs, bi, ent, eff_r, eff_c, p_r, p_c, st0 && near, sr0_0, sc0_0, snc_0);
+                        else sw_test_entry<1, BIDIR>(P, sm, sadi, base, bp, bs, bi, ent, eff_r, eff_c, p_r, p_c, st1 && near, sr0_1, sc0_1, snc_1);
+                    }
+                    if (SW_KIND(base) != 0u) v = sw_eval(&P, base, bp, bs, bi);
+                } else {
+                    PixState st;
+                    st.v0 = st.v1 = st.v2 = -1;
+                    st.sadi = __int_as_float(0x7f800000);
+                    st.written = false;
+                    sw_dense_pixel(P, st, q_r, q_c, dmax);
+                    if (st.written) v = (unsigned)(st.v0 & 255) | ((unsigned)(st.v1 & 255) << 8) | ((unsigned)(st.v2 & 255) << 16);
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < SW_TH; ++jj) if (jj == j) val[jj] = v;
+        }
     }
-    // hole list, one atomic per warp
-    const bool hole = inside && !st.written && q_r >= P.fill_begin && q_r < P.fill_end;
-    const unsigned bal = __ballot_sync(0xffffffffu, hole);
-    if (bal) {
-        const int lane = tid & 31;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&P.counters[1], __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (hole) P.hole_list[base + __popc(bal & ((1u << lane) - 1u))] = q_r * W + q_c;
+
+    // ---- 4. outputs: uint8 frame, packed hole-fill image, hole runs (one atomic pair per tile) ----
+    // The per-row values go through shared memory (keys[] is dead after the sort) so that this loop can
+    // stay rolled: the unrolled form was a quarter of the kernel's code.
+    static_assert(SW_MAXK >= SW_TH * 32, "value buffer aliases keys[]");
+    unsigned *vbuf = sm.keys;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < SW_TH; ++j) vbuf[j * 32 + lane] = val[j];
+    __syncwarp();
+    const bool words_ok = (W & 3) == 0;                       // row starts 4-byte aligned: coalesced word stores
+    int n_holes = 0, n_starts = 0;
+    // pass 1: stores + per-row hole / run-start ballots (kept in shared memory: dps[] is dead too)
+    unsigned *balbuf = sm.dps;                                 // [0..7] hole ballots, [8..15] run-start ballots
+#pragma unroll 1
+    for (int j = 0; j < SW_TH; ++j) {
+        const int q_r = ty0 + j;
+        if (q_r >= P.y_end) { if (lane == 0) { balbuf[j] = 0u; balbuf[8 + j] = 0u; } continue; }     // warp-uniform
+        const size_t q = (size_t)q_r * W + q_c;
+        const unsigned vj = vbuf[j * 32 + lane];
+        const unsigned rgb = vj & 0xffffffu;
+        const bool is_hole = (vj >> 24) != 0u;
+        if (words_ok) {
+            unsigned char *rb = reinterpret_cast<unsigned char *>(sm.rowbuf);
+            rb[lane * 3] = (unsigned char)rgb; rb[lane * 3 + 1] = (unsigned char)(rgb >> 8); rb[lane * 3 + 2] = (unsigned char)(rgb >> 16);
+            __syncwarp();
+            const int n_words = (min(32, W - tx0) * 3) >> 2;   // W % 4 == 0 and tx0 % 32 == 0: whole words
+            if (lane < n_words) reinterpret_cast<unsigned *>(P.out + ((size_t)q_r * W + tx0) * 3)[lane] = sm.rowbuf[lane];
+            __syncwarp();
+        } else if (col_in) {
+            uint8_t *o = P.out + q * 3;
+            o[0] = (uint8_t)rgb; o[1] = (uint8_t)(rgb >> 8); o[2] = (uint8_t)(rgb >> 16);     // New_IF = uint8(IF)  (:65 / :57)
+        }
+        if (col_in) {
+            unsigned word = rgb;
+            if (is_hole) {                                     // :70 / :63: a hole is first replaced by the target pixel
+                const uint8_t *t = P.tgt + q * 3;
+                word = (unsigned)t[0] | ((unsigned)t[1] << 8) | ((unsigned)t[2] << 16) | (1u << 24);
+            }
+            P.fill[q] = word;
+        }
+        // hole runs: consecutive hole lanes become one (first pixel, length) entry, capped at HF_MAXRUN
+        const bool hole = col_in && is_hole && q_r >= P.fill_begin && q_r < P.fill_end;
+        const unsigned bal = __ballot_sync(0xffffffffu, hole);
+        const bool start = hole && ((lane & (HF_MAXRUN - 1)) == 0 || !((bal >> (lane - 1)) & 1u));
+        const unsigned sb = __ballot_sync(0xffffffffu, start);
+        if (lane == 0) { balbuf[j] = bal; balbuf[8 + j] = sb; }
+        n_holes += __popc(bal); n_starts += __popc(sb);
+    }
+    if (n_starts) {                                            // warp-uniform
+        __syncwarp();
+        int pos0 = 0;
+        if (lane == 0) {
+            pos0 = atomicAdd(&P.counters[4], n_starts);
+            atomicAdd(&P.counters[1], n_holes);
+        }
+        pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+#pragma unroll 1
+        for (int j = 0; j < SW_TH; ++j) {
+            const unsigned bal = balbuf[j], sb = balbuf[8 + j];
+            if ((sb >> lane) & 1u) {
+                const unsigned inv = ~(bal >> lane);
+                const int len = min(inv ? __ffs(inv) - 1 : 32, HF_MAXRUN - (lane & (HF_MAXRUN - 1)));
+                const int pos = pos0 + __popc(sb & lt_mask);
+                P.hole_list[2 * pos] = (ty0 + j) * W + q_c;
+                P.hole_list[2 * pos + 1] = len;
+            }
+            pos0 += __popc(sb);
+        }
     }
 }
 
@@ -338,20 +609,22 @@ mci_splat_kernel(const MciParams P)
 // window.  Equivalent rule for hole h (W6): a window pixel contributes its splat value if it is
 // not a hole, the TARGET-frame pixel if it is a hole at raster <= h, nothing otherwise.
 // np.median: middle element, or the f64 mean of the two middles truncated on the uint8 store.
-// One warp per hole; the k-th smallest byte is found by bisection on the value.
-// One warp per hole.  The warp histograms the contributing window pixels per channel in shared
-// memory (3 x 256 counters), then each lane owns 8 bins: a warp prefix scan locates the lane and
-// bin holding rank (n-1)/2 and rank n/2.
-#define HF_WARPS 4
-
-__device__ __forceinline__ int hist_select(const unsigned *__restrict__ hist, int lane, int k_lo, int k_hi, int &v_hi)
+//
+// One warp per run of <= HF_MAXRUN horizontally adjacent holes.  The union of the run's windows
+// (<= 21 x 28 packed words of P.fill) is staged in shared memory with independent coalesced loads;
+// the first hole histograms its whole window, every next hole (one pixel to the right, same rows)
+// slides it: the column entering on the right is added, the column leaving on the left is removed,
+// and the hole itself switches from "later hole, excluded" to "replaced by the target pixel" --
+// ~43 shared-memory updates instead of 441 global reads.  The three channel histograms share one
+// word per bin (10 bits each, counts <= 441), so one warp prefix scan ranks all three channels.
+__device__ __forceinline__ void hist_select3(const unsigned *__restrict__ hist, int lane, int k_lo, int k_hi, unsigned (&res)[3])
 {
     const uint4 a = *reinterpret_cast<const uint4 *>(hist + lane * 8);
     const uint4 c = *reinterpret_cast<const uint4 *>(hist + lane * 8 + 4);
     const unsigned cnt[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
     unsigned local = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) local += cnt[i];
+    for (int i = 0; i < 8; ++i) local += cnt[i];          // packed add: no field exceeds 441
     unsigned incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -359,69 +632,108 @@ __device__ __forceinline__ int hist_select(const unsigned *__restrict__ hist, in
         if (lane >= o) incl += t;
     }
     const unsigned excl = incl - local;
-    int found_lo = -1, found_hi = -1;
-    if ((unsigned)k_lo >= excl && (unsigned)k_lo < incl) {
-        unsigned run = excl;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { run += cnt[i]; if (found_lo < 0 && (unsigned)k_lo < run) found_lo = lane * 8 + i; }
-    }
-    if ((unsigned)k_hi >= excl && (unsigned)k_hi < incl) {
-        unsigned run = excl;
+    for (int ch = 0; ch < 3; ++ch) {
+        const int sh = 10 * ch;
+        const unsigned ex = (excl >> sh) & 1023u, in = (incl >> sh) & 1023u;
+        int found_lo = -1, found_hi = -1;
+        if (((unsigned)k_lo >= ex && (unsigned)k_lo < in) || ((unsigned)k_hi >= ex && (unsigned)k_hi < in)) {
+            unsigned run = ex;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { run += cnt[i]; if (found_hi < 0 && (unsigned)k_hi < run) found_hi = lane * 8 + i; }
+            for (int i = 0; i < 8; ++i) {
+                const unsigned prev = run;
+                run += (cnt[i] >> sh) & 1023u;
+                if ((unsigned)k_lo >= prev && (unsigned)k_lo < run) found_lo = lane * 8 + i;
+                if ((unsigned)k_hi >= prev && (unsigned)k_hi < run) found_hi = lane * 8 + i;
+            }
+        }
+        const int v_lo = __reduce_max_sync(0xffffffffu, found_lo);
+        const int v_hi = __reduce_max_sync(0xffffffffu, found_hi);
+        res[ch] = (unsigned)((v_lo + v_hi) >> 1);         // np.median: (a+b)/2.0, truncated on the uint8 store
     }
-    v_hi = __reduce_max_sync(0xffffffffu, found_hi);
-    return __reduce_max_sync(0xffffffffu, found_lo);
+}
+
+__device__ __forceinline__ void hist_add(unsigned *hist, unsigned word)
+{
+    atomicAdd(&hist[word & 255u], 1u);
+    atomicAdd(&hist[(word >> 8) & 255u], 1u << 10);
+    atomicAdd(&hist[(word >> 16) & 255u], 1u << 20);
+}
+__device__ __forceinline__ void hist_sub(unsigned *hist, unsigned word)
+{
+    atomicSub(&hist[word & 255u], 1u);
+    atomicSub(&hist[(word >> 8) & 255u], 1u << 10);
+    atomicSub(&hist[(word >> 16) & 255u], 1u << 20);
 }
 
 __global__ void __launch_bounds__(HF_WARPS * 32)
-mci_holefill_kernel(const uint8_t *__restrict__ tgt, uint8_t *out, const uint8_t *__restrict__ mask,
+mci_holefill_kernel(const uint32_t *__restrict__ fill, uint8_t *__restrict__ out,
                     const int *__restrict__ hole_list, const int *__restrict__ counters, int H, int W)
 {
-    __shared__ __align__(16) unsigned hist_all[HF_WARPS][3][256];
+    __shared__ __align__(16) unsigned hist_all[HF_WARPS][256];
+    __shared__ unsigned win_all[HF_WARPS][21 * HF_TWP];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    unsigned (*hist)[256] = hist_all[wib];
-    const int n_holes = counters[1];
-    for (int hi = warp; hi < n_holes; hi += nwarps) {
-        const int h = hole_list[hi];
-        const int u = h / W, v = h - u * W;
-        const int u0 = max(0, u - 10), u1 = min(H, u + 11), v0 = max(0, v - 10), v1 = min(W, v + 11);
-        const int ww = v1 - v0, total = (u1 - u0) * ww;
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-            *reinterpret_cast<uint4 *>(&hist[0][0] + (i * 32 + lane) * 4) = make_uint4(0u, 0u, 0u, 0u);
-        __syncwarp();
-        int cnt = 0;
-        for (int e = lane; e < total; e += 32) {
-            const int a = u0 + e / ww, b = v0 + e % ww;
-            const int idx = a * W + b;
-            const uint8_t *p = nullptr;
-            if (!mask[idx]) p = out + (size_t)idx * 3;            // splat value
-            else if (idx <= h) p = tgt + (size_t)idx * 3;         // earlier hole: already replaced by the target pixel
-            if (p) {
-                atomicAdd(&hist[0][p[0]], 1u);
-                atomicAdd(&hist[1][p[1]], 1u);
-                atomicAdd(&hist[2][p[2]], 1u);
-                ++cnt;
+    unsigned *hist = hist_all[wib], *win = win_all[wib];
+    const int n_runs = counters[4];
+    for (int ri = warp; ri < n_runs; ri += nwarps) {
+        const int h0 = hole_list[2 * ri], len = hole_list[2 * ri + 1];
+        const int u = h0 / W, vs = h0 - u * W;
+        const int u0 = max(0, u - 10), u1 = min(H, u + 11), nrows = u1 - u0;
+        const int c0 = max(0, vs - 10), c1 = min(W, vs + len + 10), tw = c1 - c0;       // union of the run's windows
+        *reinterpret_cast<uint4 *>(hist + lane * 8) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(hist + lane * 8 + 4) = make_uint4(0u, 0u, 0u, 0u);
+        {
+            const int total = nrows * tw;                                          // <= 588
+            const unsigned rcp = (65536u + (unsigned)tw - 1u) / (unsigned)tw;         // e / tw as a multiply (exact for e < 588, tw <= 28)
+            for (int e = lane; e < total; e += 32) {
+                const int ra = (int)(((unsigned)e * rcp) >> 16), cb = e - ra * tw;
+                win[ra * HF_TWP + cb] = fill[(size_t)(u0 + ra) * W + c0 + cb];
             }
         }
         __syncwarp();
-        const int n = __reduce_add_sync(0xffffffffu, cnt);        // >= 1: the hole itself contributes
-        const int k_lo = (n - 1) >> 1, k_hi = n >> 1;
-        unsigned res[3];
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            int v_hi;
-            const int v_lo = hist_select(hist[ch], lane, k_lo, k_hi, v_hi);
-            res[ch] = (unsigned)((v_lo + v_hi) >> 1);             // np.median: (a+b)/2.0, truncated on the uint8 store
+        // ---- full window of the first hole ----
+        int cnt = 0;
+        {
+            const int ww = min(W, vs + 11) - c0, total = nrows * ww;
+            const unsigned rcp = (65536u + (unsigned)ww - 1u) / (unsigned)ww;
+            for (int e = lane; e < total; e += 32) {
+                const int ra = (int)(((unsigned)e * rcp) >> 16), cb = e - ra * ww;
+                const unsigned word = win[ra * HF_TWP + cb];
+                if (!(word >> 24) || (u0 + ra) * W + c0 + cb <= h0) { hist_add(hist, word); ++cnt; }
+            }
+        }
+        int n = __reduce_add_sync(0xffffffffu, cnt);              // >= 1: the hole itself contributes
+        for (int s = 0; s < len; ++s) {
+            const int v = vs + s, h = h0 + s;
+            __syncwarp();
+            unsigned res[3];
+            hist_select3(hist, lane, (n - 1) >> 1, n >> 1, res);
+            if (lane == 0) {
+                uint8_t *o = out + (size_t)h * 3;
+                o[0] = (uint8_t)res[0]; o[1] = (uint8_t)res[1]; o[2] = (uint8_t)res[2];
+            }
+            if (s + 1 == len) break;
+            __syncwarp();
+            int delta = 0;
+            if (lane < nrows) {
+                const int a = u0 + lane;
+                if (v + 11 < W) {                                  // column entering on the right
+                    const unsigned word = win[lane * HF_TWP + (v + 11 - c0)];
+                    if (!(word >> 24) || a < u) { hist_add(hist, word); ++delta; }
+                }
+                if (v - 10 >= 0) {                                 // column leaving on the left
+                    const unsigned word = win[lane * HF_TWP + (v - 10 - c0)];
+                    if (!(word >> 24) || a <= u) { hist_sub(hist, word); --delta; }
+                }
+            } else if (lane == 31) {                               // the next hole itself: now a target pixel
+                hist_add(hist, win[(u - u0) * HF_TWP + (v + 1 - c0)]);
+                ++delta;
+            }
+            n += __reduce_add_sync(0xffffffffu, delta);
         }
         __syncwarp();
-        if (lane == 0) {
-            uint8_t *o = out + (size_t)h * 3;
-            o[0] = (uint8_t)res[0]; o[1] = (uint8_t)res[1]; o[2] = (uint8_t)res[2];
-        }
     }
 }
 
@@ -432,7 +744,7 @@ int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd
     const MVField *fl[2] = {fwd, bwd};
     const int ndir = bidir ? 2 : 1;
     int rc;
-    CK(ctx, cudaMemsetAsync(ctx->d_counters + 1, 0, 2 * sizeof(int), ctx->stream));
+    CK(ctx, cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(int), ctx->stream));   // [1] holes [2] dmax [4] hole runs
     MciParams P;
     memset(&P, 0, sizeof(P));
     for (int d = 0; d < ndir; ++d) {
@@ -444,15 +756,16 @@ int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd
         CKL(ctx);
         P.disp[d] = ctx->d_disp[d]; P.cell[d] = f->mv_cell; P.cols[d] = f->mv_cols;
         P.sad[d] = f->sad; P.scell[d] = f->sad_cell; P.scols[d] = f->sad_cols;
-        P.cshift[d] = (f->mv_cell & (f->mv_cell - 1)) == 0 ? __builtin_ctz(f->mv_cell) : -1;
-        P.sshift[d] = (f->sad_cell & (f->sad_cell - 1)) == 0 ? __builtin_ctz(f->sad_cell) : -1;
+        P.sad_nested[d] = (f->sad_cell % f->mv_cell) == 0;
+        P.cmul[d] = f->mv_cell > 1 ? (unsigned)((0x100000000ull + (unsigned)f->mv_cell - 1) / (unsigned)f->mv_cell) : 0u;
+        P.smul[d] = f->sad_cell > 1 ? (unsigned)((0x100000000ull + (unsigned)f->sad_cell - 1) / (unsigned)f->sad_cell) : 0u;
     }
     size_t npx = (size_t)H * W;
     if (ctx->hole_cap < npx) {
-        if (ctx->d_hole_mask) cudaFree(ctx->d_hole_mask);
+        if (ctx->d_fill) cudaFree(ctx->d_fill);
         if (ctx->d_hole_list) cudaFree(ctx->d_hole_list);
-        ctx->d_hole_mask = nullptr; ctx->d_hole_list = nullptr; ctx->hole_cap = 0;
-        CK(ctx, cudaMalloc(&ctx->d_hole_mask, npx));
+        ctx->d_fill = nullptr; ctx->d_hole_list = nullptr; ctx->hole_cap = 0;
+        CK(ctx, cudaMalloc(&ctx->d_fill, npx * sizeof(uint32_t)));
         CK(ctx, cudaMalloc(&ctx->d_hole_list, npx * sizeof(int)));
         ctx->hole_cap = npx;
     }
@@ -463,17 +776,18 @@ int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd
     P.y_begin = row0 - 10 > 0 ? row0 - 10 : 0;           // the 21x21 hole-fill window reads 10 rows of splat either side
     P.y_end = row1 + 10 < H ? row1 + 10 : H;
     P.src = ctx->frames[slot_src].rgb; P.tgt = ctx->frames[slot_tgt].rgb;
-    P.out = ctx->frames[out_slot].rgb; P.mask = ctx->d_hole_mask;
+    P.out = ctx->frames[out_slot].rgb; P.fill = ctx->d_fill;
     P.hole_list = ctx->d_hole_list; P.counters = ctx->d_counters;
-    dim3 grid(ceil_div_i(W, MCI_TW), ceil_div_i(P.y_end - P.y_begin, MCI_TH));
+    const int tiles_x = ceil_div_i(W, 32), n_tiles = tiles_x * ceil_div_i(P.y_end - P.y_begin, SW_TH);
     ctx->mci_timed = 0;
     if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     const int prof = memci_prof_begin(ctx, 1);
-    mci_splat_kernel<<<grid, MCI_NT, 0, ctx->stream>>>(P);
+    if (bidir) mci_splat_kernel<true><<<ceil_div_i(n_tiles, SW_WARPS), SW_WARPS * 32, 0, ctx->stream>>>(P, tiles_x, n_tiles);
+    else mci_splat_kernel<false><<<ceil_div_i(n_tiles, SW_WARPS), SW_WARPS * 32, 0, ctx->stream>>>(P, tiles_x, n_tiles);
     memci_prof_end(ctx, prof);
     CKL(ctx);
     if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->mci_timed = 1; }
-    mci_holefill_kernel<<<ctx->num_sms * 8, HF_WARPS * 32, 0, ctx->stream>>>(P.tgt, P.out, P.mask, P.hole_list, P.counters, H, W);
+    mci_holefill_kernel<<<ctx->num_sms * 6, HF_WARPS * 32, 0, ctx->stream>>>(P.fill, P.out, P.hole_list, P.counters, H, W);
     CKL(ctx);
     FrameSlot &o = ctx->frames[out_slot];
     o.valid = 1; o.luma_ok = 0; o.pyr_levels = 0;

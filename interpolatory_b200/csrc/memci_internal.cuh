@@ -56,7 +56,7 @@ struct memci_ctx {
     long long fs_last_cand, fs_last_ops;
     // MCI scratch
     short2 *d_disp[2]; size_t disp_cap[2];
-    uint8_t *d_hole_mask; int *d_hole_list; size_t hole_cap;
+    uint32_t *d_fill; int *d_hole_list; size_t hole_cap;
     float *d_dense; size_t dense_cap;  // dense MV staging for download/upload
     // timing
     int timing; cudaEvent_t ev[4]; int fs_timed, mci_timed;
@@ -88,7 +88,8 @@ int memci_mv_reserve(memci_ctx *ctx, MVField *f, int mv_cell, int mv_rows, int m
 int memci_luma_plane(memci_ctx *ctx, const uint8_t *rgb, int H, int W, int Wp, int32_t *luma);
 int memci_ensure_luma(memci_ctx *ctx, int slot);
 int memci_ensure_pyramid(memci_ctx *ctx, int slot, int levels);
-int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out, int br0, int br1);   // block rows [br0, br1); br1 < 0 = all
+int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out, int br0, int br1,
+                 MVField *out2 = nullptr);   // block rows [br0, br1); br1 < 0 = all; out2: reverse direction in the same launch
 int memci_tss_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int steps, MVField *out);
 int memci_hbma_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int win, int sub, int steps,
                    int min_bs, int cost_key, MVField *out);

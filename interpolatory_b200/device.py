@@ -104,6 +104,10 @@ class DeviceContext:
     def me_fs(self, src, tgt, block_size, target_region, mv_slot):
         self._ck(self.L.memci_me_fs(self._ctx, src, tgt, int(block_size), int(target_region), mv_slot))
 
+    def me_fs_pair(self, a, b, block_size, target_region, mv_fwd, mv_bwd):
+        """fwd = fs(a -> b) and bwd = fs(b -> a) in one launch (same results as two me_fs calls)."""
+        self._ck(self.L.memci_me_fs_pair(self._ctx, a, b, int(block_size), int(target_region), mv_fwd, mv_bwd))
+
     def me_tss(self, src, tgt, block_size, steps, mv_slot):
         self._ck(self.L.memci_me_tss(self._ctx, src, tgt, int(block_size), int(steps), mv_slot))
 
