@@ -95,11 +95,13 @@ __global__ void fs_generic_kernel(const int32_t *__restrict__ L0, const int32_t 
 }
 
 // =========================================================================================
-// Redo pass: one CTA per listed block (same exact arithmetic as fs_generic_kernel, 8 warps wide).
+// Redo pass: one CTA per listed block (same exact arithmetic as fs_generic_kernel, 32 warps wide:
+// about one candidate per thread at +-16, so the pass is a few microseconds of latency).
 // =========================================================================================
 // List entries carry the search direction in bit 30 (pair launches: direction 1 swaps the frames).
 #define FS_DIR_BIT 0x40000000
-__global__ void __launch_bounds__(256)
+#define FS_REDO_NT 1024
+__global__ void __launch_bounds__(FS_REDO_NT)
 fs_redo_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
                const uint8_t *__restrict__ rgb0, const uint8_t *__restrict__ rgb1,
                int H, int W, int Wp, int bs, int R, int nbc,
@@ -110,7 +112,7 @@ fs_redo_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
     // Shared staging, zero padded like np.pad: the block and its search window as luma1000 ints
     // (fast SAD) and as the reference's float64 luma (exact replay of flagged candidates).
     extern __shared__ double redo_sm[];
-    __shared__ unsigned long long wbest[8];
+    __shared__ unsigned long long wbest[FS_REDO_NT / 32];
     const int ww = bs + 2 * R;
     double *dref = redo_sm, *dwin = redo_sm + bs * bs;
     int *ref = reinterpret_cast<int *>(dwin + ww * ww), *win = ref + bs * bs;
@@ -173,7 +175,7 @@ fs_redo_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
         if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int w = 1; w < 8; ++w) best = wbest[w] < best ? wbest[w] : best;
+            for (int w = 1; w < FS_REDO_NT / 32; ++w) best = wbest[w] < best ? wbest[w] : best;
             if (best != KEY_NONE) {
                 const int ri = (int)((best >> 8) & 255), ci = (int)(best & 255);
                 out_vec[blk] = make_float2((float)(b.r0 + ri - s_row), (float)(b.c0 + ci - s_col));
@@ -207,6 +209,7 @@ fs_redo_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
 // =========================================================================================
 struct FsParams {
     int H, W, bs, R, Rp, m, nbr, nbc, n_tiles, box_h, n_stages, ks;   // ks = bits reserved for dist^2 in the 32-bit key   // Rp = R rounded up to 4: TMA x origin stays 16-byte aligned
+    unsigned one;                // the constant 1, opaque to ptxas (keeps IMADs from being folded into ALU adds)
     int n_tiles_dir;             // tiles of one direction; tile index >= n_tiles_dir = reverse direction (pair launch)
     const FsTile *tiles;
     float2 *out_vec[2];
@@ -290,32 +293,38 @@ __device__ inline void fs_fill_tab(FsTileTab *tab, const FsTile t, const FsParam
 // winner on (sad-1, d2) and could beat it on scan order.  S == 0 also has remainder 0; its
 // lowered key wraps to a huge value and is ignored by the min.
 //
-// The kernel is bound by the integer-ALU pipe (VABSDIFF), so everything here that can be an IMAD
-// is written as one (multiplies by run-time constants instead of shifts): the FMA pipe is idle.
-// Per candidate: 7 IMAD (fma pipe) + ~4 alu-pipe ops.  mulg = (1 << GB) << ks.
+// The kernel is bound by the integer-ALU pipe (VABSDIFF, 2 issue cycles per warp instruction), while the
+// FMA pipe idles.  So the whole per-candidate bookkeeping is written as IMAD / IMAD.HI (inline PTX keeps
+// ptxas from turning them back into ALU-pipe shifts, adds and selects); only the running minima (one
+// VIMNMX3 per two candidates and chain) stay on the ALU pipe.  Per candidate, with Sm1 = S - 1 (the SAD
+// accumulators start at 0xffffffff so that S - 1 comes for free):
+//   S    = Sm1 * 1 + 1                      hi = mulhi(S, 0x10624dd3)     q = mulhi(hi, 2^26) = S / 1000
+//   rem1 = q * -1000 + Sm1 = (S % 1000) - 1  flag = mulhi(rem1, 2) = (S % 1000 == 0)
+//   u    = two_dy0 * (GM gi) + base          t = one * (GM gi^2 + gi) + u   (one = 1 from the parameter block:
+//                                                                            a literal 1 would be folded into an add)
+//   key  = q * mulg + t                      lo = flag * -lower + key
 template <int G, bool CHECK>
-__device__ __forceinline__ void fs_finalize(const unsigned (&acc)[G], int n_valid, int dy0, int dx, unsigned mulg,
+__device__ __forceinline__ void fs_finalize(const unsigned (&acc)[G], int n_valid, int dy0, int dx, unsigned mulg, unsigned one,
                                             unsigned &kb, unsigned &kl)
 {
     constexpr unsigned GM = G <= 16 ? 16u : 64u;
     const unsigned base = ((unsigned)(dy0 * dy0 + dx * dx) + 1u) * GM;
-    const unsigned two_dy0 = (unsigned)(2 * dy0);
-    const unsigned lower = mulg + GM;                        // one SAD step + one notch, in key units
-    const unsigned base_lo = base - lower;
+    const unsigned a_dy = (unsigned)(2 * dy0) * GM;
+    const unsigned neg_lower = 0u - (mulg + GM);              // one SAD step + one notch, in key units
     kb = 0xffffffffu; kl = 0xffffffffu;
 #pragma unroll
     for (int gi = 0; gi < G; ++gi) {
-        const unsigned S = acc[gi];
-        const unsigned q = S / 1000u;                         // IMAD.HI + one shift
-        unsigned rem, dk, dkl, key, lo, t;
-        // inline PTX keeps these as IMADs (the compiler would turn them into ALU-pipe shifts/adds/selects)
-        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(rem) : "r"(q), "r"(0xfffffc18u), "r"(S));                       // S - 1000 q
-        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(dk) : "r"(two_dy0), "r"(GM * (unsigned)gi), "r"(base + (GM * (unsigned)(gi * gi) + (unsigned)gi)));
-        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(dkl) : "r"(two_dy0), "r"(GM * (unsigned)gi), "r"(base_lo + (GM * (unsigned)(gi * gi) + (unsigned)gi)));
-        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(q), "r"(mulg), "r"(dk));
-        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lo) : "r"(q), "r"(mulg), "r"(dkl));                            // key - lower
-        asm("min.u32 %0, %1, 1;" : "=r"(t) : "r"(rem));
-        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lo) : "r"(t), "r"(lower), "r"(lo));                             // back to key unless rem == 0
+        const unsigned Sm1 = acc[gi];
+        unsigned S, hi, q, rem1, flag, u, t, key, lo;
+        asm("mad.lo.u32 %0, %1, %2, 1;" : "=r"(S) : "r"(Sm1), "r"(one));
+        asm("mul.hi.u32 %0, %1, 0x10624dd3;" : "=r"(hi) : "r"(S));
+        asm("mul.hi.u32 %0, %1, 0x4000000;" : "=r"(q) : "r"(hi));
+        asm("mad.lo.u32 %0, %1, 0xfffffc18, %2;" : "=r"(rem1) : "r"(q), "r"(Sm1));
+        asm("mul.hi.u32 %0, %1, 2;" : "=r"(flag) : "r"(rem1));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(u) : "r"(a_dy), "r"((unsigned)gi), "r"(base));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(one), "r"(GM * (unsigned)(gi * gi) + (unsigned)gi), "r"(u));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(key) : "r"(q), "r"(mulg), "r"(t));
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(lo) : "r"(flag), "r"(neg_lower), "r"(key));
         if (CHECK) { if (gi >= n_valid) { key = 0xffffffffu; lo = 0xffffffffu; } }   // rows past the window lose
         kb = min(kb, key);
         kl = min(kl, lo);
@@ -475,7 +484,7 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                     const int wr0 = wrow_base + g * G;
                     unsigned acc[G];
 #pragma unroll
-                    for (int i = 0; i < G; ++i) acc[i] = 0u;
+                    for (int i = 0; i < G; ++i) acc[i] = 0xffffffffu;      // S - 1: see fs_finalize
 #pragma unroll 1
                     for (int sub = 0; sub < m * m; ++sub) {
                         const int si = SINGLE ? 0 : sub / m, sj = SINGLE ? 0 : sub - si * m;
@@ -510,8 +519,8 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                     const int n_valid = n_dy - g * G;       // > 0
                     const int dy0 = dy_lo + g * G;
                     unsigned kb32, kl32;
-                    if (n_valid >= G) fs_finalize<G, false>(acc, n_valid, dy0, dx, mulg, kb32, kl32);
-                    else fs_finalize<G, true>(acc, n_valid, dy0, dx, mulg, kb32, kl32);
+                    if (n_valid >= G) fs_finalize<G, false>(acc, n_valid, dy0, dx, mulg, p.one, kb32, kl32);
+                    else fs_finalize<G, true>(acc, n_valid, dy0, dx, mulg, p.one, kb32, kl32);
                     // groups ascend in row offset: strict '<' on (sad, d2) keeps the earlier row on ties
                     if ((kb32 >> GB) < (kb_run >> GB)) { kb_run = kb32; g_run = g; }
                     klow = min(klow, kl32);
@@ -750,6 +759,7 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         } else { tm[2] = tm[0]; tm[3] = tm[1]; }
         FsParams p;
         p.H = H; p.W = W; p.bs = bs; p.R = R; p.Rp = (R + 3) & ~3; p.m = bs / 8; p.nbr = nbr; p.nbc = nbc;
+        p.one = 1u;
         p.n_tiles_dir = pl->row_tile_start[br1] - pl->row_tile_start[br0]; p.n_tiles = ndir * p.n_tiles_dir; p.box_h = pl->box_h;
         { int ks = 1; while ((1 << ks) <= 2 * R * R + 1) ++ks; p.ks = ks; }
         p.n_stages = fs_smem_bytes(bs, pl->box_h, 2, pl->G) <= 220 * 1024 ? 2 : 1;
@@ -775,7 +785,7 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         const int redo_smem = (bs * bs + (bs + 2 * R) * (bs + 2 * R)) * 12;
         if (redo_smem <= 160 * 1024) {
             CK(ctx, cudaFuncSetAttribute(fs_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, redo_smem));
-            fs_redo_kernel<<<ctx->num_sms * 2, 256, redo_smem, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbc,
+            fs_redo_kernel<<<ctx->num_sms * 2, FS_REDO_NT, redo_smem, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbc,
                                                                               ctx->d_redo_list, ctx->d_counters, out->vec, out->sad,
                                                                               p.out_vec[1], p.out_sad[1]);
         } else {

@@ -49,12 +49,17 @@ struct MciParams {
 // forward : int(round(mv * dist))        f32 product, round-half-even  (Unidirectional.py:48-49,
 //                                         Bidirectional.py:34-35; W1)
 // backward: int(round(mv * (1.0 - dist))) f64 product                   (Bidirectional.py:42-44; W2)
-__global__ void mci_disp_kernel(const float2 *__restrict__ vec, int n, float dist, int backward,
-                                short2 *__restrict__ disp, int *__restrict__ dmax)
+struct DispArgs { const float2 *vec[2]; short2 *disp[2]; int n[2]; };
+__global__ void mci_disp_kernel(const DispArgs A, float dist, int ndir, int *__restrict__ dmax)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // both directions in one launch: blockIdx.y = direction (0 forward, 1 backward)
+    const int backward = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = backward ? A.n[1] : A.n[0];
+    const float2 *vec = backward ? A.vec[1] : A.vec[0];
+    short2 *disp = backward ? A.disp[1] : A.disp[0];
     int m = 0;
-    if (i < n) {
+    if (backward < ndir && i < n) {
         float2 v = vec[i];
         int dr, dc;
         if (!backward) {
@@ -619,6 +624,10 @@ mci_splat_kernel(const __grid_constant__ MciParams P, int tiles_x, int n_tiles)
 // word per bin (10 bits each, counts <= 441), so one warp prefix scan ranks all three channels.
 __device__ __forceinline__ void hist_select3(const unsigned *__restrict__ hist, int lane, int k_lo, int k_hi, unsigned (&res)[3])
 {
+    // Each lane owns 8 bins; the three channel counts of a bin share one word (10-bit fields, counts <= 441,
+    // so bit 9 of every field is free).  "prefix >= k+1" for all three channels at once is one subtraction
+    // with that bit as a guard: (prefix | guard) - (k+1) keeps the guard bit exactly when there is no borrow.
+    const unsigned GUARD = 0x20080200u, ONES = 0x00100401u;
     const uint4 a = *reinterpret_cast<const uint4 *>(hist + lane * 8);
     const uint4 c = *reinterpret_cast<const uint4 *>(hist + lane * 8 + 4);
     const unsigned cnt[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
@@ -632,25 +641,23 @@ __device__ __forceinline__ void hist_select3(const unsigned *__restrict__ hist, 
         if (lane >= o) incl += t;
     }
     const unsigned excl = incl - local;
+    const unsigned k1_lo = (unsigned)(k_lo + 1) * ONES, k1_hi = (unsigned)(k_hi + 1) * ONES;
+    unsigned run = excl + GUARD, ge_lo = 0u, ge_hi = 0u;  // per field: how many of the lane's 8 prefixes reach rank k
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-        const int sh = 10 * ch;
-        const unsigned ex = (excl >> sh) & 1023u, in = (incl >> sh) & 1023u;
-        int found_lo = -1, found_hi = -1;
-        if (((unsigned)k_lo >= ex && (unsigned)k_lo < in) || ((unsigned)k_hi >= ex && (unsigned)k_hi < in)) {
-            unsigned run = ex;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const unsigned prev = run;
-                run += (cnt[i] >> sh) & 1023u;
-                if ((unsigned)k_lo >= prev && (unsigned)k_lo < run) found_lo = lane * 8 + i;
-                if ((unsigned)k_hi >= prev && (unsigned)k_hi < run) found_hi = lane * 8 + i;
-            }
-        }
-        const int v_lo = __reduce_max_sync(0xffffffffu, found_lo);
-        const int v_hi = __reduce_max_sync(0xffffffffu, found_hi);
-        res[ch] = (unsigned)((v_lo + v_hi) >> 1);         // np.median: (a+b)/2.0, truncated on the uint8 store
+    for (int i = 0; i < 8; ++i) {
+        run += cnt[i];
+        ge_lo += ((run - k1_lo) >> 9) & ONES;
+        ge_hi += ((run - k1_hi) >> 9) & ONES;
     }
+    // the lane holding rank k: exclusive prefix <= k < inclusive prefix; its bin is 8 - (#prefixes >= k+1)
+    const unsigned in_lo = ((incl + GUARD - k1_lo) >> 9) & ~((excl + GUARD - k1_lo) >> 9) & ONES;
+    const unsigned in_hi = ((incl + GUARD - k1_hi) >> 9) & ~((excl + GUARD - k1_hi) >> 9) & ONES;
+    const unsigned bin1 = (unsigned)(lane * 8 + 9);       // bin + 1 so that 0 means "not in this lane"
+    const unsigned v_lo = __reduce_or_sync(0xffffffffu, in_lo * bin1 - (ge_lo & (in_lo * 1023u)));
+    const unsigned v_hi = __reduce_or_sync(0xffffffffu, in_hi * bin1 - (ge_hi & (in_hi * 1023u)));
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)                         // np.median: (a+b)/2.0, truncated on the uint8 store
+        res[ch] = (((v_lo >> (10 * ch)) & 1023u) + ((v_hi >> (10 * ch)) & 1023u) - 2u) >> 1;
 }
 
 __device__ __forceinline__ void hist_add(unsigned *hist, unsigned word)
@@ -747,19 +754,23 @@ int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd
     CK(ctx, cudaMemsetAsync(ctx->d_counters + 1, 0, 4 * sizeof(int), ctx->stream));   // [1] holes [2] dmax [4] hole runs
     MciParams P;
     memset(&P, 0, sizeof(P));
+    DispArgs DA;
+    memset(&DA, 0, sizeof(DA));
+    size_t n_max = 0;
     for (int d = 0; d < ndir; ++d) {
         const MVField *f = fl[d];
         size_t n = (size_t)f->mv_rows * f->mv_cols;
         if ((rc = memci_reserve(ctx, (void **)&ctx->d_disp[d], &ctx->disp_cap[d], n * sizeof(short2)))) return rc;
-        mci_disp_kernel<<<ceil_div_i((int)n, 256), 256, 0, ctx->stream>>>(f->vec, (int)n, dist, d, ctx->d_disp[d],
-                                                                          ctx->d_counters + 2);
-        CKL(ctx);
+        DA.vec[d] = f->vec; DA.disp[d] = ctx->d_disp[d]; DA.n[d] = (int)n;
+        n_max = n > n_max ? n : n_max;
         P.disp[d] = ctx->d_disp[d]; P.cell[d] = f->mv_cell; P.cols[d] = f->mv_cols;
         P.sad[d] = f->sad; P.scell[d] = f->sad_cell; P.scols[d] = f->sad_cols;
         P.sad_nested[d] = (f->sad_cell % f->mv_cell) == 0;
         P.cmul[d] = f->mv_cell > 1 ? (unsigned)((0x100000000ull + (unsigned)f->mv_cell - 1) / (unsigned)f->mv_cell) : 0u;
         P.smul[d] = f->sad_cell > 1 ? (unsigned)((0x100000000ull + (unsigned)f->sad_cell - 1) / (unsigned)f->sad_cell) : 0u;
     }
+    mci_disp_kernel<<<dim3(ceil_div_i((int)n_max, 256), ndir), 256, 0, ctx->stream>>>(DA, dist, ndir, ctx->d_counters + 2);
+    CKL(ctx);
     size_t npx = (size_t)H * W;
     if (ctx->hole_cap < npx) {
         if (ctx->d_fill) cudaFree(ctx->d_fill);

@@ -4,6 +4,8 @@
 //   mode 1: FADD pairs (d = a-b; acc += |d|)                      -> the same op on the fp32 pipe
 //   mode 2: 8 VABSDIFF + 4 FADD pairs per step                    -> both pipes co-issued
 //   mode 3: 8 VABSDIFF + 8 FADD pairs per step
+//   modes 4..9: 8 VABSDIFF + 2 x {LDS.32, IMAD reg, IMAD imm, FADD, IADD3, VIMNMX3} per step -- what does an extra
+//               instruction cost next to the SAD stream? (px_ops counts the 8 SADs only)
 #include "memci_internal.cuh"
 
 template <int MODE>
@@ -19,9 +21,34 @@ __global__ void __launch_bounds__(512) ub_kernel(int iters, const int *__restric
         fr[j] = (float)r[j];
         fa[j] = (float)a[j];
     }
+    __shared__ int ub_sm[2048];
+    unsigned extra = 0, e0 = threadIdx.x, e1 = threadIdx.x * 3u, e2 = 7u, e3 = 11u;
+    float f0 = (float)threadIdx.x, f1 = 1.5f;
+    if (MODE == 4) { for (int i = threadIdx.x; i < 2048; i += blockDim.x) ub_sm[i] = seed[i & 63]; __syncthreads(); }
 #pragma unroll 4
     for (int it = 0; it < iters; ++it) {
-        if (MODE == 0 || MODE >= 2) {
+        if (MODE == 4) {
+            e0 += (unsigned)ub_sm[(threadIdx.x + it) & 2047];
+            e1 += (unsigned)ub_sm[(threadIdx.x + 2 * it + 512) & 2047];
+        }
+        if (MODE == 5) {
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(e0) : "r"(e2), "r"(e3));
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(e1) : "r"(e3), "r"(e2));
+        }
+        if (MODE == 6) {
+            asm volatile("mad.lo.u32 %0, %1, 0x10624dd3, %0;" : "+r"(e0) : "r"(e2));
+            asm volatile("mad.lo.u32 %0, %1, 0x3e8, %0;" : "+r"(e1) : "r"(e3));
+        }
+        if (MODE == 7) { f0 = __fadd_rn(f0, f1); f1 = __fadd_rn(f1, f0); }
+        if (MODE == 8) {
+            asm volatile("add.u32 %0, %0, %1;" : "+r"(e0) : "r"(e2));
+            asm volatile("add.u32 %0, %0, %1;" : "+r"(e1) : "r"(e3));
+        }
+        if (MODE == 9) {
+            asm volatile("min.u32 %0, %0, %1;" : "+r"(e0) : "r"(e2 + it));
+            asm volatile("min.u32 %0, %0, %1;" : "+r"(e1) : "r"(e3 + it));
+        }
+        if (MODE == 0 || MODE >= 2) {   // the SAD stream
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[j] = __sad(r[j], (int)a[(j + 1) & 7], a[j]);
         }
@@ -34,15 +61,17 @@ __global__ void __launch_bounds__(512) ub_kernel(int iters, const int *__restric
             for (int j = 0; j < 4; ++j) fa[j] = __fadd_rn(fa[j], fabsf(__fsub_rn(fr[j], fa[(j + 1) & 3])));
         }
     }
+    extra = e0 + e1 + (unsigned)f0 + (unsigned)f1;
     unsigned s = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) s += a[j] + (unsigned)fa[j];
+    s += extra;
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 extern "C" MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, float *ms, double *px_ops)
 {
-    if (!ctx || mode < 0 || mode > 3 || iters <= 0) return MEMCI_ERR_ARG;
+    if (!ctx || mode < 0 || mode > 9 || iters <= 0) return MEMCI_ERR_ARG;
     cudaSetDevice(ctx->device);
     const int grid = ctx->num_sms * 4, nt = 512;
     int *d_seed = nullptr;
@@ -60,7 +89,13 @@ extern "C" MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, f
         case 0: ub_kernel<0><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
         case 1: ub_kernel<1><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
         case 2: ub_kernel<2><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
-        default: ub_kernel<3><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        case 3: ub_kernel<3><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        case 4: ub_kernel<4><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        case 5: ub_kernel<5><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        case 6: ub_kernel<6><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        case 7: ub_kernel<7><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        case 8: ub_kernel<8><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        default: ub_kernel<9><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
         }
         ctx->launches++;
     }
@@ -71,7 +106,7 @@ extern "C" MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, f
     cudaEventElapsedTime(&t, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d_seed); cudaFree(d_out);
-    const double per_step = mode == 0 ? 8.0 : mode == 1 ? 8.0 : mode == 2 ? 12.0 : 16.0;
+    const double per_step = mode == 2 ? 12.0 : mode == 3 ? 16.0 : 8.0;
     if (ms) *ms = t;
     if (px_ops) *px_ops = per_step * (double)iters * (double)grid * nt;
     return MEMCI_OK;
