@@ -147,6 +147,20 @@ MEMCI_API int memci_mci_unidir(memci_ctx *ctx, int slot_src, int slot_tgt, int m
 MEMCI_API int memci_mci_bidir(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd,
                               int mv_bwd, float dist, int out_slot);
 
+/* Replaces the MCI half of BiDir2Interpolator.get_interpolated_frame (MCI/Bidirectional_2.py:330-345):
+ *   Ff, Ef = IEWMC(fwr_MV_field, source, target, dist, pad_size, min_block_size, upscale_MV)      (:49-144)
+ *   Fb, Eb = IEWMC(bwr_MV_field, target, source, 1 - dist, ...)
+ *   Out    = unpad_and_downconvert(BDHI(Error_adaptive_combination(Ff, Ef, Fb, Eb)))              (:147-290)
+ * dist_fwd / dist_bwd are the two float32 values the reference's njit boundary sees (dist and 1 - dist,
+ * each rounded from the Python float); weights = get_weight_kern(2 * min_block_size)[:, :, 0] (:33-47),
+ * 64 float32, row-major, copied before the call returns.  The MV slots may be block level (hbma,
+ * upscale=False) or coarser ME blocks (fs / tss: the dense field sampled at the 4x4 block origins). */
+MEMCI_API int memci_mci_bidir2(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd, int mv_bwd, float dist_fwd,
+                               float dist_bwd, int min_block_size, int pad_size, const float *weights, int out_slot);
+/* After memci_mci_bidir2: largest |int(dist * mv)| and the number of blocks whose shifted slices leave
+ * the padded arrays (the reference's numpy slices would clip and its in-place adds fail; we zero-fill). */
+MEMCI_API int memci_bidir2_stats(memci_ctx *ctx, int *max_shift, int *n_out_of_range);
+
 /* ---- spatial tiling of one frame pair into horizontal bands (8K mode) -------------
  * A band = block rows [block_row0, block_row1).  Each GPU holds full-size slots but only fills the
  * rows it owns plus the halo rows it received; these entry points restrict the work to a band. */

@@ -3,6 +3,7 @@
 import math
 
 from .Bidirectional import BiDirInterpolator
+from .Bidirectional_2 import BiDir2Interpolator
 from .Unidirectional import UniDirInterpolator
 
 
@@ -13,6 +14,6 @@ def MEMCI(target_fps, video_in_path=None, video_out_path=None, max_out_frames=ma
     if mci_mode == 'bidir':
         return BiDirInterpolator(target_fps, video_in_path, video_out_path, max_out_frames, max_cache_size, **args)
     if mci_mode == 'bidir2':
-        raise NotImplementedError("mci_mode 'bidir2' (Bidirectional_2.py) is the next row of the hot-path scope "
-                                  "table (SURVEY 8f #1) and is not built yet")
+        args['filter_mode'] = 'none'                                        # no smoothing in bidir2 (Interpolator.py:27)
+        return BiDir2Interpolator(target_fps, video_in_path, video_out_path, max_out_frames, max_cache_size, **args)
     raise Exception(f'Unknown mci_mode: {mci_mode}')

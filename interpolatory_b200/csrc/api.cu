@@ -139,6 +139,7 @@ int memci_ctx_destroy(memci_ctx *ctx)
         if (ctx->tmp_mv[i].vec) cudaFree(ctx->tmp_mv[i].vec);
         if (ctx->tmp_mv[i].sad) cudaFree(ctx->tmp_mv[i].sad);
         if (ctx->d_disp[i]) cudaFree(ctx->d_disp[i]);
+        if (ctx->d_b2blk[i]) cudaFree(ctx->d_b2blk[i]);
     }
     for (int i = 0; i < 4; ++i) {
         if (ctx->fs_plan[i].d_tiles) cudaFree(ctx->fs_plan[i].d_tiles);
@@ -360,6 +361,28 @@ int memci_mci_bidir(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd, int 
     REQ_MV(ctx, mv_fwd, 1); REQ_MV(ctx, mv_bwd, 1);
     if (out_slot == slot_src || out_slot == slot_tgt) return memci_fail(ctx, MEMCI_ERR_ARG, "output slot aliases an input slot");
     return memci_mci_run(ctx, slot_src, slot_tgt, &ctx->mvs[mv_fwd], &ctx->mvs[mv_bwd], dist, out_slot, 1, 0, -1);
+}
+
+int memci_mci_bidir2(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd, int mv_bwd, float dist_fwd, float dist_bwd,
+                     int min_block_size, int pad_size, const float *weights, int out_slot)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_FRAME(ctx, out_slot, 0);
+    REQ_MV(ctx, mv_fwd, 1); REQ_MV(ctx, mv_bwd, 1);
+    if (!weights) return memci_fail(ctx, MEMCI_ERR_ARG, "null weight kernel");
+    if (out_slot == slot_src || out_slot == slot_tgt) return memci_fail(ctx, MEMCI_ERR_ARG, "output slot aliases an input slot");
+    return memci_bidir2_run(ctx, slot_src, slot_tgt, &ctx->mvs[mv_fwd], &ctx->mvs[mv_bwd], dist_fwd, dist_bwd,
+                            min_block_size, pad_size, weights, out_slot);
+}
+
+int memci_bidir2_stats(memci_ctx *ctx, int *max_shift, int *n_out_of_range)
+{
+    REQ_CTX(ctx);
+    int h[2] = {0, 0};
+    CK(ctx, cudaMemcpyAsync(h, ctx->d_counters + 5, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (max_shift) *max_shift = h[0];
+    if (n_out_of_range) *n_out_of_range = h[1];
+    return MEMCI_OK;
 }
 
 int memci_mci_rows(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd, int mv_bwd, float dist, int out_slot,

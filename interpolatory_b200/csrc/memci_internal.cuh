@@ -51,13 +51,14 @@ struct memci_ctx {
     MVField mvs[MEMCI_NUM_MV_SLOTS];
     MVField tmp_mv[2];                 // HBMA ping-pong
     // full-search scratch
-    int *d_redo_list; int redo_cap; int *d_counters;   // [0] redo count, [1] hole count, [2] dmax, [3] tile counter
+    int *d_redo_list; int redo_cap; int *d_counters;   // [0] redo count, [1] hole count, [2] dmax, [4] hole runs, [5] bidir2 max |T|, [6] bidir2 out-of-range blocks
     FsPlan fs_plan[4];
     long long fs_last_cand, fs_last_ops;
     // MCI scratch
     short2 *d_disp[2]; size_t disp_cap[2];
     uint32_t *d_fill; int *d_hole_list; size_t hole_cap;
     float *d_dense; size_t dense_cap;  // dense MV staging for download/upload
+    int4 *d_b2blk[2]; size_t b2blk_cap[2];   // bidir2: per 4x4 block (Xb, Yb, TXb, TYb << 1 | occluded), per direction
     // timing
     int timing; cudaEvent_t ev[4]; int fs_timed, mci_timed;
     // event pool: per-launch device times of the two hot kernels inside a caller's timed region
@@ -96,6 +97,8 @@ int memci_hbma_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int win, 
 int memci_smooth_run(memci_ctx *ctx, const MVField *in, int mode, int fsz, MVField *out);
 int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd, const MVField *bwd,
                   float dist, int out_slot, int bidir, int row0, int row1);   // output rows [row0, row1); row1 < 0 = all
+int memci_bidir2_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd, const MVField *bwd,
+                     float dist_fwd, float dist_bwd, int mbs, int pad, const float *w64, int out_slot);
 int memci_mv_to_dense(memci_ctx *ctx, const MVField *f, float *d_dense);
 // returns an event pair index (>= 0) after recording the start event, or -1 when profiling is off / full
 int memci_prof_begin(memci_ctx *ctx, int kind);

@@ -170,6 +170,19 @@ class DeviceContext:
     def mci_bidir(self, src, tgt, mv_fwd, mv_bwd, dist, out_slot):
         self._ck(self.L.memci_mci_bidir(self._ctx, src, tgt, mv_fwd, mv_bwd, C.c_float(float(np.float32(dist))), out_slot))
 
+    def mci_bidir2(self, src, tgt, mv_fwd, mv_bwd, dist_fwd, dist_bwd, weights, out_slot, min_block_size=4, pad_size=16):
+        """IEWMC both ways + error-adaptive combination + BDHI + unpad (Bidirectional_2.py:330-345)."""
+        w = np.ascontiguousarray(weights, np.float32)
+        assert w.size == (2 * min_block_size) ** 2
+        self._ck(self.L.memci_mci_bidir2(self._ctx, src, tgt, mv_fwd, mv_bwd, C.c_float(float(np.float32(dist_fwd))),
+                                         C.c_float(float(np.float32(dist_bwd))), int(min_block_size), int(pad_size),
+                                         w.ctypes.data_as(C.c_void_p), out_slot))
+
+    def bidir2_stats(self):
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.L.memci_bidir2_stats(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # -- instrumentation
     def launch_count(self):
         return int(self.L.memci_launch_count(self._ctx))

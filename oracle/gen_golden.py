@@ -58,12 +58,70 @@ def gen_tss(ns):
     np.savez_compressed(os.path.join(OUT, "tss_small.npz"), **t)
 
 
+def gen_bidir2(ns):
+    """bidir2 (MCI/Bidirectional_2.py): function level (IEWMC / EAC / BDHI on fs and hbma vectors, with the
+    vectors stored so that the CPU tests need no ME) + the class API for the three me_modes."""
+    from src.Interpolators.MEMCI.MCI import Bidirectional_2 as b2
+    t = {}
+    t["weight_kern"] = b2.get_weight_kern(8)[:, :, 0].copy()
+    for (H, W) in [(72, 96), (50, 70), (37, 53)]:
+        fr = make_sequence(H, W, 2, seed=H + 1000)
+        a, b = fr[0], fr[1]
+        k = f"{H}x{W}"
+        fields = {"fs": (ns.fs.get_motion_vectors(8, 7, a, b), ns.fs.get_motion_vectors(8, 7, b, a), True),
+                  "hbma": (ns.hbma.get_motion_vectors(8, 7, 1, 2, 4, a, b, 'sad', False),
+                           ns.hbma.get_motion_vectors(8, 7, 1, 2, 4, b, a, 'sad', False), False)}
+        for me, (fwd, bwd, up) in fields.items():
+            t[f"{k}/{me}/fwd"] = blocks_of(fwd, 8) if up else fwd
+            t[f"{k}/{me}/bwd"] = blocks_of(bwd, 8) if up else bwd
+            for di, dist in enumerate((0.5, 0.39999998, 0.8)):
+                Ff, Ef = b2.IEWMC(fwd, a, b, dist, 16, 4, up)
+                Fb, Eb = b2.IEWMC(bwd, b, a, 1 - dist, 16, 4, up)
+                Fc = b2.Error_adaptive_combination(Ff, Ef, Fb, Eb)
+                out = b2.unpad_and_downconvert(b2.BDHI(Fc, 4, 16), 16)
+                if di == 0 and H == 37:          # one full set of intermediates (small)
+                    t[f"{k}/{me}/Ff"], t[f"{k}/{me}/Ef"], t[f"{k}/{me}/Fc"] = Ff, Ef, Fc
+                t[f"{k}/{me}/out{di}"] = out
+    # fill_holes on random blocks (incl. an all-hole block -> NaN)
+    rng = np.random.default_rng(42)
+    blocks = []
+    for i in range(24):
+        blk = rng.uniform(0, 255, (8, 8, 3)).astype(np.float32)
+        blk[rng.random((8, 8)) < (0.05, 0.3, 0.7)[i % 3]] = -1
+        blocks.append(blk)
+    blocks.append(np.full((8, 8, 3), -1, np.float32))
+    t["fill_holes/in"] = np.stack(blocks)
+    t["fill_holes/out"] = np.stack([b2.fill_holes(b.copy()) for b in blocks])
+
+    class SynthStream(ns.BaseVideoStream):
+        def __init__(self, frames, fps):
+            self.frames, self.nframes, self.fps, self.duration = frames, len(frames), fps, len(frames) / fps
+
+        def get_frame(self, idx):
+            return self.frames[idx]
+
+    frames = make_sequence(72, 96, 3, seed=2272)
+    for si, st in enumerate([dict(mci_mode='bidir2'),
+                             dict(mci_mode='bidir2', me_mode='fs', block_size='8', target_region='7'),
+                             dict(mci_mode='bidir2', me_mode='tss'),
+                             dict(mci_mode='bidir2', me_mode='fs', block_size='16', target_region='5', filter_mode='median')]):
+        it = ns.MEMCI(60, **dict(st))
+        it.video_stream = SynthStream(list(frames), 24)
+        it.rate_ratio = 60 / 24
+        t[f"e2e/set{si}/settings"] = np.array(repr(sorted(st.items())))
+        t[f"e2e/set{si}/out"] = np.stack([np.asarray(it.get_interpolated_frame(i)) for i in range(5)])
+    np.savez_compressed(os.path.join(OUT, "bidir2_small.npz"), **t)
+
+
 def main():
     ns = ref_harness.load()
     os.makedirs(OUT, exist_ok=True)
     if "--only-tss" in sys.argv:
         return gen_tss(ns)
+    if "--only-bidir2" in sys.argv:
+        return gen_bidir2(ns)
     gen_tss(ns)
+    gen_bidir2(ns)
     rng = np.random.default_rng(7)
 
     # ---- ratio / dist table (src/util.py:49-60) ---------------------------------

@@ -665,3 +665,214 @@ ORC_API void orc_set_num_threads(int n)
     (void)n;
 #endif
 }
+
+/* ======================================================================== */
+/* bidir2: MCI/Bidirectional_2.py (Wang et al., IEWMC + error-adaptive       */
+/* combination + block-wise directional hole interpolation)                  */
+/* ======================================================================== */
+
+/* IEWMC_helper, MCI/Bidirectional_2.py:49-127.  `mv` is the field exactly as the reference
+ * indexes it (:63-67): block level [ceil(H/mbs)][ceil(W/mbs)][3] when upscale == 0 (hbma), dense
+ * [H][W][3] sampled at the block origin otherwise.  `w` = get_weight_kern(2*mbs)[:,:,0] as float32
+ * (:33-47; the three channels carry the same weights).  Outputs F, E: float32 [H+2p][W+2p][3].
+ *
+ * numba's typing, reproduced term by term (probed against the reference):
+ *   TXb = int(dist * Xb)            float32 * int64 -> float64, truncated                 (:71-72)
+ *   SAD = MV_i[2] / SAD_norm        float32 / int64 -> float64, compared with 250         (:73,:87)
+ *   t_a = (1 - dist) * t_1          int64 - float32 -> float64 scalar, * uint8 -> float64 (:89)
+ *   t_b = dist * t_2                float32 * uint8 array -> float32                      (:92)
+ *   acc += w * (t_a + t_b)          float64, rounded to float32 on the store into acc     (:94-96)
+ *   acc += w * F1 (occluded)        float32 * uint8 -> float32                            (:98)
+ *   WM  = (w * |F1 - F2|).astype(f32)   float32 * int32 -> float64, then rounded          (:105)
+ * and the three accumulators are float32 sums in block-raster order (:100,:106,:108).
+ * Returns 0, or -1 if a shifted block leaves the padded arrays (the reference's slices would clip and
+ * its in-place adds would fail to broadcast). */
+ORC_API int orc_iewmc(const uint8_t *F1, const uint8_t *F2, const float *mv, int upscale, int H, int W,
+                      int mbs, int pad, float dist, const float *w, float *Fout, float *Eout)
+{
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad, eb = 2 * mbs, half = mbs / 2;
+    const size_t npx = (size_t)Hp * Wp;
+    float *accum = (float *)calloc(npx * 3, sizeof(float));
+    float *wmcd = (float *)calloc(npx * 3, sizeof(float));
+    float *wsum = (float *)calloc(npx * 3, sizeof(float));
+    uint8_t *P1 = (uint8_t *)calloc(npx * 3, 1), *P2 = (uint8_t *)calloc(npx * 3, 1);
+    if (!accum || !wmcd || !wsum || !P1 || !P2) { free(accum); free(wmcd); free(wsum); free(P1); free(P2); return -2; }
+    for (int r = 0; r < H; ++r) {
+        memcpy(P1 + ((size_t)(r + pad) * Wp + pad) * 3, F1 + (size_t)r * W * 3, (size_t)W * 3);
+        memcpy(P2 + ((size_t)(r + pad) * Wp + pad) * 3, F2 + (size_t)r * W * 3, (size_t)W * 3);
+    }
+    const int mv_cols = upscale ? W : ceil_div(W, mbs);
+    const double one_minus = 1.0 - (double)dist;              /* (1-dist): int64 - float32 -> float64 */
+    const long long sad_norm = (long long)mbs * mbs * 3;
+    int rc = 0;
+    for (int br = 0; br < H && rc == 0; br += mbs) {
+        for (int bc = 0; bc < W; bc += mbs) {
+            const float *m = upscale ? mv + ((size_t)br * mv_cols + bc) * 3 : mv + ((size_t)(br / mbs) * mv_cols + bc / mbs) * 3;
+            const long long Xb = (long long)m[0], Yb = (long long)m[1];
+            const long long TXb = (long long)((double)dist * (double)Xb), TYb = (long long)((double)dist * (double)Yb);
+            const double sad = (double)m[2] / (double)sad_norm;
+            const int occluded = !(sad < 250.0);
+            const long long r0 = br + pad - half, c0 = bc + pad - half;
+            if (r0 + Xb < 0 || r0 + Xb + eb > Hp || c0 + Yb < 0 || c0 + Yb + eb > Wp ||
+                r0 + TXb < 0 || r0 + TXb + eb > Hp || c0 + TYb < 0 || c0 + TYb + eb > Wp) { rc = -1; break; }
+            for (int i = 0; i < eb; ++i) {
+                for (int j = 0; j < eb; ++j) {
+                    const float wk = w[i * eb + j];
+                    const size_t s1 = ((size_t)(r0 + i) * Wp + (c0 + j)) * 3;
+                    const size_t s2 = ((size_t)(r0 + Xb + i) * Wp + (c0 + Yb + j)) * 3;
+                    const size_t t = ((size_t)(r0 + TXb + i) * Wp + (c0 + TYb + j)) * 3;
+                    for (int ch = 0; ch < 3; ++ch) {
+                        const uint8_t a = P1[s1 + ch], b = P2[s2 + ch];
+                        float av;
+                        if (!occluded) {
+                            const double ta = one_minus * (double)a;
+                            const float tb = dist * (float)b;
+                            const double tc = ta + (double)tb;
+                            av = (float)((double)wk * tc);
+                        } else {
+                            av = wk * (float)a;
+                        }
+                        accum[t + ch] = accum[t + ch] + av;
+                        const int d = (int)a - (int)b;
+                        const float wm = (float)((double)wk * (double)(d < 0 ? -d : d));
+                        wmcd[t + ch] = wmcd[t + ch] + wm;
+                        wsum[t + ch] = wsum[t + ch] + wk;
+                    }
+                }
+            }
+        }
+    }
+    if (rc == 0) {
+        for (size_t p = 0; p < npx; ++p) {                    /* normalisation, :113-122 */
+            const float ws = wsum[p * 3];
+            for (int ch = 0; ch < 3; ++ch) {
+                if (ws <= 0.f) { Fout[p * 3 + ch] = -1.f; Eout[p * 3 + ch] = -1.f; }
+                else { Fout[p * 3 + ch] = accum[p * 3 + ch] / ws; Eout[p * 3 + ch] = wmcd[p * 3 + ch] / ws; }
+            }
+        }
+    }
+    free(accum); free(wmcd); free(wsum); free(P1); free(P2);
+    return rc;
+}
+
+/* Error_adaptive_combination, MCI/Bidirectional_2.py:147-166.  alpha = 1 is an int64 literal, so
+ * (E + alpha) and the whole quotient are float64 (float32 array + int64 -> float64); Ef + Eb is a
+ * float32 sum first.  The result is rounded to float32 on the store into Fc. */
+ORC_API void orc_eac(const float *Ff, const float *Ef, const float *Fb, const float *Eb, size_t npx, float *Fc)
+{
+    for (size_t p = 0; p < npx; ++p) {
+        const int hf = Ff[p * 3] != -1.f, hb = Fb[p * 3] != -1.f;
+        for (int ch = 0; ch < 3; ++ch) {
+            const size_t k = p * 3 + ch;
+            if (hf && hb) {
+                const double num = ((double)Eb[k] + 1.0) * (double)Ff[k] + ((double)Ef[k] + 1.0) * (double)Fb[k];
+                const float es = Ef[k] + Eb[k];
+                Fc[k] = (float)(num / ((double)es + 2.0));
+            } else if (hf) Fc[k] = Ff[k];
+            else if (hb) Fc[k] = Fb[k];
+            else Fc[k] = -1.f;
+        }
+    }
+}
+
+/* fill_holes, MCI/Bidirectional_2.py:168-262, on one n x n block (row pitch `pitch` floats of 3 channels).
+ *   - ah/av/ad/ar: float32 running sums started at 0.1 in (i, j) raster order over i, j < n-1; the
+ *     counter of the anti-diagonal direction is never incremented (:193-194), so ar is divided by 0.1;
+ *   - p_array = np.full((4,3), -1) is an INT64 array: every directional estimate is truncated toward
+ *     zero when it is stored (:236-244); distances are float64 hypot;
+ *   - `A += 1 / a` and `pixel_interp += p / a` are in-place adds on float32 arrays: numba rounds the
+ *     right-hand side to float32 first and adds in float32 (probed: adding in float64 is 1 ulp off in
+ *     ~95 % of the blocks). */
+static void fill_holes_block(const float *blk, int pitch, int n, float *out, int opitch)
+{
+    float a[4][4];
+    for (int d = 0; d < 4; ++d) for (int k = 0; k < 4; ++k) a[d][k] = 0.1f;
+    for (int i = 0; i < n - 1; ++i) {
+        for (int j = 0; j < n - 1; ++j) {
+            const float *pi = blk + ((size_t)i * pitch + j) * 3;
+            if (pi[0] == -1.f) continue;
+            const float *q;
+            q = blk + ((size_t)(i + 1) * pitch + j) * 3;
+            if (q[0] != -1.f) { for (int k = 0; k < 3; ++k) a[0][k] = a[0][k] + fabsf(pi[k] - q[k]); a[0][3] = a[0][3] + 1.f; }
+            q = blk + ((size_t)i * pitch + j + 1) * 3;
+            if (q[0] != -1.f) { for (int k = 0; k < 3; ++k) a[1][k] = a[1][k] + fabsf(pi[k] - q[k]); a[1][3] = a[1][3] + 1.f; }
+            q = blk + ((size_t)(i + 1) * pitch + j + 1) * 3;
+            if (q[0] != -1.f) { for (int k = 0; k < 3; ++k) a[2][k] = a[2][k] + fabsf(pi[k] - q[k]); a[2][3] = a[2][3] + 1.f; }
+            if (i >= 1) {
+                q = blk + ((size_t)(i - 1) * pitch + j + 1) * 3;
+                if (q[0] != -1.f) { for (int k = 0; k < 3; ++k) a[3][k] = a[3][k] + fabsf(pi[k] - q[k]); }
+            }
+        }
+    }
+    float aa[4][3];
+    for (int d = 0; d < 4; ++d) for (int k = 0; k < 3; ++k) aa[d][k] = a[d][k] / a[d][3];
+    static const int dir[4][2] = {{1, 0}, {0, 1}, {1, 1}, {-1, 1}};
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) {
+            float *o = out + ((size_t)i * opitch + j) * 3;
+            const float *self = blk + ((size_t)i * pitch + j) * 3;
+            if (self[0] != -1.f) { o[0] = self[0]; o[1] = self[1]; o[2] = self[2]; continue; }
+            long long parr[4][3];
+            for (int d = 0; d < 4; ++d) {
+                parr[d][0] = parr[d][1] = parr[d][2] = -1;
+                const float *p1 = NULL, *p2 = NULL;
+                double d1 = 0.0, d2 = 0.0;
+                int n1 = i, m1 = j, n2 = i, m2 = j;
+                while (!p1 && n1 >= 0 && n1 < n && m1 >= 0 && m1 < n) {
+                    const float *q = blk + ((size_t)n1 * pitch + m1) * 3;
+                    if (q[0] != -1.f) { p1 = q; d1 = hypot((double)(i - n1), (double)(j - m1)); }
+                    n1 -= dir[d][0]; m1 -= dir[d][1];
+                }
+                while (!p2 && n2 >= 0 && n2 < n && m2 >= 0 && m2 < n) {
+                    const float *q = blk + ((size_t)n2 * pitch + m2) * 3;
+                    if (q[0] != -1.f) { p2 = q; d2 = hypot((double)(i - n2), (double)(j - m2)); }
+                    n2 += dir[d][0]; m2 += dir[d][1];
+                }
+                for (int k = 0; k < 3; ++k) {
+                    if (p1 && p2) parr[d][k] = (long long)(((d2 * (double)p1[k]) + (d1 * (double)p2[k])) / (d1 + d2));
+                    else if (p1) parr[d][k] = (long long)p1[k];
+                    else if (p2) parr[d][k] = (long long)p2[k];
+                }
+            }
+            float A[3] = {0.f, 0.f, 0.f}, pix[3] = {0.f, 0.f, 0.f};
+            for (int d = 0; d < 4; ++d) {
+                if (parr[d][0] == -1) continue;
+                for (int k = 0; k < 3; ++k) {
+                    A[k] = A[k] + 1.f / aa[d][k];
+                    pix[k] = pix[k] + (float)((double)parr[d][k] / (double)aa[d][k]);
+                }
+            }
+            for (int k = 0; k < 3; ++k) o[k] = pix[k] / A[k];
+        }
+    }
+}
+
+/* BDHI + unpad_and_downconvert, MCI/Bidirectional_2.py:265-293: 2*mbs blocks from (pad, pad); a block
+ * with a hole (channel 0 == -1) is replaced by fill_holes(block); then [pad:-pad] as uint8. */
+ORC_API void orc_bdhi_unpad(const float *Fc, int H, int W, int mbs, int pad, uint8_t *out)
+{
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad, fb = 2 * mbs;
+    float *Fo = (float *)malloc((size_t)Hp * Wp * 3 * sizeof(float));
+    memcpy(Fo, Fc, (size_t)Hp * Wp * 3 * sizeof(float));
+    for (int r = pad; r < Hp - pad; r += fb) {
+        for (int c = pad; c < Wp - pad; c += fb) {
+            const int nr = imin(fb, Hp - r), nc = imin(fb, Wp - c);
+            int hole = 0;
+            for (int i = 0; i < nr && !hole; ++i)
+                for (int j = 0; j < nc; ++j)
+                    if (Fc[((size_t)(r + i) * Wp + c + j) * 3] == -1.f) { hole = 1; break; }
+            if (hole && nr == fb && nc == fb)
+                fill_holes_block(Fc + ((size_t)r * Wp + c) * 3, Wp, fb, Fo + ((size_t)r * Wp + c) * 3, Wp);
+        }
+    }
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c)
+            for (int k = 0; k < 3; ++k) {
+                const float v = Fo[((size_t)(r + pad) * Wp + c + pad) * 3 + k];
+                out[((size_t)r * W + c) * 3 + k] = (uint8_t)(int)v;      /* float32 -> uint8 as numba lowers it */
+            }
+    free(Fo);
+}
+
+/* fill_holes on one contiguous n x n x 3 block (test hook for the validation script) */
+ORC_API void orc_fill_holes(const float *blk, int n, float *out) { fill_holes_block(blk, n, n, out, n); }

@@ -49,6 +49,10 @@ def lib():
         L.orc_smooth_dense.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p]
         L.orc_mci_unidir.argtypes = [_u8p, _u8p, _f32p, C.c_float, C.c_int, C.c_int, _u8p]
         L.orc_mci_bidir.argtypes = [_u8p, _u8p, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _u8p]
+        L.orc_iewmc.argtypes = [_u8p, _u8p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _f32p, _f32p, _f32p]
+        L.orc_eac.argtypes = [_f32p, _f32p, _f32p, _f32p, C.c_size_t, _f32p]
+        L.orc_bdhi_unpad.argtypes = [_f32p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
+        L.orc_fill_holes.argtypes = [_f32p, C.c_int, _f32p]
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
         _lib = L
@@ -183,3 +187,58 @@ def hbma_auto_steps(H, W):
         m /= 2
         s += 1
     return s
+
+
+# ---- bidir2 (MCI/Bidirectional_2.py) -------------------------------------------------------
+def weight_kern(kernlen=8):
+    """get_weight_kern (Bidirectional_2.py:33-47), one channel, float32."""
+    x = np.linspace(1, 1.1, int(kernlen / 2))
+    x = np.append(x, np.flip(x))
+    xx, yy = np.meshgrid(x, x)
+    return np.ascontiguousarray((6 * np.square(5 * (np.log2(xx) + np.log2(yy)))).astype(np.float32))
+
+
+def iewmc(mv_field, F1, F2, dist, pad_size=16, min_block_size=4, upscale_mv=True):
+    """IEWMC (Bidirectional_2.py:130-144) -> (F, E) float32 [H+2p][W+2p][3]."""
+    F1 = _frame(F1); F2 = _frame(F2)
+    H, W = F1.shape[:2]
+    mv = np.ascontiguousarray(mv_field, np.float32)
+    w = weight_kern(2 * min_block_size)
+    F = np.empty((H + 2 * pad_size, W + 2 * pad_size, 3), np.float32)
+    E = np.empty_like(F)
+    rc = lib().orc_iewmc(F1, F2, mv, int(bool(upscale_mv)), H, W, int(min_block_size), int(pad_size),
+                         C.c_float(np.float32(dist)), w, F, E)
+    _chk(rc, "orc_iewmc")
+    return F, E
+
+
+def eac(Ff, Ef, Fb, Eb):
+    """Error_adaptive_combination (Bidirectional_2.py:147-166)."""
+    a = [np.ascontiguousarray(x, np.float32) for x in (Ff, Ef, Fb, Eb)]
+    Fc = np.empty_like(a[0])
+    lib().orc_eac(a[0], a[1], a[2], a[3], a[0].shape[0] * a[0].shape[1], Fc)
+    return Fc
+
+
+def bdhi_unpad(Fc, min_block_size=4, pad_size=16):
+    """BDHI + unpad_and_downconvert (Bidirectional_2.py:265-293) -> uint8 [H][W][3]."""
+    Fc = np.ascontiguousarray(Fc, np.float32)
+    H, W = Fc.shape[0] - 2 * pad_size, Fc.shape[1] - 2 * pad_size
+    out = np.empty((H, W, 3), np.uint8)
+    lib().orc_bdhi_unpad(Fc, H, W, int(min_block_size), int(pad_size), out)
+    return out
+
+
+def bidir2_frame(src, tgt, fwd, bwd, dist, upscale_mv, pad_size=16, min_block_size=4):
+    """BiDir2Interpolator.get_interpolated_frame after ME (Bidirectional_2.py:330-345); dist is the python float."""
+    Ff, Ef = iewmc(fwd, src, tgt, dist, pad_size, min_block_size, upscale_mv)
+    Fb, Eb = iewmc(bwd, tgt, src, 1 - dist, pad_size, min_block_size, upscale_mv)
+    return bdhi_unpad(eac(Ff, Ef, Fb, Eb), min_block_size, pad_size)
+
+
+def fill_holes(block):
+    """fill_holes (Bidirectional_2.py:168-262) on one n x n x 3 float32 block."""
+    b = np.ascontiguousarray(block, np.float32)
+    out = np.empty_like(b)
+    lib().orc_fill_holes(b, b.shape[0], out)
+    return out

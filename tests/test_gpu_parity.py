@@ -383,3 +383,44 @@ def test_tss_vs_golden_and_oracle(gpu, golden, oracle):
         for i, want in enumerate(g[f"e2e/set{si}/out"]):
             assert np.array_equal(np.asarray(it.get_interpolated_frame(i)), want), (st, i)
         it.close()
+
+
+# ---------------------------------------------------------------- bidir2 (MCI/Bidirectional_2.py)
+def test_bidir2_vs_golden_and_oracle(gpu, golden, oracle):
+    """IEWMC + EAC + BDHI + unpad on the GPU: function level against the reference's frames (fs and hbma
+    vectors, three dists), whole clips through the class API (hbma / fs / tss), and against the oracle on
+    larger fresh inputs (odd sizes: the hole-fill blocks then reach into the padding)."""
+    import ast
+    from interpolatory_b200 import MEMCI, ArrayVideoStream
+    from interpolatory_b200.MCI.Bidirectional_2 import interpolate, get_weight_kern
+    g = golden("bidir2_small.npz")
+    assert np.array_equal(get_weight_kern(8), g["weight_kern"])
+    for (H, W) in SHAPES:
+        fr = make_sequence(H, W, 2, seed=H + 1000)
+        k = f"{H}x{W}"
+        for me in ("fs", "hbma"):
+            fwd, bwd = g[f"{k}/{me}/fwd"], g[f"{k}/{me}/bwd"]
+            up = me == "fs"
+            if up:
+                fwd = np.repeat(np.repeat(fwd, 8, axis=0), 8, axis=1)[:H, :W]
+                bwd = np.repeat(np.repeat(bwd, 8, axis=0), 8, axis=1)[:H, :W]
+            for di, dist in enumerate((0.5, 0.39999998, 0.8)):
+                out = interpolate(fr[0], fr[1], fwd, bwd, dist, 16, 4, up)
+                assert np.array_equal(out, g[f"{k}/{me}/out{di}"]), (k, me, dist)
+    frames = make_sequence(72, 96, 3, seed=2272)
+    for si in range(4):
+        st = dict(ast.literal_eval(str(g[f"e2e/set{si}/settings"])))
+        it = MEMCI(60, **st)
+        it.set_video_stream(ArrayVideoStream(list(frames), 24))
+        for i, want in enumerate(g[f"e2e/set{si}/out"]):
+            assert np.array_equal(np.asarray(it.get_interpolated_frame(i)), want), (st, i)
+        it.close()
+    # fresh, larger inputs against the oracle (class API for the vectors, oracle for the MCI half)
+    for (H, W, me) in ((270, 483, 'fs'), (360, 640, 'hbma'), (203, 301, 'tss')):
+        fr = make_sequence(H, W, 2, seed=H)
+        it = MEMCI(60, mci_mode='bidir2', me_mode=me)
+        it.set_video_stream(ArrayVideoStream(list(fr), 30))
+        out = np.asarray(it.get_interpolated_frame(1))
+        fwd, bwd = it.fwr_MV_field_dense, it.bwr_MV_field_dense
+        assert np.array_equal(out, oracle.bidir2_frame(fr[0], fr[1], fwd, bwd, 0.5, True)), (H, W, me)
+        it.close()

@@ -69,8 +69,10 @@ def test_factory():
     assert InterpolatorDictionary['MEMCI'] is MEMCI
     with pytest.raises(Exception, match='Unknown mci_mode'):
         MEMCI(60, mci_mode='sideways')
-    with pytest.raises(NotImplementedError):
-        MEMCI(60, mci_mode='bidir2')
+    from interpolatory_b200.MCI.Bidirectional_2 import BiDir2Interpolator
+    b2 = MEMCI(60, mci_mode='bidir2', filter_mode='median')
+    assert isinstance(b2, BiDir2Interpolator) and str(b2) == 'Uni_2' and b2.filter_mode is None      # bidir2 forces no smoothing
+    assert b2.upscale_MV is False and b2.ME_args["upscale"] is False and b2.pad_size == 16            # hbma: block-level vectors
     it = MEMCI(60, me_mode='tss', target_region='9')
     assert it.region == it.steps == 3 and it.ME_args == {"block_size": 8, "steps": 3}      # tss forces region = steps
 

@@ -181,3 +181,36 @@ def test_tss(oracle, golden):
         fr = make_sequence(H, W, 2, seed=H)
         for bs, steps in ((8, 3), (8, 1), (4, 2), (16, 4), (8, 5)):
             assert np.array_equal(oracle.tss_blocks(bs, steps, fr[0], fr[1]), g[f"{H}x{W}/tss/{bs}_{steps}"]), (H, W, bs, steps)
+
+
+# ---------------------------------------------------------------- bidir2 (MCI/Bidirectional_2.py)
+def _b2_fields(g, k, me):
+    """MV fields as the reference indexes them: dense (fs: stored on 8x8 blocks) or block level (hbma)."""
+    fwd, bwd = g[f"{k}/{me}/fwd"], g[f"{k}/{me}/bwd"]
+    if me == "fs":
+        H, W = map(int, k.split("x"))
+        fwd = np.repeat(np.repeat(fwd, 8, axis=0), 8, axis=1)[:H, :W]
+        bwd = np.repeat(np.repeat(bwd, 8, axis=0), 8, axis=1)[:H, :W]
+    return np.ascontiguousarray(fwd), np.ascontiguousarray(bwd), me == "fs"
+
+
+def test_bidir2(oracle, golden):
+    """IEWMC, Error_adaptive_combination, fill_holes / BDHI and the final uint8 frame against the reference."""
+    g = golden("bidir2_small.npz")
+    assert np.array_equal(oracle.weight_kern(8), g["weight_kern"])
+    for (H, W) in SHAPES:
+        fr = make_sequence(H, W, 2, seed=H + 1000)
+        k = f"{H}x{W}"
+        for me in ("fs", "hbma"):
+            fwd, bwd, up = _b2_fields(g, k, me)
+            for di, dist in enumerate((0.5, 0.39999998, 0.8)):
+                out = oracle.bidir2_frame(fr[0], fr[1], fwd, bwd, dist, up)
+                assert np.array_equal(out, g[f"{k}/{me}/out{di}"]), (k, me, dist)
+            if H == 37:
+                Ff, Ef = oracle.iewmc(fwd, fr[0], fr[1], 0.5, 16, 4, up)
+                Fb, Eb = oracle.iewmc(bwd, fr[1], fr[0], 1 - 0.5, 16, 4, up)
+                assert np.array_equal(Ff, g[f"{k}/{me}/Ff"]) and np.array_equal(Ef, g[f"{k}/{me}/Ef"])
+                assert np.array_equal(oracle.eac(Ff, Ef, Fb, Eb), g[f"{k}/{me}/Fc"])
+    blocks, want = g["fill_holes/in"], g["fill_holes/out"]
+    for b, w in zip(blocks, want):
+        assert np.array_equal(oracle.fill_holes(b), w, equal_nan=True)
