@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libmemci_b200.so")
+LIB_PATH = os.environ.get("MEMCI_B200_LIB") or os.path.join(_HERE, "_lib", "libmemci_b200.so")   # env override: A/B builds while tuning
 _lib = None
 
 

@@ -351,11 +351,11 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                 const FsParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full[2];
-    __shared__ __align__(8) uint64_t done[2];
-    __shared__ FsTileTab tabs[2];
-    __shared__ unsigned long long best_fast[2][FS_NBMAX];
-    __shared__ unsigned best_low[2][FS_NBMAX];
+    __shared__ __align__(8) uint64_t full[3];
+    __shared__ __align__(8) uint64_t done[3];
+    __shared__ FsTileTab tabs[3];
+    __shared__ unsigned long long best_fast[3][FS_NBMAX];
+    __shared__ unsigned best_low[3][FS_NBMAX];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int stage_ints = (p.box_h + p.bs) * FS_BOXW;
@@ -366,13 +366,10 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
     const unsigned mulg = (1u << GB) << p.ks;
 
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
-        mbar_init(&done[0], FS_NT / 32);
-        mbar_init(&done[1], FS_NT / 32);
+        for (int i = 0; i < 3; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], FS_NT / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 2 * FS_NBMAX) {
+    if (tid < 3 * FS_NBMAX) {
         (&best_fast[0][0])[tid] = KEY_NONE;
         (&best_low[0][0])[tid] = 0xffffffffu;
     }
@@ -381,11 +378,17 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
     const int first = blockIdx.x, stride = gridDim.x;
     if (first >= p.n_tiles) return;
 
-    auto issue = [&](int tile_idx, int k) {        // warp 0 only: tile table + two TMA tile loads
+    // Ring indices: tile k lives in data stage k % NS and in table / result buffer k % NB.
+    //   NS == 3 (the 8x8 +-16 case: 3 x 48 KB): warp 0 does its housekeeping AFTER its own share of tile k --
+    //     by then done[k-1] completed long ago, so it never spins -- writes tile k-1's vectors and issues the
+    //     TMA for tile k+2 into the stage tile k-1 just vacated.  Two tiles are always in flight or landed.
+    //   NS == 2: warp 0 waits for done[k-1] BEFORE tile k (it needs that stage for tile k+1).
+    //   NS == 1: load, search, output, strictly in turn.
+    const int NS = p.n_stages, NB = NS == 3 ? 3 : 2;
+    auto issue = [&](int tile_idx, int s, int j) {        // warp 0 only: tile table + two TMA tile loads
         const int dir = tile_idx >= p.n_tiles_dir ? 1 : 0;
         FsTile t = p.tiles[tile_idx - dir * p.n_tiles_dir];
-        int s = p.n_stages == 2 ? (k & 1) : 0;
-        fs_fill_tab(&tabs[k & 1], t, p, lane, dir);
+        fs_fill_tab(&tabs[j], t, p, lane, dir);
         __syncwarp();
         if (lane == 0) {
             int *win = stage0 + (size_t)s * stage_ints;
@@ -396,14 +399,14 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
         }
     };
 
-    // warp 0, lanes < nb: motion vectors of tile k out, result buffers re-armed, redo list fed
-    auto output = [&](int k) {
-        const FsTileTab *tab = &tabs[k & 1];
+    // warp 0, lanes < nb: motion vectors of the tile in buffer j out, result buffers re-armed, redo list fed
+    auto output = [&](int j) {
+        const FsTileTab *tab = &tabs[j];
         if (lane < tab->nb) {
-            const unsigned long long kb = best_fast[k & 1][lane];
-            const unsigned kl = best_low[k & 1][lane];
-            best_fast[k & 1][lane] = KEY_NONE;
-            best_low[k & 1][lane] = 0xffffffffu;
+            const unsigned long long kb = best_fast[j][lane];
+            const unsigned kl = best_low[j][lane];
+            best_fast[j][lane] = KEY_NONE;
+            best_low[j][lane] = 0xffffffffu;
             const int bc = tab->bx0 + lane;
             const int blk = tab->by * p.nbc + bc;
             const int s_row = tab->s_row, s_col = bc * p.bs;
@@ -427,25 +430,30 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
         __syncwarp();
     };
 
-    if (warp == 0) issue(first, 0);
+    if (warp == 0) {
+        issue(first, 0, 0);
+        if (NS == 3 && first + stride < p.n_tiles) issue(first + stride, 1, 1);
+    }
 
     int k = 0;
-    unsigned full_phase[2] = {0u, 0u}, done_phase[2] = {0u, 0u};
+    int s = 0, j = 0;                                  // k % NS, k % NB
+    unsigned full_phase[3] = {0u, 0u, 0u}, done_phase[3] = {0u, 0u, 0u};
     for (int tile_idx = first; tile_idx < p.n_tiles; tile_idx += stride, ++k) {
-        const int s = p.n_stages == 2 ? (k & 1) : 0;
         const int next = tile_idx + stride;
-        if (warp == 0 && p.n_stages == 2) {
+        const int jp = j == 0 ? NB - 1 : j - 1;        // buffer of tile k-1
+        const int jn = j + 1 == NB ? 0 : j + 1;        // buffer of tile k+1
+        if (warp == 0 && NS == 2) {
             if (k >= 1) {
-                mbar_wait(&done[(k - 1) & 1], done_phase[(k - 1) & 1]);
-                done_phase[(k - 1) & 1] ^= 1u;
-                output(k - 1);
+                mbar_wait(&done[jp], done_phase[jp]);
+                done_phase[jp] ^= 1u;
+                output(jp);
             }
-            if (next < p.n_tiles) issue(next, k + 1);     // streams in while this tile is searched
+            if (next < p.n_tiles) issue(next, s ^ 1, jn);     // streams in while this tile is searched
         }
 
         mbar_wait(&full[s], full_phase[s]);
         full_phase[s] ^= 1u;
-        const FsTileTab *tab = &tabs[k & 1];
+        const FsTileTab *tab = &tabs[j];
         const int *win = stage0 + (size_t)s * stage_ints;
         const int *ref = win + p.box_h * FS_BOXW;
         const int nb = tab->nb, n_items = tab->total_dx, n_dy = tab->n_dy, ndx0 = tab->uniform_ndx;
@@ -545,25 +553,37 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                 const unsigned kl_b = __reduce_min_sync(0xffffffffu, mine ? klow : 0xffffffffu);
                 if (lane == leader) {
                     const unsigned long long kw = ((unsigned long long)mh << 32) | ml;
-                    if (kw != KEY_NONE) atomicMin(&best_fast[k & 1][bb], kw);
-                    if (kl_b != 0xffffffffu) atomicMin(&best_low[k & 1][bb], kl_b >> GB);
+                    if (kw != KEY_NONE) atomicMin(&best_fast[j][bb], kw);
+                    if (kl_b != 0xffffffffu) atomicMin(&best_low[j][bb], kl_b >> GB);
                 }
                 todo &= ~__ballot_sync(0xffffffffu, mine);
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&done[k & 1]);
+        if (lane == 0) mbar_arrive(&done[j]);
 
-        if (warp == 0 && p.n_stages == 1) {
-            mbar_wait(&done[k & 1], done_phase[k & 1]);
-            done_phase[k & 1] ^= 1u;
-            output(k);
-            if (next < p.n_tiles) issue(next, k + 1);
+        if (warp == 0 && NS == 1) {
+            mbar_wait(&done[j], done_phase[j]);
+            done_phase[j] ^= 1u;
+            output(j);
+            if (next < p.n_tiles) issue(next, 0, jn);
         }
+        if (warp == 0 && NS == 3) {
+            if (k >= 1) {
+                mbar_wait(&done[jp], done_phase[jp]);     // completed about one tile ago: no spin
+                done_phase[jp] ^= 1u;
+                output(jp);
+            }
+            // tile k+2 goes where tile k-1 was (stage and buffer (k+2) % 3 == (k-1) % 3)
+            if (next + stride < p.n_tiles) issue(next + stride, jp, jp);
+        }
+        s = s + 1 == NS ? 0 : s + 1;
+        j = jn;
     }
-    if (warp == 0 && p.n_stages == 2 && k >= 1) {
-        mbar_wait(&done[(k - 1) & 1], done_phase[(k - 1) & 1]);
-        output(k - 1);
+    if (warp == 0 && NS >= 2 && k >= 1) {
+        const int jl = j == 0 ? NB - 1 : j - 1;          // buffer of the last tile
+        mbar_wait(&done[jl], done_phase[jl]);
+        output(jl);
     }
 }
 
@@ -762,7 +782,8 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         p.one = 1u;
         p.n_tiles_dir = pl->row_tile_start[br1] - pl->row_tile_start[br0]; p.n_tiles = ndir * p.n_tiles_dir; p.box_h = pl->box_h;
         { int ks = 1; while ((1 << ks) <= 2 * R * R + 1) ++ks; p.ks = ks; }
-        p.n_stages = fs_smem_bytes(bs, pl->box_h, 2, pl->G) <= 220 * 1024 ? 2 : 1;
+        p.n_stages = fs_smem_bytes(bs, pl->box_h, 3, pl->G) <= 200 * 1024 ? 3 : fs_smem_bytes(bs, pl->box_h, 2, pl->G) <= 220 * 1024 ? 2 : 1;
+        if (const char *e = getenv("MEMCI_FS_STAGES")) { int v = atoi(e); if (v >= 1 && v < p.n_stages) p.n_stages = v; }   // tuning override
         p.tiles = pl->d_tiles + pl->row_tile_start[br0];
         p.out_vec[0] = out->vec; p.out_sad[0] = out->sad;
         p.out_vec[1] = out2 ? out2->vec : out->vec; p.out_sad[1] = out2 ? out2->sad : out->sad;

@@ -24,12 +24,21 @@ __global__ void __launch_bounds__(512) ub_kernel(int iters, const int *__restric
     __shared__ int ub_sm[2048];
     unsigned extra = 0, e0 = threadIdx.x, e1 = threadIdx.x * 3u, e2 = 7u, e3 = 11u;
     float f0 = (float)threadIdx.x, f1 = 1.5f;
-    if (MODE == 4) { for (int i = threadIdx.x; i < 2048; i += blockDim.x) ub_sm[i] = seed[i & 63]; __syncthreads(); }
+    if (MODE == 4 || MODE >= 10) { for (int i = threadIdx.x; i < 2048; i += blockDim.x) ub_sm[i] = seed[i & 63]; __syncthreads(); }
 #pragma unroll 4
     for (int it = 0; it < iters; ++it) {
-        if (MODE == 4) {
-            e0 += (unsigned)ub_sm[(threadIdx.x + it) & 2047];
-            e1 += (unsigned)ub_sm[(threadIdx.x + 2 * it + 512) & 2047];
+        if (MODE == 4) {          // 2 LDS.32 with immediate offsets (no address arithmetic), results consumed by the SAD stream
+            const int *bp = ub_sm + threadIdx.x;
+            r[0] = bp[(it & 3) * 32];
+            r[1] = bp[512 + (it & 3) * 32];
+        }
+        if (MODE == 10) {         // 1 LDS.128
+            const int4 v4 = *reinterpret_cast<const int4 *>(ub_sm + (threadIdx.x & 127) * 4 + (it & 3) * 512);
+            r[0] = v4.x + (it & 3); r[1] = v4.y; r[2] = v4.z; r[3] = v4.w;
+        }
+        if (MODE == 11) {         // 4 LDS.32
+            const int *bp = ub_sm + threadIdx.x;
+            r[0] = bp[(it & 3) * 32]; r[1] = bp[512 + (it & 3) * 32]; r[2] = bp[1024 + (it & 3) * 32]; r[3] = bp[1536 - 512 + (it & 3) * 32 + 128];
         }
         if (MODE == 5) {
             asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(e0) : "r"(e2), "r"(e3));
@@ -48,7 +57,7 @@ __global__ void __launch_bounds__(512) ub_kernel(int iters, const int *__restric
             asm volatile("min.u32 %0, %0, %1;" : "+r"(e0) : "r"(e2 + it));
             asm volatile("min.u32 %0, %0, %1;" : "+r"(e1) : "r"(e3 + it));
         }
-        if (MODE == 0 || MODE >= 2) {   // the SAD stream
+        if (MODE == 0 || MODE >= 2) {   // the SAD stream (modes 4, 10, 11 refresh part of r[] from shared memory)
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[j] = __sad(r[j], (int)a[(j + 1) & 7], a[j]);
         }
@@ -71,7 +80,7 @@ __global__ void __launch_bounds__(512) ub_kernel(int iters, const int *__restric
 
 extern "C" MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, float *ms, double *px_ops)
 {
-    if (!ctx || mode < 0 || mode > 9 || iters <= 0) return MEMCI_ERR_ARG;
+    if (!ctx || mode < 0 || mode > 11 || iters <= 0) return MEMCI_ERR_ARG;
     cudaSetDevice(ctx->device);
     const int grid = ctx->num_sms * 4, nt = 512;
     int *d_seed = nullptr;
@@ -95,7 +104,9 @@ extern "C" MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, f
         case 6: ub_kernel<6><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
         case 7: ub_kernel<7><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
         case 8: ub_kernel<8><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
-        default: ub_kernel<9><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        case 9: ub_kernel<9><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        case 10: ub_kernel<10><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        default: ub_kernel<11><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
         }
         ctx->launches++;
     }

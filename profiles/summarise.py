@@ -1,6 +1,7 @@
 """Turn gpurun_out/{launches.csv,prof_*.ncu-rep} into small text summaries under profiles/."""
 import collections, csv, subprocess, sys, os
 tag = sys.argv[1]
+assert tag.startswith("r") and tag[1:].isdigit(), "usage: python profiles/summarise.py rNN"
 out = open(f"profiles/{tag}_summary.md", "w")
 def w(s=""):
     out.write(s + "\n")
@@ -12,6 +13,7 @@ w()
 w("## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`) -- cold-cache, serialised: compare SHARES")
 w()
 lines = [l for l in open("gpurun_out/launches.csv") if l.startswith('"')]
+open(f"profiles/{tag}_launches.csv", "w").writelines(lines)
 agg = collections.defaultdict(lambda: [0, 0.0])
 for row in csv.DictReader(lines):
     name = row['Kernel Name'].split('(')[0].replace('void ', '')
@@ -35,7 +37,9 @@ want = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__warps_eligible.avg.per_cycle_active',
+        'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
         'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
@@ -43,7 +47,7 @@ want = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_
         'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_sector_hit_rate.pct']
-for rep, title in (("prof_fs", "fs_tiled_kernel (dominant kernel)"), ("prof_mci", "mci_splat_kernel")):
+for rep, title in (("prof_fs", "fs_tiled_kernel (dominant kernel)"), ("prof_mci", "mci_splat_kernel"), ("prof_hf", "mci_holefill_kernel")):
     path = f"gpurun_out/{rep}.ncu-rep"
     if not os.path.exists(path):
         continue
