@@ -42,12 +42,17 @@ WORKLOADS = {
                               filter_mode='median', filter_size='4'), 24, 120, 16),
     "cfg4": (2160, 3840, dict(me_mode='fs', block_size='16', target_region='32', mci_mode='bidir'), 30, 60, 4),
     "cfg5": (4320, 7680, dict(me_mode='fs', block_size='16', target_region='32', mci_mode='bidir'), 30, 60, 1),
+    # not a BASELINE.json config: the third mci_mode on the cfg2 / cfg3 motion estimators
+    "cfg2_bidir2": (1080, 1920, dict(me_mode='fs', block_size='8', target_region='16', mci_mode='bidir2'), 30, 60, 16),
+    "cfg3_bidir2": (1080, 1920, dict(me_mode='hbma', block_size='8', target_region='7', mci_mode='bidir2'), 24, 120, 16),
 }
 WORKLOAD_TEXT = {
     "cfg2": "cfg2: 1080p full-search 8x8 blocks +-16, 30->60 fps, bidir MCI, synthetic frames",
     "cfg1": "cfg1: 640x360 full-search 8x8 +-7, 24->60 fps, bidir MCI, synthetic frames",
     "cfg3": "cfg3: 1080p HBMA (auto 4-level pyramid via class rule) + median MV smoothing, 24->120 fps, bidir MCI",
     "cfg4": "cfg4: 4K full-search 16x16 +-32, 30->60 fps, bidir MCI, synthetic frames",
+    "cfg2_bidir2": "cfg2 motion estimation (1080p full-search 8x8 +-16, 30->60 fps) with bidir2 MCI (IEWMC + EAC + BDHI)",
+    "cfg3_bidir2": "cfg3 motion estimation (1080p HBMA, auto 4-level pyramid, block-level vectors) with bidir2 MCI, 24->120 fps",
     "cfg5": "cfg5: 8K (7680x4320) single frame pair, full-search 16x16 +-32, bidir MCI, split into one horizontal band per GPU "
             "with frame-row + MV-row halo exchange (NCCL send/recv)",
 }
@@ -331,6 +336,11 @@ def main():
     ctx = DeviceContext(H, W, device=local_rank, stream=stream.cuda_stream)
     base_ptr = dev_frames.data_ptr()
 
+    bidir2 = st.get('mci_mode') == 'bidir2'
+    if bidir2:
+        from interpolatory_b200.MCI.Bidirectional_2 import get_weight_kern
+        b2_w = get_weight_kern(8)
+
     def step_resident():
         for k in range(P):
             a, b = k % 3, (k + 1) % 3
@@ -339,7 +349,10 @@ def main():
             ctx.set_frame_device(b, base_ptr + (k + 1) * frame_bytes)
             ctx.estimate_pair(params, a, b, 0, 1)
             for j, d in enumerate(dists):
-                ctx.mci_bidir(a, b, 0, 1, d, 6 + (j & 1))
+                if bidir2:
+                    ctx.mci_bidir2(a, b, 0, 1, d, np.float32(1 - float(d)), b2_w, 6 + (j & 1))
+                else:
+                    ctx.mci_bidir(a, b, 0, 1, d, 6 + (j & 1))
 
     def barrier():
         if world > 1:

@@ -70,42 +70,39 @@ __global__ void b2_blocks_kernel(const float2 *__restrict__ vec, int mv_cell, in
 __device__ __forceinline__ int floor_div4(int a) { return a >> 2; }        // arithmetic shift = floor for negatives
 
 // ---- fill_holes on one 8x8 block in shared memory (:168-262) -----------------------------------------
-// a_array: the four directional mean absolute differences, float32 running sums in raster order
-__device__ void b2_direction_stats(const float (*fc)[B2_TW][3], int c0, float (*aa)[3])
+// a_array: the four directional mean absolute differences.  The reference accumulates them as float32
+// running sums in (i, j) raster order; the 16 chains (4 directions x {3 channels, count}) are independent,
+// so 16 threads of the block's first two rows each run ONE chain in that order.  sums[d][k] then holds the
+// raw sum (k < 3) or the count (k == 3); the quotient is taken by the reader.
+__device__ void b2_direction_chain(const float (*fc)[B2_TW][3], int c0, int d, int k, float *sum_out)
 {
-    float a[4][4];
-#pragma unroll
-    for (int d = 0; d < 4; ++d)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) a[d][k] = 0.1f;
+    const int di = d == 3 ? -1 : (d == 1 ? 0 : 1), dj = d == 0 ? 0 : 1;      // (1,0) (0,1) (1,1) (-1,1)
+    float a = 0.1f;
     for (int i = 0; i < B2_EB - 1; ++i) {
+        if (d == 3 && i < 1) continue;                                      // (i-1 > -1), :192
         for (int j = 0; j < B2_EB - 1; ++j) {
             const float *pi = fc[i][c0 + j];
             if (pi[0] == -1.f) continue;
-            const float *q = fc[i + 1][c0 + j];
-            if (q[0] != -1.f) { for (int k = 0; k < 3; ++k) a[0][k] = __fadd_rn(a[0][k], fabsf(__fsub_rn(pi[k], q[k]))); a[0][3] = __fadd_rn(a[0][3], 1.f); }
-            q = fc[i][c0 + j + 1];
-            if (q[0] != -1.f) { for (int k = 0; k < 3; ++k) a[1][k] = __fadd_rn(a[1][k], fabsf(__fsub_rn(pi[k], q[k]))); a[1][3] = __fadd_rn(a[1][3], 1.f); }
-            q = fc[i + 1][c0 + j + 1];
-            if (q[0] != -1.f) { for (int k = 0; k < 3; ++k) a[2][k] = __fadd_rn(a[2][k], fabsf(__fsub_rn(pi[k], q[k]))); a[2][3] = __fadd_rn(a[2][3], 1.f); }
-            if (i >= 1) {
-                q = fc[i - 1][c0 + j + 1];
-                if (q[0] != -1.f) { for (int k = 0; k < 3; ++k) a[3][k] = __fadd_rn(a[3][k], fabsf(__fsub_rn(pi[k], q[k]))); }   // counter never incremented (:193-194)
-            }
+            const float *q = fc[i + di][c0 + j + dj];
+            if (q[0] == -1.f) continue;
+            if (k < 3) a = __fadd_rn(a, fabsf(__fsub_rn(pi[k], q[k])));
+            else if (d != 3) a = __fadd_rn(a, 1.f);                          // the anti-diagonal counter is never incremented (:193-194)
         }
     }
-#pragma unroll
-    for (int d = 0; d < 4; ++d)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) aa[d][k] = __fdiv_rn(a[d][k], a[d][3]);
+    *sum_out = a;
 }
 
 // one undetermined pixel (i, j) of the block starting at column c0: four directional estimates, truncated
 // to int64 by the reference's int array (:236-244), combined with weights 1 / a (:246-256)
-__device__ void b2_fill_pixel(const float (*fc)[B2_TW][3], int c0, const float (*aa)[3], int i, int j, float *res)
+__device__ void b2_fill_pixel(const float (*fc)[B2_TW][3], int c0, const float (*sums)[4], int i, int j, float *res)
 {
     const int dir[4][2] = {{1, 0}, {0, 1}, {1, 1}, {-1, 1}};
     float A[3] = {0.f, 0.f, 0.f}, pix[3] = {0.f, 0.f, 0.f};
+    float aa[4][3];
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) aa[d][k] = __fdiv_rn(sums[d][k], sums[d][3]);      // ah = ah[0:3] / ah[3]  (:196-199)
     for (int d = 0; d < 4; ++d) {
         const float *p1 = nullptr, *p2 = nullptr;
         double d1 = 0.0, d2 = 0.0;
@@ -133,12 +130,49 @@ __device__ void b2_fill_pixel(const float (*fc)[B2_TW][3], int c0, const float (
     for (int k = 0; k < 3; ++k) res[k] = __fdiv_rn(pix[k], A[k]);
 }
 
+// Contribution of one block to one target pixel (x, y): local offset (i, j) inside the block's 8x8 expanded
+// block, one float32 add per accumulator -- IEWMC_helper :87-108.
+__device__ __forceinline__ void b2_contribute(const B2Params &P, const int4 b, int i, int j, int y, int x,
+                                              const uint8_t *__restrict__ F1, const uint8_t *__restrict__ F2, float dist,
+                                              double one_minus, float (&acc)[3], float (&wm)[3], float &ws)
+{
+    const int H = P.H, W = P.W;
+    const float wk = P.w[i * B2_EB + j];
+    const int sy = y - b.z, sx = x - (b.w >> 1);                 // position inside the (zero-padded) frames
+    const int ty = sy + b.x, tx = sx + b.y;
+    const bool in1 = (unsigned)sy < (unsigned)H && (unsigned)sx < (unsigned)W;
+    const bool in2 = (unsigned)ty < (unsigned)H && (unsigned)tx < (unsigned)W;
+    const uint8_t *p1 = F1 + ((size_t)sy * W + sx) * 3, *p2 = F2 + ((size_t)ty * W + tx) * 3;
+    const bool occluded = b.w & 1;
+    const double wkd = (double)wk;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int a = in1 ? p1[k] : 0, bb = in2 ? p2[k] : 0;
+        float av;
+        if (!occluded) {
+            // (double)a without the conversion unit: 2^52 + a has a's bits in its low mantissa word
+            const double ad = __dsub_rn(__hiloint2double(0x43300000, a), 4503599627370496.0);
+            const double ta = __dmul_rn(one_minus, ad);                        // float64 * uint8
+            const float tb = __fmul_rn(dist, (float)bb);                       // float32 * uint8
+            av = __double2float_rn(__dmul_rn(wkd, __dadd_rn(ta, (double)tb)));
+        } else {
+            av = __fmul_rn(wk, (float)a);                                      // float32 * uint8
+        }
+        acc[k] = __fadd_rn(acc[k], av);
+        // float32(float64(w) * |d|): the float64 product of a 24-bit and an 8-bit number is exact, so the single
+        // rounding to float32 equals the float32 product
+        wm[k] = __fadd_rn(wm[k], __fmul_rn(wk, (float)abs(a - bb)));
+    }
+    ws = __fadd_rn(ws, wk);
+}
+
 __global__ void __launch_bounds__(B2_TW * B2_TH)
 b2_frame_kernel(const __grid_constant__ B2Params P)
 {
     __shared__ int4 sblk[2][B2_MAXB];
+    __shared__ unsigned stl[2][B2_MAXB];          // top row | left column << 16 of each staged block's shifted expanded block (signed 16-bit each)
     __shared__ float fc[B2_TH][B2_TW][3];
-    __shared__ float aa[B2_TW / B2_EB][4][3];
+    __shared__ float dsum[B2_TW / B2_EB][4][4];
     __shared__ int blk_hole[B2_TW / B2_EB];
 
     const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
@@ -156,18 +190,23 @@ b2_frame_kernel(const __grid_constant__ B2Params P)
         for (int i = tid; i < nrb * ncb; i += B2_TW * B2_TH) {
             const int r = i / ncb, c = i - r * ncb;
             const size_t g = (size_t)(br_lo + r) * P.nbc + bc_lo + c;
-            sblk[0][i] = P.blk[0][g];
-            sblk[1][i] = P.blk[1][g];
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const int4 b = P.blk[d][g];
+                sblk[d][i] = b;
+                stl[d][i] = (unsigned)((4 * (br_lo + r) - 2 + b.z) & 0xffff) | ((unsigned)(4 * (bc_lo + c) - 2 + (b.w >> 1)) << 16);
+            }
         }
     }
     __syncthreads();
 
     const bool in_region = x < P.Wr;            // y < Hr always (grid)
     float out_c[3] = {-1.f, -1.f, -1.f};
-    if (in_region && nrb > 0 && ncb > 0) {
+    // warp-uniform row range (y is the same for the whole warp; x differs)
+    const int brp_lo_w = max(br_lo, floor_div4(y - 5 - tmax)), brp_hi_w = min(br_hi, floor_div4(y + 2 + tmax));
+    if (nrb > 0 && ncb > 0) {
         float Fd[2][3], Ed[2][3];
         bool has[2];
-        const int brp_lo = max(br_lo, floor_div4(y - 5 - tmax)), brp_hi = min(br_hi, floor_div4(y + 2 + tmax));
         const int bcp_lo = max(bc_lo, floor_div4(x - 5 - tmax)), bcp_hi = min(bc_hi, floor_div4(x + 2 + tmax));
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
@@ -175,35 +214,30 @@ b2_frame_kernel(const __grid_constant__ B2Params P)
             const float dist = P.dist[d];
             const double one_minus = __dsub_rn(1.0, (double)dist);          // (1 - dist): int64 - float32 -> float64
             float acc[3] = {0.f, 0.f, 0.f}, wm[3] = {0.f, 0.f, 0.f}, ws = 0.f;
-            for (int br = brp_lo; br <= brp_hi; ++br) {                      // block raster order = the reference's accumulation order
-                for (int bc = bcp_lo; bc <= bcp_hi; ++bc) {
-                    const int4 b = staged ? sblk[d][(br - br_lo) * ncb + (bc - bc_lo)] : P.blk[d][(size_t)br * P.nbc + bc];
-                    const int i = y - (4 * br - 2 + b.z);
-                    if ((unsigned)i >= (unsigned)B2_EB) continue;
-                    const int j = x - (4 * bc - 2 + (b.w >> 1));
-                    if ((unsigned)j >= (unsigned)B2_EB) continue;
-                    const float wk = P.w[i * B2_EB + j];
-                    const int sy = 4 * br - 2 + i, sx = 4 * bc - 2 + j;       // position inside the (zero-padded) frames
-                    const int ty = sy + b.x, tx = sx + b.y;
-                    const bool in1 = (unsigned)sy < (unsigned)H && (unsigned)sx < (unsigned)W;
-                    const bool in2 = (unsigned)ty < (unsigned)H && (unsigned)tx < (unsigned)W;
-                    const uint8_t *p1 = F1 + ((size_t)sy * W + sx) * 3, *p2 = F2 + ((size_t)ty * W + tx) * 3;
-                    const bool occluded = b.w & 1;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const int a = in1 ? p1[k] : 0, bb = in2 ? p2[k] : 0;
-                        float av;
-                        if (!occluded) {
-                            const double ta = __dmul_rn(one_minus, (double)a);                 // float64 * uint8
-                            const float tb = __fmul_rn(dist, (float)bb);                       // float32 * uint8
-                            av = __double2float_rn(__dmul_rn((double)wk, __dadd_rn(ta, (double)tb)));
-                        } else {
-                            av = __fmul_rn(wk, (float)a);
+            // Per-lane loops over the blocks that can reach (x, y), in block raster order = the reference's accumulation
+            // order.  Lanes of a warp share y and walk bc ranges shifted with x, so neighbouring lanes test neighbouring
+            // blocks in the same iteration and hit together.  (A warp-compacted list of the blocks passing the row test
+            // was tried: fewer tests, but every entry then hits only 8 of 32 lanes -- 40 % slower.)
+            if (in_region) {
+                if (staged) {
+                    for (int br = brp_lo_w; br <= brp_hi_w; ++br) {
+                        const int row0 = (br - br_lo) * ncb - bc_lo;
+                        for (int bc = bcp_lo; bc <= bcp_hi; ++bc) {
+                            const unsigned tl = stl[d][row0 + bc];
+                            const int i = y - (short)(tl & 0xffffu), j = x - ((int)tl >> 16);
+                            if ((i | j) & ~(B2_EB - 1)) continue;                  // both in [0, 8)
+                            b2_contribute(P, sblk[d][row0 + bc], i, j, y, x, F1, F2, dist, one_minus, acc, wm, ws);
                         }
-                        acc[k] = __fadd_rn(acc[k], av);
-                        wm[k] = __fadd_rn(wm[k], __double2float_rn(__dmul_rn((double)wk, (double)abs(a - bb))));
                     }
-                    ws = __fadd_rn(ws, wk);
+                } else {
+                    for (int br = brp_lo_w; br <= brp_hi_w; ++br) {
+                        for (int bc = bcp_lo; bc <= bcp_hi; ++bc) {
+                            const int4 b = P.blk[d][(size_t)br * P.nbc + bc];
+                            const int i = y - (4 * br - 2 + b.z), j = x - (4 * bc - 2 + (b.w >> 1));
+                            if ((i | j) & ~(B2_EB - 1)) continue;
+                            b2_contribute(P, b, i, j, y, x, F1, F2, dist, one_minus, acc, wm, ws);
+                        }
+                    }
                 }
             }
             has[d] = !(ws <= 0.f);
@@ -232,9 +266,12 @@ b2_frame_kernel(const __grid_constant__ B2Params P)
     __syncthreads();
     // BDHI (:265-286): a block with a hole gets fill_holes(block); statistics by one thread per block
     const int myblk = lx >> 3;
-    if (ly == 0 && (lx & 7) == 0 && blk_hole[myblk] && tx0 + myblk * B2_EB < P.Wr) b2_direction_stats(fc, myblk * B2_EB, aa[myblk]);
+    if (ly < 2 && blk_hole[myblk] && tx0 + myblk * B2_EB < P.Wr) {
+        const int chain = ly * 8 + (lx & 7);                                   // 16 threads per block: chain = direction * 4 + channel
+        b2_direction_chain(fc, myblk * B2_EB, chain >> 2, chain & 3, &dsum[myblk][chain >> 2][chain & 3]);
+    }
     __syncthreads();
-    if (hole) b2_fill_pixel(fc, myblk * B2_EB, aa[myblk], ly, lx & 7, out_c);
+    if (hole) b2_fill_pixel(fc, myblk * B2_EB, dsum[myblk], ly, lx & 7, out_c);
     if (y < H && x < W) {
         uint8_t *o = P.out + ((size_t)y * W + x) * 3;                          // unpad_and_downconvert: astype(uint8)
         o[0] = (uint8_t)__float2int_rz(out_c[0]); o[1] = (uint8_t)__float2int_rz(out_c[1]); o[2] = (uint8_t)__float2int_rz(out_c[2]);

@@ -18,8 +18,8 @@ def pair_params_from_settings(shape, **st):
     if me not in ('fs', 'hbma', 'tss'):
         raise NotImplementedError(f"me_mode {me!r} is not part of the B200 hot path")
     mci = st.get('mci_mode', 'unidir')
-    if mci not in ('unidir', 'bidir'):
-        raise NotImplementedError(f"mci_mode {mci!r} is not part of the B200 hot path")
+    if mci not in ('unidir', 'bidir', 'bidir2'):
+        raise Exception(f'Unknown mci_mode: {mci}')
     p = PairParams()
     p.me_mode = {'fs': 0, 'hbma': 1, 'tss': 2}[me]
     p.block_size = int(st.get('block_size', 8))
@@ -27,9 +27,9 @@ def pair_params_from_settings(shape, **st):
     p.sub_region = 1
     p.steps = hbma_auto_steps(shape) if me == 'hbma' else 3
     p.min_block_size = 4
-    p.filter_mode = FILTER_MODES[st.get('filter_mode', 'none')]
+    p.filter_mode = FILTER_MODES['none' if mci == 'bidir2' else st.get('filter_mode', 'none')]      # no smoothing in bidir2
     p.filter_size = int(st.get('filter_size', 4))
-    p.bidir = 1 if mci == 'bidir' else 0
+    p.bidir = 1 if mci in ('bidir', 'bidir2') else 0
     return p
 
 
@@ -53,6 +53,10 @@ class PairPipeline:
         self.H, self.W = int(H), int(W)
         self.params = pair_params_from_settings((H, W), **settings)
         self.bidir = bool(self.params.bidir)
+        self.bidir2 = settings.get('mci_mode', 'unidir') == 'bidir2'
+        if self.bidir2:
+            from .MCI.Bidirectional_2 import get_weight_kern
+            self._w = get_weight_kern(2 * self.params.min_block_size)
         self.ctxs = [DeviceContext(H, W, device) for _ in range(max(1, int(n_contexts)))]
 
     def close(self):
@@ -94,7 +98,11 @@ class PairPipeline:
                 ctx.estimate_pair(self.params, a, b, 0, 1)
                 for j, d in enumerate(dists):
                     o = 6 + (j & 1)
-                    if self.bidir:
+                    if self.bidir2:
+                        # the class passes the python floats dist and 1 - dist (Bidirectional_2.py:331-332)
+                        ctx.mci_bidir2(a, b, 0, 1, np.float32(d), np.float32(1 - float(d)), self._w, o,
+                                       self.params.min_block_size, 4 * self.params.min_block_size)
+                    elif self.bidir:
                         ctx.mci_bidir(a, b, 0, 1, d, o)
                     else:
                         ctx.mci_unidir(a, b, 0, d, o)

@@ -34,8 +34,11 @@ def make_sequence(H, W, n_frames, seed=0):
     pr, pc, ph, pw = H // 5, W // 2, 24 * s, 32 * s
     strip_w = 24 * s
     base_patch = None
+    period = margin // (3 * s)          # frames until the crop would leave the canvas: the pan then bounces back
     for t in range(n_frames):
-        oy, ox = 2 * t * s, 3 * t * s
+        tt = t % (2 * period)
+        tt = tt if tt <= period else 2 * period - tt
+        oy, ox = 2 * tt * s, 3 * tt * s
         f = canvas[oy:oy + H, ox:ox + W].copy()
         f += rng.normal(0.0, 2.0, size=f.shape).astype(np.float32)
         # (iv) fast strip on the right edge: jumps 40*s px per frame vertically
