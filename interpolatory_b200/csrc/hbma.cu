@@ -8,6 +8,8 @@
 // (float)((double)S1000 / 1000.0) reproduces it unless the value sits within the f64
 // accumulation error of a float32 rounding boundary; those candidates, and every
 // SSD candidate, are replayed in float64 in the reference's operation order.
+#include <stdlib.h>
+
 #include "memci_internal.cuh"
 
 struct BwRes { float r, c, cost; };
@@ -300,6 +302,144 @@ __global__ void hbma_densify_kernel(const int32_t *__restrict__ L1, const int32_
     }
 }
 
+// ---- increase_vec_density, fast path (sub_win == 1, SAD, block size 4 or 8) -------------------------
+// One warp per PARENT block: its four children share the three candidate vectors (parent unscaled,
+// horizontal neighbour, vertical neighbour -- hbma.py:107-115), so the 2BS x 2BS source tile and one
+// (2BS+2)^2 target region per vector are staged once (zero filled outside the frame = np.pad) and the
+// 4 x 3 x 9 = 108 candidates run as four passes of 27 lanes.  All index arithmetic is compile-time
+// (the generic kernel spends most of its ~1000 instructions per child on runtime divisions and staging).
+// Same arithmetic as the generic kernel: float32 cost from the integer SAD unless it sits on a rounding
+// boundary (then the f64 replay), key = (cost bits, d2, ri, ci), strict '<' across the three vectors.
+template <int BS>
+__global__ void __launch_bounds__(HBMA_WARPS * 32)
+hbma_densify_parent_kernel(const int32_t *__restrict__ L1, const int32_t *__restrict__ L2,
+                           const uint8_t *__restrict__ rgb1, const uint8_t *__restrict__ rgb2,
+                           int H, int W, int Wp, double eps, int vec_scale,
+                           const float2 *__restrict__ in_vec, int in_rows, int in_cols, int in_pitch,
+                           float2 *__restrict__ out_vec, float *__restrict__ out_cost,
+                           int out_rows, int out_cols, int out_pitch)
+{
+    constexpr int SB = 2 * BS, RS = 2 * BS + 2, RSP = RS + 1, SM_INTS = SB * SB + 3 * RS * RSP;
+    __shared__ int sm_all[HBMA_WARPS][SM_INTS];
+    int *src = sm_all[threadIdx.x >> 5], *reg = src + SB * SB;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int prow_n = (out_rows + 1) >> 1, pcol_n = (out_cols + 1) >> 1;
+    const float epsf = (float)eps;
+    // candidate of this lane inside a pass: vector k, refinement offset (ri, ci) of the 3x3 window
+    const int k_l = lane / 9, m_l = lane - k_l * 9, ri_l = m_l / 3, ci_l = m_l - ri_l * 3;
+    for (int pb = warp; pb < prow_n * pcol_n; pb += nwarps) {
+        const int row = pb / pcol_n, col = pb - row * pcol_n;
+        const bool parent_ok = row < in_rows && col < in_cols;
+        int r_max = 0, c_max = 0;
+        float2 v[3] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        const int im_r0 = row * SB, im_c0 = col * SB;
+        int R0[3] = {0, 0, 0}, C0[3] = {0, 0, 0};
+        if (parent_ok) {
+            // second child row/col is skipped when the parent touches the frame edge (:117-124, Q5)
+            r_max = ((row + 1) * SB >= H) ? row * 2 + 1 : (row + 1) * 2;
+            c_max = ((col + 1) * SB >= W) ? col * 2 + 1 : (col + 1) * 2;
+            v[0] = in_vec[(size_t)row * in_pitch + col];                          // parent, unscaled (:107, Q4)
+            const int hc = col >= 1 ? col - 1 : min(col + 1, in_cols - 1);
+            const int vr = row >= 1 ? row - 1 : min(row + 1, in_rows - 1);
+            const float2 h = in_vec[(size_t)row * in_pitch + hc];
+            const float2 u = in_vec[(size_t)vr * in_pitch + col];
+            const float sc = (float)vec_scale;
+            v[1] = make_float2(__fmul_rn(h.x, sc), __fmul_rn(h.y, sc));
+            v[2] = make_float2(__fmul_rn(u.x, sc), __fmul_rn(u.y, sc));
+            for (int i = lane; i < SB * SB; i += 32) {
+                const int r = im_r0 + i / SB, c = im_c0 + i % SB;
+                src[i] = (r < H && c < W) ? L1[(size_t)r * Wp + c] : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                R0[k] = (int)((double)im_r0 + (double)v[k].x) - 1;                // search centre of child (0,0), minus sub_win
+                C0[k] = (int)((double)im_c0 + (double)v[k].y) - 1;
+                for (int i = lane; i < RS * RS; i += 32) {
+                    const int rr = i / RS, cc = i - rr * RS;
+                    const int r = R0[k] + rr, c = C0[k] + cc;
+                    reg[k * RS * RSP + rr * RSP + cc] = (r >= 0 && c >= 0 && r < H && c < W) ? L2[(size_t)r * Wp + c] : 0;
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int child = 0; child < 4; ++child) {
+            const int a = child >> 1, b = child & 1;
+            const int o_r = row * 2 + a, o_c = col * 2 + b;
+            if (o_r >= out_rows || o_c >= out_cols) continue;                     // warp-uniform
+            const bool evaluated = parent_ok && o_r < r_max && o_c < c_max;
+            float2 o = make_float2(0.f, 0.f);
+            float oc = 0.f;
+            if (evaluated) {
+                const int im_r = o_r * BS, im_c = o_c * BS;
+                unsigned hi = 0xffffffffu, lo = 0xffffffffu;
+                int mn_r = 0, mn_c = 0;
+                if (lane < 27) {
+                    const float2 vk = k_l == 0 ? v[0] : (k_l == 1 ? v[1] : v[2]);
+                    const int idr = (int)((double)im_r + (double)vk.x);           // f64 sum, trunc to int32 (:134)
+                    const int idc = (int)((double)im_c + (double)vk.y);
+                    if (!(idr >= H || idc >= W || idr < 0 || idc < 0)) {          // :36-37
+                        int max_r = 2, min_r = -1, max_c = 2, min_c = -1;         // sub_win == 1
+                        if (idr + 1 + BS >= H) max_r = max(1, H - idr - BS);      // :53-54
+                        if (idr - 1 < 0) min_r += 1 - idr;                        // :55-56
+                        if (idc + 1 + BS >= W) max_c = max(1, W - idc - BS);
+                        if (idc - 1 < 0) min_c += 1 - idc;
+                        mn_r = min_r; mn_c = min_c;
+                        if (ri_l < max_r - min_r && ci_l < max_c - min_c) {
+                            const int r_off = min_r + ri_l, c_off = min_c + ci_l;
+                            const int R0k = k_l == 0 ? R0[0] : (k_l == 1 ? R0[1] : R0[2]);
+                            const int C0k = k_l == 0 ? C0[0] : (k_l == 1 ? C0[1] : C0[2]);
+                            const int rr0 = idr + r_off - R0k, cc0 = idc + c_off - C0k;      // inside the staged region for integral vectors
+                            float cost;
+                            bool ok = false;
+                            if (rr0 >= 0 && cc0 >= 0 && rr0 + BS <= RS && cc0 + BS <= RS) {
+                                const int *sp = src + (a * BS) * SB + b * BS;
+                                const int *rp = reg + k_l * RS * RSP + rr0 * RSP + cc0;
+                                unsigned S = 0;
+#pragma unroll
+                                for (int i = 0; i < BS; ++i)
+#pragma unroll
+                                    for (int j = 0; j < BS; ++j) S = __sad(sp[i * SB + j], rp[i * RSP + j], S);
+                                ok = cost_from_S(S, epsf, cost);
+                            }
+                            if (!ok) cost = (float)exact_cost_f64(rgb1, rgb2, H, W, im_r, im_c, idr + r_off, idc + c_off, BS, 0);
+                            hi = __float_as_uint(cost);
+                            lo = ((unsigned)(r_off * r_off + c_off * c_off) << 16) | ((unsigned)ri_l << 8) | (unsigned)ci_l;
+                        }
+                    }
+                }
+                float lowest = __int_as_float(0x7f800000);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const bool mine = k_l == k;
+                    const unsigned mh = __reduce_min_sync(0xffffffffu, mine ? hi : 0xffffffffu);
+                    const unsigned ml = __reduce_min_sync(0xffffffffu, (mine && hi == mh) ? lo : 0xffffffffu);
+                    // the winner's lane also knows its window origin (min_r, min_c): fetch it from that lane
+                    const unsigned who = __ballot_sync(0xffffffffu, mine && hi == mh && lo == ml && hi != 0xffffffffu);
+                    if (who) {                                                    // out-of-frame centre: [0,0,inf], never selected (:36-37, :135)
+                        const int wl = __ffs(who) - 1;
+                        const int wr = __shfl_sync(0xffffffffu, mn_r, wl), wc = __shfl_sync(0xffffffffu, mn_c, wl);
+                        const float cost = __uint_as_float(mh);
+                        if (cost < lowest) {                                      // strict: first vector wins ties (:135)
+                            lowest = cost;
+                            oc = cost;
+                            o = make_float2(__fadd_rn((float)(wr + (int)((ml >> 8) & 255u)), v[k].x),
+                                            __fadd_rn((float)(wc + (int)(ml & 255u)), v[k].y));
+                        }
+                    }
+                }
+            }
+            if (lane == 0) {
+                out_vec[(size_t)o_r * out_pitch + o_c] = o;
+                out_cost[(size_t)o_r * out_pitch + o_c] = oc;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void hbma_compact_kernel(const float2 *__restrict__ in_vec, const float *__restrict__ in_cost, int pitch,
                                     int rows, int cols, float2 *__restrict__ out_vec, float *__restrict__ out_sad)
 {
@@ -378,6 +518,19 @@ int memci_hbma_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int win, 
     auto densify = [&](int lvl, int b, int vec_scale) -> int {
         int orows = ceil_div_i(hs[lvl], b), ocols = ceil_div_i(ws[lvl], b);   // the slice kept by the reference
         int opitch = cols * 2;
+        if (sub == 1 && cost_key == 0 && (b == 4 || b == 8) && !getenv("MEMCI_HBMA_GENERIC")) {     // parent-level fast path
+            if (b == 8)
+                hbma_densify_parent_kernel<8><<<grid, nt, 0, ctx->stream>>>(
+                    LUMA(f1, lvl), LUMA(f2, lvl), RGB(f1, lvl), RGB(f2, lvl), hs[lvl], ws[lvl], WP(lvl), hbma_eps(b), vec_scale,
+                    ctx->tmp_mv[cur].vec, rows, cols, pitch, ctx->tmp_mv[cur ^ 1].vec, ctx->tmp_mv[cur ^ 1].sad, orows, ocols, opitch);
+            else
+                hbma_densify_parent_kernel<4><<<grid, nt, 0, ctx->stream>>>(
+                    LUMA(f1, lvl), LUMA(f2, lvl), RGB(f1, lvl), RGB(f2, lvl), hs[lvl], ws[lvl], WP(lvl), hbma_eps(b), vec_scale,
+                    ctx->tmp_mv[cur].vec, rows, cols, pitch, ctx->tmp_mv[cur ^ 1].vec, ctx->tmp_mv[cur ^ 1].sad, orows, ocols, opitch);
+            CKL(ctx);
+            cur ^= 1; rows = orows; cols = ocols; pitch = opitch;
+            return MEMCI_OK;
+        }
         int smi = b * b + 3 * (b + 2 * sub) * (b + 2 * sub);          // fused three-vector search
         if (smi > 1536) smi = sm_ints_for(b, sub);
         hbma_densify_kernel<<<grid, nt, smi * HBMA_WARPS * sizeof(int), ctx->stream>>>(
