@@ -10,13 +10,16 @@ bidirectional MCI.  A step = one pass of the hot path over a batch of P independ
 pass-through source frames of the 60 fps output involve no computation and are not counted in
 `value` (interpolated frames/s); `output_frames_per_s` adds them back.
 
-value    : inputs resident in HBM before the timed region, outputs left in HBM; CUDA events.
+value    : inputs resident in HBM before the timed region, outputs left in HBM; the step's P pairs are spread over
+           C contexts (= CUDA streams, --contexts) so that one pair's small kernels overlap another pair's search;
+           timed with CUDA events on a timing stream that fans out to / in from the C streams.
 e2e      : same work through the public pipeline API with page-locked HOST buffers, the H2D copy
            of every source frame and the D2H copy of every interpolated frame inside the timed region.
 roofline : dominant kernel (fs_tiled_kernel): SAD pixel-ops per launch (exact candidate count of the
-           reference's own bounds x 64) / mean launch time from CUDA events recorded around every
-           launch inside the timed region, against the VABSDIFF issue rate measured by a microbenchmark
-           in this run.  The kernel is integer-ALU bound, not HBM bound; its HBM view and
+           reference's own bounds x 64 x 2 directions) / mean launch time from CUDA events recorded around
+           every launch of a single-stream pass of the same step (`single_stream`: timed next to another
+           stream's persistent grid a launch would include queueing), against the VABSDIFF issue rate
+           measured by a microbenchmark in this run.  The kernel is integer-ALU bound, not HBM bound; its HBM view and
            the HBM-bound MCI splat kernel are reported beside it.
 cpu_baseline / --impl reference: the C restatement of the reference (oracle/, validated bit-exact
            against the reference) on the host cores, OpenMP over block rows, one full-size pair per sample.
@@ -293,7 +296,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0, help="frame pairs per step per GPU (default: per workload)")
-    ap.add_argument("--contexts", type=int, default=3, help="device contexts (streams) of the e2e pipeline")
+    ap.add_argument("--contexts", type=int, default=4, help="device contexts (CUDA streams) of the resident and the e2e pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -341,45 +344,88 @@ def main():
         from interpolatory_b200.MCI.Bidirectional_2 import get_weight_kern
         b2_w = get_weight_kern(8)
 
-    def step_resident():
-        for k in range(P):
-            a, b = k % 3, (k + 1) % 3
-            if k == 0:
-                ctx.set_frame_device(a, base_ptr)
-            ctx.set_frame_device(b, base_ptr + (k + 1) * frame_bytes)
-            ctx.estimate_pair(params, a, b, 0, 1)
-            for j, d in enumerate(dists):
-                if bidir2:
-                    ctx.mci_bidir2(a, b, 0, 1, d, np.float32(1 - float(d)), b2_w, 6 + (j & 1))
-                else:
-                    ctx.mci_bidir(a, b, 0, 1, d, 6 + (j & 1))
+    def enqueue_pair(c, k):
+        """pair k (frames k, k+1 of the resident clip) on context c: 2 motion fields + nd interpolated frames"""
+        a, b = k % 3, (k + 1) % 3
+        if c.first:                                        # first pair of this context's run: both frames are new
+            c.set_frame_device(a, base_ptr + k * frame_bytes)
+            c.first = False
+        c.set_frame_device(b, base_ptr + (k + 1) * frame_bytes)
+        c.estimate_pair(params, a, b, 0, 1)
+        for j, d in enumerate(dists):
+            if bidir2:
+                c.mci_bidir2(a, b, 0, 1, d, np.float32(1 - float(d)), b2_w, 6 + (j & 1))
+            else:
+                c.mci_bidir(a, b, 0, 1, d, 6 + (j & 1))
+
+    def step_resident(ctxs):
+        """One step = P pairs.  Each context (one CUDA stream) takes a contiguous run of pairs; the runs are enqueued
+        round-robin so that the small kernels and the tail of one pair overlap another pair's full search."""
+        C = len(ctxs)
+        bounds = [round(i * P / C) for i in range(C + 1)]
+        pos = [bounds[i] for i in range(C)]
+        for c in ctxs:
+            c.first = True
+        live = True
+        while live:
+            live = False
+            for i, c in enumerate(ctxs):
+                if pos[i] < bounds[i + 1]:
+                    enqueue_pair(c, pos[i])
+                    pos[i] += 1
+                    live = True
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- pass 1, ONE stream: per-launch device times of the two hot kernels (roofline numerators).  A launch timed
+    #      while another stream's persistent grid drains would include queueing, so the kernels are timed alone. ----
     for _ in range(max(args.warmup, 1)):
-        step_resident()
+        step_resident([ctx])
     barrier()
     n_cand, px_ops, _ = ctx.fs_stats()
-
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    ctx.reset_launch_count()
-    ctx.profile_start(args.steps * P * (2 + nd) + 16)
+    prof_steps = max(1, min(args.steps, 2))
+    ctx.profile_start(prof_steps * P * (2 + nd) + 16)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for _ in range(args.steps):
-        step_resident()
+    for _ in range(prof_steps):
+        step_resident([ctx])
     e1.record(stream)
     barrier()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count()
+    ms_single = e0.elapsed_time(e1) / prof_steps
     fs_ms_sum, fs_n, mci_ms_sum, mci_n = ctx.profile_collect()
-    n_holes = ctx.mci_stats()
-    resident_last = ctx.download_frame(6 + ((nd - 1) & 1)).copy()
+
+    # ---- pass 2, the measured value: the same P pairs per step over C contexts / streams (inputs resident in HBM) ----
+    n_res = max(1, min(args.contexts, P))
+    streams = [stream] + [torch.cuda.Stream() for _ in range(n_res - 1)]
+    ctxs = [ctx] + [DeviceContext(H, W, device=local_rank, stream=s_.cuda_stream) for s_ in streams[1:]]
+    tstream = torch.cuda.Stream()
+    for _ in range(max(args.warmup, 1)):
+        step_resident(ctxs)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    for c in ctxs:
+        c.reset_launch_count()
+    barrier()
+    e0.record(tstream)
+    for s_ in streams:
+        s_.wait_event(e0)                      # every stream starts after e0 ...
+    for _ in range(args.steps):
+        step_resident(ctxs)
+    for s_ in streams:
+        ev = torch.cuda.Event()
+        ev.record(s_)
+        tstream.wait_event(ev)                 # ... and e1 completes after the last one finishes
+    e1.record(tstream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = sum(c.launch_count() for c in ctxs)
+    n_holes = ctxs[-1].mci_stats()
+    resident_last = ctxs[-1].download_frame(6 + ((nd - 1) & 1)).copy()
 
     # ---- e2e: host buffers, H2D + D2H inside the timed region, through the public pipeline API ----
     pin_in = PinnedBuffer((P + 1, H, W, 3))
@@ -392,7 +438,8 @@ def main():
     l0 = pipe.launch_count()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        pipe.run(pin_in.array, dists, pin_out.array)
+        pipe.run(pin_in.array, dists, pin_out.array, sync=False)      # every step: H2D of its P+C frames, D2H of its P*nd frames
+    pipe.sync()
     barrier()
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop()
@@ -426,7 +473,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
             "config": {"workload": WORKLOAD_TEXT[args.workload], "pairs_per_step_per_gpu": P, "H": H, "W": W,
-                       "settings": st, "interpolated_per_pair": nd,
+                       "settings": st, "interpolated_per_pair": nd, "streams": n_res,
                        "sharding": "pair index, independent per rank, no collective",
                        "l2_policy": f"inputs larger than L2: {((P + 1) * frame_bytes + 3 * H * W * 4) / 1e6:.0f} MB of frames + luma planes "
                                     "streamed per step vs 126 MB L2"},
@@ -457,7 +504,11 @@ def main():
                 "bytes_per_launch": mci_bytes, "launches_timed": mci_n, "avg_launch_ms": mci_avg_s * 1e3,
                 "holes_last_frame": n_holes, "traffic": load_traffic("mci_splat_kernel") if args.workload == "cfg2" else None,
             },
-            "kernel_share_of_step": {"fs_tiled": fs_ms_sum / ms if ms else None, "mci_splat": mci_ms_sum / ms if ms else None},
+            "single_stream": {"value": world * P * nd / (ms_single * 1e-3), "ms_per_step": ms_single, "steps": prof_steps,
+                              "note": "same step on one CUDA stream; the per-launch kernel times of `roofline` / `roofline_mci` "
+                                      "come from this pass (a launch timed next to another stream's persistent grid would include queueing)"},
+            "kernel_share_of_step": {"fs_tiled": fs_ms_sum / (ms_single * prof_steps), "mci_splat": mci_ms_sum / (ms_single * prof_steps),
+                                     "of": "single_stream step"},
         }
         if world == 1 and not args.no_cpu_baseline:
             dt, cores = cpu_reference_sample(H, W, st, dists, frames)
@@ -467,7 +518,8 @@ def main():
         print(json.dumps(line), flush=True)
 
     pipe.close()
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if world > 1:
         dist.destroy_process_group()
 

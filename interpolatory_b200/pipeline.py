@@ -71,10 +71,12 @@ class PairPipeline:
         for c in self.ctxs:
             c.sync()
 
-    def run(self, frames, dists, out):
+    def run(self, frames, dists, out, sync=True):
         """frames: uint8 [F, H, W, 3] (page-locked for real overlap); dists: float32 dist of each
         interpolated frame inside a pair; out: uint8 [(F-1)*len(dists), H, W, 3], filled in pair
-        order.  Returns after everything has been enqueued AND completed."""
+        order.  Returns after everything has been enqueued AND (sync=True) completed; with sync=False
+        the caller streams several batches back to back and calls sync() once (each context is one
+        stream, so a batch never overtakes the previous one's reads or writes of the same buffers)."""
         n_pairs = len(frames) - 1
         nd = len(dists)
         C = min(len(self.ctxs), n_pairs)
@@ -108,5 +110,6 @@ class PairPipeline:
                         ctx.mci_unidir(a, b, 0, d, o)
                     ctx.download_frame(o, out[k * nd + j], sync=False)
                 pos[c] += 1
-        self.sync()
+        if sync:
+            self.sync()
         return out
