@@ -345,7 +345,7 @@ __device__ __forceinline__ void sw_test_entry(const MciParams &P, const SwShared
 }
 
 template <bool BIDIR>
-__global__ void __launch_bounds__(SW_WARPS * 32, 5)
+__global__ void __launch_bounds__(SW_WARPS * 32, 4)      // 128 registers: any tighter cap spills the 40-register decision state (measured slower)
 mci_splat_kernel(const __grid_constant__ MciParams P, int tiles_x, int n_tiles)
 {
     __shared__ SwShared sm_all[SW_WARPS];
