@@ -141,8 +141,8 @@ def cpu_reference_sample(H, W, st, dists, frames, threads=None):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     O.build()
-    if threads:
-        O.set_num_threads(threads)
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would pin the port to one thread)
+    O.set_num_threads(threads or len(os.sched_getaffinity(0)))
     a, b = frames[0], frames[1]
     bs, R = int(st['block_size']), int(st['target_region'])
     t0 = time.perf_counter()
