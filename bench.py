@@ -354,7 +354,7 @@ def main():
         c.estimate_pair(params, a, b, 0, 1)
         for j, d in enumerate(dists):
             if bidir2:
-                c.mci_bidir2(a, b, 0, 1, d, np.float32(1 - float(d)), b2_w, 6 + (j & 1))
+                c.mci_bidir2(a, b, 0, 1, np.float32(d), np.float32(1 - d), b2_w, 6 + (j & 1))
             else:
                 c.mci_bidir(a, b, 0, 1, d, 6 + (j & 1))
 

@@ -34,8 +34,11 @@ def pair_params_from_settings(shape, **st):
 
 
 def interpolation_dists(rate_ratio):
-    """dist values (float32) of the interpolated frames between two source frames, in output
-    order, exactly as the class API derives them (util.get_first_frame_idx_and_ratio, W0)."""
+    """dist values of the interpolated frames between two source frames, in output order, exactly as the
+    class API derives them (util.get_first_frame_idx_and_ratio, W0): Python floats `1. - ratio` (float64
+    arithmetic on the float32 ratio).  The device calls round them to float32 at the boundary like the
+    reference's njit signatures do; bidir2 also needs float32(1 - dist) of the UNROUNDED value
+    (Bidirectional_2.py:331-332), which is why the float64 is kept here."""
     out, idx = [], 1
     while True:
         first, ratio = get_first_frame_idx_and_ratio(idx, rate_ratio)
@@ -43,7 +46,7 @@ def interpolation_dists(rate_ratio):
             break
         dist = 1. - ratio
         if dist != 0.:
-            out.append(np.float32(dist))
+            out.append(float(dist))
         idx += 1
     return out
 
@@ -102,7 +105,7 @@ class PairPipeline:
                     o = 6 + (j & 1)
                     if self.bidir2:
                         # the class passes the python floats dist and 1 - dist (Bidirectional_2.py:331-332)
-                        ctx.mci_bidir2(a, b, 0, 1, np.float32(d), np.float32(1 - float(d)), self._w, o,
+                        ctx.mci_bidir2(a, b, 0, 1, np.float32(d), np.float32(1 - d), self._w, o,
                                        self.params.min_block_size, 4 * self.params.min_block_size)
                     elif self.bidir:
                         ctx.mci_bidir(a, b, 0, 1, d, o)

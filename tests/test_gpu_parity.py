@@ -424,3 +424,66 @@ def test_bidir2_vs_golden_and_oracle(gpu, golden, oracle):
         fwd, bwd = it.fwr_MV_field_dense, it.bwr_MV_field_dense
         assert np.array_equal(out, oracle.bidir2_frame(fr[0], fr[1], fwd, bwd, 0.5, True)), (H, W, me)
         it.close()
+
+
+def test_fs_pair_launch_equals_two_launches(gpu):
+    """memci_me_fs_pair (both directions in one persistent launch, one redo pass) against two memci_me_fs calls,
+    on sizes that exercise clipped tiles, the generic (non multiple of 8) kernel and 16-px blocks."""
+    from interpolatory_b200.device import DeviceContext
+    for (H, W, bs, R) in ((270, 483, 8, 16), (131, 97, 8, 7), (120, 200, 6, 5), (256, 320, 16, 20)):
+        fr = make_sequence(H, W, 2, seed=H + W)
+        ctx = DeviceContext(H, W)
+        ctx.upload_frame(0, fr[0]); ctx.upload_frame(1, fr[1])
+        ctx.me_fs(0, 1, bs, R, 2); ctx.me_fs(1, 0, bs, R, 3)
+        ctx.me_fs_pair(0, 1, bs, R, 0, 1)
+        for a, b in ((0, 2), (1, 3)):
+            got, want = ctx.download_mv_blocks(a), ctx.download_mv_blocks(b)
+            assert np.array_equal(got[1], want[1]) and np.array_equal(got[3], want[3]), (H, W, bs, R, a)
+        ctx.close()
+
+
+def test_pipeline_bidir2_equals_class_api(gpu):
+    """PairPipeline (the e2e path of bench.py) with mci_mode=bidir2 against BiDir2Interpolator frame by frame
+    (24 -> 120 fps: the same four dists inside every pair, which is what the pipeline API assumes)."""
+    from interpolatory_b200 import MEMCI, ArrayVideoStream
+    from interpolatory_b200.pipeline import PairPipeline, interpolation_dists
+    H, W = 136, 200
+    frames = make_sequence(H, W, 4, seed=77)
+    st = dict(me_mode='hbma', mci_mode='bidir2')
+    dists = interpolation_dists(120 / 24)
+    assert len(dists) == 4
+    pipe = PairPipeline(H, W, n_contexts=2, **st)
+    out = np.empty((3 * len(dists), H, W, 3), np.uint8)
+    pipe.run(frames, dists, out)
+    pipe.close()
+    it = MEMCI(120, **st)
+    it.set_video_stream(ArrayVideoStream(list(frames), 24))
+    k = 0
+    for i in range(1, 15):
+        first, ratio = it_first_ratio(i, 120 / 24)
+        if (1. - ratio) == 0.:
+            continue                                       # pass-through source frame
+        got = np.asarray(it.get_interpolated_frame(i))
+        assert np.array_equal(got, out[k]), (i, k)
+        k += 1
+    assert k == 12
+    it.close()
+
+
+def it_first_ratio(idx, rr):
+    from interpolatory_b200.util import get_first_frame_idx_and_ratio
+    return get_first_frame_idx_and_ratio(idx, rr)
+
+
+def test_bidir2_out_of_range_blocks_raise(gpu):
+    """A vector that shifts an expanded block outside the padded frame: the reference's slices would clip and its
+    in-place add fail; we raise as well (after zero-filling on the device)."""
+    from interpolatory_b200.MCI.Bidirectional_2 import interpolate
+    H, W = 64, 96
+    fr = make_sequence(H, W, 2, seed=3)
+    mv = np.zeros((H, W, 3), np.float32)
+    ok = interpolate(fr[0], fr[1], mv, mv, 0.5, 16, 4, True)
+    assert ok.shape == (H, W, 3)
+    mv[0:8, 0:8, 0] = -40.0                    # 14 + (-40) < 0: leaves the 16-px padding
+    with pytest.raises(Exception, match='outside the padded frame'):
+        interpolate(fr[0], fr[1], mv, mv, 0.5, 16, 4, True)
