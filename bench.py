@@ -135,6 +135,27 @@ class ClockSampler:
                 "window": "device-resident timed region + e2e timed region"}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank to the CPU cores NVML reports as local to its GPU, BEFORE any page-locked buffer is allocated:
+    the buffers then live on that NUMA node and the H2D / D2H DMA does not cross the socket interconnect (the e2e
+    leg at 8 ranks is host-bound).  Best effort: silently keeps the inherited affinity if NVML has no answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            bind_to_gpu_numa_node.original = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------
 def cpu_reference_sample(H, W, st, dists, frames, threads=None):
     """One full-size pair through the CPU restatement of the reference; returns seconds."""
@@ -296,7 +317,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=0, help="frame pairs per step per GPU (default: per workload)")
-    ap.add_argument("--contexts", type=int, default=4, help="device contexts (CUDA streams) of the resident and the e2e pipeline")
+    ap.add_argument("--contexts", type=int, default=8, help="device contexts (CUDA streams) of the resident and the e2e pipeline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -320,6 +341,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the MEMCI path has no CPU fallback")
     lib()                                         # fail loudly if the CUDA library is missing
+    bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -479,7 +501,7 @@ def main():
                                     "streamed per step vs 126 MB L2"},
             "output_frames_per_s": value * out_per_interp,
             "sad_gops": (2 * px_ops * world * P * args.steps) / (ms_all * 1e-3) / 1e9,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": (P + n_ctx) * frame_bytes,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": (P + 1) * frame_bytes,
                     "d2h_bytes_per_step": P * nd * frame_bytes, "contexts": n_ctx,
                     "output_frames_per_s": e2e_value * out_per_interp},
             "gpu_launches": int(launches),
@@ -511,6 +533,8 @@ def main():
                                      "of": "single_stream step"},
         }
         if world == 1 and not args.no_cpu_baseline:
+            if getattr(bind_to_gpu_numa_node, "original", None):
+                os.sched_setaffinity(0, bind_to_gpu_numa_node.original)        # the CPU baseline may use every host core
             dt, cores = cpu_reference_sample(H, W, st, dists, frames)
             line["cpu_baseline"] = {"value": nd / dt, "unit": "frames/s", "cores": cores, "kind": "port",
                                     "sample": f"1 full-size frame pair of the same workload ({dt:.2f} s): C restatement of the "

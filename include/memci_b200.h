@@ -89,6 +89,25 @@ MEMCI_API int memci_download_frame(memci_ctx *ctx, int slot, uint8_t *host_hwc);
 /* Device pointer of a frame slot's uint8[H][W][3] buffer (NULL on bad slot). */
 MEMCI_API void *memci_frame_device_ptr(memci_ctx *ctx, int slot);
 
+/* ---- frame staging (decode-to-device path) -------------------------------------------------
+ * Replaces the host-side hand-over of decoded frames, VideoStream.get_frame -> interpolator
+ * (src/VideoStream.py:61, base.py:103), for streaming use: every source frame crosses PCIe ONCE on the
+ * stager's own H2D stream and is handed to any context with a device-to-device copy that waits on the
+ * upload's event; output frames drain through the stager's D2H stream while the context's stream goes on
+ * with the next pair.  Host buffers must be page-locked (memci_host_alloc) for the copies to overlap. */
+typedef struct memci_stager memci_stager;
+MEMCI_API int memci_stager_create(int device, int H, int W, int n_slots, memci_stager **out);
+MEMCI_API int memci_stager_destroy(memci_stager *st);
+/* Async H2D of one uint8[H][W][3] frame into ring slot `slot` (waits until every context that took the
+ * slot's previous frame has copied it). */
+MEMCI_API int memci_stager_upload(memci_stager *st, int slot, const uint8_t *host_hwc);
+/* Ring slot -> frame slot of `ctx` (D2D on the context's stream, after the upload; at most 4 takers per upload). */
+MEMCI_API int memci_frame_from_stager(memci_ctx *ctx, int frame_slot, memci_stager *st, int slot);
+/* Frame slot -> host through the stager's D2H stream; the slot is rewritten only after the copy (the MCI
+ * entry points wait for it).  memci_stager_sync() before reading the host buffer. */
+MEMCI_API int memci_download_frame_via(memci_ctx *ctx, int slot, uint8_t *host_hwc, memci_stager *st);
+MEMCI_API int memci_stager_sync(memci_stager *st);
+
 /* ---- motion estimation ------------------------------------------------------ */
 
 /* Replaces ME/full_search.py:61 get_motion_vectors(block_size, target_region, im1, im2)

@@ -36,6 +36,12 @@ _PROTOS = {
     "memci_set_frame_device": ([_P, _I, _P], _I),
     "memci_download_frame": ([_P, _I, _P], _I),
     "memci_frame_device_ptr": ([_P, _I], _P),
+    "memci_stager_create": ([_I, _I, _I, _I, C.POINTER(_P)], _I),
+    "memci_stager_destroy": ([_P], _I),
+    "memci_stager_upload": ([_P, _I, _P], _I),
+    "memci_frame_from_stager": ([_P, _I, _P, _I], _I),
+    "memci_download_frame_via": ([_P, _I, _P, _P], _I),
+    "memci_stager_sync": ([_P], _I),
     "memci_me_fs": ([_P, _I, _I, _I, _I, _I], _I),
     "memci_me_fs_pair": ([_P, _I, _I, _I, _I, _I, _I], _I),
     "memci_me_tss": ([_P, _I, _I, _I, _I, _I], _I),

@@ -146,6 +146,10 @@ int memci_ctx_destroy(memci_ctx *ctx)
         free(ctx->fs_plan[i].row_tile_start); free(ctx->fs_plan[i].row_cand);
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     }
+    for (int i = 0; i < MEMCI_NUM_FRAME_SLOTS; ++i) {
+        if (ctx->ev_out_ready[i]) cudaEventDestroy(ctx->ev_out_ready[i]);
+        if (ctx->ev_out_copied[i]) cudaEventDestroy(ctx->ev_out_copied[i]);
+    }
     if (ctx->d_redo_list) cudaFree(ctx->d_redo_list);
     if (ctx->d_counters) cudaFree(ctx->d_counters);
     if (ctx->d_fill) cudaFree(ctx->d_fill);
@@ -209,6 +213,125 @@ int memci_download_frame(memci_ctx *ctx, int slot, uint8_t *host)
     REQ_CTX(ctx); REQ_FRAME(ctx, slot, 1);
     if (!host) return memci_fail(ctx, MEMCI_ERR_ARG, "null host frame");
     CK(ctx, cudaMemcpyAsync(host, ctx->frames[slot].rgb, (size_t)ctx->H * ctx->W * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    return MEMCI_OK;
+}
+
+// ---- frame staging: host frames cross PCIe once, on copy streams of their own -------------------------
+// A stager owns a ring of device frame buffers, an H2D stream and a D2H stream.  Source frames are uploaded
+// once (memci_stager_upload) and handed to any number of contexts with a device-to-device copy that waits
+// on the upload's event (memci_frame_from_stager); output frames leave through the D2H stream
+// (memci_download_frame_via) while the context's own stream goes on with the next pair.  A ring slot is
+// overwritten only after every context that took the frame has copied it, an output slot only after its
+// D2H copy has finished (memci_wait_slot_free, called by the MCI entry points).
+#define STAGER_MAX_CONSUMERS 4
+struct memci_stager {
+    int device, H, W, n;
+    cudaStream_t h2d, d2h;
+    uint8_t **buf;
+    cudaEvent_t *ready;
+    cudaEvent_t *consumed;      // [n][STAGER_MAX_CONSUMERS]
+    int *n_consumed;
+};
+
+int memci_stager_create(int device, int H, int W, int n_slots, memci_stager **out)
+{
+    if (!out || H <= 0 || W <= 0 || n_slots <= 0) return MEMCI_ERR_ARG;
+    *out = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) return memci_fail(nullptr, MEMCI_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    memci_stager *st = (memci_stager *)calloc(1, sizeof(memci_stager));
+    if (!st) return MEMCI_ERR_NOMEM;
+    st->device = device; st->H = H; st->W = W; st->n = n_slots;
+    st->buf = (uint8_t **)calloc(n_slots, sizeof(uint8_t *));
+    st->ready = (cudaEvent_t *)calloc(n_slots, sizeof(cudaEvent_t));
+    st->consumed = (cudaEvent_t *)calloc((size_t)n_slots * STAGER_MAX_CONSUMERS, sizeof(cudaEvent_t));
+    st->n_consumed = (int *)calloc(n_slots, sizeof(int));
+    bool ok = st->buf && st->ready && st->consumed && st->n_consumed &&
+              cudaStreamCreateWithFlags(&st->h2d, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&st->d2h, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < n_slots; ++i) {
+        ok = cudaMalloc(&st->buf[i], (size_t)H * W * 3 + 16) == cudaSuccess &&
+             cudaEventCreateWithFlags(&st->ready[i], cudaEventDisableTiming) == cudaSuccess;
+        for (int c = 0; ok && c < STAGER_MAX_CONSUMERS; ++c)
+            ok = cudaEventCreateWithFlags(&st->consumed[i * STAGER_MAX_CONSUMERS + c], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) { memci_stager_destroy(st); return memci_fail(nullptr, MEMCI_ERR_NOMEM, "stager allocation failed"); }
+    *out = st;
+    return MEMCI_OK;
+}
+
+int memci_stager_destroy(memci_stager *st)
+{
+    if (!st) return MEMCI_OK;
+    cudaSetDevice(st->device);
+    if (st->h2d) { cudaStreamSynchronize(st->h2d); cudaStreamDestroy(st->h2d); }
+    if (st->d2h) { cudaStreamSynchronize(st->d2h); cudaStreamDestroy(st->d2h); }
+    for (int i = 0; i < st->n; ++i) {
+        if (st->buf && st->buf[i]) cudaFree(st->buf[i]);
+        if (st->ready && st->ready[i]) cudaEventDestroy(st->ready[i]);
+        for (int c = 0; st->consumed && c < STAGER_MAX_CONSUMERS; ++c)
+            if (st->consumed[i * STAGER_MAX_CONSUMERS + c]) cudaEventDestroy(st->consumed[i * STAGER_MAX_CONSUMERS + c]);
+    }
+    free(st->buf); free(st->ready); free(st->consumed); free(st->n_consumed); free(st);
+    return MEMCI_OK;
+}
+
+int memci_stager_upload(memci_stager *st, int slot, const uint8_t *host)
+{
+    if (!st || !host || slot < 0 || slot >= st->n) return MEMCI_ERR_ARG;
+    cudaSetDevice(st->device);
+    // the previous tenant of this ring slot must have been copied out by everyone who asked for it
+    for (int c = 0; c < st->n_consumed[slot]; ++c)
+        if (cudaStreamWaitEvent(st->h2d, st->consumed[slot * STAGER_MAX_CONSUMERS + c], 0) != cudaSuccess) return MEMCI_ERR_CUDA;
+    st->n_consumed[slot] = 0;
+    if (cudaMemcpyAsync(st->buf[slot], host, (size_t)st->H * st->W * 3, cudaMemcpyHostToDevice, st->h2d) != cudaSuccess) return MEMCI_ERR_CUDA;
+    if (cudaEventRecord(st->ready[slot], st->h2d) != cudaSuccess) return MEMCI_ERR_CUDA;
+    return MEMCI_OK;
+}
+
+int memci_frame_from_stager(memci_ctx *ctx, int frame_slot, memci_stager *st, int slot)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, frame_slot, 0);
+    if (!st || slot < 0 || slot >= st->n) return memci_fail(ctx, MEMCI_ERR_ARG, "bad stager slot %d", slot);
+    if (st->H != ctx->H || st->W != ctx->W || st->device != ctx->device) return memci_fail(ctx, MEMCI_ERR_ARG, "stager and context differ in device or frame size");
+    if (st->n_consumed[slot] >= STAGER_MAX_CONSUMERS) return memci_fail(ctx, MEMCI_ERR_STATE, "stager slot %d handed out more than %d times", slot, STAGER_MAX_CONSUMERS);
+    CK(ctx, cudaStreamWaitEvent(ctx->stream, st->ready[slot], 0));
+    CK(ctx, cudaMemcpyAsync(ctx->frames[frame_slot].rgb, st->buf[slot], (size_t)ctx->H * ctx->W * 3, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(ctx, cudaEventRecord(st->consumed[slot * STAGER_MAX_CONSUMERS + st->n_consumed[slot]++], ctx->stream));
+    frame_touched(ctx->frames[frame_slot]);
+    return MEMCI_OK;
+}
+
+int memci_download_frame_via(memci_ctx *ctx, int slot, uint8_t *host, memci_stager *st)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot, 1);
+    if (!host || !st) return memci_fail(ctx, MEMCI_ERR_ARG, "null host frame / stager");
+    if (!ctx->ev_out_ready[slot]) {
+        CK(ctx, cudaEventCreateWithFlags(&ctx->ev_out_ready[slot], cudaEventDisableTiming));
+        CK(ctx, cudaEventCreateWithFlags(&ctx->ev_out_copied[slot], cudaEventDisableTiming));
+    }
+    CK(ctx, cudaEventRecord(ctx->ev_out_ready[slot], ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(st->d2h, ctx->ev_out_ready[slot], 0));
+    CK(ctx, cudaMemcpyAsync(host, ctx->frames[slot].rgb, (size_t)ctx->H * ctx->W * 3, cudaMemcpyDeviceToHost, st->d2h));
+    CK(ctx, cudaEventRecord(ctx->ev_out_copied[slot], st->d2h));
+    ctx->out_pending[slot] = 1;
+    return MEMCI_OK;
+}
+
+// output slot still being copied out by a stager -> the context's stream waits for that copy
+static int memci_wait_slot_free(memci_ctx *ctx, int slot)
+{
+    if (slot >= 0 && slot < MEMCI_NUM_FRAME_SLOTS && ctx->out_pending[slot]) {
+        CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out_copied[slot], 0));
+        ctx->out_pending[slot] = 0;
+    }
+    return MEMCI_OK;
+}
+
+int memci_stager_sync(memci_stager *st)
+{
+    if (!st) return MEMCI_ERR_ARG;
+    cudaSetDevice(st->device);
+    if (cudaStreamSynchronize(st->h2d) != cudaSuccess || cudaStreamSynchronize(st->d2h) != cudaSuccess) return MEMCI_ERR_CUDA;
     return MEMCI_OK;
 }
 
@@ -352,6 +475,7 @@ int memci_mci_unidir(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_slot, fl
 {
     REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_FRAME(ctx, out_slot, 0); REQ_MV(ctx, mv_slot, 1);
     if (out_slot == slot_src || out_slot == slot_tgt) return memci_fail(ctx, MEMCI_ERR_ARG, "output slot aliases an input slot");
+    { int rc_ = memci_wait_slot_free(ctx, out_slot); if (rc_) return rc_; }
     return memci_mci_run(ctx, slot_src, slot_tgt, &ctx->mvs[mv_slot], nullptr, dist, out_slot, 0, 0, -1);
 }
 
@@ -360,6 +484,7 @@ int memci_mci_bidir(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd, int 
     REQ_CTX(ctx); REQ_FRAME(ctx, slot_src, 1); REQ_FRAME(ctx, slot_tgt, 1); REQ_FRAME(ctx, out_slot, 0);
     REQ_MV(ctx, mv_fwd, 1); REQ_MV(ctx, mv_bwd, 1);
     if (out_slot == slot_src || out_slot == slot_tgt) return memci_fail(ctx, MEMCI_ERR_ARG, "output slot aliases an input slot");
+    { int rc_ = memci_wait_slot_free(ctx, out_slot); if (rc_) return rc_; }
     return memci_mci_run(ctx, slot_src, slot_tgt, &ctx->mvs[mv_fwd], &ctx->mvs[mv_bwd], dist, out_slot, 1, 0, -1);
 }
 
@@ -370,6 +495,7 @@ int memci_mci_bidir2(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd, int
     REQ_MV(ctx, mv_fwd, 1); REQ_MV(ctx, mv_bwd, 1);
     if (!weights) return memci_fail(ctx, MEMCI_ERR_ARG, "null weight kernel");
     if (out_slot == slot_src || out_slot == slot_tgt) return memci_fail(ctx, MEMCI_ERR_ARG, "output slot aliases an input slot");
+    { int rc_ = memci_wait_slot_free(ctx, out_slot); if (rc_) return rc_; }
     return memci_bidir2_run(ctx, slot_src, slot_tgt, &ctx->mvs[mv_fwd], &ctx->mvs[mv_bwd], dist_fwd, dist_bwd,
                             min_block_size, pad_size, weights, out_slot);
 }
@@ -392,6 +518,7 @@ int memci_mci_rows(memci_ctx *ctx, int slot_src, int slot_tgt, int mv_fwd, int m
     REQ_MV(ctx, mv_fwd, 1);
     if (bidir) REQ_MV(ctx, mv_bwd, 1);
     if (out_slot == slot_src || out_slot == slot_tgt) return memci_fail(ctx, MEMCI_ERR_ARG, "output slot aliases an input slot");
+    { int rc_ = memci_wait_slot_free(ctx, out_slot); if (rc_) return rc_; }
     return memci_mci_run(ctx, slot_src, slot_tgt, &ctx->mvs[mv_fwd], bidir ? &ctx->mvs[mv_bwd] : nullptr, dist, out_slot,
                          bidir ? 1 : 0, row0, row1);
 }

@@ -63,6 +63,9 @@ struct memci_ctx {
     int timing; cudaEvent_t ev[4]; int fs_timed, mci_timed;
     // event pool: per-launch device times of the two hot kernels inside a caller's timed region
     cudaEvent_t *pool; int pool_cap, pool_n; unsigned char *pool_kind;   // pairs (2i, 2i+1); kind 0 = fs, 1 = mci
+    // asynchronous drain of output frames through a stager's D2H stream: slot may be rewritten only after its copy
+    cudaEvent_t ev_out_ready[MEMCI_NUM_FRAME_SLOTS], ev_out_copied[MEMCI_NUM_FRAME_SLOTS];
+    unsigned char out_pending[MEMCI_NUM_FRAME_SLOTS];
     long long launches;
     int sticky;                        // sticky CUDA error
     char err[512];

@@ -97,6 +97,13 @@ class DeviceContext:
             self.sync()
         return out
 
+    def frame_from_stager(self, slot, stager, ring_slot):
+        self._ck(self.L.memci_frame_from_stager(self._ctx, slot, stager._st, int(ring_slot)))
+
+    def download_frame_via(self, slot, out, stager):
+        """Async D2H through the stager's copy stream; stager.sync() before reading `out`."""
+        self._ck(self.L.memci_download_frame_via(self._ctx, slot, _ptr(out), stager._st))
+
     def frame_ptr(self, slot):
         return self.L.memci_frame_device_ptr(self._ctx, slot)
 
@@ -241,3 +248,42 @@ def clear_contexts():
     for c in list(_CTX_CACHE.values()):
         c.close()
     _CTX_CACHE.clear()
+
+
+class FrameStager:
+    """Ring of device frame buffers with H2D / D2H streams of their own (include/memci_b200.h, frame staging):
+    a source frame crosses PCIe once and is handed to the contexts device-to-device."""
+
+    def __init__(self, H, W, n_slots, device=0):
+        self.L = N.lib()
+        self.H, self.W, self.n = int(H), int(W), int(n_slots)
+        st = C.c_void_p()
+        rc = self.L.memci_stager_create(int(device), self.H, self.W, self.n, C.byref(st))
+        if rc != 0:
+            raise N.MemciError(f"memci_stager_create failed ({rc})")
+        self._st = st
+
+    def upload(self, ring_slot, frame):
+        a = np.ascontiguousarray(frame, dtype=np.uint8)
+        if a.shape != (self.H, self.W, 3):
+            raise ValueError(f"frame shape {a.shape} != {(self.H, self.W, 3)}")
+        rc = self.L.memci_stager_upload(self._st, int(ring_slot), _ptr(a))
+        if rc != 0:
+            raise N.MemciError(f"memci_stager_upload failed ({rc})")
+        return a
+
+    def sync(self):
+        rc = self.L.memci_stager_sync(self._st)
+        if rc != 0:
+            raise N.MemciError(f"memci_stager_sync failed ({rc})")
+
+    def close(self):
+        if getattr(self, "_st", None):
+            self.L.memci_stager_destroy(self._st)
+            self._st = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

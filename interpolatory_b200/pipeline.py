@@ -8,7 +8,7 @@ frame crosses PCIe once (twice at the run boundaries); nothing is exchanged betw
 import numpy as np
 
 from ._native import PairParams
-from .device import DeviceContext, FILTER_MODES
+from .device import DeviceContext, FILTER_MODES, FrameStager
 from .util import get_first_frame_idx_and_ratio, hbma_auto_steps
 
 
@@ -52,8 +52,15 @@ def interpolation_dists(rate_ratio):
 
 
 class PairPipeline:
+    """Throughput path: the source frames of a batch are uploaded ONCE by a FrameStager (its own H2D stream, a
+    ring of device buffers, in the order the pairs need them) and handed device-to-device to the contexts; each
+    context (one CUDA stream) takes a contiguous run of pairs, so a frame's luma plane is computed once per
+    context that uses it; interpolated frames drain through the stager's D2H stream.  Compute streams never wait
+    for PCIe except for data they actually need, and successive batches pipeline (a ring slot is rewritten as
+    soon as the previous batch's takers have copied it)."""
+
     def __init__(self, H, W, device=0, n_contexts=3, **settings):
-        self.H, self.W = int(H), int(W)
+        self.H, self.W, self.device = int(H), int(W), device
         self.params = pair_params_from_settings((H, W), **settings)
         self.bidir = bool(self.params.bidir)
         self.bidir2 = settings.get('mci_mode', 'unidir') == 'bidir2'
@@ -61,11 +68,15 @@ class PairPipeline:
             from .MCI.Bidirectional_2 import get_weight_kern
             self._w = get_weight_kern(2 * self.params.min_block_size)
         self.ctxs = [DeviceContext(H, W, device) for _ in range(max(1, int(n_contexts)))]
+        self.stager = None
 
     def close(self):
         for c in self.ctxs:
             c.close()
         self.ctxs = []
+        if self.stager is not None:
+            self.stager.close()
+            self.stager = None
 
     def launch_count(self):
         return sum(c.launch_count() for c in self.ctxs)
@@ -73,46 +84,52 @@ class PairPipeline:
     def sync(self):
         for c in self.ctxs:
             c.sync()
+        if self.stager is not None:
+            self.stager.sync()
 
     def run(self, frames, dists, out, sync=True):
-        """frames: uint8 [F, H, W, 3] (page-locked for real overlap); dists: float32 dist of each
-        interpolated frame inside a pair; out: uint8 [(F-1)*len(dists), H, W, 3], filled in pair
-        order.  Returns after everything has been enqueued AND (sync=True) completed; with sync=False
-        the caller streams several batches back to back and calls sync() once (each context is one
-        stream, so a batch never overtakes the previous one's reads or writes of the same buffers)."""
-        n_pairs = len(frames) - 1
+        """frames: uint8 [F, H, W, 3] (page-locked for real overlap); dists: dist of each interpolated frame
+        inside a pair (Python floats, see interpolation_dists); out: uint8 [(F-1)*len(dists), H, W, 3], filled
+        in pair order.  Returns after everything has been enqueued AND (sync=True) completed; with sync=False
+        the caller streams several batches back to back and calls sync() once."""
+        n_frames = len(frames)
+        n_pairs = n_frames - 1
         nd = len(dists)
+        if self.stager is None or self.stager.n < n_frames:
+            if self.stager is not None:
+                self.sync()
+                self.stager.close()
+            self.stager = FrameStager(self.H, self.W, n_frames, self.device)
+        st = self.stager
         C = min(len(self.ctxs), n_pairs)
         bounds = [round(i * n_pairs / C) for i in range(C + 1)]
-        pos = [bounds[i] for i in range(C)]
-        started = [False] * C
-        live = True
-        while live:
-            live = False
-            for c in range(C):
-                k = pos[c]
-                if k >= bounds[c + 1]:
-                    continue
-                live = True
-                ctx = self.ctxs[c]
-                a, b = k % 3, (k + 1) % 3
-                if not started[c]:
-                    ctx.upload_frame(a, frames[k])
-                    started[c] = True
-                ctx.upload_frame(b, frames[k + 1])
-                ctx.estimate_pair(self.params, a, b, 0, 1)
-                for j, d in enumerate(dists):
-                    o = 6 + (j & 1)
-                    if self.bidir2:
-                        # the class passes the python floats dist and 1 - dist (Bidirectional_2.py:331-332)
-                        ctx.mci_bidir2(a, b, 0, 1, np.float32(d), np.float32(1 - d), self._w, o,
-                                       self.params.min_block_size, 4 * self.params.min_block_size)
-                    elif self.bidir:
-                        ctx.mci_bidir(a, b, 0, 1, d, o)
-                    else:
-                        ctx.mci_unidir(a, b, 0, d, o)
-                    ctx.download_frame(o, out[k * nd + j], sync=False)
-                pos[c] += 1
+        # enqueue order: the runs advance in lock step; uploads are issued in the order that order needs them
+        order = [(c, bounds[c] + r) for r in range(max(bounds[c + 1] - bounds[c] for c in range(C))) for c in range(C)
+                 if bounds[c] + r < bounds[c + 1]]
+        staged = set()
+        for c, k in order:
+            for f in (k, k + 1):
+                if f not in staged:
+                    st.upload(f, frames[f])              # ring slot = frame index within the batch
+                    staged.add(f)
+        for c, k in order:
+            ctx = self.ctxs[c]
+            a, b = k % 3, (k + 1) % 3
+            if k == bounds[c]:
+                ctx.frame_from_stager(a, st, k)           # first pair of the run: both frames are new to this context
+            ctx.frame_from_stager(b, st, k + 1)
+            ctx.estimate_pair(self.params, a, b, 0, 1)
+            for j, d in enumerate(dists):
+                o = 6 + (j & 1)
+                if self.bidir2:
+                    # the class passes the python floats dist and 1 - dist (Bidirectional_2.py:331-332)
+                    ctx.mci_bidir2(a, b, 0, 1, np.float32(d), np.float32(1 - d), self._w, o,
+                                   self.params.min_block_size, 4 * self.params.min_block_size)
+                elif self.bidir:
+                    ctx.mci_bidir(a, b, 0, 1, d, o)
+                else:
+                    ctx.mci_unidir(a, b, 0, d, o)
+                ctx.download_frame_via(o, out[k * nd + j], st)
         if sync:
             self.sync()
         return out
