@@ -174,6 +174,7 @@ b2_frame_kernel(const __grid_constant__ B2Params P)
     __shared__ float fc[B2_TH][B2_TW][3];
     __shared__ float dsum[B2_TW / B2_EB][4][4];
     __shared__ int blk_hole[B2_TW / B2_EB];
+    __shared__ int tile_tmax[2][2];               // largest |T| per direction and axis among the staged blocks: tighter per-pixel loops than the frame-wide maximum
 
     const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
     const int tx0 = blockIdx.x * B2_TW, ty0 = blockIdx.y * B2_TH;
@@ -186,7 +187,10 @@ b2_frame_kernel(const __grid_constant__ B2Params P)
     const int nrb = br_hi - br_lo + 1, ncb = bc_hi - bc_lo + 1;
     const bool staged = nrb > 0 && ncb > 0 && nrb * ncb <= B2_MAXB;
     if (tid < B2_TW / B2_EB) blk_hole[tid] = 0;
+    if (tid < 4) (&tile_tmax[0][0])[tid] = 0;
+    __syncthreads();
     if (staged) {
+        int tm[2][2] = {{0, 0}, {0, 0}};
         for (int i = tid; i < nrb * ncb; i += B2_TW * B2_TH) {
             const int r = i / ncb, c = i - r * ncb;
             const size_t g = (size_t)(br_lo + r) * P.nbc + bc_lo + c;
@@ -195,25 +199,32 @@ b2_frame_kernel(const __grid_constant__ B2Params P)
                 const int4 b = P.blk[d][g];
                 sblk[d][i] = b;
                 stl[d][i] = (unsigned)((4 * (br_lo + r) - 2 + b.z) & 0xffff) | ((unsigned)(4 * (bc_lo + c) - 2 + (b.w >> 1)) << 16);
+                tm[d][0] = max(tm[d][0], abs(b.z)); tm[d][1] = max(tm[d][1], abs(b.w >> 1));
             }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int m = __reduce_max_sync(0xffffffffu, tm[q >> 1][q & 1]);
+            if (lx == 0 && m > 0) atomicMax(&tile_tmax[q >> 1][q & 1], m);
         }
     }
     __syncthreads();
 
     const bool in_region = x < P.Wr;            // y < Hr always (grid)
     float out_c[3] = {-1.f, -1.f, -1.f};
-    // warp-uniform row range (y is the same for the whole warp; x differs)
-    const int brp_lo_w = max(br_lo, floor_div4(y - 5 - tmax)), brp_hi_w = min(br_hi, floor_div4(y + 2 + tmax));
     if (nrb > 0 && ncb > 0) {
         float Fd[2][3], Ed[2][3];
         bool has[2];
-        const int bcp_lo = max(bc_lo, floor_div4(x - 5 - tmax)), bcp_hi = min(bc_hi, floor_div4(x + 2 + tmax));
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
             const uint8_t *F1 = P.f1[d], *F2 = P.f2[d];
             const float dist = P.dist[d];
             const double one_minus = __dsub_rn(1.0, (double)dist);          // (1 - dist): int64 - float32 -> float64
             float acc[3] = {0.f, 0.f, 0.f}, wm[3] = {0.f, 0.f, 0.f}, ws = 0.f;
+            // every block that can reach the tile is staged, so the staged maxima bound this tile's loops exactly
+            const int tr = staged ? tile_tmax[d][0] : tmax, tc = staged ? tile_tmax[d][1] : tmax;
+            const int brp_lo_w = max(br_lo, floor_div4(y - 5 - tr)), brp_hi_w = min(br_hi, floor_div4(y + 2 + tr));    // warp-uniform
+            const int bcp_lo = max(bc_lo, floor_div4(x - 5 - tc)), bcp_hi = min(bc_hi, floor_div4(x + 2 + tc));
             // Per-lane loops over the blocks that can reach (x, y), in block raster order = the reference's accumulation
             // order.  Lanes of a warp share y and walk bc ranges shifted with x, so neighbouring lanes test neighbouring
             // blocks in the same iteration and hit together.  (A warp-compacted list of the blocks passing the row test
