@@ -78,11 +78,52 @@ __global__ void __launch_bounds__(512) ub_kernel(int iters, const int *__restric
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// mode 12: the full-search kernel's own SAD pattern -- 64 reference registers, G = 11 accumulators, G + 7 window rows
+// of 8 pixels per group, pixel-major order -- with the window pixels synthesised in registers (no shared memory) and
+// no bookkeeping: what the register-tiled stream itself can reach at the kernel's occupancy (512 threads, 1 CTA / SM).
+__global__ void __launch_bounds__(512, 1) ub_fs_pattern_kernel(int iters, const int *__restrict__ seed, unsigned *__restrict__ out)
+{
+    constexpr int G = 11;
+    int r[8][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[k][j] = seed[(threadIdx.x + k * 8 + j) & 63] + k;
+    unsigned total = 0;
+    int base = seed[threadIdx.x & 63];
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        unsigned acc[G];
+#pragma unroll
+        for (int i = 0; i < G; ++i) acc[i] = 0xffffffffu;
+#pragma unroll
+        for (int w = 0; w < G + 7; ++w) {
+            int px[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) px[j] = base + w * 8 + j + it;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int gi = 0; gi < G; ++gi) {
+                    const int kk = w - gi;
+                    if (kk >= 0 && kk < 8) acc[gi] = __sad(r[kk][j], px[j], acc[gi]);
+                }
+        }
+        unsigned m = 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < G; ++i) m = min(m, acc[i]);
+        total += m;
+        base += (int)(m & 3u);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = total;
+}
+
 extern "C" MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, float *ms, double *px_ops)
 {
-    if (!ctx || mode < 0 || mode > 11 || iters <= 0) return MEMCI_ERR_ARG;
+    if (!ctx || mode < 0 || mode > 14 || iters <= 0) return MEMCI_ERR_ARG;
     cudaSetDevice(ctx->device);
-    const int grid = ctx->num_sms * 4, nt = 512;
+    // modes 13 / 14: the mode-12 kernel with 2 / 1 warps per scheduler
+    const int grid = mode >= 12 ? ctx->num_sms : ctx->num_sms * 4, nt = mode == 13 ? 256 : mode == 14 ? 128 : 512;
     int *d_seed = nullptr;
     unsigned *d_out = nullptr;
     int h_seed[64];
@@ -106,6 +147,7 @@ extern "C" MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, f
         case 8: ub_kernel<8><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
         case 9: ub_kernel<9><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
         case 10: ub_kernel<10><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        case 12: case 13: case 14: ub_fs_pattern_kernel<<<grid, nt, 0, ctx->stream>>>(iters / 16, d_seed, d_out); break;
         default: ub_kernel<11><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
         }
         ctx->launches++;
@@ -117,7 +159,7 @@ extern "C" MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, f
     cudaEventElapsedTime(&t, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d_seed); cudaFree(d_out);
-    const double per_step = mode == 2 ? 12.0 : mode == 3 ? 16.0 : 8.0;
+    const double per_step = mode == 2 ? 12.0 : mode == 3 ? 16.0 : mode >= 12 ? 704.0 / 16.0 : 8.0;
     if (ms) *ms = t;
     if (px_ops) *px_ops = per_step * (double)iters * (double)grid * nt;
     return MEMCI_OK;
