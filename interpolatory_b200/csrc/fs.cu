@@ -189,11 +189,11 @@ fs_redo_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
 // =========================================================================================
 // Tiled kernel.
 //
-// A tile = nb horizontally adjacent blocks of one block row.  Thread 0 stages, with two TMA
+// A tile = nb horizontally adjacent blocks of one block row.  The lead warp stages, with two TMA
 // tile loads (cp.async.bulk.tensor.2d, zero fill outside the frame = the reference's np.pad),
 //   win[box_h][256]  luma1000 of the target frame, rows s_row-R .. s_row+bs+R-1, cols x0-R ..
 //   ref[bs][256]     luma1000 of the source frame, the nb blocks themselves
-// into one of two shared-memory stages while the previous tile is being searched.
+// into one of up to three shared-memory stages while earlier tiles are being searched.
 //
 // Work item = (block b, column offset dx, group g of G consecutive row offsets).  A thread
 // keeps the 8x8 reference sub-block in 64 registers and G accumulators, walks the G+7 window
@@ -205,7 +205,7 @@ fs_redo_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
 //
 // Argmin: per item in registers, then one shared-memory atomicMin per item on the 64-bit key.
 // Flagged candidates are tracked with SAD-1 as a lower bound; a block whose best lower bound
-// beats its best fast key is appended to the redo list and re-resolved by fs_generic_kernel.
+// beats its best fast key is appended to the redo list and re-resolved by fs_redo_kernel.
 // =========================================================================================
 struct FsParams {
     int H, W, bs, R, Rp, m, nbr, nbc, n_tiles, box_h, n_stages, ks;   // ks = bits reserved for dist^2 in the 32-bit key   // Rp = R rounded up to 4: TMA x origin stays 16-byte aligned
@@ -342,7 +342,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 // warp reduction, shared-memory atomic) is paid once per 8*8*(2R+1) SAD pixel-ops.
 //
 // Synchronisation is mbarrier-only: full[s] = "tile data landed in stage s" (TMA complete_tx),
-// done[j] = "all 16 warps finished searching the tile using result buffer j".  Only warp 0
+// done[j] = "all 16 warps finished searching the tile using result buffer j".  Only the lead warp
 // ever waits on done[] (it writes the tile's motion vectors, re-arms the stage and issues the
 // next TMA), so a warp that finishes early moves straight on to the next tile.
 template <int G, bool SINGLE>
@@ -386,7 +386,7 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
     //   NS == 2: warp 0 waits for done[k-1] BEFORE tile k (it needs that stage for tile k+1).
     //   NS == 1: load, search, output, strictly in turn.
     const int NS = p.n_stages, NB = NS == 3 ? 3 : 2;
-    auto issue = [&](int tile_idx, int s, int j) {        // warp 0 only: tile table + two TMA tile loads
+    auto issue = [&](int tile_idx, int s, int j) {        // lead warp only: tile table + two TMA tile loads
         const int dir = tile_idx >= p.n_tiles_dir ? 1 : 0;
         FsTile t = p.tiles[tile_idx - dir * p.n_tiles_dir];
         fs_fill_tab(&tabs[j], t, p, lane, dir);

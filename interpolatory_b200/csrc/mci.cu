@@ -3,19 +3,20 @@
 // The reference is a raster-order SCATTER: every source pixel p splats forward (and backward)
 // onto q = p + round(mv * dist), and what lands on q depends on the ORDER of arrival (strict /
 // non-strict SAD priority, SAD-weighted blend with whatever is already there).  We restate it
-// as an order-preserving GATHER, one thread per target pixel q:
+// as an order-preserving GATHER over the target pixels q:
 //
 //   * an "event" at q is a (source pixel p, direction) pair whose splat hits q;
 //   * events reach q in raster order of p, forward before backward at the same p;
 //   * with e = q - p the effective displacement (wrap-around of negative targets folded in,
 //     W1), raster order of p is DESCENDING lexicographic order of e -- independent of q.
 //
-// So each 32x8 tile of targets collects the set of distinct (e, direction) values of the MV
-// cells that can reach it (MVs are piecewise constant on cells, so the set is tiny: ~2-6
+// So each 32x8 tile of targets (one warp) collects the set of distinct (e, direction) values of the
+// MV cells that can reach it (MVs are piecewise constant on cells, so the set is tiny: ~2-6
 // entries for coherent motion), sorts it once, and every pixel walks that sorted list, testing
 // "does the pixel at q - e really carry displacement e?" and replaying the reference's state
-// machine (SAD_interpolated_frame / Interpolated_Frame) in registers.  Holes (pixels no event
-// reached) are recorded and filled by a second kernel with the 21x21 masked median.
+// machine (SAD_interpolated_frame / Interpolated_Frame) as a decision record in registers; the
+// pixel values are fetched afterwards.  Holes (pixels no event reached) are recorded as runs and
+// filled by a second kernel with the 21x21 masked median (sliding histogram along the run).
 #include <type_traits>
 
 #include "memci_internal.cuh"
