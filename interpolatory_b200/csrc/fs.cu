@@ -210,6 +210,7 @@ fs_redo_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
 struct FsParams {
     int H, W, bs, R, Rp, m, nbr, nbc, n_tiles, box_h, n_stages, ks;   // ks = bits reserved for dist^2 in the 32-bit key   // Rp = R rounded up to 4: TMA x origin stays 16-byte aligned
     int lead_warp;               // the warp that writes the tile's vectors and issues the TMA loads
+    unsigned long long *trace;   // debug (MEMCI_FS_TRACE=file): per (tile, warp) of CTA 0: clock at wait / start / end of the column
     unsigned one;                // the constant 1, opaque to ptxas (keeps IMADs from being folded into ALU adds)
     int n_tiles_dir;             // tiles of one direction; tile index >= n_tiles_dir = reverse direction (pair launch)
     const FsTile *tiles;
@@ -452,8 +453,11 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
             if (next < p.n_tiles) issue(next, s ^ 1, jn);     // streams in while this tile is searched
         }
 
+        unsigned long long t_wait = 0, t_start = 0;
+        if (p.trace && blockIdx.x == 0 && lane == 0) t_wait = clock64();
         mbar_wait(&full[s], full_phase[s]);
         full_phase[s] ^= 1u;
+        if (p.trace && blockIdx.x == 0 && lane == 0) t_start = clock64();
         const FsTileTab *tab = &tabs[j];
         const int *win = stage0 + (size_t)s * stage_ints;
         const int *ref = win + p.box_h * FS_BOXW;
@@ -561,6 +565,10 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
             }
         }
         __syncwarp();
+        if (p.trace && blockIdx.x == 0 && lane == 0 && k < 64) {
+            unsigned long long *t = p.trace + ((size_t)k * (FS_NT / 32) + warp) * 3;
+            t[0] = t_wait; t[1] = t_start; t[2] = clock64();
+        }
         if (lane == 0) mbar_arrive(&done[j]);
 
         if (warp == p.lead_warp && NS == 1) {
@@ -785,6 +793,10 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         // issues the next loads early instead of late (1.8 % on the 1080p kernel; start-up staggering of the warps and per-item
         // result slots reduced by the lead warp were measured too: no gain)
         p.lead_warp = FS_NT / 32 - 1;
+        p.trace = nullptr;
+        const char *trace_path = getenv("MEMCI_FS_TRACE");
+        const size_t trace_n = (size_t)64 * (FS_NT / 32) * 3;
+        if (trace_path) { CK(ctx, cudaMalloc(&p.trace, trace_n * 8)); CK(ctx, cudaMemsetAsync(p.trace, 0, trace_n * 8, ctx->stream)); }
         p.n_tiles_dir = pl->row_tile_start[br1] - pl->row_tile_start[br0]; p.n_tiles = ndir * p.n_tiles_dir; p.box_h = pl->box_h;
         { int ks = 1; while ((1 << ks) <= 2 * R * R + 1) ++ks; p.ks = ks; }
         p.n_stages = fs_smem_bytes(bs, pl->box_h, 3, pl->G) <= 200 * 1024 ? 3 : fs_smem_bytes(bs, pl->box_h, 2, pl->G) <= 220 * 1024 ? 2 : 1;
@@ -805,6 +817,16 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         default: rc = fs_launch_tiled<11>(ctx, tm, p, smem); break;
         }
         memci_prof_end(ctx, prof);
+        if (p.trace) {                                   // debug dump: one line per (tile, warp)
+            unsigned long long *h = (unsigned long long *)malloc(trace_n * 8);
+            cudaStreamSynchronize(ctx->stream);
+            cudaMemcpy(h, p.trace, trace_n * 8, cudaMemcpyDeviceToHost);
+            if (FILE *f = fopen(trace_path, "w")) {
+                for (size_t i = 0; i < trace_n / 3; ++i) fprintf(f, "%zu %zu %llu %llu %llu\n", i / (FS_NT / 32), i % (FS_NT / 32), h[3 * i], h[3 * i + 1], h[3 * i + 2]);
+                fclose(f);
+            }
+            free(h); cudaFree(p.trace);
+        }
         if (rc) return rc;
         if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->fs_timed = 1; }
         // exact pass over the (normally few) blocks on the redo list

@@ -6,6 +6,8 @@
 //   mode 3: 8 VABSDIFF + 8 FADD pairs per step
 //   modes 4..9: 8 VABSDIFF + 2 x {LDS.32, IMAD reg, IMAD imm, FADD, IADD3, VIMNMX3} per step -- what does an extra
 //               instruction cost next to the SAD stream? (px_ops counts the 8 SADs only)
+#include <stdlib.h>
+
 #include "memci_internal.cuh"
 
 template <int MODE>
@@ -123,7 +125,8 @@ extern "C" MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, f
     if (!ctx || mode < 0 || mode > 14 || iters <= 0) return MEMCI_ERR_ARG;
     cudaSetDevice(ctx->device);
     // modes 13 / 14: the mode-12 kernel with 2 / 1 warps per scheduler
-    const int grid = mode >= 12 ? ctx->num_sms : ctx->num_sms * 4, nt = mode == 13 ? 256 : mode == 14 ? 128 : 512;
+    int grid = mode >= 12 ? ctx->num_sms : ctx->num_sms * 4, nt = mode == 13 ? 256 : mode == 14 ? 128 : 512;
+    if (const char *e = getenv("MEMCI_UB_CTAS_PER_SM")) grid = ctx->num_sms * atoi(e);        // occupancy experiments
     int *d_seed = nullptr;
     unsigned *d_out = nullptr;
     int h_seed[64];
