@@ -487,3 +487,42 @@ def test_bidir2_out_of_range_blocks_raise(gpu):
     mv[0:8, 0:8, 0] = -40.0                    # 14 + (-40) < 0: leaves the 16-px padding
     with pytest.raises(Exception, match='outside the padded frame'):
         interpolate(fr[0], fr[1], mv, mv, 0.5, 16, 4, True)
+
+
+def test_cfg3_1080p_full_size_vs_oracle(gpu, oracle):
+    """cfg3 at full size (1080p, HBMA with the class API's auto depth 4, median smoothing, the four 24->120 dists):
+    the parent-level densify kernel, the splat's 4x4-cell lists, dense hole runs (dist 0.8) and bidir2 on the same
+    vectors, against the oracle."""
+    from interpolatory_b200.device import DeviceContext
+    from interpolatory_b200._native import PairParams
+    from interpolatory_b200.MCI.Bidirectional_2 import get_weight_kern
+    from interpolatory_b200.util import hbma_auto_steps
+    H, W = 1080, 1920
+    fr = make_sequence(H, W, 2, seed=7)
+    a, b = fr[0], fr[1]
+    steps = hbma_auto_steps((H, W))
+    assert steps == 4
+    ctx = DeviceContext(H, W)
+    try:
+        ctx.upload_frame(0, a); ctx.upload_frame(1, b)
+        # block-level vectors (what bidir2 consumes: upscale=False)
+        ctx.estimate_pair(PairParams(1, 8, 7, 1, steps, 4, 0, 4, 1), 0, 1, 0, 1)
+        fb = oracle.hbma(8, 7, 1, steps, 4, a, b, 'sad', False)
+        bb = oracle.hbma(8, 7, 1, steps, 4, b, a, 'sad', False)
+        for slot, ref in ((0, fb), (1, bb)):
+            _, vec, _, sad = ctx.download_mv_blocks(slot)
+            assert np.array_equal(vec, ref[:, :, :2]) and np.array_equal(sad, ref[:, :, 2]), slot
+        ctx.mci_bidir2(0, 1, 0, 1, np.float32(0.4), np.float32(1 - 0.4), get_weight_kern(8), 7)
+        assert np.array_equal(ctx.download_frame(7), oracle.bidir2_frame(a, b, fb, bb, 0.4, False))
+        assert ctx.bidir2_stats()[1] == 0
+        # median-smoothed dense fields (what unidir / bidir consume)
+        ctx.estimate_pair(PairParams(1, 8, 7, 1, steps, 4, 2, 4, 1), 0, 1, 0, 1)
+        fd = oracle.smooth('median', oracle.hbma(8, 7, 1, steps, 4, a, b), 4)
+        bd = oracle.smooth('median', oracle.hbma(8, 7, 1, steps, 4, b, a), 4)
+        for dist in (0.19999999, 0.8):
+            ctx.mci_bidir(0, 1, 0, 1, np.float32(dist), 7)
+            assert np.array_equal(ctx.download_frame(7), oracle.bidir_helper(a, b, fd, bd, np.float32(dist))), dist
+        ctx.mci_unidir(0, 1, 0, np.float32(0.6), 7)
+        assert np.array_equal(ctx.download_frame(7), oracle.unidir_helper(a, b, fd, np.float32(0.6)))
+    finally:
+        ctx.close()
