@@ -5,6 +5,8 @@ and the device->host copy of the previous output overlap the kernels of the curr
 Frame pairs are independent: a context takes a contiguous run of pairs, so each source
 frame crosses PCIe once (twice at the run boundaries); nothing is exchanged between contexts.
 """
+import math
+
 import numpy as np
 
 from ._native import PairParams
@@ -87,14 +89,57 @@ class PairPipeline:
         if self.stager is not None:
             self.stager.sync()
 
+    def plan_clip(self, n_frames, fps_in, fps_out):
+        """Output schedule of a whole clip, exactly as BaseInterpolator.interpolate_video walks it (base.py:78-115):
+        one entry per output frame, (source frame index, dist) with dist == 0 for a pass-through source frame."""
+        rate_ratio = fps_out / fps_in
+        n_out = int(math.floor((n_frames / fps_in) * fps_out))
+        plan = []
+        for idx in range(n_out):
+            first, ratio = get_first_frame_idx_and_ratio(idx, rate_ratio)
+            dist = 1. - ratio
+            if math.isclose(dist, 0.):
+                plan.append((first, 0.0))
+            elif first + 1 < n_frames:
+                plan.append((first, float(dist)))
+            else:
+                break                                     # the reference would read past the last frame here
+        return plan
+
+    def run_clip(self, frames, fps_in, fps_out, out, sync=True):
+        """Any rate ratio (e.g. 24 -> 60, where the dists differ from pair to pair): fills out[i] for every output
+        frame i of plan_clip(); pass-through frames are copied on the host, interpolated ones go through the same
+        staged, multi-context path as run().  Returns the plan."""
+        plan = self.plan_clip(len(frames), fps_in, fps_out)
+        per_pair = {}
+        for i, (k, d) in enumerate(plan):
+            if d == 0.0:
+                out[i] = frames[k]
+            else:
+                per_pair.setdefault(k, []).append((i, d))
+        if per_pair:
+            self._run_pairs(frames, per_pair, out)
+        if sync:
+            self.sync()
+        return plan
+
     def run(self, frames, dists, out, sync=True):
         """frames: uint8 [F, H, W, 3] (page-locked for real overlap); dists: dist of each interpolated frame
         inside a pair (Python floats, see interpolation_dists); out: uint8 [(F-1)*len(dists), H, W, 3], filled
         in pair order.  Returns after everything has been enqueued AND (sync=True) completed; with sync=False
         the caller streams several batches back to back and calls sync() once."""
-        n_frames = len(frames)
-        n_pairs = n_frames - 1
         nd = len(dists)
+        per_pair = {k: [(k * nd + j, d) for j, d in enumerate(dists)] for k in range(len(frames) - 1)}
+        self._run_pairs(frames, per_pair, out)
+        if sync:
+            self.sync()
+        return out
+
+    def _run_pairs(self, frames, per_pair, out):
+        """per_pair: {pair index k: [(output index, dist), ...]}; pairs without work are skipped."""
+        n_frames = len(frames)
+        pairs = sorted(per_pair)
+        n_pairs = len(pairs)
         if self.stager is None or self.stager.n < n_frames:
             if self.stager is not None:
                 self.sync()
@@ -107,19 +152,23 @@ class PairPipeline:
         order = [(c, bounds[c] + r) for r in range(max(bounds[c + 1] - bounds[c] for c in range(C))) for c in range(C)
                  if bounds[c] + r < bounds[c + 1]]
         staged = set()
-        for c, k in order:
+        for c, r in order:
+            k = pairs[r]
             for f in (k, k + 1):
                 if f not in staged:
                     st.upload(f, frames[f])              # ring slot = frame index within the batch
                     staged.add(f)
-        for c, k in order:
+        prev = {}                                        # context -> pair it processed last
+        for c, r in order:
+            k = pairs[r]
             ctx = self.ctxs[c]
             a, b = k % 3, (k + 1) % 3
-            if k == bounds[c]:
-                ctx.frame_from_stager(a, st, k)           # first pair of the run: both frames are new to this context
+            if prev.get(c) != k - 1:
+                ctx.frame_from_stager(a, st, k)           # not the successor of this context's last pair: both frames are new to it
             ctx.frame_from_stager(b, st, k + 1)
+            prev[c] = k
             ctx.estimate_pair(self.params, a, b, 0, 1)
-            for j, d in enumerate(dists):
+            for j, (oi, d) in enumerate(per_pair[k]):
                 o = 6 + (j & 1)
                 if self.bidir2:
                     # the class passes the python floats dist and 1 - dist (Bidirectional_2.py:331-332)
@@ -129,7 +178,4 @@ class PairPipeline:
                     ctx.mci_bidir(a, b, 0, 1, d, o)
                 else:
                     ctx.mci_unidir(a, b, 0, d, o)
-                ctx.download_frame_via(o, out[k * nd + j], st)
-        if sync:
-            self.sync()
-        return out
+                ctx.download_frame_via(o, out[oi], st)

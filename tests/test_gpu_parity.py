@@ -526,3 +526,24 @@ def test_cfg3_1080p_full_size_vs_oracle(gpu, oracle):
         assert np.array_equal(ctx.download_frame(7), oracle.unidir_helper(a, b, fd, np.float32(0.6)))
     finally:
         ctx.close()
+
+
+def test_run_clip_24_to_60_equals_class_api(gpu):
+    """PairPipeline.run_clip on a rate ratio whose dists differ from pair to pair (24 -> 60, BASELINE cfg1's ratio):
+    every output frame -- pass-through and interpolated -- equals the class API's get_interpolated_frame(i)."""
+    from interpolatory_b200 import MEMCI, ArrayVideoStream
+    from interpolatory_b200.pipeline import PairPipeline
+    H, W = 120, 168
+    frames = make_sequence(H, W, 5, seed=321)
+    st = dict(me_mode='fs', block_size='8', target_region='7', mci_mode='bidir')
+    pipe = PairPipeline(H, W, n_contexts=3, **st)
+    plan = pipe.plan_clip(len(frames), 24, 60)
+    out = np.zeros((len(plan), H, W, 3), np.uint8)
+    pipe.run_clip(frames, 24, 60, out)
+    pipe.close()
+    it = MEMCI(60, **st)
+    it.set_video_stream(ArrayVideoStream(list(frames), 24))
+    assert len(plan) >= 10 and sum(1 for _, d in plan if d == 0.0) >= 2
+    for i in range(len(plan)):
+        assert np.array_equal(np.asarray(it.get_interpolated_frame(i)), out[i]), (i, plan[i])
+    it.close()
