@@ -190,10 +190,21 @@ int memci_host_free(void *p)
 // ---- frames ----------------------------------------------------------------------------
 static void frame_touched(FrameSlot &f) { f.valid = 1; f.luma_ok = 0; f.pyr_levels = 0; }
 
+// output slot still being copied out by a stager -> the context's stream waits for that copy
+static int memci_wait_slot_free(memci_ctx *ctx, int slot)
+{
+    if (slot >= 0 && slot < MEMCI_NUM_FRAME_SLOTS && ctx->out_pending[slot]) {
+        CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out_copied[slot], 0));
+        ctx->out_pending[slot] = 0;
+    }
+    return MEMCI_OK;
+}
+
 int memci_upload_frame(memci_ctx *ctx, int slot, const uint8_t *host)
 {
     REQ_CTX(ctx); REQ_FRAME(ctx, slot, 0);
     if (!host) return memci_fail(ctx, MEMCI_ERR_ARG, "null host frame");
+    { int rc_ = memci_wait_slot_free(ctx, slot); if (rc_) return rc_; }
     CK(ctx, cudaMemcpyAsync(ctx->frames[slot].rgb, host, (size_t)ctx->H * ctx->W * 3, cudaMemcpyHostToDevice, ctx->stream));
     frame_touched(ctx->frames[slot]);
     return MEMCI_OK;
@@ -203,6 +214,7 @@ int memci_set_frame_device(memci_ctx *ctx, int slot, const void *dev)
 {
     REQ_CTX(ctx); REQ_FRAME(ctx, slot, 0);
     if (!dev) return memci_fail(ctx, MEMCI_ERR_ARG, "null device frame");
+    { int rc_ = memci_wait_slot_free(ctx, slot); if (rc_) return rc_; }
     CK(ctx, cudaMemcpyAsync(ctx->frames[slot].rgb, dev, (size_t)ctx->H * ctx->W * 3, cudaMemcpyDeviceToDevice, ctx->stream));
     frame_touched(ctx->frames[slot]);
     return MEMCI_OK;
@@ -231,6 +243,7 @@ struct memci_stager {
     cudaEvent_t *ready;
     cudaEvent_t *consumed;      // [n][STAGER_MAX_CONSUMERS]
     int *n_consumed;
+    unsigned char *has_data;
 };
 
 int memci_stager_create(int device, int H, int W, int n_slots, memci_stager **out)
@@ -245,7 +258,8 @@ int memci_stager_create(int device, int H, int W, int n_slots, memci_stager **ou
     st->ready = (cudaEvent_t *)calloc(n_slots, sizeof(cudaEvent_t));
     st->consumed = (cudaEvent_t *)calloc((size_t)n_slots * STAGER_MAX_CONSUMERS, sizeof(cudaEvent_t));
     st->n_consumed = (int *)calloc(n_slots, sizeof(int));
-    bool ok = st->buf && st->ready && st->consumed && st->n_consumed &&
+    st->has_data = (unsigned char *)calloc(n_slots, 1);
+    bool ok = st->buf && st->ready && st->consumed && st->n_consumed && st->has_data &&
               cudaStreamCreateWithFlags(&st->h2d, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&st->d2h, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; ok && i < n_slots; ++i) {
@@ -271,7 +285,7 @@ int memci_stager_destroy(memci_stager *st)
         for (int c = 0; st->consumed && c < STAGER_MAX_CONSUMERS; ++c)
             if (st->consumed[i * STAGER_MAX_CONSUMERS + c]) cudaEventDestroy(st->consumed[i * STAGER_MAX_CONSUMERS + c]);
     }
-    free(st->buf); free(st->ready); free(st->consumed); free(st->n_consumed); free(st);
+    free(st->buf); free(st->ready); free(st->consumed); free(st->n_consumed); free(st->has_data); free(st);
     return MEMCI_OK;
 }
 
@@ -285,6 +299,7 @@ int memci_stager_upload(memci_stager *st, int slot, const uint8_t *host)
     st->n_consumed[slot] = 0;
     if (cudaMemcpyAsync(st->buf[slot], host, (size_t)st->H * st->W * 3, cudaMemcpyHostToDevice, st->h2d) != cudaSuccess) return MEMCI_ERR_CUDA;
     if (cudaEventRecord(st->ready[slot], st->h2d) != cudaSuccess) return MEMCI_ERR_CUDA;
+    st->has_data[slot] = 1;
     return MEMCI_OK;
 }
 
@@ -294,6 +309,8 @@ int memci_frame_from_stager(memci_ctx *ctx, int frame_slot, memci_stager *st, in
     if (!st || slot < 0 || slot >= st->n) return memci_fail(ctx, MEMCI_ERR_ARG, "bad stager slot %d", slot);
     if (st->H != ctx->H || st->W != ctx->W || st->device != ctx->device) return memci_fail(ctx, MEMCI_ERR_ARG, "stager and context differ in device or frame size");
     if (st->n_consumed[slot] >= STAGER_MAX_CONSUMERS) return memci_fail(ctx, MEMCI_ERR_STATE, "stager slot %d handed out more than %d times", slot, STAGER_MAX_CONSUMERS);
+    if (!st->has_data[slot]) return memci_fail(ctx, MEMCI_ERR_STATE, "stager slot %d was never uploaded", slot);
+    { int rc_ = memci_wait_slot_free(ctx, frame_slot); if (rc_) return rc_; }
     CK(ctx, cudaStreamWaitEvent(ctx->stream, st->ready[slot], 0));
     CK(ctx, cudaMemcpyAsync(ctx->frames[frame_slot].rgb, st->buf[slot], (size_t)ctx->H * ctx->W * 3, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(ctx, cudaEventRecord(st->consumed[slot * STAGER_MAX_CONSUMERS + st->n_consumed[slot]++], ctx->stream));
@@ -314,16 +331,6 @@ int memci_download_frame_via(memci_ctx *ctx, int slot, uint8_t *host, memci_stag
     CK(ctx, cudaMemcpyAsync(host, ctx->frames[slot].rgb, (size_t)ctx->H * ctx->W * 3, cudaMemcpyDeviceToHost, st->d2h));
     CK(ctx, cudaEventRecord(ctx->ev_out_copied[slot], st->d2h));
     ctx->out_pending[slot] = 1;
-    return MEMCI_OK;
-}
-
-// output slot still being copied out by a stager -> the context's stream waits for that copy
-static int memci_wait_slot_free(memci_ctx *ctx, int slot)
-{
-    if (slot >= 0 && slot < MEMCI_NUM_FRAME_SLOTS && ctx->out_pending[slot]) {
-        CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out_copied[slot], 0));
-        ctx->out_pending[slot] = 0;
-    }
     return MEMCI_OK;
 }
 

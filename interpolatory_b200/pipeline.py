@@ -73,6 +73,8 @@ class PairPipeline:
         self.stager = None
 
     def close(self):
+        if self.ctxs:
+            self.sync()                                  # the D2H stream may still be reading a context's output slot
         for c in self.ctxs:
             c.close()
         self.ctxs = []
