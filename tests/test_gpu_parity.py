@@ -547,3 +547,23 @@ def test_run_clip_24_to_60_equals_class_api(gpu):
     for i in range(len(plan)):
         assert np.array_equal(np.asarray(it.get_interpolated_frame(i)), out[i]), (i, plan[i])
     it.close()
+
+
+@pytest.mark.parametrize("H,W", [(8, 8), (16, 24), (9, 40), (33, 17)])
+def test_tiny_frames_vs_oracle(gpu, oracle, H, W):
+    """Frames smaller than a tile / a search window / a hole-fill window: every kernel's edge clamps."""
+    from interpolatory_b200.ME.full_search import get_motion_vectors as fs
+    from interpolatory_b200.MCI.Bidirectional import helper as bi
+    from interpolatory_b200.MCI.Unidirectional import helper as uni
+    from interpolatory_b200.MCI.Bidirectional_2 import interpolate as b2
+    rng = np.random.default_rng(H * 100 + W)
+    a = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    b = np.roll(a, (1, 2), axis=(0, 1))
+    b[:2] = rng.integers(0, 256, (2, W, 3), dtype=np.uint8)
+    for bs, R in ((8, 3), (4, 2)):
+        f, g = fs(bs, R, a, b), fs(bs, R, b, a)
+        assert np.array_equal(f, oracle.fs(bs, R, a, b)) and np.array_equal(g, oracle.fs(bs, R, b, a)), (bs, R)
+        for dist in (0.5, 0.8):
+            assert np.array_equal(bi(a, b, f, g, np.float32(dist)), oracle.bidir_helper(a, b, f, g, np.float32(dist)))
+            assert np.array_equal(uni(a, b, f, np.float32(dist)), oracle.unidir_helper(a, b, f, np.float32(dist)))
+        assert np.array_equal(b2(a, b, f, g, 0.5, 16, 4, True), oracle.bidir2_frame(a, b, f, g, 0.5, True))
