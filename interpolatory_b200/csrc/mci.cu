@@ -17,6 +17,7 @@
 // machine (SAD_interpolated_frame / Interpolated_Frame) as a decision record in registers; the
 // pixel values are fetched afterwards.  Holes (pixels no event reached) are recorded as runs and
 // filled by a second kernel with the 21x21 masked median (sliding histogram along the run).
+#include <stdlib.h>
 #include <type_traits>
 
 #include "memci_internal.cuh"
@@ -44,6 +45,7 @@ struct MciParams {
     int scell[2], scols[2];
     unsigned smul[2];
     int sad_nested[2];           // scell % cell == 0: every pixel of an MV cell reads the same SAD cell
+    int force_path;              // debug (MEMCI_MCI_PATH): 0 auto, 1 never the staged fast path, 2 always the dense enumeration
 };
 
 // ---- per-cell integer displacement ---------------------------------------------------------
@@ -360,11 +362,13 @@ mci_splat_kernel(const __grid_constant__ MciParams P, int tiles_x, int n_tiles)
     const int H = P.H, W = P.W;
     const bool col_in = q_c < W;
     const int dmax = P.counters[2];
-    const bool keys_fit = (H + dmax <= MCI_KOFF) && (W + dmax <= MCI_KOFF) && dmax <= MCI_KOFF;
+    // A wrapped effective displacement lies in [H - dmax, H - 1], an un-wrapped one in [-dmax, dmax]: on a frame
+    // no larger than 2 * dmax the two ranges meet and one key would stand for two different cell displacements.
+    const bool keys_fit = (H + dmax <= MCI_KOFF) && (W + dmax <= MCI_KOFF) && dmax <= MCI_KOFF && H > 2 * dmax && W > 2 * dmax;
     const unsigned lt_mask = (1u << lane) - 1u;
 
     int n = 0;
-    bool overflow = !keys_fit;
+    bool overflow = !keys_fit || P.force_path == 2;
     bool any_far = false;                                      // a wrapped entry made it into the list
     if (lane < 2) { sm.s_r0[lane] = 0; sm.s_c0[lane] = 0; sm.s_nc[lane] = 1; sm.staged[lane] = 0; }
     __syncwarp();
@@ -465,7 +469,7 @@ mci_splat_kernel(const __grid_constant__ MciParams P, int tiles_x, int n_tiles)
     const bool st0 = sm.staged[0] != 0, st1 = sm.staged[1] != 0;
     // fast path: every entry un-wrapped and its cells (displacement + SAD) staged; unidirectional tiles must
     // also be out of reach of the self-write rule (a vector leaving the frame at the bottom / right, :56-58)
-    const bool fast = !overflow && !any_far && st0 && P.sad_nested[0] &&
+    const bool fast = P.force_path == 0 && !overflow && !any_far && st0 && P.sad_nested[0] &&
                       (BIDIR ? (st1 && P.sad_nested[1]) : (ty0 + SW_TH - 1 + dmax < H && tx0 + 31 + dmax < W));
     if (fast) {
         float sadi[SW_TH], bs[SW_TH], bi[SW_TH];
@@ -784,6 +788,7 @@ int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd
     if (row1 < 0) { row0 = 0; row1 = H; }
     if (row0 < 0 || row1 > H || row0 >= row1) return memci_fail(ctx, MEMCI_ERR_ARG, "row range [%d, %d) outside [0, %d)", row0, row1, H);
     P.H = H; P.W = W; P.bidir = bidir; P.ndir = ndir; P.dist = dist;
+    if (const char *e = getenv("MEMCI_MCI_PATH")) P.force_path = atoi(e);
     P.fill_begin = row0; P.fill_end = row1;
     P.y_begin = row0 - 10 > 0 ? row0 - 10 : 0;           // the 21x21 hole-fill window reads 10 rows of splat either side
     P.y_end = row1 + 10 < H ? row1 + 10 : H;

@@ -567,3 +567,36 @@ def test_tiny_frames_vs_oracle(gpu, oracle, H, W):
             assert np.array_equal(bi(a, b, f, g, np.float32(dist)), oracle.bidir_helper(a, b, f, g, np.float32(dist)))
             assert np.array_equal(uni(a, b, f, np.float32(dist)), oracle.unidir_helper(a, b, f, np.float32(dist)))
         assert np.array_equal(b2(a, b, f, g, 0.5, 16, 4, True), oracle.bidir2_frame(a, b, f, g, 0.5, True))
+
+
+def test_splat_fuzz_vs_oracle(gpu, oracle, monkeypatch):
+    """Random block-constant MV fields through both MCI helpers against the oracle: cell sizes 1/2/4/6/8, vectors up to
+    +-60 px (wrapped and out-of-frame targets, neighbourhoods too large to stage, key lists that overflow into the dense
+    fallback, frames no larger than twice the largest displacement), fractional vectors, SAD ties and infinite SADs,
+    several dists; each case through the kernel's automatic path choice and with the generic / dense paths forced."""
+    from interpolatory_b200.MCI.Bidirectional import helper as bi
+    from interpolatory_b200.MCI.Unidirectional import helper as uni
+    rng = np.random.default_rng(2024)
+    cases = [(64, 96, 8, 2), (64, 96, 8, 20), (90, 130, 4, 8), (72, 72, 6, 12), (48, 160, 1, 3), (120, 96, 8, 60), (56, 88, 4, 40),
+             (40, 40, 4, 30), (33, 70, 1, 16), (64, 64, 8, 31), (64, 64, 8, 32), (70, 50, 2, 24)]
+    for (H, W, g, D) in cases:
+        a = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        b = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        nr, nc = -(-H // g), -(-W // g)
+        fields = []
+        for _ in range(2):
+            v = rng.integers(-D, D + 1, (nr, nc, 2)).astype(np.float32)
+            if g == 4:
+                v += rng.choice([0.0, 0.25, 0.5], (nr, nc, 2)).astype(np.float32)      # fractional (mean-smoothed) vectors
+            sad = rng.integers(0, 6, (nr, nc, 1)).astype(np.float32) * 100.0              # many ties
+            sad[rng.random((nr, nc, 1)) < 0.03] = np.inf
+            f = np.concatenate([v, sad], axis=2)
+            fields.append(np.ascontiguousarray(np.kron(f, np.ones((g, g, 1), np.float32))[:H, :W]))
+        f_, b_ = fields
+        for dist in (0.5, 0.19999999, 0.8):
+            d = np.float32(dist)
+            want_u, want_b = oracle.unidir_helper(a, b, f_, d), oracle.bidir_helper(a, b, f_, b_, d)
+            for path in ("0", "1", "2"):            # MEMCI_MCI_PATH: 0 automatic, 1 no staged fast path, 2 dense enumeration
+                monkeypatch.setenv("MEMCI_MCI_PATH", path)
+                assert np.array_equal(uni(a, b, f_, d), want_u), (H, W, g, D, dist, 'unidir', path)
+                assert np.array_equal(bi(a, b, f_, b_, d), want_b), (H, W, g, D, dist, 'bidir', path)
