@@ -569,6 +569,8 @@ ORC_API int orc_mci_unidir(const uint8_t *src, const uint8_t *tgt, const float *
             long long u_i = (long long)u + (long long)rintf(pr);         /* round half even  :48-49 */
             long long v_i = (long long)v + (long long)rintf(pc);
             if (u_i < H && v_i < W) {                                   /* :51 */
+                /* below -H / -W numba's unchecked wraparound writes outside the array: undefined in the reference */
+                if (u_i < -(long long)H || v_i < -(long long)W) { free(IF); free(SADI); return -3; }
                 size_t q = (size_t)wrap_idx((int)u_i, H) * W + wrap_idx((int)v_i, W);
                 if (m[2] <= SADI[q]) {                                  /* :52 */
                     IF[q * 3 + 0] = s[0]; IF[q * 3 + 1] = s[1]; IF[q * 3 + 2] = s[2];
@@ -607,6 +609,7 @@ ORC_API int orc_mci_bidir(const uint8_t *src, const uint8_t *tgt, const float *f
                 long long u_i = (long long)u + (long long)rintf(pr);    /* :34-35 */
                 long long v_i = (long long)v + (long long)rintf(pc);
                 if (u_i < H && v_i < W) {
+                    if (u_i < -(long long)H || v_i < -(long long)W) { free(IF); free(SADI); return -3; }   /* undefined in the reference */
                     size_t q = (size_t)wrap_idx((int)u_i, H) * W + wrap_idx((int)v_i, W);
                     if (f[2] < SADI[q]) {                               /* :37 strict */
                         IF[q * 3 + 0] = s[0]; IF[q * 3 + 1] = s[1]; IF[q * 3 + 2] = s[2];
@@ -619,6 +622,7 @@ ORC_API int orc_mci_bidir(const uint8_t *src, const uint8_t *tgt, const float *f
                 long long u_i = (long long)u + (long long)rint(pr);     /* :43-44 */
                 long long v_i = (long long)v + (long long)rint(pc);
                 if (u_i < H && v_i < W) {
+                    if (u_i < -(long long)H || v_i < -(long long)W) { free(IF); free(SADI); return -3; }   /* undefined in the reference */
                     size_t q = (size_t)wrap_idx((int)u_i, H) * W + wrap_idx((int)v_i, W);
                     float bs = b[2], si = SADI[q];
                     if (bs < si) {                                      /* :46 */

@@ -600,3 +600,119 @@ def test_splat_fuzz_vs_oracle(gpu, oracle, monkeypatch):
                 monkeypatch.setenv("MEMCI_MCI_PATH", path)
                 assert np.array_equal(uni(a, b, f_, d), want_u), (H, W, g, D, dist, 'unidir', path)
                 assert np.array_equal(bi(a, b, f_, b_, d), want_b), (H, W, g, D, dist, 'bidir', path)
+
+
+def _fuzz_field(rng, H, W, g, D, frac, sg=None, holes=0.03):
+    """Dense [H, W, 3] field, (dy, dx) constant on g x g cells and SAD constant on sg x sg cells."""
+    nr, nc = -(-H // g), -(-W // g)
+    v = rng.integers(-D, D + 1, (nr, nc, 2)).astype(np.float32)
+    if rng.integers(0, 3) == 0:                                   # few distinct vectors, like a real field
+        v = np.repeat(np.repeat(v[::3, ::3], 3, 0), 3, 1)[:nr, :nc]
+    if frac:
+        v += rng.choice([0.0, 0.25, 0.5, 1 / 3], (nr, nc, 2)).astype(np.float32)
+    sg = sg or g
+    sr, sc = -(-H // sg), -(-W // sg)
+    sad = rng.integers(0, 6, (sr, sc, 1)).astype(np.float32) * float(rng.choice([100.0, 1.0, 37.5]))
+    sad[rng.random((sr, sc, 1)) < holes] = np.inf
+    mv = np.kron(v, np.ones((g, g, 1), np.float32))[:H, :W]
+    sd = np.kron(sad, np.ones((sg, sg, 1), np.float32))[:H, :W]
+    return np.ascontiguousarray(np.concatenate([mv, sd], axis=2))
+
+
+def test_mci_fuzz_random_geometry(gpu, oracle, monkeypatch):
+    """Seeded random geometry for all three MCI modes: frame sizes 8..150 x 8..200, independent MV cell sizes per
+    direction (1, 2, 4, 5, 6, 8, 16), SAD cells that nest in the MV cells or not, vectors up to +-100 px, random dist,
+    a random forced splat path.  Where the reference itself is undefined (a negative index below -H: numba writes out
+    of bounds) the oracle reports it and the case is skipped; bidir2 cases that leave the 16-px pad must raise on both
+    sides."""
+    from interpolatory_b200.MCI.Bidirectional import helper as bi
+    from interpolatory_b200.MCI.Unidirectional import helper as uni
+    from interpolatory_b200.MCI.Bidirectional_2 import interpolate as b2
+    rng = np.random.default_rng(11)
+    n_mci = n_b2 = n_b2_raise = 0
+    for _ in range(120):
+        H, W = int(rng.integers(8, 150)), int(rng.integers(8, 200))
+        a = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        b = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        gf, gb = int(rng.choice([1, 2, 4, 8, 16, 5])), int(rng.choice([1, 2, 4, 8, 16, 6]))
+        D = int(rng.choice([0, 1, 3, 8, 20, 45, 100]))
+        sgf = gf * int(rng.choice([1, 1, 2])) if rng.integers(0, 2) else int(rng.choice([3, 4, 8]))
+        f_ = _fuzz_field(rng, H, W, gf, D, rng.integers(0, 2), sgf)
+        b_ = _fuzz_field(rng, H, W, gb, D, rng.integers(0, 2))
+        dist = np.float32(rng.choice([0.5, 0.19999999, 0.8, 0.4, 0.6, 1 / 3, 0.99]))
+        path = str(rng.integers(0, 3))
+        monkeypatch.setenv("MEMCI_MCI_PATH", path)
+        cfg = (H, W, gf, gb, D, sgf, float(dist), path)
+        try:
+            want_u, want_b = oracle.unidir_helper(a, b, f_, dist), oracle.bidir_helper(a, b, f_, b_, dist)
+        except RuntimeError:
+            want_u = None                                          # undefined in the reference
+        if want_u is not None:
+            assert np.array_equal(uni(a, b, f_, dist), want_u), ('unidir',) + cfg
+            assert np.array_equal(bi(a, b, f_, b_, dist), want_b), ('bidir',) + cfg
+            n_mci += 1
+        up = bool(rng.integers(0, 2)); D2 = int(rng.choice([0, 2, 6, 14])); dd = float(rng.choice([0.5, 0.4, 0.8, 0.25]))
+        if up:
+            g2 = int(rng.choice([4, 8, 16]))
+            f2, b2_ = _fuzz_field(rng, H, W, g2, D2, rng.integers(0, 2), holes=0), _fuzz_field(rng, H, W, g2, D2, rng.integers(0, 2), holes=0)
+        else:
+            nr, nc = -(-H // 4), -(-W // 4)
+            f2, b2_ = _fuzz_field(rng, nr, nc, 1, D2, rng.integers(0, 2), holes=0), _fuzz_field(rng, nr, nc, 1, D2, rng.integers(0, 2), holes=0)
+        try:
+            want2 = oracle.bidir2_frame(a, b, f2, b2_, dd, up)
+        except RuntimeError:
+            want2 = None
+        if want2 is None:
+            with pytest.raises(Exception, match="shifted outside the padded frame"):
+                b2(a, b, f2, b2_, dd, 16, 4, up)
+            n_b2_raise += 1
+        else:
+            assert np.array_equal(b2(a, b, f2, b2_, dd, 16, 4, up), want2), ('bidir2', H, W, up, D2, dd)
+            n_b2 += 1
+    assert n_mci >= 80 and n_b2 >= 60 and n_b2_raise >= 5
+
+
+def test_me_fuzz_vs_oracle(gpu, oracle):
+    """Seeded random sizes and parameters for full search, three-step search, HBMA (sad / ssd, upscale or not) and the
+    three smoothing filters, on five kinds of frames: noise, two grey levels (every SAD a tie and an exact integer),
+    flat, shifted noise plus a grey offset, and the synthetic sequence."""
+    from interpolatory_b200.ME.full_search import get_motion_vectors as fs
+    from interpolatory_b200.ME.tss import get_motion_vectors as tss
+    from interpolatory_b200.ME.hbma import get_motion_vectors as hbma
+    from interpolatory_b200.smoothing import smooth
+    rng = np.random.default_rng(7)
+
+    def frames(kind, H, W):
+        if kind == 0:
+            return rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+        if kind == 1:
+            return np.repeat(rng.integers(0, 2, (2, H, W, 1), dtype=np.uint8) * 50 + 20, 3, axis=3)
+        if kind == 2:
+            a = np.empty((2, H, W, 3), np.uint8); a[0] = 77; a[1] = 80
+            return a
+        if kind == 3:
+            a = np.repeat(rng.integers(0, 200, (H, W, 1), dtype=np.uint8), 3, axis=2)
+            b = (np.roll(a, (int(rng.integers(-5, 6)), int(rng.integers(-5, 6))), (0, 1)).astype(np.int32) + int(rng.integers(0, 5))).astype(np.uint8)
+            return np.stack([a, b])
+        return make_sequence(H, W, 2, seed=int(rng.integers(1 << 30)))
+
+    for _ in range(600):
+        H, W = int(rng.integers(8, 200)), int(rng.integers(8, 260))
+        kind = int(rng.integers(0, 5))
+        if kind == 4 and (H < 48 or W < 48):
+            kind = 0
+        a, b = frames(kind, H, W)
+        bs = int(rng.choice([2, 3, 4, 5, 6, 8, 8, 8, 12, 16, 16, 24, 32]))
+        R = int(rng.integers(0, 24))
+        assert np.array_equal(fs(bs, R, a, b), oracle.fs(bs, R, a, b)), ('fs', H, W, kind, bs, R)
+        steps = int(rng.integers(1, 6))
+        assert np.array_equal(tss(bs, steps, a, b), oracle.tss(bs, steps, a, b)), ('tss', H, W, kind, bs, steps)
+        hb, win, sub, st = int(rng.choice([4, 8, 8, 16, 32])), int(rng.integers(1, 10)), int(rng.integers(1, 4)), int(rng.integers(0, 4))
+        mbs, cost, up = int(rng.choice([2, 4, 4, 8])), str(rng.choice(['sad', 'ssd'])), bool(rng.integers(0, 2))
+        assert np.array_equal(hbma(hb, win, sub, st, mbs, a, b, cost, up), oracle.hbma(hb, win, sub, st, mbs, a, b, cost, up)), \
+            ('hbma', H, W, kind, hb, win, sub, st, mbs, cost, up)
+        g = int(rng.choice([1, 2, 4, 8, 16]))
+        mv = _fuzz_field(rng, H, W, g, 20, rng.integers(0, 2))
+        fsz = int(rng.choice([1, 2, 4, 8, 16, 3]))
+        for mode in ("mean", "median", "weighted"):
+            assert np.array_equal(np.asarray(smooth(mode, mv, fsz)), oracle.smooth(mode, mv, fsz)), ('smooth', H, W, g, fsz, mode)

@@ -214,3 +214,18 @@ def test_bidir2(oracle, golden):
     blocks, want = g["fill_holes/in"], g["fill_holes/out"]
     for b, w in zip(blocks, want):
         assert np.array_equal(oracle.fill_holes(b), w, equal_nan=True)
+
+
+def test_oracle_reports_undefined_wraparound(oracle):
+    """A displaced index below -H is an out-of-bounds write in the reference (numba does not bounds-check the
+    wraparound); the oracle refuses the case instead of guessing."""
+    H, W = 16, 24
+    a = np.zeros((H, W, 3), np.uint8)
+    mv = np.zeros((H, W, 3), np.float32)
+    mv[..., 0] = -40.0
+    with pytest.raises(RuntimeError):
+        oracle.unidir_helper(a, a, mv, np.float32(0.5))
+    with pytest.raises(RuntimeError):
+        oracle.bidir_helper(a, a, mv, mv, np.float32(0.5))
+    mv[..., 0] = -31.0                                           # 0 + rint(-15.5) = -16 = -H: still a valid wrap
+    oracle.unidir_helper(a, a, mv, np.float32(0.5))
