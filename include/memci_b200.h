@@ -180,6 +180,17 @@ MEMCI_API int memci_mci_bidir2(memci_ctx *ctx, int slot_src, int slot_tgt, int m
  * the padded arrays (the reference's numpy slices would clip and its in-place adds fail; we zero-fill). */
 MEMCI_API int memci_bidir2_stats(memci_ctx *ctx, int *max_shift, int *n_out_of_range);
 
+/* ---- frame quality (Middlebury harness) --------------------------------------------------- */
+/* Replaces the two skimage calls of the reference's benchmark harness (src/Benchmark.py:46-47 in benchmark(),
+ * :105-106 in get_middle_frame()) for two uint8 RGB frames resident in slots:
+ *   *mse  = skimage.metrics.mean_squared_error(a, b)   (exact: integer sum / (3 H W));
+ *           peak_signal_noise_ratio(a, b, data_range=255) = 10 log10(255^2 / mse) is left to the caller
+ *   *ssim = skimage.metrics.structural_similarity(a, b, data_range=255, multichannel=True): win_size 7, uniform
+ *           window, sample covariance, K1 0.01, K2 0.03, mean over the frame cropped by 3 px and the 3 channels.
+ * Either pointer may be NULL.  Synchronises the context's stream.  Frames smaller than 7 x 7: MEMCI_ERR_ARG
+ * (skimage raises ValueError: win_size exceeds image extent). */
+MEMCI_API int memci_quality(memci_ctx *ctx, int slot_a, int slot_b, double *mse, double *ssim);
+
 /* ---- spatial tiling of one frame pair into horizontal bands (8K mode) -------------
  * A band = block rows [block_row0, block_row1).  Each GPU holds full-size slots but only fills the
  * rows it owns plus the halo rows it received; these entry points restrict the work to a band. */

@@ -57,6 +57,7 @@ _PROTOS = {
     "memci_mci_bidir": ([_P, _I, _I, _I, _I, C.c_float, _I], _I),
     "memci_mci_bidir2": ([_P, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P, _I], _I),
     "memci_bidir2_stats": ([_P, C.POINTER(_I), C.POINTER(_I)], _I),
+    "memci_quality": ([_P, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)], _I),
     "memci_me_fs_rows": ([_P, _I, _I, _I, _I, _I, _I, _I], _I),
     "memci_mci_rows": ([_P, _I, _I, _I, _I, C.c_float, _I, _I, _I, _I], _I),
     "memci_upload_frame_rows": ([_P, _I, _P, _I, _I], _I),

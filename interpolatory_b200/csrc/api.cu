@@ -141,6 +141,7 @@ int memci_ctx_destroy(memci_ctx *ctx)
         if (ctx->d_disp[i]) cudaFree(ctx->d_disp[i]);
         if (ctx->d_b2blk[i]) cudaFree(ctx->d_b2blk[i]);
     }
+    if (ctx->d_quality) cudaFree(ctx->d_quality);
     for (int i = 0; i < 4; ++i) {
         if (ctx->fs_plan[i].d_tiles) cudaFree(ctx->fs_plan[i].d_tiles);
         free(ctx->fs_plan[i].row_tile_start); free(ctx->fs_plan[i].row_cand);
@@ -515,6 +516,19 @@ int memci_bidir2_stats(memci_ctx *ctx, int *max_shift, int *n_out_of_range)
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     if (max_shift) *max_shift = h[0];
     if (n_out_of_range) *n_out_of_range = h[1];
+    return MEMCI_OK;
+}
+
+int memci_quality(memci_ctx *ctx, int slot_a, int slot_b, double *mse, double *ssim)
+{
+    REQ_CTX(ctx); REQ_FRAME(ctx, slot_a, 1); REQ_FRAME(ctx, slot_b, 1);
+    const int H = ctx->H, W = ctx->W;
+    if (H < 7 || W < 7) return memci_fail(ctx, MEMCI_ERR_ARG, "win_size exceeds image extent (%d x %d frame, 7 x 7 window)", H, W);
+    double h[2] = {0.0, 0.0};
+    int rc = memci_quality_run(ctx, slot_a, slot_b, h);
+    if (rc) return rc;
+    if (mse) *mse = h[0] / ((double)H * (double)W * 3.0);
+    if (ssim) *ssim = h[1] / ((double)(H - 6) * (double)(W - 6) * 3.0);
     return MEMCI_OK;
 }
 

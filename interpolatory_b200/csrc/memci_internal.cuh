@@ -58,6 +58,7 @@ struct memci_ctx {
     short2 *d_disp[2]; size_t disp_cap[2];
     uint32_t *d_fill; int *d_hole_list; size_t hole_cap;
     float *d_dense; size_t dense_cap;  // dense MV staging for download/upload
+    void *d_quality; size_t quality_cap;     // PSNR / SSIM partial sums
     int4 *d_b2blk[2]; size_t b2blk_cap[2];   // bidir2: per 4x4 block (Xb, Yb, TXb, TYb << 1 | occluded), per direction
     // timing
     int timing; cudaEvent_t ev[4]; int fs_timed, mci_timed;
@@ -102,6 +103,7 @@ int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd
                   float dist, int out_slot, int bidir, int row0, int row1);   // output rows [row0, row1); row1 < 0 = all
 int memci_bidir2_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd, const MVField *bwd,
                      float dist_fwd, float dist_bwd, int mbs, int pad, const float *w64, int out_slot);
+int memci_quality_run(memci_ctx *ctx, int slot_a, int slot_b, double *h_result);   // h_result[0] = sum of squared differences, [1] = sum of SSIM map
 int memci_mv_to_dense(memci_ctx *ctx, const MVField *f, float *d_dense);
 // returns an event pair index (>= 0) after recording the start event, or -1 when profiling is off / full
 int memci_prof_begin(memci_ctx *ctx, int kind);

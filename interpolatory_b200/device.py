@@ -190,6 +190,13 @@ class DeviceContext:
         self._ck(self.L.memci_bidir2_stats(self._ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    # -- frame quality (Middlebury harness)
+    def quality(self, slot_a, slot_b):
+        """(mean squared error, mean SSIM) of two resident frames; see memci_quality in include/memci_b200.h."""
+        mse, ssim = C.c_double(), C.c_double()
+        self._ck(self.L.memci_quality(self._ctx, slot_a, slot_b, C.byref(mse), C.byref(ssim)))
+        return mse.value, ssim.value
+
     # -- instrumentation
     def launch_count(self):
         return int(self.L.memci_launch_count(self._ctx))

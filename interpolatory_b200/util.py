@@ -9,6 +9,38 @@ def eprint(s):
     print(s, file=sys.stderr)
 
 
+progress_file_path = None
+
+# src/Globals.py: the flags the harness and the interpolators consult
+debug_flags = {
+    'debug_IO': False,
+    'debug_interpolator': False,
+    'debug_progress': True,
+    'debug_timer': False,
+    'debug_benchmark_progress': True,
+    'debug_MEMCI_args': True,
+}
+
+
+def sToMMSS(s):
+    """seconds -> 'M:SS' (src/util.py:13-16)."""
+    return f"{int(s / 60)}:{str(int(s % 60)).rjust(2, '0')}"
+
+
+def getETA(elapsed_seconds, processed_frames, all_frames):
+    """Remaining time at the rate so far (src/util.py:22-26)."""
+    remaining = all_frames - processed_frames
+    return sToMMSS(0 if processed_frames == 0 else int(float(elapsed_seconds) / processed_frames * remaining))
+
+
+def signal_progress(s):
+    """Overwrite the progress file the GUI polls, if one is set (src/util.py:29-34)."""
+    if progress_file_path is not None:
+        with open(progress_file_path, 'w') as f:
+            f.write(s)
+            f.flush()
+
+
 def get_first_frame_idx_and_ratio(idx, rate_ratio):
     """(index of the last source frame at or before output frame `idx`, 1 - fractional position).
 

@@ -716,3 +716,78 @@ def test_me_fuzz_vs_oracle(gpu, oracle):
         fsz = int(rng.choice([1, 2, 4, 8, 16, 3]))
         for mode in ("mean", "median", "weighted"):
             assert np.array_equal(np.asarray(smooth(mode, mv, fsz)), oracle.smooth(mode, mv, fsz)), ('smooth', H, W, g, fsz, mode)
+
+
+# ---------------------------------------------------------------- Middlebury harness: PSNR / SSIM on the device
+SSIM_RTOL = 1e-9      # float64 on both sides; the box sums are exact integers here, running f64 sums in scipy
+
+
+def test_quality_metrics_vs_oracle(gpu):
+    """memci_quality through metrics.py against the restated skimage algorithm (oracle/quality.py): MSE exactly,
+    SSIM within SSIM_RTOL, on noise, near-identical, flat and synthetic frames, sizes off the 32 x 8 tile grid."""
+    import quality as Q
+    from interpolatory_b200 import metrics as M
+    rng = np.random.default_rng(17)
+    for (H, W) in [(7, 7), (8, 40), (37, 53), (100, 131), (360, 640), (480, 584)]:
+        a = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        noisy = np.clip(a.astype(np.int32) + rng.integers(-12, 13, a.shape), 0, 255).astype(np.uint8)
+        flat = np.full((H, W, 3), 93, np.uint8)
+        cases = [(a, noisy), (a, a), (a, rng.integers(0, 256, a.shape, dtype=np.uint8)), (flat, a), (flat, flat + 4)]
+        if H >= 48 and W >= 48:
+            fr = make_sequence(H, W, 2, seed=H)
+            cases.append((fr[0], fr[1]))
+        for x, y in cases:
+            mse, ssim = M.frame_quality(x, y)
+            assert mse == Q.mean_squared_error(x, y)
+            want = Q.structural_similarity(x, y)
+            assert abs(ssim - want) <= SSIM_RTOL * abs(want), (H, W, ssim, want)
+            assert M.structural_similarity(x, y, data_range=255, multichannel=True) == ssim
+            p, wp = M.peak_signal_noise_ratio(x, y, data_range=255), Q.peak_signal_noise_ratio(x, y)
+            assert p == wp or abs(p - wp) <= 1e-12 * abs(wp)
+    with pytest.raises(ValueError):
+        M.structural_similarity(np.zeros((6, 20, 3), np.uint8), np.zeros((6, 20, 3), np.uint8), data_range=255, multichannel=True)
+    with pytest.raises(NotImplementedError):
+        M.structural_similarity(a, a, data_range=255, multichannel=True, gaussian_weights=True)
+
+
+def test_middlebury_harness(gpu, tmp_path, capsys):
+    """benchmark() and get_middle_frame() (src/Benchmark.py:18-114) over a synthetic <name>/frame10.png,
+    frame10i11.png, frame11.png dataset: written PNGs equal get_benchmark_frame, results.txt / printed JSON carry
+    the oracle's mean PSNR and SSIM of those frames."""
+    import json
+    import quality as Q
+    from PIL import Image
+    from interpolatory_b200 import MEMCI
+    from interpolatory_b200.Benchmark import benchmark, get_middle_frame
+    data, outd = tmp_path / "middlebury", tmp_path / "out"
+    outd.mkdir()
+    truths = {}
+    for i, (name, (H, W)) in enumerate({"Alpha": (96, 128), "Beta": (120, 90), "Gamma": (75, 141)}.items()):
+        fr = make_sequence(H, W, 3, seed=400 + i)
+        (data / name).mkdir(parents=True)
+        for fn, im in (("frame10", fr[0]), ("frame10i11", fr[1]), ("frame11", fr[2])):
+            Image.fromarray(im).save(data / name / f"{fn}.png")
+        truths[name] = fr
+    for settings in (dict(me_mode='fs', mci_mode='bidir'), dict(me_mode='hbma', mci_mode='bidir2')):
+        it = MEMCI(2, **settings)
+        res = benchmark(it, str(outd), dataset_dir=str(data))
+        ps, ss = [], []
+        for name, fr in truths.items():
+            want = np.asarray(MEMCI(2, **settings).get_benchmark_frame(fr[0], fr[2]))
+            got = np.asarray(Image.open(outd / f"{name}.png"))
+            assert np.array_equal(got, want), (settings, name)
+            ps.append(Q.peak_signal_noise_ratio(fr[1], want)); ss.append(Q.structural_similarity(fr[1], want))
+        assert abs(res['PSNR'] - np.mean(ps)) < 1e-9 and abs(res['SSIM'] - np.mean(ss)) < 1e-9
+        on_disk = json.loads((outd / "results.txt").read_text())
+        assert on_disk['PSNR'] == res['PSNR'] and on_disk['SSIM'] == res['SSIM'] and 'Time taken' in on_disk
+        assert json.loads(capsys.readouterr().out.strip().splitlines()[-1])['SSIM'] == res['SSIM']
+        fr = truths["Alpha"]
+        r2 = get_middle_frame(it, str(data / "Alpha" / "frame10.png"), str(data / "Alpha" / "frame11.png"),
+                              str(outd / "mid.png"), str(data / "Alpha" / "frame10i11.png"))
+        assert abs(r2['SSIM'] - ss[0]) < 1e-9 and abs(r2['PSNR'] - ps[0]) < 1e-9
+        # ground truth = the frame just written: PSNR is reported as the string the reference prints (:111-112)
+        assert get_middle_frame(it, str(data / "Alpha" / "frame10.png"), str(data / "Alpha" / "frame11.png"),
+                                str(outd / "same.png"), str(outd / "same.png")) == {'PSNR': 'Infinity', 'SSIM': 1.0}
+        it.close()
+    with pytest.raises(FileNotFoundError):
+        benchmark(MEMCI(2), None, dataset_dir=str(tmp_path / "nothing"))

@@ -229,3 +229,22 @@ def test_oracle_reports_undefined_wraparound(oracle):
         oracle.bidir_helper(a, a, mv, mv, np.float32(0.5))
     mv[..., 0] = -31.0                                           # 0 + rint(-15.5) = -16 = -H: still a valid wrap
     oracle.unidir_helper(a, a, mv, np.float32(0.5))
+
+
+def test_quality_oracle_known_answers():
+    """The PSNR / SSIM restatement (oracle/quality.py; skimage itself is absent, parity unpinned) against the SSIM
+    definition evaluated window by window and against closed-form answers."""
+    import quality as Q
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 256, (19, 23, 3), dtype=np.uint8)
+    b = np.clip(a.astype(np.int32) + rng.integers(-30, 31, a.shape), 0, 255).astype(np.uint8)
+    assert Q.structural_similarity(a, a) == 1.0
+    assert Q.peak_signal_noise_ratio(a, a) == np.inf
+    assert abs(Q.structural_similarity(a, b) - Q.ssim_by_definition(a, b)) < 1e-12
+    c = np.full((16, 16, 3), 100, np.uint8); d = np.full((16, 16, 3), 110, np.uint8)
+    assert abs(Q.peak_signal_noise_ratio(c, d) - 10 * np.log10(255.0 ** 2 / 100.0)) < 1e-12
+    # two constant frames: variances vanish, S = (2 ux uy + C1) / (ux^2 + uy^2 + C1)
+    C1 = (0.01 * 255) ** 2
+    assert abs(Q.structural_similarity(c, d) - (2 * 100 * 110 + C1) / (100 ** 2 + 110 ** 2 + C1)) < 1e-12
+    with pytest.raises(ValueError):
+        Q.structural_similarity(a[:6], b[:6])
