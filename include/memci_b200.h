@@ -244,6 +244,10 @@ MEMCI_API int memci_reset_launch_count(memci_ctx *ctx);
  * (candidates * block_size^2) and blocks re-resolved by the exact float64 path. */
 MEMCI_API int memci_fs_stats(memci_ctx *ctx, long long *n_candidates, long long *px_ops,
                              int *n_redo_blocks);
+/* After a full search that took the two-phase path (8-bit prefilter + exact refinement, csrc/fs8.cu): how many
+ * candidates survived the prefilter and were evaluated exactly, and whether the survivor list overflowed (the exact
+ * kernel then searched the pair instead).  Both 0 if the last search did not use the prefilter. */
+MEMCI_API int memci_fs_prefilter_stats(memci_ctx *ctx, int *n_survivors, int *overflowed);
 /* Number of holes filled by the last MCI call (synchronises the stream). */
 MEMCI_API int memci_mci_stats(memci_ctx *ctx, int *n_holes);
 /* Device-side time of the last memci_me_fs main kernel / MCI splat kernel, measured

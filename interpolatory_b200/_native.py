@@ -69,6 +69,7 @@ _PROTOS = {
     "memci_launch_count": ([_P], C.c_longlong),
     "memci_reset_launch_count": ([_P], _I),
     "memci_fs_stats": ([_P, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(_I)], _I),
+    "memci_fs_prefilter_stats": ([_P, C.POINTER(_I), C.POINTER(_I)], _I),
     "memci_mci_stats": ([_P, C.POINTER(_I)], _I),
     "memci_enable_kernel_timing": ([_P, _I], _I),
     "memci_last_kernel_ms": ([_P, C.POINTER(C.c_float), C.POINTER(C.c_float)], _I),

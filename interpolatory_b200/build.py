@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libmemci_b200.so")
-SOURCES = ["api.cu", "frames.cu", "fs.cu", "hbma.cu", "smooth.cu", "mci.cu", "bidir2.cu", "tss.cu", "quality.cu", "microbench.cu"]
+SOURCES = ["api.cu", "frames.cu", "fs.cu", "fs8.cu", "hbma.cu", "smooth.cu", "mci.cu", "bidir2.cu", "tss.cu", "quality.cu", "microbench.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]

@@ -126,6 +126,7 @@ int memci_ctx_destroy(memci_ctx *ctx)
         FrameSlot &f = ctx->frames[i];
         if (f.rgb) cudaFree(f.rgb);
         if (f.luma) cudaFree(f.luma);
+        if (f.luma8) cudaFree(f.luma8);
         for (int l = 0; l <= MEMCI_MAX_PYR; ++l) {
             if (f.pyr_rgb[l]) cudaFree(f.pyr_rgb[l]);
             if (f.pyr_luma[l]) cudaFree(f.pyr_luma[l]);
@@ -142,6 +143,8 @@ int memci_ctx_destroy(memci_ctx *ctx)
         if (ctx->d_b2blk[i]) cudaFree(ctx->d_b2blk[i]);
     }
     if (ctx->d_quality) cudaFree(ctx->d_quality);
+    if (ctx->d_fs8_list) cudaFree(ctx->d_fs8_list);
+    if (ctx->d_fs8_best) cudaFree(ctx->d_fs8_best);
     for (int i = 0; i < 4; ++i) {
         if (ctx->fs_plan[i].d_tiles) cudaFree(ctx->fs_plan[i].d_tiles);
         free(ctx->fs_plan[i].row_tile_start); free(ctx->fs_plan[i].row_cand);
@@ -189,7 +192,7 @@ int memci_host_free(void *p)
 }
 
 // ---- frames ----------------------------------------------------------------------------
-static void frame_touched(FrameSlot &f) { f.valid = 1; f.luma_ok = 0; f.pyr_levels = 0; }
+static void frame_touched(FrameSlot &f) { f.valid = 1; f.luma_ok = 0; f.luma8_ok = 0; f.pyr_levels = 0; }
 
 // output slot still being copied out by a stager -> the context's stream waits for that copy
 static int memci_wait_slot_free(memci_ctx *ctx, int slot)
@@ -658,10 +661,25 @@ int memci_fs_stats(memci_ctx *ctx, long long *n_cand, long long *px_ops, int *n_
     REQ_CTX(ctx);
     if (n_cand) *n_cand = ctx->fs_last_cand;
     if (px_ops) *px_ops = ctx->fs_last_ops;
-    if (n_redo) {
-        CK(ctx, cudaMemcpyAsync(n_redo, ctx->d_counters, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_redo) {                                       // float64 replays: redo-list blocks (exact kernel) + flagged survivors (prefilter path)
+        int h[12];
+        CK(ctx, cudaMemcpyAsync(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        *n_redo = ctx->fs_used_prefilter ? h[11] : h[0];
+    }
+    return MEMCI_OK;
+}
+
+int memci_fs_prefilter_stats(memci_ctx *ctx, int *n_survivors, int *overflowed)
+{
+    REQ_CTX(ctx);
+    int h[2] = {0, 0};
+    if (ctx->fs_used_prefilter) {
+        CK(ctx, cudaMemcpyAsync(h, ctx->d_counters + 8, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    if (overflowed) *overflowed = h[0];
+    if (n_survivors) *n_survivors = h[1];
     return MEMCI_OK;
 }
 

@@ -324,6 +324,6 @@ int memci_bidir2_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *
     b2_frame_kernel<<<grid, B2_TW * B2_TH, 0, ctx->stream>>>(P);
     CKL(ctx);
     FrameSlot &o = ctx->frames[out_slot];
-    o.valid = 1; o.luma_ok = 0; o.pyr_levels = 0;
+    o.valid = 1; o.luma_ok = 0; o.luma8_ok = 0; o.pyr_levels = 0;
     return MEMCI_OK;
 }

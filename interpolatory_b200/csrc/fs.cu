@@ -100,7 +100,7 @@ __global__ void fs_generic_kernel(const int32_t *__restrict__ L0, const int32_t 
 // =========================================================================================
 // List entries carry the search direction in bit 30 (pair launches: direction 1 swaps the frames).
 #define FS_DIR_BIT 0x40000000
-#define FS_REDO_NT 1024
+#define FS_REDO_NT 256
 __global__ void __launch_bounds__(FS_REDO_NT)
 fs_redo_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
                const uint8_t *__restrict__ rgb0, const uint8_t *__restrict__ rgb1,
@@ -219,6 +219,7 @@ struct FsParams {
     int *redo_list;
     int *counters;
     int redo_cap;
+    const int *gate;             // non-null: run only if *gate != 0 (the prefilter path's survivor list overflowed)
 };
 
 struct FsTileTab {
@@ -359,6 +360,7 @@ fs_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
     __shared__ unsigned long long best_fast[3][FS_NBMAX];
     __shared__ unsigned best_low[3][FS_NBMAX];
 
+    if (p.gate && *p.gate == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int stage_ints = (p.box_h + p.bs) * FS_BOXW;
     int *const stage0 = reinterpret_cast<int *>(smem_raw);
@@ -776,8 +778,20 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         CK(ctx, cudaMalloc(&ctx->d_redo_list, sizeof(int) * 2 * (size_t)nbr * nbc));
         ctx->redo_cap = 2 * nbr * nbc;
     }
-    CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));
     ctx->fs_timed = 0;
+    // Two-phase exact search (fs8.cu): 8-bit prefilter + exact refinement of the survivors; the exact tiled kernel below
+    // then runs only if the survivor list overflowed (device-side gate, no host round trip).
+    const char *pf_env = getenv("MEMCI_FS_PREFILTER");
+    const bool use8 = pl->n_tiles > 0 && !(pf_env && atoi(pf_env) == 0) && memci_fs8_eligible(ctx, bs, R);
+    int prof = -1;
+    int *redo_count = use8 ? ctx->d_counters + 11 : ctx->d_counters;     // the prefilter path zeroes [8..11] in one memset
+    ctx->fs_used_prefilter = use8 ? 1 : 0;
+    if (!use8) CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));
+    if (use8) {
+        if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+        prof = memci_prof_begin(ctx, 0);
+        if ((rc = memci_fs8_run(ctx, slot_src, slot_tgt, bs, R, out, br0, br1, out2))) return rc;
+    }
     if (pl->n_tiles > 0) {
         CUtensorMap tm[4];                     // src/tgt of direction 0, src/tgt of direction 1
         if ((rc = make_tmap(ctx, &tm[0], fs.luma, H, W, Wp, FS_BOXW, bs))) return rc;
@@ -804,10 +818,13 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         p.tiles = pl->d_tiles + pl->row_tile_start[br0];
         p.out_vec[0] = out->vec; p.out_sad[0] = out->sad;
         p.out_vec[1] = out2 ? out2->vec : out->vec; p.out_sad[1] = out2 ? out2->sad : out->sad;
-        p.redo_list = ctx->d_redo_list; p.counters = ctx->d_counters; p.redo_cap = ctx->redo_cap;
+        p.redo_list = ctx->d_redo_list; p.counters = redo_count; p.redo_cap = ctx->redo_cap;
+        p.gate = use8 ? ctx->d_counters + 8 : nullptr;
         const int smem = fs_smem_bytes(bs, pl->box_h, p.n_stages, pl->G);
-        if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-        const int prof = memci_prof_begin(ctx, 0);
+        if (!use8) {
+            if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+            prof = memci_prof_begin(ctx, 0);
+        }
         switch (pl->G) {
         case 5: rc = fs_launch_tiled<5>(ctx, tm, p, smem); break;
         case 8: rc = fs_launch_tiled<8>(ctx, tm, p, smem); break;
@@ -833,12 +850,12 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         const int redo_smem = (bs * bs + (bs + 2 * R) * (bs + 2 * R)) * 12;
         if (redo_smem <= 160 * 1024) {
             CK(ctx, cudaFuncSetAttribute(fs_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, redo_smem));
-            fs_redo_kernel<<<ctx->num_sms * 2, FS_REDO_NT, redo_smem, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbc,
-                                                                              ctx->d_redo_list, ctx->d_counters, out->vec, out->sad,
+            fs_redo_kernel<<<ctx->num_sms * 8, FS_REDO_NT, redo_smem, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbc,
+                                                                              ctx->d_redo_list, redo_count, out->vec, out->sad,
                                                                               p.out_vec[1], p.out_sad[1]);
         } else {
             fs_generic_kernel<<<ctx->num_sms, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, 0, 0, nbc,
-                                                                     ctx->d_redo_list, ctx->d_counters, out->vec, out->sad,
+                                                                     ctx->d_redo_list, redo_count, out->vec, out->sad,
                                                                      p.out_vec[1], p.out_sad[1]);
         }
         CKL(ctx);

@@ -807,6 +807,6 @@ int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd
     mci_holefill_kernel<<<ctx->num_sms * 6, HF_WARPS * 32, 0, ctx->stream>>>(P.fill, P.out, P.hole_list, P.counters, H, W);
     CKL(ctx);
     FrameSlot &o = ctx->frames[out_slot];
-    o.valid = 1; o.luma_ok = 0; o.pyr_levels = 0;
+    o.valid = 1; o.luma_ok = 0; o.luma8_ok = 0; o.pyr_levels = 0;
     return MEMCI_OK;
 }

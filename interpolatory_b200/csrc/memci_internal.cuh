@@ -11,6 +11,7 @@
 #include "../../include/memci_b200.h"
 
 #define MEMCI_MAX_PYR 12
+#define MEMCI_L8_PAD 96              // zero border (pixels / rows) around the 8-bit luma plane of the full-search prefilter
 
 struct MVField {
     int valid;
@@ -25,6 +26,8 @@ struct FrameSlot {
     uint8_t *rgb;                      // [H][W][3]
     int32_t *luma;                     // [H][Wp] luma*1000 = 299R+587G+114B (exact integer)
     int luma_ok;
+    uint8_t *luma8;                    // round(luma) as uint8, [H + 2 PAD][Wp + 2 PAD], zero border (fs8.cu); allocated on first use
+    int luma8_ok;
     // HBMA pyramid cache (levels 1..pyr_levels), invalidated on upload
     int pyr_levels;
     uint8_t *pyr_rgb[MEMCI_MAX_PYR + 1];
@@ -51,9 +54,12 @@ struct memci_ctx {
     MVField mvs[MEMCI_NUM_MV_SLOTS];
     MVField tmp_mv[2];                 // HBMA ping-pong
     // full-search scratch
-    int *d_redo_list; int redo_cap; int *d_counters;   // [0] redo count, [1] hole count, [2] dmax, [4] hole runs, [5] bidir2 max |T|, [6] bidir2 out-of-range blocks
+    int *d_redo_list; int redo_cap; int *d_counters;   // [0] redo count, [1] hole count, [2] dmax, [4] hole runs, [5] bidir2 max |T|, [6] bidir2 out-of-range blocks, [8] fs8 list overflow, [9] fs8 survivors, [11] redo count of the fs8 path
     FsPlan fs_plan[4];
+    unsigned *d_fs8_list; size_t fs8_list_cap;          // prefilter survivors (bytes)
+    unsigned long long *d_fs8_best; size_t fs8_best_cap; // per (direction, block) minimum key of the refine pass (bytes)
     long long fs_last_cand, fs_last_ops;
+    int fs_used_prefilter;             // the last full search took the two-phase path (fs8.cu)
     // MCI scratch
     short2 *d_disp[2]; size_t disp_cap[2];
     uint32_t *d_fill; int *d_hole_list; size_t hole_cap;
@@ -95,6 +101,8 @@ int memci_ensure_luma(memci_ctx *ctx, int slot);
 int memci_ensure_pyramid(memci_ctx *ctx, int slot, int levels);
 int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out, int br0, int br1,
                  MVField *out2 = nullptr);   // block rows [br0, br1); br1 < 0 = all; out2: reverse direction in the same launch
+int memci_fs8_eligible(memci_ctx *ctx, int bs, int R);
+int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out, int br0, int br1, MVField *out2);
 int memci_tss_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int steps, MVField *out);
 int memci_hbma_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int win, int sub, int steps,
                    int min_bs, int cost_key, MVField *out);

@@ -26,10 +26,10 @@ __global__ void __launch_bounds__(512) ub_kernel(int iters, const int *__restric
     __shared__ int ub_sm[2048];
     unsigned extra = 0, e0 = threadIdx.x, e1 = threadIdx.x * 3u, e2 = 7u, e3 = 11u;
     float f0 = (float)threadIdx.x, f1 = 1.5f;
-    if (MODE == 4 || MODE >= 10) { for (int i = threadIdx.x; i < 2048; i += blockDim.x) ub_sm[i] = seed[i & 63]; __syncthreads(); }
+    if (MODE == 4 || (MODE >= 10 && MODE != 15)) { for (int i = threadIdx.x; i < 2048; i += blockDim.x) ub_sm[i] = seed[i & 63]; __syncthreads(); }
 #pragma unroll 4
     for (int it = 0; it < iters; ++it) {
-        if (MODE == 4) {          // 2 LDS.32 with immediate offsets (no address arithmetic), results consumed by the SAD stream
+        if (MODE == 4 || MODE == 16) {          // 2 LDS.32 with immediate offsets (no address arithmetic), results consumed by the SAD stream
             const int *bp = ub_sm + threadIdx.x;
             r[0] = bp[(it & 3) * 32];
             r[1] = bp[512 + (it & 3) * 32];
@@ -59,7 +59,10 @@ __global__ void __launch_bounds__(512) ub_kernel(int iters, const int *__restric
             asm volatile("min.u32 %0, %0, %1;" : "+r"(e0) : "r"(e2 + it));
             asm volatile("min.u32 %0, %0, %1;" : "+r"(e1) : "r"(e3 + it));
         }
-        if (MODE == 0 || MODE >= 2) {   // the SAD stream (modes 4, 10, 11 refresh part of r[] from shared memory)
+        if (MODE == 15 || MODE == 16) {   // packed 8-bit form: VABSDIFF4.U8.ACC = 4 pixel pairs per instruction
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = __vsadu4((unsigned)r[j], a[(j + 1) & 7]) + a[j];
+        } else if (MODE == 0 || MODE >= 2) {   // the SAD stream (modes 4, 10, 11 refresh part of r[] from shared memory)
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[j] = __sad(r[j], (int)a[(j + 1) & 7], a[j]);
         }
@@ -122,10 +125,10 @@ __global__ void __launch_bounds__(512, 1) ub_fs_pattern_kernel(int iters, const 
 
 extern "C" MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, float *ms, double *px_ops)
 {
-    if (!ctx || mode < 0 || mode > 14 || iters <= 0) return MEMCI_ERR_ARG;
+    if (!ctx || mode < 0 || mode > 16 || iters <= 0) return MEMCI_ERR_ARG;
     cudaSetDevice(ctx->device);
     // modes 13 / 14: the mode-12 kernel with 2 / 1 warps per scheduler
-    int grid = mode >= 12 ? ctx->num_sms : ctx->num_sms * 4, nt = mode == 13 ? 256 : mode == 14 ? 128 : 512;
+    int grid = (mode >= 12 && mode <= 14) ? ctx->num_sms : ctx->num_sms * 4, nt = mode == 13 ? 256 : mode == 14 ? 128 : 512;
     if (const char *e = getenv("MEMCI_UB_CTAS_PER_SM")) grid = ctx->num_sms * atoi(e);        // occupancy experiments
     int *d_seed = nullptr;
     unsigned *d_out = nullptr;
@@ -150,6 +153,8 @@ extern "C" MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, f
         case 8: ub_kernel<8><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
         case 9: ub_kernel<9><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
         case 10: ub_kernel<10><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        case 15: ub_kernel<15><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
+        case 16: ub_kernel<16><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
         case 12: case 13: case 14: ub_fs_pattern_kernel<<<grid, nt, 0, ctx->stream>>>(iters / 16, d_seed, d_out); break;
         default: ub_kernel<11><<<grid, nt, 0, ctx->stream>>>(iters, d_seed, d_out); break;
         }
@@ -162,7 +167,7 @@ extern "C" MEMCI_API int memci_microbench(memci_ctx *ctx, int mode, int iters, f
     cudaEventElapsedTime(&t, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d_seed); cudaFree(d_out);
-    const double per_step = mode == 2 ? 12.0 : mode == 3 ? 16.0 : mode >= 12 ? 704.0 / 16.0 : 8.0;
+    const double per_step = mode >= 15 ? 32.0 : mode == 2 ? 12.0 : mode == 3 ? 16.0 : mode >= 12 ? 704.0 / 16.0 : 8.0;
     if (ms) *ms = t;
     if (px_ops) *px_ops = per_step * (double)iters * (double)grid * nt;
     return MEMCI_OK;

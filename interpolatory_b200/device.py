@@ -209,6 +209,12 @@ class DeviceContext:
         self._ck(self.L.memci_fs_stats(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def fs_prefilter_stats(self):
+        """(survivors of the 8-bit prefilter, list overflowed?) of the last full search."""
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.L.memci_fs_prefilter_stats(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def mci_stats(self):
         n = C.c_int()
         self._ck(self.L.memci_mci_stats(self._ctx, C.byref(n)))

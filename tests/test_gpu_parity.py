@@ -791,3 +791,64 @@ def test_middlebury_harness(gpu, tmp_path, capsys):
         it.close()
     with pytest.raises(FileNotFoundError):
         benchmark(MEMCI(2), None, dataset_dir=str(tmp_path / "nothing"))
+
+
+# ---------------------------------------------------------------- full search: two-phase path (8-bit prefilter + exact refinement)
+@pytest.mark.parametrize("H,W,bs,R", [(120, 200, 8, 16), (97, 131, 8, 7), (270, 483, 8, 16), (136, 264, 16, 12), (360, 640, 16, 32)])
+def test_fs_prefilter_path_equals_exact_kernel_and_oracle(gpu, oracle, monkeypatch, H, W, bs, R):
+    """The default full search prunes with an 8-bit prefilter and evaluates the survivors exactly (csrc/fs8.cu); with
+    MEMCI_FS_PREFILTER=0 the exact tiled kernel searches every candidate.  Both must give the oracle's field, the
+    prefilter must actually prune, and a survivor list that overflows (forced here with a tiny segment capacity; flat
+    frames do it on their own) must fall back to the exact kernel on the device."""
+    from interpolatory_b200.device import DeviceContext
+    fr = make_sequence(H, W, 2, seed=11 * H + W)
+    ctx = DeviceContext(H, W)
+    ctx.upload_frame(0, fr[0]); ctx.upload_frame(1, fr[1])
+    want = [oracle.fs_blocks(bs, R, fr[0], fr[1]), oracle.fs_blocks(bs, R, fr[1], fr[0])]
+
+    def run():
+        ctx.me_fs_pair(0, 1, bs, R, 0, 1)
+        out = [ctx.download_mv_blocks(0), ctx.download_mv_blocks(1)]
+        return [np.concatenate([o[1], o[3][:, :, None]], axis=2) for o in out]
+
+    monkeypatch.setenv("MEMCI_FS_PREFILTER", "1")
+    got = run()
+    n_surv, overflow = ctx.fs_prefilter_stats()
+    n_cand = ctx.fs_stats()[0]
+    assert overflow == 0 and 0 < n_surv < 0.2 * n_cand, (n_surv, n_cand)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    # no room on the survivor list: blocks go to the block-level redo pass, and past its limit the pair falls back
+    for cap in ("40", "0"):
+        monkeypatch.setenv("MEMCI_F8_SEG_CAP", cap)
+        got = run()
+        if cap == "0":
+            assert ctx.fs_prefilter_stats()[1] == 1
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w), cap
+    monkeypatch.delenv("MEMCI_F8_SEG_CAP")
+    monkeypatch.setenv("MEMCI_FS_PREFILTER", "0")
+    got = run()
+    assert ctx.fs_prefilter_stats() == (0, 0)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+    # one direction, and a block-row range (the band-split entry point), through the prefilter
+    monkeypatch.setenv("MEMCI_FS_PREFILTER", "1")
+    ctx.me_fs(1, 0, bs, R, 2)
+    o = ctx.download_mv_blocks(2)
+    assert np.array_equal(np.concatenate([o[1], o[3][:, :, None]], axis=2), want[1])
+    ctx.close()
+
+
+def test_fs_prefilter_flat_and_tie_frames(gpu, oracle):
+    """Content where the prefilter cannot prune: flat frames (every candidate survives, the list overflows), two grey
+    levels (every SAD an exact multiple of 1000: all survivors are flagged and go to the float64 redo pass)."""
+    from interpolatory_b200.ME.full_search import get_motion_vectors as fs
+    rng = np.random.default_rng(3)
+    H, W = 96, 160
+    flat = np.empty((2, H, W, 3), np.uint8); flat[0] = 77; flat[1] = 80
+    two = np.repeat(rng.integers(0, 2, (2, H, W, 1), dtype=np.uint8) * 50 + 20, 3, axis=3)
+    grad = np.repeat((np.arange(W, dtype=np.uint8)[None, :, None] + np.zeros((H, 1, 1), np.uint8)), 3, axis=2)
+    for a, b in ((flat[0], flat[1]), (two[0], two[1]), (grad, np.roll(grad, 3, axis=1)), (flat[0], two[1])):
+        for bs, R in ((8, 16), (16, 9), (8, 3)):
+            assert np.array_equal(fs(bs, R, a, b), oracle.fs(bs, R, a, b)), (bs, R)
