@@ -22,7 +22,6 @@
 
 #include "memci_internal.cuh"
 
-#define F8_NT 256
 #define F8_G 11
 #define F8_NBMAX 32
 #define F8_MAXSEG 1024          // CTAs of the prefilter grid = segments of the survivor list
@@ -30,7 +29,6 @@
 struct F8Params {
     int H, W, bs, m, R, Rp, nbr, nbc;
     int nb_tile, tiles_per_row, n_tiles_dir, br0, ndir;
-    int ablate;                  // debug (MEMCI_F8_ABLATE): 1 no reloads after the first tile, 2 no survivor emission, 8 no search
     int pitch8;                  // bytes per row of the padded L8 planes
     int win_rows;                // staged window rows incl. slack for the last group
     int rs;                      // words per window row (per pre-shifted plane)
@@ -110,8 +108,8 @@ __device__ __forceinline__ void f8_accumulate(unsigned (&acc)[F8_G], const unsig
 // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  While a tile is searched, the raw window
 // and source rows of the CTA's next tile stream into shared memory with cp.async; after the search they are expanded
 // into the four byte-shifted planes (shared -> shared), so no global-memory latency sits between two tiles.
-template <bool M1>
-__global__ void __launch_bounds__(F8_NT, 4)
+template <bool M1, int F8_NT>
+__global__ void __launch_bounds__(F8_NT, 1024 / F8_NT)
 fs8_prefilter_kernel(const F8Params p)
 {
     extern __shared__ __align__(16) unsigned f8_smem[];
@@ -124,7 +122,7 @@ fs8_prefilter_kernel(const F8Params p)
     unsigned *planes = f8_smem;                                    // [4][plane_words]
     unsigned *raw = planes + 4 * p.plane_words;                    // [win_rows][rs + 1]   next tile's window, unshifted
     unsigned *ref0 = raw + p.win_rows * raw_rs;                    // [2][bs][ref_rs]      source blocks, current / next tile
-    unsigned short *A = reinterpret_cast<unsigned short *>(ref0 + 2 * bs * p.ref_rs);   // [F8_NT][a_stride]
+    unsigned short *A = reinterpret_cast<unsigned short *>(ref0 + 2 * bs * p.ref_rs);   // [threads][a_stride]
     const int n_tiles = p.n_tiles_dir * p.ndir;
 
     auto tile_of = [&](int t, int &dir, int &by, int &bx0, int &nb) {
@@ -197,7 +195,7 @@ fs8_prefilter_kernel(const F8Params p)
 
     for (;;) {
         const int tn = t + gridDim.x;
-        if (tn < n_tiles && !(p.ablate & 1)) issue_loads(tn, cur ^ 1);                // streams in while this tile is searched
+        if (tn < n_tiles) issue_loads(tn, cur ^ 1);                // streams in while this tile is searched
 
         unsigned *bmin = bmin_s[cur];
         const int *pre = pre_s[cur], *dx_lo_s = dx_lo_ss[cur];
@@ -214,7 +212,7 @@ fs8_prefilter_kernel(const F8Params p)
         int b = 0, dxi = 0;
         unsigned cmin = 0xffffffffu;
         unsigned short *col = A + (size_t)tid * p.a_stride;
-        if (active && !(p.ablate & 8)) {
+        if (active) {
             if (uniform_s[cur] > 0) b = tid / uniform_s[cur];
             else while (b + 1 < nb && pre[b + 1] <= tid) ++b;
             dxi = tid - pre[b];
@@ -277,7 +275,7 @@ fs8_prefilter_kernel(const F8Params p)
         //      segment lengths at the end ----
         {
             const unsigned thr = active ? bmin[b] + (unsigned)p.T : 0u;
-            const unsigned flagged0 = __ballot_sync(0xffffffffu, active && cmin <= thr && !(p.ablate & 2));
+            const unsigned flagged0 = __ballot_sync(0xffffffffu, active && cmin <= thr);
             const unsigned head_own = (dir ? 0x80000000u : 0u) | ((unsigned)(by * p.nbc + bx0 + b) << 14) | (unsigned)dxi;
             const unsigned short *cw = A + (size_t)(tid & ~31) * p.a_stride;
             for (unsigned f = flagged0; f; f &= f - 1) {
@@ -316,9 +314,9 @@ fs8_prefilter_kernel(const F8Params p)
         if (tn >= n_tiles) break;
         f8_cp_async_wait_all();
         __syncwarp();                                              // the warp's own rows of the next tile landed; planes are free since the barrier above
-        if (!(p.ablate & 1)) build(tn, cur ^ 1); else if (warp == 0) bmin_s[cur][lane] = 0xffffffffu;
+        build(tn, cur ^ 1);
         __syncthreads();
-        t = tn; if (!(p.ablate & 1)) cur ^= 1;
+        t = tn; cur ^= 1;
     }
     __syncthreads();
     if (tid == 0) { p.seg_counts[blockIdx.x] = min(seg_count, (unsigned)p.seg_cap); atomicAdd(&p.counters[9], (int)seg_count); }
@@ -492,7 +490,7 @@ int memci_ensure_luma8(memci_ctx *ctx, int slot)
 
 // Is the prefilter path applicable?  Block sizes 8k, list entry fields (17-bit block, 7-bit offsets), border of the
 // padded plane, one candidate column per thread, shared memory.
-static int f8_smem_bytes(int bs, int R, int nb_tile, int *rs_out, int *plane_words_out, int *ref_rs_out, int *a_stride_out, int *win_rows_out)
+static int f8_smem_bytes(int nt, int bs, int R, int nb_tile, int *rs_out, int *plane_words_out, int *ref_rs_out, int *a_stride_out, int *win_rows_out)
 {
     const int Rp = (R + 3) & ~3;
     const int n_dy = 2 * R + 1;
@@ -504,7 +502,18 @@ static int f8_smem_bytes(int bs, int R, int nb_tile, int *rs_out, int *plane_wor
     const int ref_rs = nb_tile * bs / 4;
     const int a_stride = (n_groups * F8_G + 3) & ~3;
     *rs_out = rs; *plane_words_out = plane_words; *ref_rs_out = ref_rs; *a_stride_out = a_stride; *win_rows_out = win_rows;
-    return (4 * plane_words + win_rows * (rs + 1) + 2 * bs * ref_rs) * 4 + F8_NT * a_stride * 2;
+    return (4 * plane_words + win_rows * (rs + 1) + 2 * bs * ref_rs) * 4 + nt * a_stride * 2;
+}
+
+// CTA size: 512 threads (two CTAs per SM, wider tiles: 15 blocks of 33 column offsets fill 97 % of the lanes at +-16)
+// when the shared memory of two such CTAs fits, else 256 threads (four per SM).  MEMCI_F8_NT overrides (tuning).
+static int f8_threads(int bs, int R)
+{
+    if (const char *e = getenv("MEMCI_F8_NT")) { const int v = atoi(e); if (v == 256 || v == 512) return v; }
+    int a, b, c, d, e2;
+    int nb_tile = 512 / (2 * R + 1);
+    if (nb_tile > F8_NBMAX) nb_tile = F8_NBMAX;
+    return (nb_tile >= 1 && f8_smem_bytes(512, bs, R, nb_tile, &a, &b, &c, &d, &e2) <= 110 * 1024) ? 512 : 256;
 }
 
 int memci_fs8_eligible(memci_ctx *ctx, int bs, int R)
@@ -512,11 +521,12 @@ int memci_fs8_eligible(memci_ctx *ctx, int bs, int R)
     if ((bs != 8 && bs != 16) || R < 1 || R > 63 || R + bs + 16 > MEMCI_L8_PAD) return 0;      // A fits uint16 up to 16 x 16 blocks
     const long long n_blk = (long long)ceil_div_i(ctx->H, bs) * ceil_div_i(ctx->W, bs);
     if (n_blk >= (1 << 17)) return 0;
-    int nb_tile = F8_NT / (2 * R + 1);
+    const int nt = f8_threads(bs, R);
+    int nb_tile = nt / (2 * R + 1);
     if (nb_tile < 1) return 0;
     int a, b, c, d, e;
     if (nb_tile > F8_NBMAX) nb_tile = F8_NBMAX;
-    return f8_smem_bytes(bs, R, nb_tile, &a, &b, &c, &d, &e) <= 110 * 1024;
+    return f8_smem_bytes(nt, bs, R, nb_tile, &a, &b, &c, &d, &e) <= 110 * 1024;
 }
 
 // Enqueue prefilter + refine + output for block rows [br0, br1).  counters[8] is left non-zero when the survivor
@@ -531,15 +541,15 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     F8Params p;
     memset(&p, 0, sizeof(p));
     p.H = H; p.W = W; p.bs = bs; p.m = bs / 8; p.R = R; p.Rp = (R + 3) & ~3; p.nbr = nbr; p.nbc = nbc;
-    p.nb_tile = F8_NT / (2 * R + 1);
+    const int nt = f8_threads(bs, R);
+    p.nb_tile = nt / (2 * R + 1);
     if (p.nb_tile > F8_NBMAX) p.nb_tile = F8_NBMAX;
     if (p.nb_tile > nbc) p.nb_tile = nbc;
     p.tiles_per_row = ceil_div_i(nbc, p.nb_tile);
     p.n_tiles_dir = p.tiles_per_row * (br1 - br0); p.br0 = br0; p.ndir = ndir;
     p.pitch8 = ctx->Wp + 2 * MEMCI_L8_PAD;
-    const int smem = f8_smem_bytes(bs, R, p.nb_tile, &p.rs, &p.plane_words, &p.ref_rs, &p.a_stride, &p.win_rows);
+    const int smem = f8_smem_bytes(nt, bs, R, p.nb_tile, &p.rs, &p.plane_words, &p.ref_rs, &p.a_stride, &p.win_rows);
     p.T = 2 * bs * bs + 1;
-    if (const char *e = getenv("MEMCI_F8_ABLATE")) p.ablate = atoi(e);
     const FrameSlot &fs = ctx->frames[slot_src], &ft = ctx->frames[slot_tgt];
     const size_t org = (size_t)MEMCI_L8_PAD * p.pitch8 + MEMCI_L8_PAD;
     p.l8_src[0] = fs.luma8 + org; p.l8_tgt[0] = ft.luma8 + org;
@@ -560,12 +570,14 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     CK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4 * sizeof(int), ctx->stream));   // [8] overflow [9] survivors [11] redo count
     static int attr_set = 0;
     if (!attr_set) {
-        CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         attr_set = 1;
     }
     const int n_tiles = p.n_tiles_dir * ndir;
-    int per_sm = 4;
+    int per_sm = 1024 / nt;
     if (const char *e = getenv("MEMCI_F8_CTAS")) per_sm = atoi(e);          // tuning: persistent CTAs per SM
     int grid = n_tiles < per_sm * ctx->num_sms ? n_tiles : per_sm * ctx->num_sms;
     if (grid > F8_MAXSEG) grid = F8_MAXSEG;
@@ -573,8 +585,13 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     p.list = ctx->d_fs8_list + F8_MAXSEG;
     p.seg_cap = (int)((have / 4 - F8_MAXSEG) / grid);
     if (const char *e = getenv("MEMCI_F8_SEG_CAP")) { const int v = atoi(e); if (v >= 0 && v < p.seg_cap) p.seg_cap = v; }   // tests: force the overflow fallback
-    if (bs == 8) fs8_prefilter_kernel<true><<<grid, F8_NT, smem, ctx->stream>>>(p);
-    else fs8_prefilter_kernel<false><<<grid, F8_NT, smem, ctx->stream>>>(p);
+    if (nt == 512) {
+        if (bs == 8) fs8_prefilter_kernel<true, 512><<<grid, 512, smem, ctx->stream>>>(p);
+        else fs8_prefilter_kernel<false, 512><<<grid, 512, smem, ctx->stream>>>(p);
+    } else {
+        if (bs == 8) fs8_prefilter_kernel<true, 256><<<grid, 256, smem, ctx->stream>>>(p);
+        else fs8_prefilter_kernel<false, 256><<<grid, 256, smem, ctx->stream>>>(p);
+    }
     CKL(ctx);
     fs8_refine_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(fs.luma, ft.luma, H, W, ctx->Wp, bs, R, nbc, n_blk,
                                                                  p.list, p.seg_cap, p.seg_counts, grid, ctx->d_counters, ctx->d_fs8_best,
