@@ -15,12 +15,13 @@ value    : inputs resident in HBM before the timed region, outputs left in HBM; 
            timed with CUDA events on a timing stream that fans out to / in from the C streams.
 e2e      : same work through the public pipeline API with page-locked HOST buffers, the H2D copy
            of every source frame and the D2H copy of every interpolated frame inside the timed region.
-roofline : dominant kernel (fs_tiled_kernel): SAD pixel-ops per launch (exact candidate count of the
-           reference's own bounds x 64 x 2 directions) / mean launch time from CUDA events recorded around
-           every launch of a single-stream pass of the same step (`single_stream`: timed next to another
-           stream's persistent grid a launch would include queueing), against the VABSDIFF issue rate
-           measured by a microbenchmark in this run.  The kernel is integer-ALU bound, not HBM bound; its HBM view and
-           the HBM-bound MCI splat kernel are reported beside it.
+roofline : dominant kernel (fs8_prefilter_kernel, phase 1 of the two-phase exact full search): SAD pixel-ops per launch
+           (exact candidate count of the reference's own bounds x 64 x 2 directions) / mean launch time from CUDA events
+           recorded around every launch of a single-stream pass of the same step (`single_stream`: timed next to
+           another stream's persistent grid a launch would include queueing), against the VABSDIFF4.U8.ACC issue rate
+           measured by a microbenchmark in this run.  Integer-ALU bound, not HBM bound.
+           `roofline_fs_exact` is the exact kernel (fs_tiled_kernel, prefilter off) against the 32-bit VABSDIFF rate,
+           `roofline_mci` the HBM-bound MCI splat kernel.
 cpu_baseline / --impl reference: the C restatement of the reference (oracle/, validated bit-exact
            against the reference) on the host cores, OpenMP over block rows, one full-size pair per sample.
 """
@@ -419,6 +420,20 @@ def main():
     barrier()
     ms_single = e0.elapsed_time(e1) / prof_steps
     fs_ms_sum, fs_n, mci_ms_sum, mci_n = ctx.profile_collect()
+    n_surv, pf_overflow = ctx.fs_prefilter_stats()
+    n_redo = ctx.fs_stats()[2]
+    used_prefilter = n_surv > 0 or pf_overflow > 0
+
+    # ---- pass 1b: the exact full-search kernel alone (prefilter off), for the second roofline line ----
+    exact_ms_sum = exact_n = 0
+    if used_prefilter:
+        os.environ["MEMCI_FS_PREFILTER"] = "0"
+        step_resident([ctx]); barrier()
+        ctx.profile_start(P * (2 + nd) + 16)
+        step_resident([ctx]); barrier()
+        exact_ms_sum, exact_n, _, _ = ctx.profile_collect()
+        del os.environ["MEMCI_FS_PREFILTER"]
+        step_resident([ctx]); barrier()
 
     # ---- pass 2, the measured value: the same P pairs per step over C contexts / streams (inputs resident in HBM) ----
     n_res = max(1, min(args.contexts, P))
@@ -473,6 +488,8 @@ def main():
     # ---- roofline denominator: VABSDIFF issue rate measured now, on this GPU ----
     ub_ms, ub_ops = min((ctx.microbench(0, 8192) for _ in range(3)), key=lambda x: x[0])
     peak_tops = ub_ops / (ub_ms * 1e-3) / 1e12
+    ub4_ms, ub4_ops = min((ctx.microbench(15, 8192) for _ in range(3)), key=lambda x: x[0])
+    peak4_tops = ub4_ops / (ub4_ms * 1e-3) / 1e12               # VABSDIFF4.U8.ACC: four pixel pairs per instruction
 
     t_max = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -507,7 +524,20 @@ def main():
             "gpu_launches": int(launches),
             "gpu_launches_e2e": int(e2e_launches),
             "clocks": clk,
-            "roofline": {
+            "roofline": ({
+                "kernel": "fs8_prefilter_kernel (8-bit luma-SAD of every candidate + survivor selection; phase 1 of the exact two-phase full search)",
+                "bound": "int_alu",
+                "achieved": achieved_tops, "peak": peak4_tops, "unit": "T SAD px-op/s",
+                "frac": (achieved_tops / peak4_tops) if achieved_tops else None,
+                "peak_source": "VABSDIFF4.U8.ACC issue-rate microbenchmark measured in this run (memci_microbench mode 15)",
+                "ops_per_launch": px_ops, "candidates_per_launch": n_cand, "launches_timed": fs_n,
+                "avg_launch_ms": fs_avg_s * 1e3,
+                "survivors_per_launch": n_surv, "survivor_fraction": n_surv / max(n_cand, 1), "redo_blocks_per_launch": n_redo,
+                "list_overflowed": bool(pf_overflow),
+                "traffic": load_traffic("fs8_prefilter_kernel") if args.workload == "cfg2" else None,
+                "vs_exact_arithmetic_peak": {"peak": peak_tops, "frac": (achieved_tops / peak_tops) if achieved_tops else None,
+                                             "note": "same algorithmic px-ops against the 32-bit VABSDIFF rate the exact kernel is bound by"},
+            } if used_prefilter else {
                 "kernel": "fs_tiled_kernel (full-search luma-SAD + argmin)", "bound": "int_alu",
                 "achieved": achieved_tops, "peak": peak_tops, "unit": "T SAD px-op/s",
                 "frac": (achieved_tops / peak_tops) if achieved_tops else None,
@@ -518,7 +548,14 @@ def main():
                 "hbm_view": {"algorithmic_bytes_per_launch": luma_bytes, "achieved_gbs": luma_bytes / fs_avg_s / 1e9 if fs_n else None,
                              "peak_gbs": peaks["hbm_gbs"], "frac": (luma_bytes / fs_avg_s / 1e9) / peaks["hbm_gbs"] if fs_n else None,
                              "peak_source": peak_src},
-            },
+            }),
+            "roofline_fs_exact": ({
+                "kernel": "fs_tiled_kernel (the exact kernel: every candidate at 18-bit luma; runs when the prefilter is off or its survivor list overflows)",
+                "bound": "int_alu", "achieved": px_ops / ((exact_ms_sum / exact_n) * 1e-3) / 1e12, "peak": peak_tops, "unit": "T SAD px-op/s",
+                "frac": px_ops / ((exact_ms_sum / exact_n) * 1e-3) / 1e12 / peak_tops, "avg_launch_ms": exact_ms_sum / exact_n, "launches_timed": exact_n,
+                "peak_source": "VABSDIFF issue-rate microbenchmark measured in this run (memci_microbench mode 0)",
+                "traffic": load_traffic("fs_tiled_kernel") if args.workload == "cfg2" else None,
+            } if exact_n else None),
             "roofline_mci": {
                 "kernel": "mci_splat_kernel (warp/blend, order-preserving gather)", "bound": "hbm",
                 "achieved": mci_bytes / mci_avg_s / 1e9 if mci_n else None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -529,7 +566,7 @@ def main():
             "single_stream": {"value": world * P * nd / (ms_single * 1e-3), "ms_per_step": ms_single, "steps": prof_steps,
                               "note": "same step on one CUDA stream; the per-launch kernel times of `roofline` / `roofline_mci` "
                                       "come from this pass (a launch timed next to another stream's persistent grid would include queueing)"},
-            "kernel_share_of_step": {"fs_tiled": fs_ms_sum / (ms_single * prof_steps), "mci_splat": mci_ms_sum / (ms_single * prof_steps),
+            "kernel_share_of_step": {("fs8_prefilter" if used_prefilter else "fs_tiled"): fs_ms_sum / (ms_single * prof_steps), "mci_splat": mci_ms_sum / (ms_single * prof_steps),
                                      "of": "single_stream step"},
         }
         if world == 1 and not args.no_cpu_baseline:

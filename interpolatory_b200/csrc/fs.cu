@@ -789,8 +789,7 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
     if (!use8) CK(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(int), ctx->stream));
     if (use8) {
         if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-        prof = memci_prof_begin(ctx, 0);
-        if ((rc = memci_fs8_run(ctx, slot_src, slot_tgt, bs, R, out, br0, br1, out2))) return rc;
+        if ((rc = memci_fs8_run(ctx, slot_src, slot_tgt, bs, R, out, br0, br1, out2))) return rc;   // per-launch profile events: around the prefilter kernel
     }
     if (pl->n_tiles > 0) {
         CUtensorMap tm[4];                     // src/tgt of direction 0, src/tgt of direction 1
@@ -833,7 +832,7 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         case 33: rc = fs_launch_tiled<33>(ctx, tm, p, smem); break;
         default: rc = fs_launch_tiled<11>(ctx, tm, p, smem); break;
         }
-        memci_prof_end(ctx, prof);
+        if (!use8) memci_prof_end(ctx, prof);
         if (p.trace) {                                   // debug dump: one line per (tile, warp)
             unsigned long long *h = (unsigned long long *)malloc(trace_n * 8);
             cudaStreamSynchronize(ctx->stream);

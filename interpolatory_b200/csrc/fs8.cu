@@ -131,9 +131,7 @@ fs8_prefilter_kernel(const F8Params p)
         by = p.br0 + trow; bx0 = (tt - trow * p.tiles_per_row) * p.nb_tile;
         nb = min(p.nb_tile, p.nbc - bx0);
     };
-    auto issue_loads = [&](int t, int buf) {
-        int dir, by, bx0, nb;
-        tile_of(t, dir, by, bx0, nb);
+    auto issue_loads = [&](int dir, int by, int bx0, int nb, int buf) {
         const int s_row = by * bs;
         const uint8_t *g = (dir ? p.l8_tgt[1] : p.l8_tgt[0]) + (ptrdiff_t)(s_row - R) * p.pitch8 + (bx0 * bs - p.Rp);
         const int n_w = (nb * bs + 2 * p.Rp) / 4 + 2;              // words per row incl. the one the last funnel shift reads
@@ -149,10 +147,8 @@ fs8_prefilter_kernel(const F8Params p)
                 f8_cp_async4(ref + r * p.ref_rs + j, reinterpret_cast<const unsigned *>(gs + (ptrdiff_t)r * p.pitch8) + j);
     };
     // raw -> four byte-shifted planes; tile geometry (warp 0)
-    auto build = [&](int t, int par) {
+    auto build = [&](int by, int bx0, int nb, int par) {
         unsigned *bmin = bmin_s[par]; int *pre = pre_s[par], *dx_lo_s = dx_lo_ss[par];
-        int dir, by, bx0, nb;
-        tile_of(t, dir, by, bx0, nb);
         const int n_w = (nb * bs + 2 * p.Rp) / 4 + 1;
         for (int r = warp; r < p.win_rows; r += F8_NT / 32) {
             const unsigned *src = raw + r * raw_rs;
@@ -187,20 +183,24 @@ fs8_prefilter_kernel(const F8Params p)
     int t = blockIdx.x;
     if (t >= n_tiles) return;
     int cur = 0;
-    issue_loads(t, 0);
+    int dir, by, bx0, nb;                                          // geometry of the tile being searched
+    tile_of(t, dir, by, bx0, nb);
+    issue_loads(dir, by, bx0, nb, 0);
     f8_cp_async_wait_all();
     __syncwarp();
-    build(t, 0);                                                  // every warp expands the rows it copied itself
+    build(by, bx0, nb, 0);                                        // every warp expands the rows it copied itself
     __syncthreads();
 
     for (;;) {
         const int tn = t + gridDim.x;
-        if (tn < n_tiles) issue_loads(tn, cur ^ 1);                // streams in while this tile is searched
+        int dir_n = 0, by_n = 0, bx0_n = 0, nb_n = 0;              // ... and of the CTA's next tile
+        if (tn < n_tiles) {
+            tile_of(tn, dir_n, by_n, bx0_n, nb_n);
+            issue_loads(dir_n, by_n, bx0_n, nb_n, cur ^ 1);        // streams in while this tile is searched
+        }
 
         unsigned *bmin = bmin_s[cur];
         const int *pre = pre_s[cur], *dx_lo_s = dx_lo_ss[cur];
-        int dir, by, bx0, nb;
-        tile_of(t, dir, by, bx0, nb);
         const int s_row = by * bs;
         const unsigned *ref = ref0 + cur * bs * p.ref_rs;
         const FsBounds8 b0 = f8_bounds(p.H, p.W, bs, R, s_row, bx0 * bs);
@@ -282,10 +282,15 @@ fs8_prefilter_kernel(const F8Params p)
                 const int src = __ffs(f) - 1;
                 const unsigned thr_c = __shfl_sync(0xffffffffu, thr, src);
                 const unsigned head = __shfl_sync(0xffffffffu, head_own, src);
-                const unsigned short *cs = cw + src * p.a_stride;
+                // lane l looks at row offsets 2l and 2l + 1 (one 32-bit load): 64 offsets per pass
+                const unsigned *cs = reinterpret_cast<const unsigned *>(cw + src * p.a_stride);
                 int hits = 0;
-                for (int i0 = 0; i0 < n_dy; i0 += 32)
-                    hits += __popc(__ballot_sync(0xffffffffu, i0 + lane < n_dy && cs[i0 + lane] <= thr_c));
+                for (int i0 = 0; i0 < n_dy; i0 += 64) {
+                    const int i = i0 + 2 * lane;
+                    const unsigned v = i < n_dy ? cs[i >> 1] : 0xffffffffu;
+                    hits += __popc(__ballot_sync(0xffffffffu, (v & 0xffffu) <= thr_c)) +
+                            __popc(__ballot_sync(0xffffffffu, i + 1 < n_dy && (v >> 16) <= thr_c));
+                }
                 int pos = 0;
                 if (lane == 0) {
                     // A column that survives whole is flat content: nothing to prune in this block.  It, and any block
@@ -302,21 +307,26 @@ fs8_prefilter_kernel(const F8Params p)
                 }
                 pos = __shfl_sync(0xffffffffu, pos, 0);
                 if (pos < 0) continue;
-                for (int i0 = 0; i0 < n_dy; i0 += 32) {
-                    const int i = i0 + lane;
-                    const bool hit = i < n_dy && cs[i] <= thr_c;
-                    const unsigned hb = __ballot_sync(0xffffffffu, hit);
-                    if (hit) seg[pos + __popc(hb & ((1u << lane) - 1u))] = head | ((unsigned)i << 7);
-                    pos += __popc(hb);
+                for (int i0 = 0; i0 < n_dy; i0 += 64) {
+                    const int i = i0 + 2 * lane;
+                    const unsigned v = i < n_dy ? cs[i >> 1] : 0xffffffffu;
+                    const bool h0 = (v & 0xffffu) <= thr_c, h1 = i + 1 < n_dy && (v >> 16) <= thr_c;
+                    const unsigned b0m = __ballot_sync(0xffffffffu, h0), b1m = __ballot_sync(0xffffffffu, h1);
+                    const unsigned below = (1u << lane) - 1u;
+                    const int off = __popc(b0m & below) + __popc(b1m & below);      // entries of lower lanes come first (order is irrelevant to the result)
+                    if (h0) seg[pos + off] = head | ((unsigned)i << 7);
+                    if (h1) seg[pos + off + (h0 ? 1 : 0)] = head | ((unsigned)(i + 1) << 7);
+                    pos += __popc(b0m) + __popc(b1m);
                 }
             }
         }
         if (tn >= n_tiles) break;
         f8_cp_async_wait_all();
         __syncwarp();                                              // the warp's own rows of the next tile landed; planes are free since the barrier above
-        build(tn, cur ^ 1);
+        build(by_n, bx0_n, nb_n, cur ^ 1);
         __syncthreads();
         t = tn; cur ^= 1;
+        dir = dir_n; by = by_n; bx0 = bx0_n; nb = nb_n;
     }
     __syncthreads();
     if (tid == 0) { p.seg_counts[blockIdx.x] = min(seg_count, (unsigned)p.seg_cap); atomicAdd(&p.counters[9], (int)seg_count); }
@@ -585,6 +595,7 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     p.list = ctx->d_fs8_list + F8_MAXSEG;
     p.seg_cap = (int)((have / 4 - F8_MAXSEG) / grid);
     if (const char *e = getenv("MEMCI_F8_SEG_CAP")) { const int v = atoi(e); if (v >= 0 && v < p.seg_cap) p.seg_cap = v; }   // tests: force the overflow fallback
+    const int prof = memci_prof_begin(ctx, 0);
     if (nt == 512) {
         if (bs == 8) fs8_prefilter_kernel<true, 512><<<grid, 512, smem, ctx->stream>>>(p);
         else fs8_prefilter_kernel<false, 512><<<grid, 512, smem, ctx->stream>>>(p);
@@ -592,6 +603,7 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
         if (bs == 8) fs8_prefilter_kernel<true, 256><<<grid, 256, smem, ctx->stream>>>(p);
         else fs8_prefilter_kernel<false, 256><<<grid, 256, smem, ctx->stream>>>(p);
     }
+    memci_prof_end(ctx, prof);
     CKL(ctx);
     fs8_refine_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(fs.luma, ft.luma, H, W, ctx->Wp, bs, R, nbc, n_blk,
                                                                  p.list, p.seg_cap, p.seg_counts, grid, ctx->d_counters, ctx->d_fs8_best,

@@ -47,7 +47,7 @@ want = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_
         'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_sector_hit_rate.pct']
-for rep, title in (("prof_fs", "fs_tiled_kernel (dominant kernel)"), ("prof_mci", "mci_splat_kernel"), ("prof_hf", "mci_holefill_kernel")):
+for rep, title in (("prof_fs8", "fs8_prefilter_kernel (dominant kernel: 8-bit prefilter of the two-phase full search)"), ("prof_fs", "fs_tiled_kernel (the exact kernel, MEMCI_FS_PREFILTER=0)"), ("prof_mci", "mci_splat_kernel"), ("prof_hf", "mci_holefill_kernel")):
     path = f"gpurun_out/{rep}.ncu-rep"
     if not os.path.exists(path):
         continue
@@ -65,7 +65,7 @@ for rep, title in (("prof_fs", "fs_tiled_kernel (dominant kernel)"), ("prof_mci"
     w()
 import json
 traffic = {}
-for rep, kname in (("prof_fs", "fs_tiled_kernel"), ("prof_mci", "mci_splat_kernel")):
+for rep, kname in (("prof_fs8", "fs8_prefilter_kernel"), ("prof_fs", "fs_tiled_kernel"), ("prof_mci", "mci_splat_kernel")):
     path = f"gpurun_out/{rep}.ncu-rep"
     if not os.path.exists(path):
         continue
