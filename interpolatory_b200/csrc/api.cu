@@ -665,7 +665,7 @@ int memci_fs_stats(memci_ctx *ctx, long long *n_cand, long long *px_ops, int *n_
         int h[12];
         CK(ctx, cudaMemcpyAsync(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
-        *n_redo = ctx->fs_used_prefilter ? h[11] : h[0];
+        *n_redo = ctx->fs_used_prefilter ? h[10] + h[11] : h[0];     // float64 replays of flagged survivors + redo blocks
     }
     return MEMCI_OK;
 }

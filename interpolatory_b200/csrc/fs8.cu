@@ -342,6 +342,7 @@ __device__ __forceinline__ unsigned long long f8_key(unsigned sad, unsigned d2, 
 // Blocks already on the redo list (dense blocks, earlier flagged sums) are skipped.
 __global__ void __launch_bounds__(256)
 fs8_refine_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
+                  const uint8_t *__restrict__ rgb0, const uint8_t *__restrict__ rgb1,
                   int H, int W, int Wp, int bs, int R, int nbc, int n_blk,
                   const unsigned *__restrict__ list, int seg_cap, const unsigned *__restrict__ seg_counts, int n_seg,
                   int *__restrict__ counters,
@@ -419,10 +420,38 @@ fs8_refine_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1
         }
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+        // Flagged sum (S a positive multiple of 1000): the reference's float64 accumulation may land just below the
+        // integer and truncate to S / 1000 - 1 (fs.cu).  8 x 8 blocks are replayed here in the reference's operation
+        // order -- each lane forms the |dL| terms of its row, then the 64 terms are added row by row, column by column --
+        // larger blocks go to the block-level redo pass.
+        const bool flagged = on && S != 0u && (S / 1000u) * 1000u == S;
+        unsigned sad = S / 1000u;
+        if (bs == 8 && __any_sync(0xffffffffu, flagged)) {
+            double tr[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) tr[c] = 0.0;
+            if (flagged) {
+                const uint8_t *rgb_s = dir ? rgb1 : rgb0, *rgb_t = dir ? rgb0 : rgb1;
+                const int r1 = s_row + pr, r2 = t_row + pr;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int c1 = s_col + c, c2 = t_col + c;
+                    double l1 = 0.0, l2 = 0.0;
+                    if (r1 < H && c1 < W) { const uint8_t *q = rgb_s + ((size_t)r1 * W + c1) * 3; l1 = luma_f64(q[0], q[1], q[2]); }
+                    if (r2 < H && c2 < W) { const uint8_t *q = rgb_t + ((size_t)r2 * W + c2) * 3; l2 = luma_f64(q[0], q[1], q[2]); }
+                    tr[c] = fabs(__dsub_rn(l1, l2));
+                }
+            }
+            double acc = 0.0;
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, tr[c], i, 8));
+            }
+            if (flagged) { sad = (unsigned)acc; if (pr == 0) atomicAdd(&counters[10], 1); }
+        }
         if (on && pr == 0) {
-            const unsigned sad = S / 1000u;
-            if (S != 0 && sad * 1000u == S) {
-                // flagged: the f64 sum may truncate to sad - 1 (fs.cu).  The whole block goes to the exact redo pass, once.
+            if (flagged && bs != 8) {
                 if (atomicExch(&redo_mark[(size_t)dir * n_blk + blk], 0u) != 0u) {
                     const int pos = atomicAdd(&counters[11], 1);
                     if (pos < redo_cap) redo_list[pos] = blk | (dir ? 0x40000000 : 0);           // FS_DIR_BIT
@@ -577,7 +606,7 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     p.counters = ctx->d_counters;
     p.redo_mark = reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2);
     p.redo_list = ctx->d_redo_list; p.redo_cap = ctx->redo_cap; p.redo_limit = n_blk * ndir / 16 + 64;
-    CK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4 * sizeof(int), ctx->stream));   // [8] overflow [9] survivors [11] redo count
+    CK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4 * sizeof(int), ctx->stream));   // [8] overflow [9] survivors [10] float64 replays [11] redo blocks
     static int attr_set = 0;
     if (!attr_set) {
         CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
@@ -605,7 +634,7 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     }
     memci_prof_end(ctx, prof);
     CKL(ctx);
-    fs8_refine_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(fs.luma, ft.luma, H, W, ctx->Wp, bs, R, nbc, n_blk,
+    fs8_refine_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, ctx->Wp, bs, R, nbc, n_blk,
                                                                  p.list, p.seg_cap, p.seg_counts, grid, ctx->d_counters, ctx->d_fs8_best,
                                                                  reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2), ctx->d_redo_list, ctx->redo_cap);
     CKL(ctx);

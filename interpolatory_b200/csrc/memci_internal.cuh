@@ -54,7 +54,7 @@ struct memci_ctx {
     MVField mvs[MEMCI_NUM_MV_SLOTS];
     MVField tmp_mv[2];                 // HBMA ping-pong
     // full-search scratch
-    int *d_redo_list; int redo_cap; int *d_counters;   // [0] redo count, [1] hole count, [2] dmax, [4] hole runs, [5] bidir2 max |T|, [6] bidir2 out-of-range blocks, [8] fs8 list overflow, [9] fs8 survivors, [11] redo count of the fs8 path
+    int *d_redo_list; int redo_cap; int *d_counters;   // [0] redo count, [1] hole count, [2] dmax, [4] hole runs, [5] bidir2 max |T|, [6] bidir2 out-of-range blocks, [8] fs8 list overflow, [9] fs8 survivors, [10] fs8 float64 replays, [11] redo blocks of the fs8 path
     FsPlan fs_plan[4];
     unsigned *d_fs8_list; size_t fs8_list_cap;          // prefilter survivors (bytes)
     unsigned long long *d_fs8_best; size_t fs8_best_cap; // per (direction, block) minimum key of the refine pass (bytes)
