@@ -143,6 +143,7 @@ int memci_ctx_destroy(memci_ctx *ctx)
         if (ctx->d_b2blk[i]) cudaFree(ctx->d_b2blk[i]);
     }
     if (ctx->d_quality) cudaFree(ctx->d_quality);
+    if (ctx->h_fs8_feedback) { cudaFreeHost(ctx->h_fs8_feedback); cudaEventDestroy(ctx->ev_fs8_feedback); }
     if (ctx->d_fs8_list) cudaFree(ctx->d_fs8_list);
     if (ctx->d_fs8_best) cudaFree(ctx->d_fs8_best);
     for (int i = 0; i < 4; ++i) {

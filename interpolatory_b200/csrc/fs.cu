@@ -782,7 +782,18 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
     // Two-phase exact search (fs8.cu): 8-bit prefilter + exact refinement of the survivors; the exact tiled kernel below
     // then runs only if the survivor list overflowed (device-side gate, no host round trip).
     const char *pf_env = getenv("MEMCI_FS_PREFILTER");
-    const bool use8 = pl->n_tiles > 0 && !(pf_env && atoi(pf_env) == 0) && memci_fs8_eligible(ctx, bs, R);
+    bool use8 = pl->n_tiles > 0 && !(pf_env && atoi(pf_env) == 0) && memci_fs8_eligible(ctx, bs, R);
+    // Content feedback: the prefilter only pays where it prunes.  The counters of a recent two-phase search come back
+    // through an asynchronous copy; if they show an overflow, many redo blocks or more than 5 % survivors, the next
+    // 32 searches go straight to the exact kernel (then the prefilter is probed again).  MEMCI_FS_PREFILTER=1 pins it on.
+    if (use8 && !(pf_env && atoi(pf_env) == 1)) {
+        if (ctx->fs8_feedback_pending && cudaEventQuery(ctx->ev_fs8_feedback) == cudaSuccess) {
+            const int *h = ctx->h_fs8_feedback;
+            ctx->fs8_feedback_pending = 0;
+            if (h[0] != 0 || (long long)h[1] * 20 > ctx->fs8_feedback_cand || h[3] > nbr * nbc * ndir / 32) ctx->fs8_backoff = 32;
+        }
+        if (ctx->fs8_backoff > 0) { --ctx->fs8_backoff; use8 = false; }
+    }
     int prof = -1;
     int *redo_count = use8 ? ctx->d_counters + 11 : ctx->d_counters;     // the prefilter path zeroes [8..11] in one memset
     ctx->fs_used_prefilter = use8 ? 1 : 0;
@@ -869,6 +880,16 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
             CKL(ctx);
         }
         if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->fs_timed = 1; }
+    }
+    if (use8 && !ctx->fs8_feedback_pending) {
+        if (!ctx->h_fs8_feedback) {
+            CK(ctx, cudaHostAlloc((void **)&ctx->h_fs8_feedback, 4 * sizeof(int), cudaHostAllocDefault));
+            CK(ctx, cudaEventCreateWithFlags(&ctx->ev_fs8_feedback, cudaEventDisableTiming));
+        }
+        CK(ctx, cudaMemcpyAsync(ctx->h_fs8_feedback, ctx->d_counters + 8, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaEventRecord(ctx->ev_fs8_feedback, ctx->stream));
+        ctx->fs8_feedback_pending = 1;
+        ctx->fs8_feedback_cand = ctx->fs_last_cand;
     }
     out->valid = 1;
     if (out2) out2->valid = 1;

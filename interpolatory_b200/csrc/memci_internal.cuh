@@ -60,6 +60,9 @@ struct memci_ctx {
     unsigned long long *d_fs8_best; size_t fs8_best_cap; // per (direction, block) minimum key of the refine pass (bytes)
     long long fs_last_cand, fs_last_ops;
     int fs_used_prefilter;             // the last full search took the two-phase path (fs8.cu)
+    // content feedback for the two-phase path: counters [8..11] of a recent search, copied back asynchronously
+    int *h_fs8_feedback; cudaEvent_t ev_fs8_feedback; int fs8_feedback_pending; long long fs8_feedback_cand;
+    int fs8_backoff;                   // > 0: that many searches skip the prefilter (the last feedback said it does not pay on this content)
     // MCI scratch
     short2 *d_disp[2]; size_t disp_cap[2];
     uint32_t *d_fill; int *d_hole_list; size_t hole_cap;

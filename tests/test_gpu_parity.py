@@ -852,3 +852,25 @@ def test_fs_prefilter_flat_and_tie_frames(gpu, oracle):
     for a, b in ((flat[0], flat[1]), (two[0], two[1]), (grad, np.roll(grad, 3, axis=1)), (flat[0], two[1])):
         for bs, R in ((8, 16), (16, 9), (8, 3)):
             assert np.array_equal(fs(bs, R, a, b), oracle.fs(bs, R, a, b)), (bs, R)
+
+
+def test_fs_prefilter_backs_off_on_flat_content(gpu, oracle, monkeypatch):
+    """Content feedback: a search whose prefilter could not prune (flat frames: the survivor list overflows and the exact
+    kernel redoes the pair) makes the next searches skip the prefilter; textured content keeps it on."""
+    from interpolatory_b200.device import DeviceContext
+    monkeypatch.delenv("MEMCI_FS_PREFILTER", raising=False)
+    H, W = 96, 160
+    flat = np.empty((2, H, W, 3), np.uint8); flat[0] = 77; flat[1] = 80
+    tex = make_sequence(H, W, 2, seed=9)
+    for frames, expect_on in ((tex, True), (flat, False)):
+        ctx = DeviceContext(H, W)
+        ctx.upload_frame(0, frames[0]); ctx.upload_frame(1, frames[1])
+        want = oracle.fs_blocks(8, 16, frames[0], frames[1])
+        used = []
+        for _ in range(4):
+            ctx.me_fs(0, 1, 8, 16, 0)
+            _, vec, _, sad = ctx.download_mv_blocks(0)          # synchronises: the feedback copy has landed
+            assert np.array_equal(vec, want[:, :, :2]) and np.array_equal(sad, want[:, :, 2])
+            used.append(ctx.fs_prefilter_stats() != (0, 0))
+        assert used[0] and used[1:] == [expect_on] * 3, used
+        ctx.close()
