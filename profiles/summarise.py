@@ -27,6 +27,12 @@ w("| kernel | launches | total us | avg us | share of hot-path kernels |")
 w("|---|---:|---:|---:|---:|")
 for k, v in sorted(step.items(), key=lambda kv: -kv[1][1]):
     w(f"| {k} | {v[0]} | {v[1]/1e3:.1f} | {v[1]/v[0]/1e3:.1f} | {v[1]/tot:.3f} |")
+w()
+w("Note: the profiled command also runs bench.py's exact-kernel pass (`roofline_fs_exact`: one warm-up + one timed step with")
+w("MEMCI_FS_PREFILTER=0), so `fs_tiled_kernel` appears with 8 real launches (~270 us each) on top of the 28 gated launches of")
+w("the two-phase path, which return at once (~3 us: the kernel only runs when the survivor list overflowed).  Shares of the")
+w("two-phase step proper: take `fs_tiled_kernel` as 28 x 3 us.")
+w()
 for k, v in agg.items():
     if k.startswith('ub_kernel'):
         w(f"| ({k}: roofline microbenchmark, not part of a step) | {v[0]} | {v[1]/1e3:.1f} | {v[1]/v[0]/1e3:.1f} | - |")
