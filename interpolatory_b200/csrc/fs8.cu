@@ -11,12 +11,14 @@
 //     survivors = { c : A(c) <= A_min + 2n + 1 }.
 // The reference's winner is always among them; every survivor is then evaluated exactly (same arithmetic, same
 // total order as fs.cu) and the minimum key taken.  The result is bit-identical; only the amount of exact work
-// depends on the content (textured frames: ~0.3 % of the candidates survive; flat frames: all of them, and the
-// caller falls back to the exact kernel when the survivor list overflows).
+// depends on the content (textured frames: ~0.5 % of the candidates survive; flat frames: all of them -- those blocks go
+// to the block-level redo pass, and past a limit the exact kernel searches the pair, gated on a device-side flag).
 //
-//   fs8_prefilter_kernel  CTA per tile of adjacent blocks of one block row; thread = (block, dx) candidate column
-//   fs8_refine_kernel     thread per survivor: exact luma-SAD (+ float64 replay of flagged sums), 64-bit atomicMin
-//   fs8_output_kernel     thread per block: key -> (dy, dx, sad)
+//   fs8_prefilter_kernel  persistent CTAs over tiles of adjacent blocks of one block row; thread = (block, dx) candidate
+//                         column; survivors appended to per-CTA segments of the list
+//   fs8_refine_kernel     8 lanes per survivor: exact luma-SAD (+ float64 replay of flagged sums), 64-bit atomicMin
+//   fs8_output_kernel     thread per block: key -> (dy, dx, sad); decides the pair-level fallback; re-arms the buffers
+// Blocks that cannot be pruned (flat content, segment overflow, flagged sums of 16 x 16 blocks) go to fs_redo_kernel (fs.cu).
 #include <stdlib.h>
 #include <type_traits>
 
@@ -607,13 +609,12 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     p.redo_mark = reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2);
     p.redo_list = ctx->d_redo_list; p.redo_cap = ctx->redo_cap; p.redo_limit = n_blk * ndir / 16 + 64;
     CK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4 * sizeof(int), ctx->stream));   // [8] overflow [9] survivors [10] float64 replays [11] redo blocks
-    static int attr_set = 0;
-    if (!attr_set) {
+    if (!ctx->fs8_attr_set) {                                      // per context: the attribute belongs to the device
         CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        attr_set = 1;
+        ctx->fs8_attr_set = 1;
     }
     const int n_tiles = p.n_tiles_dir * ndir;
     int per_sm = 1024 / nt;

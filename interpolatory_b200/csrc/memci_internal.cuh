@@ -62,6 +62,7 @@ struct memci_ctx {
     int fs_used_prefilter;             // the last full search took the two-phase path (fs8.cu)
     // content feedback for the two-phase path: counters [8..11] of a recent search, copied back asynchronously
     int *h_fs8_feedback; cudaEvent_t ev_fs8_feedback; int fs8_feedback_pending; long long fs8_feedback_cand;
+    int fs8_attr_set;                  // dynamic shared-memory attribute of the prefilter kernels set on this context's device
     int fs8_backoff;                   // > 0: that many searches skip the prefilter (the last feedback said it does not pay on this content)
     // MCI scratch
     short2 *d_disp[2]; size_t disp_cap[2];
