@@ -30,7 +30,8 @@
 
 struct F8Params {
     int H, W, bs, m, R, Rp, nbr, nbc;
-    int nb_tile, tiles_per_row, n_tiles_dir, br0, ndir;
+    int nb_tile, tiles_per_row, n_tiles_dir, br0, br1, ndir;
+    int rpt;                     // block rows per tile (2 when the taller window fits: staging and barriers per block halve)
     int pitch8;                  // bytes per row of the padded L8 planes
     int win_rows;                // staged window rows incl. slack for the last group
     int rs;                      // words per window row (per pre-shifted plane)
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(F8_NT, 1024 / F8_NT)
 fs8_prefilter_kernel(const F8Params p)
 {
     extern __shared__ __align__(16) unsigned f8_smem[];
-    __shared__ unsigned bmin_s[2][F8_NBMAX];     // per tile parity: the next tile's geometry is written while slow warps still emit
+    __shared__ unsigned bmin_s[2][2][F8_NBMAX];  // [tile parity][block row of the tile]; per tile parity: the next tile's geometry is written while slow warps still emit
     __shared__ int pre_s[2][F8_NBMAX + 1], dx_lo_ss[2][F8_NBMAX];
     __shared__ unsigned seg_count;
     __shared__ int uniform_s[2];                                   // > 0: every block of the tile has that many column offsets
@@ -123,14 +124,15 @@ fs8_prefilter_kernel(const F8Params p)
     const int bs = p.bs, R = p.R, raw_rs = p.rs + 1;
     unsigned *planes = f8_smem;                                    // [4][plane_words]
     unsigned *raw = planes + 4 * p.plane_words;                    // [win_rows][rs + 1]   next tile's window, unshifted
-    unsigned *ref0 = raw + p.win_rows * raw_rs;                    // [2][bs][ref_rs]      source blocks, current / next tile
-    unsigned short *A = reinterpret_cast<unsigned short *>(ref0 + 2 * bs * p.ref_rs);   // [threads][a_stride]
+    const int ref_rows = p.rpt * bs;
+    unsigned *ref0 = raw + p.win_rows * raw_rs;                    // [2][rpt * bs][ref_rs]  source blocks, current / next tile
+    unsigned short *A = reinterpret_cast<unsigned short *>(ref0 + 2 * ref_rows * p.ref_rs);   // [threads][a_stride]
     const int n_tiles = p.n_tiles_dir * p.ndir;
 
     auto tile_of = [&](int t, int &dir, int &by, int &bx0, int &nb) {
         dir = t >= p.n_tiles_dir ? 1 : 0;
         const int tt = t - dir * p.n_tiles_dir, trow = tt / p.tiles_per_row;
-        by = p.br0 + trow; bx0 = (tt - trow * p.tiles_per_row) * p.nb_tile;
+        by = p.br0 + trow * p.rpt; bx0 = (tt - trow * p.tiles_per_row) * p.nb_tile;      // first block row of the tile
         nb = min(p.nb_tile, p.nbc - bx0);
     };
     auto issue_loads = [&](int dir, int by, int bx0, int nb, int buf) {
@@ -142,15 +144,15 @@ fs8_prefilter_kernel(const F8Params p)
             for (int j = lane; j < n_w; j += 32) f8_cp_async4(raw + r * raw_rs + j, row + j);
         }
         const uint8_t *gs = (dir ? p.l8_src[1] : p.l8_src[0]) + (ptrdiff_t)s_row * p.pitch8 + bx0 * bs;
-        unsigned *ref = ref0 + buf * bs * p.ref_rs;
+        unsigned *ref = ref0 + buf * ref_rows * p.ref_rs;
         const int n_r = nb * bs / 4;
-        for (int r = warp; r < bs; r += F8_NT / 32)
+        for (int r = warp; r < ref_rows; r += F8_NT / 32)                  // rows past the frame are zero in the padded plane
             for (int j = lane; j < n_r; j += 32)
                 f8_cp_async4(ref + r * p.ref_rs + j, reinterpret_cast<const unsigned *>(gs + (ptrdiff_t)r * p.pitch8) + j);
     };
     // raw -> four byte-shifted planes; tile geometry (warp 0)
     auto build = [&](int by, int bx0, int nb, int par) {
-        unsigned *bmin = bmin_s[par]; int *pre = pre_s[par], *dx_lo_s = dx_lo_ss[par];
+        int *pre = pre_s[par], *dx_lo_s = dx_lo_ss[par];
         const int n_w = (nb * bs + 2 * p.Rp) / 4 + 1;
         for (int r = warp; r < p.win_rows; r += F8_NT / 32) {
             const unsigned *src = raw + r * raw_rs;
@@ -173,7 +175,7 @@ fs8_prefilter_kernel(const F8Params p)
             int incl = n_dx;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            pre[lane + 1] = incl; dx_lo_s[lane] = dxl; bmin[lane] = 0xffffffffu;
+            pre[lane + 1] = incl; dx_lo_s[lane] = dxl; bmin_s[par][0][lane] = 0xffffffffu; bmin_s[par][1][lane] = 0xffffffffu;
             const int n0 = __shfl_sync(0xffffffffu, n_dx, 0);
             const bool uni = __all_sync(0xffffffffu, lane >= nb || n_dx == n0);
             if (lane == 0) { pre[0] = 0; uniform_s[par] = (uni && n0 > 0) ? n0 : 0; }
@@ -201,31 +203,35 @@ fs8_prefilter_kernel(const F8Params p)
             issue_loads(dir_n, by_n, bx0_n, nb_n, cur ^ 1);        // streams in while this tile is searched
         }
 
-        unsigned *bmin = bmin_s[cur];
         const int *pre = pre_s[cur], *dx_lo_s = dx_lo_ss[cur];
-        const int s_row = by * bs;
-        const unsigned *ref = ref0 + cur * bs * p.ref_rs;
-        const FsBounds8 b0 = f8_bounds(p.H, p.W, bs, R, s_row, bx0 * bs);
-        const int n_dy = max(b0.r1 - b0.r0, 0);
         const int n_items = pre[nb];
-        const int wrow_base = b0.r0 - (s_row - R);
-        const int n_groups = (n_dy + F8_G - 1) / F8_G;
-        const bool active = tid < n_items && n_dy > 0;
-        int b = 0, dxi = 0;
-        unsigned cmin = 0xffffffffu;
-        unsigned short *col = A + (size_t)tid * p.a_stride;
-        if (active) {
+        int b = 0, dxi = 0, dx = 0;                                // the thread's candidate column: the same for every block row of the tile
+        if (tid < n_items) {
             if (uniform_s[cur] > 0) b = tid / uniform_s[cur];
             else while (b + 1 < nb && pre[b + 1] <= tid) ++b;
             dxi = tid - pre[b];
-            const int dx = dx_lo_s[b] + dxi;
+            dx = dx_lo_s[b] + dxi;
+        }
+        unsigned short *col = A + (size_t)tid * p.a_stride;
+        const int nv = min(p.rpt, p.br1 - by);
+#pragma unroll 1
+        for (int v = 0; v < nv; ++v) {
+        unsigned *bmin = bmin_s[cur][v];
+        const int s_row = (by + v) * bs;
+        const unsigned *ref = ref0 + (cur * ref_rows + v * bs) * p.ref_rs;
+        const FsBounds8 b0 = f8_bounds(p.H, p.W, bs, R, s_row, bx0 * bs);
+        const int n_dy = max(b0.r1 - b0.r0, 0);
+        const int wrow_base = b0.r0 - (by * bs - R);               // window rows count from the tile's first block row
+        const bool active = tid < n_items && n_dy > 0;
+        unsigned cmin = 0xffffffffu;
+        if (active) {
             unsigned rl[8], rh[8];
             if (M1) {
                 const unsigned *rp = ref + ((b * 8) >> 2);
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
-                    const uint2 v = *reinterpret_cast<const uint2 *>(rp + kk * p.ref_rs);
-                    rl[kk] = v.x; rh[kk] = v.y;
+                    const uint2 rv = *reinterpret_cast<const uint2 *>(rp + kk * p.ref_rs);
+                    rl[kk] = rv.x; rh[kk] = rv.y;
                 }
             }
             const int wc0 = b * bs + dx + p.Rp;                    // byte offset inside a window row
@@ -245,8 +251,8 @@ fs8_prefilter_kernel(const F8Params p)
                         const unsigned *rp = ref + (si * 8) * p.ref_rs + ((b * bs + sj * 8) >> 2);
 #pragma unroll
                         for (int kk = 0; kk < 8; ++kk) {
-                            const uint2 v = *reinterpret_cast<const uint2 *>(rp + kk * p.ref_rs);
-                            rl[kk] = v.x; rh[kk] = v.y;
+                            const uint2 rv = *reinterpret_cast<const uint2 *>(rp + kk * p.ref_rs);
+                            rl[kk] = rv.x; rh[kk] = rv.y;
                         }
                         const int wc = wc0 + sj * 8;
                         f8_accumulate(acc, rl, rh, planes + (wc & 3) * p.plane_words + (wrow_base + g * F8_G + si * 8) * p.rs + (wc >> 2), p.rs);
@@ -278,7 +284,7 @@ fs8_prefilter_kernel(const F8Params p)
         {
             const unsigned thr = active ? bmin[b] + (unsigned)p.T : 0u;
             const unsigned flagged0 = __ballot_sync(0xffffffffu, active && cmin <= thr);
-            const unsigned head_own = (dir ? 0x80000000u : 0u) | ((unsigned)(by * p.nbc + bx0 + b) << 14) | (unsigned)dxi;
+            const unsigned head_own = (dir ? 0x80000000u : 0u) | ((unsigned)((by + v) * p.nbc + bx0 + b) << 14) | (unsigned)dxi;
             const unsigned short *cw = A + (size_t)(tid & ~31) * p.a_stride;
             for (unsigned f = flagged0; f; f &= f - 1) {
                 const int src = __ffs(f) - 1;
@@ -289,9 +295,9 @@ fs8_prefilter_kernel(const F8Params p)
                 int hits = 0;
                 for (int i0 = 0; i0 < n_dy; i0 += 64) {
                     const int i = i0 + 2 * lane;
-                    const unsigned v = i < n_dy ? cs[i >> 1] : 0xffffffffu;
-                    hits += __popc(__ballot_sync(0xffffffffu, (v & 0xffffu) <= thr_c)) +
-                            __popc(__ballot_sync(0xffffffffu, i + 1 < n_dy && (v >> 16) <= thr_c));
+                    const unsigned pv = i < n_dy ? cs[i >> 1] : 0xffffffffu;
+                    hits += __popc(__ballot_sync(0xffffffffu, i < n_dy && (pv & 0xffffu) <= thr_c)) +
+                            __popc(__ballot_sync(0xffffffffu, i + 1 < n_dy && (pv >> 16) <= thr_c));
                 }
                 int pos = 0;
                 if (lane == 0) {
@@ -311,8 +317,8 @@ fs8_prefilter_kernel(const F8Params p)
                 if (pos < 0) continue;
                 for (int i0 = 0; i0 < n_dy; i0 += 64) {
                     const int i = i0 + 2 * lane;
-                    const unsigned v = i < n_dy ? cs[i >> 1] : 0xffffffffu;
-                    const bool h0 = (v & 0xffffu) <= thr_c, h1 = i + 1 < n_dy && (v >> 16) <= thr_c;
+                    const unsigned pv = i < n_dy ? cs[i >> 1] : 0xffffffffu;
+                    const bool h0 = i < n_dy && (pv & 0xffffu) <= thr_c, h1 = i + 1 < n_dy && (pv >> 16) <= thr_c;
                     const unsigned b0m = __ballot_sync(0xffffffffu, h0), b1m = __ballot_sync(0xffffffffu, h1);
                     const unsigned below = (1u << lane) - 1u;
                     const int off = __popc(b0m & below) + __popc(b1m & below);      // entries of lower lanes come first (order is irrelevant to the result)
@@ -322,6 +328,7 @@ fs8_prefilter_kernel(const F8Params p)
                 }
             }
         }
+        }                                                          // block rows of the tile
         if (tn >= n_tiles) break;
         f8_cp_async_wait_all();
         __syncwarp();                                              // the warp's own rows of the next tile landed; planes are free since the barrier above
@@ -531,30 +538,41 @@ int memci_ensure_luma8(memci_ctx *ctx, int slot)
 
 // Is the prefilter path applicable?  Block sizes 8k, list entry fields (17-bit block, 7-bit offsets), border of the
 // padded plane, one candidate column per thread, shared memory.
-static int f8_smem_bytes(int nt, int bs, int R, int nb_tile, int *rs_out, int *plane_words_out, int *ref_rs_out, int *a_stride_out, int *win_rows_out)
+static int f8_smem_bytes(int nt, int rpt, int bs, int R, int nb_tile, int *rs_out, int *plane_words_out, int *ref_rs_out, int *a_stride_out, int *win_rows_out)
 {
     const int Rp = (R + 3) & ~3;
     const int n_dy = 2 * R + 1;
     const int n_groups = (n_dy + F8_G - 1) / F8_G;
-    const int win_rows = bs + 2 * R + (n_groups * F8_G - n_dy) + 1;
+    const int win_rows = rpt * bs + 2 * R + (n_groups * F8_G - n_dy) + 1;
     const int rs = (nb_tile * bs + 2 * Rp) / 4 + 1;
     int plane_words = win_rows * rs;
     plane_words += (8 - (plane_words & 31) + 32) & 31;
     const int ref_rs = nb_tile * bs / 4;
     const int a_stride = (n_groups * F8_G + 3) & ~3;
     *rs_out = rs; *plane_words_out = plane_words; *ref_rs_out = ref_rs; *a_stride_out = a_stride; *win_rows_out = win_rows;
-    return (4 * plane_words + win_rows * (rs + 1) + 2 * bs * ref_rs) * 4 + nt * a_stride * 2;
+    return (4 * plane_words + win_rows * (rs + 1) + 2 * rpt * bs * ref_rs) * 4 + nt * a_stride * 2;
 }
 
-// CTA size: 512 threads (two CTAs per SM, wider tiles: 15 blocks of 33 column offsets fill 97 % of the lanes at +-16)
-// when the shared memory of two such CTAs fits, else 256 threads (four per SM).  MEMCI_F8_NT overrides (tuning).
-static int f8_threads(int bs, int R)
+// CTA shape: 512 threads (two CTAs per SM, wider tiles: 15 blocks of 33 column offsets fill 97 % of the lanes at +-16)
+// when the shared memory of two such CTAs fits, else 256 threads; two block rows per tile when that still fits.
+// MEMCI_F8_NT / MEMCI_F8_RPT override (tuning).
+static void f8_shape(int bs, int R, int *nt_out, int *rpt_out)
 {
-    if (const char *e = getenv("MEMCI_F8_NT")) { const int v = atoi(e); if (v == 256 || v == 512) return v; }
     int a, b, c, d, e2;
-    int nb_tile = 512 / (2 * R + 1);
-    if (nb_tile > F8_NBMAX) nb_tile = F8_NBMAX;
-    return (nb_tile >= 1 && f8_smem_bytes(512, bs, R, nb_tile, &a, &b, &c, &d, &e2) <= 110 * 1024) ? 512 : 256;
+    int nt = 256, rpt = 1;
+    {
+        int nb_tile = 512 / (2 * R + 1);
+        if (nb_tile > F8_NBMAX) nb_tile = F8_NBMAX;
+        if (nb_tile >= 1 && f8_smem_bytes(512, 1, bs, R, nb_tile, &a, &b, &c, &d, &e2) <= 110 * 1024) nt = 512;
+    }
+    if (const char *e = getenv("MEMCI_F8_NT")) { const int v = atoi(e); if (v == 256 || v == 512) nt = v; }
+    {
+        int nb_tile = nt / (2 * R + 1);
+        if (nb_tile > F8_NBMAX) nb_tile = F8_NBMAX;
+        if (nb_tile >= 1 && R + 2 * bs + 16 <= MEMCI_L8_PAD && f8_smem_bytes(nt, 2, bs, R, nb_tile, &a, &b, &c, &d, &e2) <= 110 * 1024) rpt = 2;
+    }
+    if (const char *e = getenv("MEMCI_F8_RPT")) { const int v = atoi(e); if (v == 1) rpt = 1; }
+    *nt_out = nt; *rpt_out = rpt;
 }
 
 int memci_fs8_eligible(memci_ctx *ctx, int bs, int R)
@@ -562,12 +580,13 @@ int memci_fs8_eligible(memci_ctx *ctx, int bs, int R)
     if ((bs != 8 && bs != 16) || R < 1 || R > 63 || R + bs + 16 > MEMCI_L8_PAD) return 0;      // A fits uint16 up to 16 x 16 blocks
     const long long n_blk = (long long)ceil_div_i(ctx->H, bs) * ceil_div_i(ctx->W, bs);
     if (n_blk >= (1 << 17)) return 0;
-    const int nt = f8_threads(bs, R);
+    int nt, rpt;
+    f8_shape(bs, R, &nt, &rpt);
     int nb_tile = nt / (2 * R + 1);
     if (nb_tile < 1) return 0;
     int a, b, c, d, e;
     if (nb_tile > F8_NBMAX) nb_tile = F8_NBMAX;
-    return f8_smem_bytes(nt, bs, R, nb_tile, &a, &b, &c, &d, &e) <= 110 * 1024;
+    return f8_smem_bytes(nt, rpt, bs, R, nb_tile, &a, &b, &c, &d, &e) <= 110 * 1024;
 }
 
 // Enqueue prefilter + refine + output for block rows [br0, br1).  counters[8] is left non-zero when the survivor
@@ -582,14 +601,16 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     F8Params p;
     memset(&p, 0, sizeof(p));
     p.H = H; p.W = W; p.bs = bs; p.m = bs / 8; p.R = R; p.Rp = (R + 3) & ~3; p.nbr = nbr; p.nbc = nbc;
-    const int nt = f8_threads(bs, R);
+    int nt, rpt;
+    f8_shape(bs, R, &nt, &rpt);
+    p.rpt = rpt;
     p.nb_tile = nt / (2 * R + 1);
     if (p.nb_tile > F8_NBMAX) p.nb_tile = F8_NBMAX;
     if (p.nb_tile > nbc) p.nb_tile = nbc;
     p.tiles_per_row = ceil_div_i(nbc, p.nb_tile);
-    p.n_tiles_dir = p.tiles_per_row * (br1 - br0); p.br0 = br0; p.ndir = ndir;
+    p.n_tiles_dir = p.tiles_per_row * ceil_div_i(br1 - br0, rpt); p.br0 = br0; p.br1 = br1; p.ndir = ndir;
     p.pitch8 = ctx->Wp + 2 * MEMCI_L8_PAD;
-    const int smem = f8_smem_bytes(nt, bs, R, p.nb_tile, &p.rs, &p.plane_words, &p.ref_rs, &p.a_stride, &p.win_rows);
+    const int smem = f8_smem_bytes(nt, rpt, bs, R, p.nb_tile, &p.rs, &p.plane_words, &p.ref_rs, &p.a_stride, &p.win_rows);
     p.T = 2 * bs * bs + 1;
     const FrameSlot &fs = ctx->frames[slot_src], &ft = ctx->frames[slot_tgt];
     const size_t org = (size_t)MEMCI_L8_PAD * p.pitch8 + MEMCI_L8_PAD;

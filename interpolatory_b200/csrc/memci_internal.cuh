@@ -11,7 +11,7 @@
 #include "../../include/memci_b200.h"
 
 #define MEMCI_MAX_PYR 12
-#define MEMCI_L8_PAD 96              // zero border (pixels / rows) around the 8-bit luma plane of the full-search prefilter
+#define MEMCI_L8_PAD 128             // zero border (pixels / rows) around the 8-bit luma plane of the full-search prefilter
 
 struct MVField {
     int valid;

@@ -849,7 +849,8 @@ def test_fs_prefilter_flat_and_tie_frames(gpu, oracle):
     flat = np.empty((2, H, W, 3), np.uint8); flat[0] = 77; flat[1] = 80
     two = np.repeat(rng.integers(0, 2, (2, H, W, 1), dtype=np.uint8) * 50 + 20, 3, axis=3)
     grad = np.repeat((np.arange(W, dtype=np.uint8)[None, :, None] + np.zeros((H, 1, 1), np.uint8)), 3, axis=2)
-    for a, b in ((flat[0], flat[1]), (two[0], two[1]), (grad, np.roll(grad, 3, axis=1)), (flat[0], two[1])):
+    white, black = np.full((H, W, 3), 255, np.uint8), np.zeros((H, W, 3), np.uint8)      # 16 x 16: A = 65280, threshold past the uint16 sentinel
+    for a, b in ((flat[0], flat[1]), (two[0], two[1]), (grad, np.roll(grad, 3, axis=1)), (flat[0], two[1]), (white, black), (white, two[1])):
         for bs, R in ((8, 16), (16, 9), (8, 3)):
             assert np.array_equal(fs(bs, R, a, b), oracle.fs(bs, R, a, b)), (bs, R)
 
