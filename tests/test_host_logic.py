@@ -167,3 +167,27 @@ def test_band_plan_covers_every_needed_row():
         if (H, n) == (4320, 8):
             f, m = plan.bytes_moved()
             assert f < 40e6 and m < 2e6                                         # halo traffic is latency-, not bandwidth-bound
+
+
+def test_metrics_argument_checks_need_no_device():
+    """metrics.py mirrors two skimage functions for one configuration and refuses the rest before touching the GPU."""
+    import numpy as np
+    import pytest
+    from interpolatory_b200 import metrics as M
+    a = np.zeros((16, 16, 3), np.uint8)
+    with pytest.raises(ValueError):
+        M.structural_similarity(a, a[:8], data_range=255, multichannel=True)
+    with pytest.raises(NotImplementedError):
+        M.structural_similarity(a.astype(np.float32), a.astype(np.float32), data_range=255, multichannel=True)
+    with pytest.raises(NotImplementedError):
+        M.peak_signal_noise_ratio(a, a, data_range=1.0)
+    with pytest.raises(ValueError):
+        M.frame_quality(a[:6], a[:6])
+    assert M.psnr_from_mse(0.0) == float('inf')
+    assert abs(M.psnr_from_mse(100.0) - 10 * np.log10(255.0 ** 2 / 100.0)) < 1e-12
+
+
+def test_harness_helpers():
+    from interpolatory_b200.util import sToMMSS, getETA
+    assert sToMMSS(0) == '0:00' and sToMMSS(61) == '1:01' and sToMMSS(600) == '10:00'
+    assert getETA(10, 0, 5) == '0:00' and getETA(10, 2, 6) == '0:20'
