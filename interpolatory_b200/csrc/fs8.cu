@@ -616,9 +616,12 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     const size_t org = (size_t)MEMCI_L8_PAD * p.pitch8 + MEMCI_L8_PAD;
     p.l8_src[0] = fs.luma8 + org; p.l8_tgt[0] = ft.luma8 + org;
     p.l8_src[1] = ft.luma8 + org; p.l8_tgt[1] = fs.luma8 + org;
-    // survivor list: an eighth of the candidates (textured content needs well under 1 %)
+    // survivor list: an eighth of the candidates, at most 16 M entries (64 MB).  Textured content needs about 0.5 %, but the
+    // list is cut into one segment per prefilter CTA and flat regions load a few segments heavily; a segment that fills
+    // up sends its blocks to the redo pass, so the size is a performance knob, not a correctness one.
     const size_t cand_max = (size_t)n_blk * (2 * R + 1) * (2 * R + 1) * 2;
     size_t cap = cand_max / 8 < (1u << 20) ? (1u << 20) : cand_max / 8;
+    if (cap > (16u << 20)) cap = 16u << 20;
     size_t have = ctx->fs8_list_cap;
     if ((rc = memci_reserve(ctx, (void **)&ctx->d_fs8_list, &have, (cap + F8_MAXSEG) * 4))) return rc;
     ctx->fs8_list_cap = have;
