@@ -216,118 +216,118 @@ fs8_prefilter_kernel(const F8Params p)
         const int nv = min(p.rpt, p.br1 - by);
 #pragma unroll 1
         for (int v = 0; v < nv; ++v) {
-        unsigned *bmin = bmin_s[cur][v];
-        const int s_row = (by + v) * bs;
-        const unsigned *ref = ref0 + (cur * ref_rows + v * bs) * p.ref_rs;
-        const FsBounds8 b0 = f8_bounds(p.H, p.W, bs, R, s_row, bx0 * bs);
-        const int n_dy = max(b0.r1 - b0.r0, 0);
-        const int wrow_base = b0.r0 - (by * bs - R);               // window rows count from the tile's first block row
-        const bool active = tid < n_items && n_dy > 0;
-        unsigned cmin = 0xffffffffu;
-        if (active) {
-            unsigned rl[8], rh[8];
-            if (M1) {
-                const unsigned *rp = ref + ((b * 8) >> 2);
-#pragma unroll
-                for (int kk = 0; kk < 8; ++kk) {
-                    const uint2 rv = *reinterpret_cast<const uint2 *>(rp + kk * p.ref_rs);
-                    rl[kk] = rv.x; rh[kk] = rv.y;
-                }
-            }
-            const int wc0 = b * bs + dx + p.Rp;                    // byte offset inside a window row
-            // full groups first, then (clipped windows only) the one group that sticks out of the valid row range: two
-            // separate copies of the loop body, so that the common one carries no masking selects
-            auto group = [&](int g, auto masked) {
-                unsigned acc[F8_G];
-#pragma unroll
-                for (int i = 0; i < F8_G; ++i) acc[i] = 0u;
+            unsigned *bmin = bmin_s[cur][v];
+            const int s_row = (by + v) * bs;
+            const unsigned *ref = ref0 + (cur * ref_rows + v * bs) * p.ref_rs;
+            const FsBounds8 b0 = f8_bounds(p.H, p.W, bs, R, s_row, bx0 * bs);
+            const int n_dy = max(b0.r1 - b0.r0, 0);
+            const int wrow_base = b0.r0 - (by * bs - R);               // window rows count from the tile's first block row
+            const bool active = tid < n_items && n_dy > 0;
+            unsigned cmin = 0xffffffffu;
+            if (active) {
+                unsigned rl[8], rh[8];
                 if (M1) {
-                    f8_accumulate(acc, rl, rh, planes + (wc0 & 3) * p.plane_words + (wrow_base + g * F8_G) * p.rs + (wc0 >> 2), p.rs);
-                } else {
-                    const int m = p.m;
-#pragma unroll 1
-                    for (int sub = 0; sub < m * m; ++sub) {
-                        const int si = sub / m, sj = sub - si * m;
-                        const unsigned *rp = ref + (si * 8) * p.ref_rs + ((b * bs + sj * 8) >> 2);
+                    const unsigned *rp = ref + ((b * 8) >> 2);
 #pragma unroll
-                        for (int kk = 0; kk < 8; ++kk) {
-                            const uint2 rv = *reinterpret_cast<const uint2 *>(rp + kk * p.ref_rs);
-                            rl[kk] = rv.x; rh[kk] = rv.y;
-                        }
-                        const int wc = wc0 + sj * 8;
-                        f8_accumulate(acc, rl, rh, planes + (wc & 3) * p.plane_words + (wrow_base + g * F8_G + si * 8) * p.rs + (wc >> 2), p.rs);
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const uint2 rv = *reinterpret_cast<const uint2 *>(rp + kk * p.ref_rs);
+                        rl[kk] = rv.x; rh[kk] = rv.y;
                     }
                 }
-                f8_finish_group<decltype(masked)::value>(acc, n_dy - g * F8_G, col + g * F8_G, cmin);
-            };
-            const int n_full = n_dy / F8_G;
+                const int wc0 = b * bs + dx + p.Rp;                    // byte offset inside a window row
+                // full groups first, then (clipped windows only) the one group that sticks out of the valid row range: two
+                // separate copies of the loop body, so that the common one carries no masking selects
+                auto group = [&](int g, auto masked) {
+                    unsigned acc[F8_G];
+#pragma unroll
+                    for (int i = 0; i < F8_G; ++i) acc[i] = 0u;
+                    if (M1) {
+                        f8_accumulate(acc, rl, rh, planes + (wc0 & 3) * p.plane_words + (wrow_base + g * F8_G) * p.rs + (wc0 >> 2), p.rs);
+                    } else {
+                        const int m = p.m;
 #pragma unroll 1
-            for (int g = 0; g < n_full; ++g) group(g, std::false_type{});
-            if (n_full * F8_G < n_dy) group(n_full, std::true_type{});
-        }
-        // ---- block minima: segmented warp reduction, one shared-memory atomic per (warp, block) ----
-        {
-            unsigned todo = __ballot_sync(0xffffffffu, active);
-            while (todo) {
-                const int leader = __ffs(todo) - 1;
-                const int bb = __shfl_sync(0xffffffffu, b, leader);
-                const bool mine = active && b == bb;
-                const unsigned mn = __reduce_min_sync(0xffffffffu, mine ? cmin : 0xffffffffu);
-                if (lane == leader) atomicMin(&bmin[bb], mn);
-                todo &= ~__ballot_sync(0xffffffffu, mine);
-            }
-        }
-        __syncthreads();
-        // ---- survivors: the warp visits its flagged columns one at a time, lanes = row offsets.  Each CTA appends to
-        //      its own segment of the list (shared-memory cursor, no global atomics); fs8_refine_kernel gets the
-        //      segment lengths at the end ----
-        {
-            const unsigned thr = active ? bmin[b] + (unsigned)p.T : 0u;
-            const unsigned flagged0 = __ballot_sync(0xffffffffu, active && cmin <= thr);
-            const unsigned head_own = (dir ? 0x80000000u : 0u) | ((unsigned)((by + v) * p.nbc + bx0 + b) << 14) | (unsigned)dxi;
-            const unsigned short *cw = A + (size_t)(tid & ~31) * p.a_stride;
-            for (unsigned f = flagged0; f; f &= f - 1) {
-                const int src = __ffs(f) - 1;
-                const unsigned thr_c = __shfl_sync(0xffffffffu, thr, src);
-                const unsigned head = __shfl_sync(0xffffffffu, head_own, src);
-                // lane l looks at row offsets 2l and 2l + 1 (one 32-bit load): 64 offsets per pass
-                const unsigned *cs = reinterpret_cast<const unsigned *>(cw + src * p.a_stride);
-                int hits = 0;
-                for (int i0 = 0; i0 < n_dy; i0 += 64) {
-                    const int i = i0 + 2 * lane;
-                    const unsigned pv = i < n_dy ? cs[i >> 1] : 0xffffffffu;
-                    hits += __popc(__ballot_sync(0xffffffffu, i < n_dy && (pv & 0xffffu) <= thr_c)) +
-                            __popc(__ballot_sync(0xffffffffu, i + 1 < n_dy && (pv >> 16) <= thr_c));
-                }
-                int pos = 0;
-                if (lane == 0) {
-                    // A column that survives whole is flat content: nothing to prune in this block.  It, and any block
-                    // whose survivors no longer fit the segment, goes to the exact block-level redo pass instead (once).
-                    pos = hits == n_dy ? -1 : (int)atomicAdd(&seg_count, (unsigned)hits);
-                    if (pos >= 0 && pos + hits > p.seg_cap) { atomicSub(&seg_count, (unsigned)hits); pos = -1; }
-                    if (pos < 0) {
-                        const unsigned slot = (head >> 31) * (unsigned)(p.nbr * p.nbc) + ((head >> 14) & 0x1ffffu);
-                        if (atomicExch(&p.redo_mark[slot], 0u) != 0u) {
-                            const int rp = atomicAdd(&p.counters[11], 1);
-                            if (rp < p.redo_cap) p.redo_list[rp] = (int)((head >> 14) & 0x1ffffu) | ((head >> 31) ? 0x40000000 : 0);   // FS_DIR_BIT
+                        for (int sub = 0; sub < m * m; ++sub) {
+                            const int si = sub / m, sj = sub - si * m;
+                            const unsigned *rp = ref + (si * 8) * p.ref_rs + ((b * bs + sj * 8) >> 2);
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk) {
+                                const uint2 rv = *reinterpret_cast<const uint2 *>(rp + kk * p.ref_rs);
+                                rl[kk] = rv.x; rh[kk] = rv.y;
+                            }
+                            const int wc = wc0 + sj * 8;
+                            f8_accumulate(acc, rl, rh, planes + (wc & 3) * p.plane_words + (wrow_base + g * F8_G + si * 8) * p.rs + (wc >> 2), p.rs);
                         }
                     }
-                }
-                pos = __shfl_sync(0xffffffffu, pos, 0);
-                if (pos < 0) continue;
-                for (int i0 = 0; i0 < n_dy; i0 += 64) {
-                    const int i = i0 + 2 * lane;
-                    const unsigned pv = i < n_dy ? cs[i >> 1] : 0xffffffffu;
-                    const bool h0 = i < n_dy && (pv & 0xffffu) <= thr_c, h1 = i + 1 < n_dy && (pv >> 16) <= thr_c;
-                    const unsigned b0m = __ballot_sync(0xffffffffu, h0), b1m = __ballot_sync(0xffffffffu, h1);
-                    const unsigned below = (1u << lane) - 1u;
-                    const int off = __popc(b0m & below) + __popc(b1m & below);      // entries of lower lanes come first (order is irrelevant to the result)
-                    if (h0) seg[pos + off] = head | ((unsigned)i << 7);
-                    if (h1) seg[pos + off + (h0 ? 1 : 0)] = head | ((unsigned)(i + 1) << 7);
-                    pos += __popc(b0m) + __popc(b1m);
+                    f8_finish_group<decltype(masked)::value>(acc, n_dy - g * F8_G, col + g * F8_G, cmin);
+                };
+                const int n_full = n_dy / F8_G;
+#pragma unroll 1
+                for (int g = 0; g < n_full; ++g) group(g, std::false_type{});
+                if (n_full * F8_G < n_dy) group(n_full, std::true_type{});
+            }
+            // ---- block minima: segmented warp reduction, one shared-memory atomic per (warp, block) ----
+            {
+                unsigned todo = __ballot_sync(0xffffffffu, active);
+                while (todo) {
+                    const int leader = __ffs(todo) - 1;
+                    const int bb = __shfl_sync(0xffffffffu, b, leader);
+                    const bool mine = active && b == bb;
+                    const unsigned mn = __reduce_min_sync(0xffffffffu, mine ? cmin : 0xffffffffu);
+                    if (lane == leader) atomicMin(&bmin[bb], mn);
+                    todo &= ~__ballot_sync(0xffffffffu, mine);
                 }
             }
-        }
+            __syncthreads();
+            // ---- survivors: the warp visits its flagged columns one at a time, lanes = row offsets.  Each CTA appends to
+            //      its own segment of the list (shared-memory cursor, no global atomics); fs8_refine_kernel gets the
+            //      segment lengths at the end ----
+            {
+                const unsigned thr = active ? bmin[b] + (unsigned)p.T : 0u;
+                const unsigned flagged0 = __ballot_sync(0xffffffffu, active && cmin <= thr);
+                const unsigned head_own = (dir ? 0x80000000u : 0u) | ((unsigned)((by + v) * p.nbc + bx0 + b) << 14) | (unsigned)dxi;
+                const unsigned short *cw = A + (size_t)(tid & ~31) * p.a_stride;
+                for (unsigned f = flagged0; f; f &= f - 1) {
+                    const int src = __ffs(f) - 1;
+                    const unsigned thr_c = __shfl_sync(0xffffffffu, thr, src);
+                    const unsigned head = __shfl_sync(0xffffffffu, head_own, src);
+                    // lane l looks at row offsets 2l and 2l + 1 (one 32-bit load): 64 offsets per pass
+                    const unsigned *cs = reinterpret_cast<const unsigned *>(cw + src * p.a_stride);
+                    int hits = 0;
+                    for (int i0 = 0; i0 < n_dy; i0 += 64) {
+                        const int i = i0 + 2 * lane;
+                        const unsigned pv = i < n_dy ? cs[i >> 1] : 0xffffffffu;
+                        hits += __popc(__ballot_sync(0xffffffffu, i < n_dy && (pv & 0xffffu) <= thr_c)) +
+                                __popc(__ballot_sync(0xffffffffu, i + 1 < n_dy && (pv >> 16) <= thr_c));
+                    }
+                    int pos = 0;
+                    if (lane == 0) {
+                        // A column that survives whole is flat content: nothing to prune in this block.  It, and any block
+                        // whose survivors no longer fit the segment, goes to the exact block-level redo pass instead (once).
+                        pos = hits == n_dy ? -1 : (int)atomicAdd(&seg_count, (unsigned)hits);
+                        if (pos >= 0 && pos + hits > p.seg_cap) { atomicSub(&seg_count, (unsigned)hits); pos = -1; }
+                        if (pos < 0) {
+                            const unsigned slot = (head >> 31) * (unsigned)(p.nbr * p.nbc) + ((head >> 14) & 0x1ffffu);
+                            if (atomicExch(&p.redo_mark[slot], 0u) != 0u) {
+                                const int rp = atomicAdd(&p.counters[11], 1);
+                                if (rp < p.redo_cap) p.redo_list[rp] = (int)((head >> 14) & 0x1ffffu) | ((head >> 31) ? 0x40000000 : 0);   // FS_DIR_BIT
+                            }
+                        }
+                    }
+                    pos = __shfl_sync(0xffffffffu, pos, 0);
+                    if (pos < 0) continue;
+                    for (int i0 = 0; i0 < n_dy; i0 += 64) {
+                        const int i = i0 + 2 * lane;
+                        const unsigned pv = i < n_dy ? cs[i >> 1] : 0xffffffffu;
+                        const bool h0 = i < n_dy && (pv & 0xffffu) <= thr_c, h1 = i + 1 < n_dy && (pv >> 16) <= thr_c;
+                        const unsigned b0m = __ballot_sync(0xffffffffu, h0), b1m = __ballot_sync(0xffffffffu, h1);
+                        const unsigned below = (1u << lane) - 1u;
+                        const int off = __popc(b0m & below) + __popc(b1m & below);      // entries of lower lanes come first (order is irrelevant to the result)
+                        if (h0) seg[pos + off] = head | ((unsigned)i << 7);
+                        if (h1) seg[pos + off + (h0 ? 1 : 0)] = head | ((unsigned)(i + 1) << 7);
+                        pos += __popc(b0m) + __popc(b1m);
+                    }
+                }
+            }
         }                                                          // block rows of the tile
         if (tn >= n_tiles) break;
         f8_cp_async_wait_all();

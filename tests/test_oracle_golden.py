@@ -248,3 +248,46 @@ def test_quality_oracle_known_answers():
     assert abs(Q.structural_similarity(c, d) - (2 * 100 * 110 + C1) / (100 ** 2 + 110 ** 2 + C1)) < 1e-12
     with pytest.raises(ValueError):
         Q.structural_similarity(a[:6], b[:6])
+
+
+def test_prefilter_bound_holds_for_the_oracle_winner(oracle):
+    """The pruning rule of the two-phase full search (csrc/fs8.cu), checked on the CPU against the oracle: with luma rounded
+    to 8 bits, A = sum |L8a - L8b| stays within bs^2 of S1000 / 1000 for every candidate, and the reference's winner always
+    satisfies A(winner) <= min A + 2 bs^2 + 1 -- on texture, noise, two grey levels (ties, flagged sums) and flat frames."""
+    rng = np.random.default_rng(21)
+    H, W = 72, 104
+
+    def l1000(f):
+        f = f.astype(np.int64)
+        return 299 * f[..., 0] + 587 * f[..., 1] + 114 * f[..., 2]
+
+    two = np.repeat(rng.integers(0, 2, (2, H, W, 1), dtype=np.uint8) * 50 + 20, 3, axis=3)
+    flat = np.empty((2, H, W, 3), np.uint8); flat[0] = 77; flat[1] = 80
+    cases = [make_sequence(H, W, 2, seed=5), rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8), two, flat]
+    for fr in cases:
+        for bs, R in ((8, 7), (16, 5)):
+            want = oracle.fs_blocks(bs, R, fr[0], fr[1])
+            La, Lb = l1000(fr[0]), l1000(fr[1])
+            pad = lambda x: np.pad(x, ((0, bs), (0, bs)))                  # the reference's zero padding
+            La, Lb = pad(La), pad(Lb)
+            A8, B8 = (La + 500) // 1000, (Lb + 500) // 1000
+            n = bs * bs
+            for br in range(want.shape[0]):
+                for bc in range(want.shape[1]):
+                    if not np.isfinite(want[br, bc, 2]):
+                        continue
+                    r, c = br * bs, bc * bs
+                    tmr = r + 1 if r + bs >= H else H - bs
+                    tmc = c + 1 if c + bs >= H else W - bs                 # full_search.py:37 compares with H
+                    rows = range(max(r - R, 0), min(tmr, r + R + 1))
+                    cols = range(max(c - R, 0), min(tmc, c + R + 1))
+                    a_min, a_win = None, None
+                    for tr in rows:
+                        for tc in cols:
+                            S = int(np.abs(La[r:r + bs, c:c + bs] - Lb[tr:tr + bs, tc:tc + bs]).sum())
+                            A = int(np.abs(A8[r:r + bs, c:c + bs] - B8[tr:tr + bs, tc:tc + bs]).sum())
+                            assert abs(S / 1000.0 - A) <= n
+                            a_min = A if a_min is None else min(a_min, A)
+                            if tr - r == want[br, bc, 0] and tc - c == want[br, bc, 1]:
+                                a_win = A
+                    assert a_win is not None and a_win <= a_min + 2 * n + 1, (bs, R, br, bc)
