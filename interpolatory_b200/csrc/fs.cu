@@ -95,8 +95,8 @@ __global__ void fs_generic_kernel(const int32_t *__restrict__ L0, const int32_t 
 }
 
 // =========================================================================================
-// Redo pass: one CTA per listed block (same exact arithmetic as fs_generic_kernel, 32 warps wide:
-// about one candidate per thread at +-16, so the pass is a few microseconds of latency).
+// Redo pass: one CTA per listed block (same exact arithmetic as fs_generic_kernel; 8 warps, about four candidates
+// per thread at +-16, eight CTAs per SM so that several hundred listed blocks run in one wave).
 // =========================================================================================
 // List entries carry the search direction in bit 30 (pair launches: direction 1 swaps the frames).
 #define FS_DIR_BIT 0x40000000
