@@ -427,12 +427,16 @@ def main():
     # ---- pass 1b: the exact full-search kernel alone (prefilter off), for the second roofline line ----
     exact_ms_sum = exact_n = 0
     if used_prefilter:
+        prev = os.environ.get("MEMCI_FS_PREFILTER")
         os.environ["MEMCI_FS_PREFILTER"] = "0"
         step_resident([ctx]); barrier()
         ctx.profile_start(P * (2 + nd) + 16)
         step_resident([ctx]); barrier()
         exact_ms_sum, exact_n, _, _ = ctx.profile_collect()
-        del os.environ["MEMCI_FS_PREFILTER"]
+        if prev is None:
+            del os.environ["MEMCI_FS_PREFILTER"]
+        else:
+            os.environ["MEMCI_FS_PREFILTER"] = prev
         step_resident([ctx]); barrier()
 
     # ---- pass 2, the measured value: the same P pairs per step over C contexts / streams (inputs resident in HBM) ----
