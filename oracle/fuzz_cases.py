@@ -1,0 +1,45 @@
+"""TEST INFRASTRUCTURE ONLY.  Seeded adversarial MCI inputs shared by oracle/validate_fuzz_vs_reference.py (which runs them
+through the unmodified reference and writes tests/golden/fuzz_reference_sha.npz) and tests/test_oracle_golden.py (which
+checks the C oracle against those hashes): random frame sizes, MV cells of different sizes per direction, SAD cells that
+nest in the MV cells or not, vectors up to +-100 px (wrapped and out-of-frame targets), fractional vectors, SAD ties and
+infinite SADs, odd dists."""
+import hashlib
+
+import numpy as np
+
+
+def fuzz_field(rng, H, W, g, D, frac, sg=None, holes=0.03):
+    """Dense [H, W, 3] field, (dy, dx) constant on g x g cells and SAD constant on sg x sg cells."""
+    nr, nc = -(-H // g), -(-W // g)
+    v = rng.integers(-D, D + 1, (nr, nc, 2)).astype(np.float32)
+    if rng.integers(0, 3) == 0:
+        v = np.repeat(np.repeat(v[::3, ::3], 3, 0), 3, 1)[:nr, :nc]
+    if frac:
+        v += rng.choice([0.0, 0.25, 0.5, 1 / 3], (nr, nc, 2)).astype(np.float32)
+    sg = sg or g
+    sr, sc = -(-H // sg), -(-W // sg)
+    sad = rng.integers(0, 6, (sr, sc, 1)).astype(np.float32) * float(rng.choice([100.0, 1.0, 37.5]))
+    sad[rng.random((sr, sc, 1)) < holes] = np.inf
+    mv = np.kron(v, np.ones((g, g, 1), np.float32))[:H, :W]
+    sd = np.kron(sad, np.ones((sg, sg, 1), np.float32))[:H, :W]
+    return np.ascontiguousarray(np.concatenate([mv, sd], axis=2))
+
+
+def mci_cases(seed, rounds):
+    """Yield (index, src, tgt, fwd field, bwd field, float32 dist)."""
+    rng = np.random.default_rng(seed)
+    for it in range(rounds):
+        H, W = int(rng.integers(8, 150)), int(rng.integers(8, 200))
+        a = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        b = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        gf, gb = int(rng.choice([1, 2, 4, 8, 16, 5])), int(rng.choice([1, 2, 4, 8, 16, 6]))
+        D = int(rng.choice([0, 1, 3, 8, 20, 45, 100]))
+        sgf = gf * int(rng.choice([1, 1, 2])) if rng.integers(0, 2) else int(rng.choice([3, 4, 8]))
+        f_ = fuzz_field(rng, H, W, gf, D, rng.integers(0, 2), sgf)
+        b_ = fuzz_field(rng, H, W, gb, D, rng.integers(0, 2))
+        dist = np.float32(rng.choice([0.5, 0.19999999, 0.8, 0.4, 0.6, 1 / 3, 0.99]))
+        yield it, a, b, f_, b_, dist
+
+
+def sha(x):
+    return hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest()

@@ -1,0 +1,109 @@
+"""The seeded random MV-field geometry of tests/test_gpu_parity.py::test_mci_fuzz_random_geometry (wrapped and out-of-frame
+targets, fractional vectors, MV / SAD cells of different sizes, SAD ties and infinite SADs) and random full-search / TSS / HBMA /
+smoothing parameters, run through the UNMODIFIED reference in the build container and compared bit for bit with the C oracle.
+Not part of the pytest suite (needs /root/reference + numba); run:  python oracle/validate_fuzz_vs_reference.py [rounds]
+`--write-golden` also runs oracle/fuzz_cases.py's seeded MCI cases through the reference and stores the SHA-256 of its frames
+in tests/golden/fuzz_reference_sha.npz, which tests/test_oracle_golden.py checks the oracle (and the GPU suite the kernels) against."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+import oracle as O          # noqa: E402
+import ref_harness          # noqa: E402
+from interpolatory_b200.synth import make_sequence  # noqa: E402
+
+
+def fuzz_field(rng, H, W, g, D, frac, sg=None, holes=0.03):
+    nr, nc = -(-H // g), -(-W // g)
+    v = rng.integers(-D, D + 1, (nr, nc, 2)).astype(np.float32)
+    if rng.integers(0, 3) == 0:
+        v = np.repeat(np.repeat(v[::3, ::3], 3, 0), 3, 1)[:nr, :nc]
+    if frac:
+        v += rng.choice([0.0, 0.25, 0.5, 1 / 3], (nr, nc, 2)).astype(np.float32)
+    sg = sg or g
+    sr, sc = -(-H // sg), -(-W // sg)
+    sad = rng.integers(0, 6, (sr, sc, 1)).astype(np.float32) * float(rng.choice([100.0, 1.0, 37.5]))
+    sad[rng.random((sr, sc, 1)) < holes] = np.inf
+    mv = np.kron(v, np.ones((g, g, 1), np.float32))[:H, :W]
+    sd = np.kron(sad, np.ones((sg, sg, 1), np.float32))[:H, :W]
+    return np.ascontiguousarray(np.concatenate([mv, sd], axis=2))
+
+
+def write_golden(ns, seed=2025, rounds=96):
+    import fuzz_cases as F
+    out = {"seed": np.int64(seed), "rounds": np.int64(rounds)}
+    n = 0
+    for it, a, b, f_, b_, dist in F.mci_cases(seed, rounds):
+        try:
+            O.unidir_helper(a, b, f_, dist); O.bidir_helper(a, b, f_, b_, dist)
+        except RuntimeError:
+            out[f"{it}/undefined"] = np.int64(1)       # a displaced index below -H: out-of-bounds write in the reference
+            continue
+        out[f"{it}/unidir"] = F.sha(np.asarray(ns.uni.helper(a, b, f_, dist)))
+        out[f"{it}/bidir"] = F.sha(np.asarray(ns.bi.helper(a, b, f_, b_, dist)))
+        n += 1
+    path = os.path.join(os.path.dirname(HERE), "tests", "golden", "fuzz_reference_sha.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {n} defined cases of {rounds}")
+
+
+def main():
+    args = [x for x in sys.argv[1:] if not x.startswith("--")]
+    rounds = int(args[0]) if args else 120
+    ns = ref_harness.load()
+    if "--write-golden" in sys.argv:
+        write_golden(ns)
+        return 0
+    rng = np.random.default_rng(11)
+    bad = n_mci = n_undef = n_me = 0
+    for it in range(rounds):
+        H, W = int(rng.integers(8, 150)), int(rng.integers(8, 200))
+        a = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        b = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        gf, gb = int(rng.choice([1, 2, 4, 8, 16, 5])), int(rng.choice([1, 2, 4, 8, 16, 6]))
+        D = int(rng.choice([0, 1, 3, 8, 20, 45, 100]))
+        sgf = gf * int(rng.choice([1, 1, 2])) if rng.integers(0, 2) else int(rng.choice([3, 4, 8]))
+        f_ = fuzz_field(rng, H, W, gf, D, rng.integers(0, 2), sgf)
+        b_ = fuzz_field(rng, H, W, gb, D, rng.integers(0, 2))
+        dist = np.float32(rng.choice([0.5, 0.19999999, 0.8, 0.4, 0.6, 1 / 3, 0.99]))
+        try:
+            mine_u, mine_b = O.unidir_helper(a, b, f_, dist), O.bidir_helper(a, b, f_, b_, dist)
+        except RuntimeError:
+            n_undef += 1            # a displaced index below -H: the reference writes out of bounds there, not run
+            continue
+        ref_u = ns.uni.helper(a, b, f_, dist)
+        ref_b = ns.bi.helper(a, b, f_, b_, dist)
+        n_mci += 1
+        for name, r, m in (("unidir", ref_u, mine_u), ("bidir", ref_b, mine_b)):
+            if not np.array_equal(np.asarray(r), m):
+                bad += 1
+                print("FAIL", name, (H, W, gf, gb, D, sgf, float(dist)), int((np.asarray(r) != m).any(axis=2).sum()))
+        if it % 4 == 0:             # motion estimation / smoothing with random parameters (slower in the reference)
+            Hs, Ws = min(H, 80), min(W, 96)
+            if Hs >= 48 and Ws >= 48:
+                fr = make_sequence(Hs, Ws, 2, seed=int(rng.integers(1 << 30)))
+            else:
+                fr = rng.integers(0, 256, (2, Hs, Ws, 3), dtype=np.uint8)
+            bs = int(rng.choice([2, 4, 5, 8, 16])); R = int(rng.integers(0, 9)); steps = int(rng.integers(1, 4))
+            checks = [("fs", ns.fs.get_motion_vectors(bs, R, fr[0], fr[1]), O.fs(bs, R, fr[0], fr[1])),
+                      ("tss", ns.tss.get_motion_vectors(bs, steps, fr[0], fr[1]), O.tss(bs, steps, fr[0], fr[1]))]
+            mv = fuzz_field(rng, Hs, Ws, int(rng.choice([1, 2, 4, 8])), 20, rng.integers(0, 2))
+            fsz = int(rng.choice([1, 2, 4, 8, 3]))
+            for mode in ("mean", "median", "weighted"):
+                checks.append((f"smooth {mode}", ns.smooth(ns.filters[mode], mv.copy(), fsz), O.smooth(mode, mv, fsz)))
+            for name, r, m in checks:
+                n_me += 1
+                if not np.array_equal(np.asarray(r), m):
+                    bad += 1
+                    print("FAIL", name, (Hs, Ws, bs, R, steps, fsz))
+    print(f"{n_mci} MCI geometries x 2 helpers, {n_me} ME / smoothing cases, {n_undef} undefined in the reference (skipped): "
+          f"{'ALL OK' if bad == 0 else str(bad) + ' FAILED'}")
+    return 0 if bad == 0 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -875,3 +875,18 @@ def test_fs_prefilter_backs_off_on_flat_content(gpu, oracle, monkeypatch):
             used.append(ctx.fs_prefilter_stats() != (0, 0))
         assert used[0] and used[1:] == [expect_on] * 3, used
         ctx.close()
+
+
+def test_mci_vs_reference_hashes_on_fuzz_geometry(gpu, golden, monkeypatch):
+    """The same 82 adversarial inputs through the CUDA helpers, against the hashes of the reference's own frames
+    (no oracle in between), with each splat path forced in turn."""
+    import fuzz_cases as F
+    from interpolatory_b200.MCI.Bidirectional import helper as bi
+    from interpolatory_b200.MCI.Unidirectional import helper as uni
+    g = golden("fuzz_reference_sha.npz")
+    for it, a, b, f_, b_, dist in F.mci_cases(int(g["seed"]), int(g["rounds"])):
+        if f"{it}/undefined" in g:
+            continue
+        monkeypatch.setenv("MEMCI_MCI_PATH", str(it % 3))
+        assert F.sha(uni(a, b, f_, dist)) == str(g[f"{it}/unidir"]), it
+        assert F.sha(bi(a, b, f_, b_, dist)) == str(g[f"{it}/bidir"]), it

@@ -291,3 +291,21 @@ def test_prefilter_bound_holds_for_the_oracle_winner(oracle):
                             if tr - r == want[br, bc, 0] and tc - c == want[br, bc, 1]:
                                 a_win = A
                     assert a_win is not None and a_win <= a_min + 2 * n + 1, (bs, R, br, bc)
+
+
+def test_oracle_vs_reference_hashes_on_fuzz_geometry(oracle, golden):
+    """82 seeded adversarial MCI inputs (oracle/fuzz_cases.py: wraps, out-of-frame targets, fractional vectors, mismatched
+    MV / SAD cells, ties, infinite SADs) that were run through the unmodified reference (oracle/validate_fuzz_vs_reference.py
+    --write-golden): the oracle reproduces every frame, and refuses exactly the cases the reference leaves undefined."""
+    import fuzz_cases as F
+    g = golden("fuzz_reference_sha.npz")
+    n = 0
+    for it, a, b, f_, b_, dist in F.mci_cases(int(g["seed"]), int(g["rounds"])):
+        if f"{it}/undefined" in g:
+            with pytest.raises(RuntimeError):
+                oracle.unidir_helper(a, b, f_, dist); oracle.bidir_helper(a, b, f_, b_, dist)
+            continue
+        assert F.sha(oracle.unidir_helper(a, b, f_, dist)) == str(g[f"{it}/unidir"]), it
+        assert F.sha(oracle.bidir_helper(a, b, f_, b_, dist)) == str(g[f"{it}/bidir"]), it
+        n += 1
+    assert n >= 80
