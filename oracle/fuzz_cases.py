@@ -41,5 +41,25 @@ def mci_cases(seed, rounds):
         yield it, a, b, f_, b_, dist
 
 
+def bidir2_cases(seed, rounds):
+    """Yield (index, src, tgt, fwd, bwd, python-float dist, upscale_MV): random fields small enough to stay inside the
+    16-px pad most of the time (dense fields on 4 / 8 / 16-px cells, or block-level fields as HBMA hands them over)."""
+    rng = np.random.default_rng(seed)
+    for it in range(rounds):
+        H, W = int(rng.integers(8, 120)), int(rng.integers(8, 160))
+        a = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        b = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        up = bool(rng.integers(0, 2)); D2 = int(rng.choice([0, 2, 6, 14])); dd = float(rng.choice([0.5, 0.4, 0.8, 0.25]))
+        if up:
+            g2 = int(rng.choice([4, 8, 16]))
+            f2 = fuzz_field(rng, H, W, g2, D2, rng.integers(0, 2), holes=0)
+            b2 = fuzz_field(rng, H, W, g2, D2, rng.integers(0, 2), holes=0)
+        else:
+            nr, nc = -(-H // 4), -(-W // 4)
+            f2 = fuzz_field(rng, nr, nc, 1, D2, rng.integers(0, 2), holes=0)
+            b2 = fuzz_field(rng, nr, nc, 1, D2, rng.integers(0, 2), holes=0)
+        yield it, a, b, f2, b2, dd, up
+
+
 def sha(x):
     return hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest()

@@ -46,6 +46,25 @@ def write_golden(ns, seed=2025, rounds=96):
         out[f"{it}/unidir"] = F.sha(np.asarray(ns.uni.helper(a, b, f_, dist)))
         out[f"{it}/bidir"] = F.sha(np.asarray(ns.bi.helper(a, b, f_, b_, dist)))
         n += 1
+    # bidir2: IEWMC both ways + error-adaptive combination + BDHI + unpad (MCI/Bidirectional_2.py:330-345)
+    from src.Interpolators.MEMCI.MCI import Bidirectional_2 as b2
+    out["b2_seed"] = np.int64(seed + 1); out["b2_rounds"] = np.int64(64)
+    n2 = n2_fail = 0
+    for it, a, b, f2, bw2, dd, up in F.bidir2_cases(seed + 1, 64):
+        try:
+            mine = O.bidir2_frame(a, b, f2, bw2, dd, up)
+        except RuntimeError:
+            out[f"b2/{it}/out_of_pad"] = np.int64(1)   # a shifted block leaves the padded frame: the reference raises too
+            continue
+        Ff, Ef = b2.IEWMC(f2, a, b, dd, 16, 4, up)
+        Fb, Eb = b2.IEWMC(bw2, b, a, 1 - dd, 16, 4, up)
+        ref = b2.unpad_and_downconvert(b2.BDHI(b2.Error_adaptive_combination(Ff, Ef, Fb, Eb), 4, 16), 16)
+        if not np.array_equal(np.asarray(ref), mine):
+            n2_fail += 1
+            print("FAIL bidir2", it, a.shape, dd, up)
+        out[f"b2/{it}/out"] = F.sha(np.asarray(ref))
+        n2 += 1
+    print(f"bidir2: {n2} cases vs oracle, {n2_fail} mismatches")
     path = os.path.join(os.path.dirname(HERE), "tests", "golden", "fuzz_reference_sha.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {n} defined cases of {rounds}")

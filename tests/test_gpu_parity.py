@@ -890,3 +890,17 @@ def test_mci_vs_reference_hashes_on_fuzz_geometry(gpu, golden, monkeypatch):
         monkeypatch.setenv("MEMCI_MCI_PATH", str(it % 3))
         assert F.sha(uni(a, b, f_, dist)) == str(g[f"{it}/unidir"]), it
         assert F.sha(bi(a, b, f_, b_, dist)) == str(g[f"{it}/bidir"]), it
+
+
+def test_bidir2_vs_reference_hashes_on_fuzz_fields(gpu, golden):
+    """The same random bidir2 inputs through the CUDA path against the hashes of the reference's own frames; where the
+    reference raises (a block shifted out of the pad) the GPU path raises too."""
+    import fuzz_cases as F
+    from interpolatory_b200.MCI.Bidirectional_2 import interpolate as b2
+    g = golden("fuzz_reference_sha.npz")
+    for it, a, b, f2, bw2, dd, up in F.bidir2_cases(int(g["b2_seed"]), int(g["b2_rounds"])):
+        if f"b2/{it}/out_of_pad" in g:
+            with pytest.raises(Exception, match="shifted outside the padded frame"):
+                b2(a, b, f2, bw2, dd, 16, 4, up)
+            continue
+        assert F.sha(b2(a, b, f2, bw2, dd, 16, 4, up)) == str(g[f"b2/{it}/out"]), it

@@ -309,3 +309,19 @@ def test_oracle_vs_reference_hashes_on_fuzz_geometry(oracle, golden):
         assert F.sha(oracle.bidir_helper(a, b, f_, b_, dist)) == str(g[f"{it}/bidir"]), it
         n += 1
     assert n >= 80
+
+
+def test_oracle_bidir2_vs_reference_hashes_on_fuzz_fields(oracle, golden):
+    """64 seeded random bidir2 inputs run through the unmodified reference (IEWMC x 2, error-adaptive combination, BDHI,
+    unpad): the oracle reproduces every frame and fails exactly where the reference raises (a block shifted out of the pad)."""
+    import fuzz_cases as F
+    g = golden("fuzz_reference_sha.npz")
+    n = 0
+    for it, a, b, f2, bw2, dd, up in F.bidir2_cases(int(g["b2_seed"]), int(g["b2_rounds"])):
+        if f"b2/{it}/out_of_pad" in g:
+            with pytest.raises(RuntimeError):
+                oracle.bidir2_frame(a, b, f2, bw2, dd, up)
+            continue
+        assert F.sha(oracle.bidir2_frame(a, b, f2, bw2, dd, up)) == str(g[f"b2/{it}/out"]), it
+        n += 1
+    assert n >= 45
