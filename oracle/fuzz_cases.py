@@ -61,5 +61,30 @@ def bidir2_cases(seed, rounds):
         yield it, a, b, f2, b2, dd, up
 
 
+def me_cases(seed, rounds):
+    """Yield (index, frame pair, dict of parameters) for full search, TSS, HBMA and the three smoothing filters."""
+    rng = np.random.default_rng(seed)
+    from interpolatory_b200.synth import make_sequence
+    for it in range(rounds):
+        H, W = int(rng.integers(8, 100)), int(rng.integers(8, 130))
+        kind = int(rng.integers(0, 4))
+        if kind == 0 and H >= 48 and W >= 48:
+            fr = make_sequence(H, W, 2, seed=int(rng.integers(1 << 30)))
+        elif kind == 1:
+            fr = np.repeat(rng.integers(0, 2, (2, H, W, 1), dtype=np.uint8) * 50 + 20, 3, axis=3)      # ties, exact-integer SADs
+        elif kind == 2:
+            a = np.repeat(rng.integers(0, 200, (H, W, 1), dtype=np.uint8), 3, axis=2)                    # shifted + grey offset
+            b = (np.roll(a, (int(rng.integers(-4, 5)), int(rng.integers(-4, 5))), (0, 1)).astype(np.int32) + int(rng.integers(0, 5))).astype(np.uint8)
+            fr = np.stack([a, b])
+        else:
+            fr = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+        prm = dict(bs=int(rng.choice([2, 3, 4, 5, 6, 8, 8, 12, 16])), R=int(rng.integers(0, 12)), steps=int(rng.integers(1, 5)),
+                   hb=int(rng.choice([4, 8, 8, 16])), win=int(rng.integers(1, 8)), sub=int(rng.integers(1, 4)), hsteps=int(rng.integers(0, 4)),
+                   mbs=int(rng.choice([2, 4, 4, 8])), cost=str(rng.choice(['sad', 'ssd'])), up=bool(rng.integers(0, 2)),
+                   g=int(rng.choice([1, 2, 4, 8])), fsz=int(rng.choice([1, 2, 4, 8, 3])), frac=int(rng.integers(0, 2)))
+        mv = fuzz_field(rng, H, W, prm['g'], 20, prm['frac'])
+        yield it, fr, prm, mv
+
+
 def sha(x):
     return hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest()

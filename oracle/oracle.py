@@ -140,6 +140,28 @@ def hbma(block_size, win_size, sub_win_size, steps, min_block_size, im1, im2, co
     return out
 
 
+def hbma_undefined_in_reference(H, W, block_size, steps, min_block_size):
+    """True where the reference's HBMA reads out of bounds (numba does not bounds-check): increase_vec_density_jit
+    takes `mvs[row + 1]` / `mvs[row, col + 1]` as the neighbour of the first row / column (hbma.py:108-115), which does
+    not exist when the coarser field has a single block row or column.  The oracle (and the CUDA path) clamp there."""
+    sizes = [(H, W)]
+    for _ in range(steps):
+        h, w = sizes[-1]
+        sizes.append(((h + 1) // 2, (w + 1) // 2))
+    rows, cols = -(-sizes[-1][0] // block_size), -(-sizes[-1][1] // block_size)
+    for (h, w) in sizes[-2::-1]:                       # densify through the pyramid at constant block size
+        if rows == 1 or cols == 1:
+            return True
+        rows, cols = -(-h // block_size), -(-w // block_size)
+    bs = block_size
+    while bs > min_block_size:                         # then halve the block size at full resolution
+        if rows == 1 or cols == 1:
+            return True
+        bs >>= 1
+        rows, cols = -(-H // bs), -(-W // bs)
+    return False
+
+
 _MODES = {None: 0, "none": 0, "mean": 1, "median": 2, "weighted": 3}
 
 

@@ -65,6 +65,35 @@ def write_golden(ns, seed=2025, rounds=96):
         out[f"b2/{it}/out"] = F.sha(np.asarray(ref))
         n2 += 1
     print(f"bidir2: {n2} cases vs oracle, {n2_fail} mismatches")
+    # motion estimation and smoothing with random parameters
+    out["me_seed"] = np.int64(seed + 2); out["me_rounds"] = np.int64(60)
+    n3 = n3_fail = 0
+    for it, fr, q, mv in F.me_cases(seed + 2, 60):
+        a, b = fr[0], fr[1]
+        calls = {
+            "fs": (lambda: ns.fs.get_motion_vectors(q['bs'], q['R'], a, b), lambda: O.fs(q['bs'], q['R'], a, b)),
+            "tss": (lambda: ns.tss.get_motion_vectors(q['bs'], q['steps'], a, b), lambda: O.tss(q['bs'], q['steps'], a, b)),
+            "hbma": (lambda: ns.hbma.get_motion_vectors(q['hb'], q['win'], q['sub'], q['hsteps'], q['mbs'], a, b, q['cost'], q['up']),
+                     lambda: O.hbma(q['hb'], q['win'], q['sub'], q['hsteps'], q['mbs'], a, b, q['cost'], q['up'])),
+        }
+        for mode in ("mean", "median", "weighted"):
+            calls[f"smooth_{mode}"] = (lambda mode=mode: ns.smooth(ns.filters[mode], mv.copy(), q['fsz']), lambda mode=mode: O.smooth(mode, mv, q['fsz']))
+        for name, (fr_ref, fr_mine) in calls.items():
+            if name == "hbma" and O.hbma_undefined_in_reference(a.shape[0], a.shape[1], q['hb'], q['hsteps'], q['mbs']):
+                out[f"me/{it}/hbma/undefined"] = np.int64(1)      # single block row / column: out-of-bounds neighbour read
+                continue
+            try:
+                ref = np.asarray(fr_ref())
+            except Exception as e:                     # parameters the reference itself rejects / crashes on: recorded, not compared
+                out[f"me/{it}/{name}/raises"] = type(e).__name__
+                continue
+            mine = fr_mine()
+            if ref.shape != mine.shape or not np.array_equal(ref, mine):
+                n3_fail += 1
+                print("FAIL", name, it, a.shape, q)
+            out[f"me/{it}/{name}"] = F.sha(ref.astype(np.float32))
+            n3 += 1
+    print(f"ME / smoothing: {n3} cases vs oracle, {n3_fail} mismatches")
     path = os.path.join(os.path.dirname(HERE), "tests", "golden", "fuzz_reference_sha.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {n} defined cases of {rounds}")

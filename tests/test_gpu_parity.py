@@ -904,3 +904,27 @@ def test_bidir2_vs_reference_hashes_on_fuzz_fields(gpu, golden):
                 b2(a, b, f2, bw2, dd, 16, 4, up)
             continue
         assert F.sha(b2(a, b, f2, bw2, dd, 16, 4, up)) == str(g[f"b2/{it}/out"]), it
+
+
+def test_me_vs_reference_hashes_on_random_parameters(gpu, golden):
+    """Full search, TSS, HBMA and the smoothing filters with random parameters against the hashes of the reference's own
+    fields (oracle/validate_fuzz_vs_reference.py --write-golden); HBMA cases where the reference reads out of bounds are
+    left out."""
+    import fuzz_cases as F
+    from interpolatory_b200.ME.full_search import get_motion_vectors as fs
+    from interpolatory_b200.ME.tss import get_motion_vectors as tss
+    from interpolatory_b200.ME.hbma import get_motion_vectors as hbma
+    from interpolatory_b200.smoothing import smooth
+    g = golden("fuzz_reference_sha.npz")
+    for it, fr, q, mv in F.me_cases(int(g["me_seed"]), int(g["me_rounds"])):
+        a, b = fr[0], fr[1]
+        calls = {"fs": lambda: fs(q['bs'], q['R'], a, b),
+                 "tss": lambda: tss(q['bs'], q['steps'], a, b),
+                 "hbma": lambda: hbma(q['hb'], q['win'], q['sub'], q['hsteps'], q['mbs'], a, b, q['cost'], q['up'])}
+        for mode in ("mean", "median", "weighted"):
+            calls[f"smooth_{mode}"] = lambda mode=mode: smooth(mode, mv, q['fsz'])
+        for name, f in calls.items():
+            key = f"me/{it}/{name}"
+            if key + "/undefined" in g or key + "/raises" in g:
+                continue
+            assert F.sha(np.asarray(f(), np.float32)) == str(g[key]), (it, name, q)

@@ -325,3 +325,29 @@ def test_oracle_bidir2_vs_reference_hashes_on_fuzz_fields(oracle, golden):
         assert F.sha(oracle.bidir2_frame(a, b, f2, bw2, dd, up)) == str(g[f"b2/{it}/out"]), it
         n += 1
     assert n >= 45
+
+
+def test_oracle_me_vs_reference_hashes_on_random_parameters(oracle, golden):
+    """60 seeded frame pairs with random full-search / TSS / HBMA (sad, ssd, upscale or not) / smoothing parameters, run
+    through the unmodified reference: the oracle reproduces every field.  HBMA cases with a single block row or column at
+    some level are left out: the reference reads a neighbour out of bounds there (oracle.hbma_undefined_in_reference)."""
+    import fuzz_cases as F
+    g = golden("fuzz_reference_sha.npz")
+    n = 0
+    for it, fr, q, mv in F.me_cases(int(g["me_seed"]), int(g["me_rounds"])):
+        a, b = fr[0], fr[1]
+        calls = {"fs": lambda: oracle.fs(q['bs'], q['R'], a, b),
+                 "tss": lambda: oracle.tss(q['bs'], q['steps'], a, b),
+                 "hbma": lambda: oracle.hbma(q['hb'], q['win'], q['sub'], q['hsteps'], q['mbs'], a, b, q['cost'], q['up'])}
+        for mode in ("mean", "median", "weighted"):
+            calls[f"smooth_{mode}"] = lambda mode=mode: oracle.smooth(mode, mv, q['fsz'])
+        for name, f in calls.items():
+            key = f"me/{it}/{name}"
+            if key + "/undefined" in g:
+                assert name == "hbma" and oracle.hbma_undefined_in_reference(a.shape[0], a.shape[1], q['hb'], q['hsteps'], q['mbs'])
+                continue
+            if key + "/raises" in g:
+                continue
+            assert F.sha(np.asarray(f(), np.float32)) == str(g[key]), (it, name, q)
+            n += 1
+    assert n >= 300
