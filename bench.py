@@ -521,7 +521,7 @@ def main():
                        "l2_policy": f"inputs larger than L2: {((P + 1) * frame_bytes + 3 * H * W * 4) / 1e6:.0f} MB of frames + luma planes "
                                     "streamed per step vs 126 MB L2"},
             "output_frames_per_s": value * out_per_interp,
-            "sad_gops": (2 * px_ops * world * P * args.steps) / (ms_all * 1e-3) / 1e9,
+            "sad_gops": (px_ops * world * P * args.steps) / (ms_all * 1e-3) / 1e9,    # px_ops already covers both directions of a pair
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": (P + 1) * frame_bytes,
                     "d2h_bytes_per_step": P * nd * frame_bytes, "contexts": n_ctx,
                     "output_frames_per_s": e2e_value * out_per_interp},

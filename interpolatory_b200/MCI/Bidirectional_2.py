@@ -61,7 +61,7 @@ class BiDir2Interpolator(MEMCIBaseInterpolator):
         target_frame = self.video_stream.get_frame(source_frame_idx + 1)
         dev = self._device(np.asarray(source_frame).shape)
         s = self._frame_slot(dev, source_frame_idx, source_frame)
-        t = self._frame_slot(dev, source_frame_idx + 1, target_frame)
+        t = self._frame_slot(dev, source_frame_idx + 1, target_frame, keep=(source_frame_idx,))
         if not self.MV_field_idx < idx / self.rate_ratio < self.MV_field_idx + 1:      # :308
             # hbma: auto depth (:311-317) and block-level vectors (upscale=False); no smoothing in bidir2
             dev.estimate_pair(self._pair_params(np.asarray(source_frame).shape, True), s, t, _MV_FWD, _MV_BWD)

@@ -79,19 +79,24 @@ class MEMCIBaseInterpolator(BaseInterpolator):
             self._resident = {}
         return self._dev
 
-    def _frame_slot(self, dev, frame_idx, frame):
-        """Device slot holding source frame `frame_idx` (uploaded once per stream position)."""
+    def _frame_slot(self, dev, frame_idx, frame, keep=()):
+        """Device slot holding source frame `frame_idx` (uploaded once per stream position).  Least recently
+        used eviction; the frames named in `keep` (the other frame of the pair being interpolated) are never
+        evicted, so random access -- get_interpolated_frame(idx) with idx going backwards, which the reference's
+        VideoStream supports (src/VideoStream.py:61-96) -- cannot make both frames of a pair share one slot."""
         if self._resident_stream is not self.video_stream:
             self._resident = {}
             self._resident_stream = self.video_stream
         if frame_idx in self._resident:
-            return self._resident[frame_idx]
+            slot = self._resident.pop(frame_idx)                 # re-insert: dict order = recency
+            self._resident[frame_idx] = slot
+            return slot
         used = set(self._resident.values())
         free = [s for s in _FRAME_SLOTS if s not in used]
         if free:
             slot = free[0]
         else:
-            victim = min(self._resident)                         # oldest source index
+            victim = next(k for k in self._resident if k not in keep)     # least recently used, never a pinned frame
             slot = self._resident.pop(victim)
         dev.upload_frame(slot, frame)
         dev.sync()                                               # pageable host memory: copy is done

@@ -34,7 +34,7 @@ class UniDirInterpolator(MEMCIBaseInterpolator):
         target_frame = self.video_stream.get_frame(source_frame_idx + 1)
         dev = self._device(np.asarray(source_frame).shape)
         s = self._frame_slot(dev, source_frame_idx, source_frame)
-        t = self._frame_slot(dev, source_frame_idx + 1, target_frame)
+        t = self._frame_slot(dev, source_frame_idx + 1, target_frame, keep=(source_frame_idx,))
         # motion field cache: valid while idx stays strictly between its two source frames (:109)
         if not self.MV_field_idx < idx / self.rate_ratio < self.MV_field_idx + 1:
             dev.estimate_pair(self._pair_params(np.asarray(source_frame).shape, False), s, t, _MV_FWD, _MV_BWD)

@@ -62,3 +62,17 @@ def make_sequence(H, W, n_frames, seed=0):
 def make_pair(H, W, seed=0):
     fr = make_sequence(H, W, 2, seed)
     return fr[0], fr[1]
+
+
+def make_pair_tiled(H, W, seed=0, tiles=4):
+    """Full-size pair for the 4K / 8K parity and bench workloads: a (H/tiles x W/tiles) synthetic pair tiled
+    tiles x tiles (so the motion stays inside a +-32 search at 8K, where make_sequence's pan would be 36 px per
+    frame), with independent seeded +-3 grey-level noise per frame that breaks the periodicity."""
+    base = make_sequence(H // tiles, W // tiles, 2, seed)
+    rng = np.random.default_rng(seed + 7919)
+    out = []
+    for t in range(2):
+        f = np.tile(base[t], (tiles, tiles, 1)).astype(np.int16)
+        f += rng.integers(-3, 4, size=(H, W, 1), dtype=np.int16)
+        out.append(np.clip(f, 0, 255).astype(np.uint8))
+    return out[0], out[1]

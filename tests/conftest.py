@@ -38,3 +38,17 @@ def native_lib():
     B.build()
     from interpolatory_b200 import _native
     return _native.lib()
+
+
+@pytest.fixture(scope="session")
+def middlebury():
+    """The reference's 12 Middlebury evaluation triples (benchmarks/middlebury/*/frame10|frame11|frame10i11.png,
+    committed byte for byte in tests/golden/middlebury_pairs.npz by oracle/gen_middlebury.py) decoded to uint8 RGB,
+    as imageio.imread delivers them to src/Benchmark.py:39-42.  Returns {name: (frame10, frame11, ground truth)}."""
+    import io
+    from PIL import Image
+    z = np.load(os.path.join(GOLDEN, "middlebury_pairs.npz"), allow_pickle=False)
+
+    def dec(key):
+        return np.array(Image.open(io.BytesIO(z[key].tobytes())).convert("RGB"))
+    return {str(n): tuple(dec(f"{n}/{f}") for f in ("frame10", "frame11", "frame10i11")) for n in z["names"]}

@@ -327,6 +327,91 @@ def test_tiled_kernel_equals_generic_kernel_1080p(gpu):
     assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][3], res[1][3])
 
 
+def _full_size_case(gpu, monkeypatch, name, prefilter, refs):
+    """One seeded full-size pair (interpolatory_b200.synth.make_pair_tiled, the generator oracle/gen_fullsize_sha.py
+    used) through the CUDA path with the two-phase search pinned on or off; `refs` maps field / frame names to
+    either a digest (committed oracle output) or an array (oracle run live)."""
+    from interpolatory_b200.device import DeviceContext
+    from interpolatory_b200.synth import make_pair_tiled
+    H, W, bs, R, seed = {"cfg4": (2160, 3840, 16, 32, 4), "cfg5": (4320, 7680, 16, 32, 5)}[name]
+    monkeypatch.setenv("MEMCI_FS_PREFILTER", "1" if prefilter else "0")
+    a, b = make_pair_tiled(H, W, seed)
+    assert sha(np.stack([a, b])) == refs["frames_sha"], "synthetic generator drifted from the fixture"
+    ctx = DeviceContext(H, W)
+    try:
+        ctx.upload_frame(0, a); ctx.upload_frame(1, b)
+        ctx.me_fs_pair(0, 1, bs, R, 0, 1)
+        n_surv, overflow = ctx.fs_prefilter_stats()
+        if prefilter:                    # the 16 x 16 / +-32 instantiation really ran and kept its list
+            assert n_surv > 0 and not overflow, (n_surv, overflow)
+        else:
+            assert n_surv == 0 and not overflow
+        assert tuple(ctx.fs_stats()[:2]) == tuple(2 * int(x) for x in refs["work"])
+        for slot, key in ((0, "fwd"), (1, "bwd")):
+            _, vec, _, sad = ctx.download_mv_blocks(slot)
+            got = np.concatenate([vec, sad[..., None]], axis=2)
+            ref = refs[key]
+            assert (sha(got) == ref) if isinstance(ref, str) else np.array_equal(got, ref), (name, prefilter, key)
+        ctx.mci_bidir(0, 1, 0, 1, np.float32(0.5), 7)
+        got = ctx.download_frame(7)
+        assert (sha(got) == refs["bidir"]) if isinstance(refs["bidir"], str) else np.array_equal(got, refs["bidir"])
+        ctx.mci_unidir(0, 1, 0, np.float32(0.5), 7)
+        assert sha(ctx.download_frame(7)) == refs["unidir_sha"]
+    finally:
+        ctx.close()
+
+
+def test_cfg4_4k_full_size_vs_oracle(gpu, oracle, golden, monkeypatch):
+    """cfg4 at full size (2160 x 3840, fs 16 x 16 +-32, bidir): both motion fields and the interpolated frame
+    against the oracle run LIVE on the host cores (2 x 2.7e10 SAD px-ops: ~25 s with OpenMP), with the two-phase
+    search on and off; the live oracle outputs must also equal the committed digests (same oracle, other machine)."""
+    from interpolatory_b200.synth import make_pair_tiled
+    g = golden("fullsize_sha.npz")
+    H, W, bs, R = 2160, 3840, 16, 32
+    a, b = make_pair_tiled(H, W, 4)
+    fwd, bwd = oracle.fs_blocks(bs, R, a, b), oracle.fs_blocks(bs, R, b, a)
+    assert sha(fwd) == str(g["cfg4/fwd_sha"]) and sha(bwd) == str(g["cfg4/bwd_sha"])
+    frame = oracle.bidir_helper(a, b, oracle.expand_dense(fwd, bs, H, W), oracle.expand_dense(bwd, bs, H, W), np.float32(0.5))
+    assert sha(frame) == str(g["cfg4/bidir_sha"])
+    refs = {"frames_sha": str(g["cfg4/frames_sha"]), "work": g["cfg4/work"], "fwd": fwd, "bwd": bwd, "bidir": frame,
+            "unidir_sha": str(g["cfg4/unidir_sha"])}
+    for prefilter in (True, False):
+        _full_size_case(gpu, monkeypatch, "cfg4", prefilter, refs)
+
+
+@pytest.mark.parametrize("prefilter", [True, False])
+def test_cfg5_8k_full_size_vs_oracle_digests(gpu, golden, monkeypatch, prefilter):
+    """cfg5 at full size (4320 x 7680 single pair, fs 16 x 16 +-32: 129 600 blocks, 1 % under the 2^17 block
+    field of the survivor list) against the digests of the oracle's fields and frames (oracle/gen_fullsize_sha.py:
+    2 x 1.09e11 SAD px-ops, minutes of host time, so generated once and committed), two-phase search on and off."""
+    g = golden("fullsize_sha.npz")
+    refs = {"frames_sha": str(g["cfg5/frames_sha"]), "work": g["cfg5/work"], "fwd": str(g["cfg5/fwd_sha"]),
+            "bwd": str(g["cfg5/bwd_sha"]), "bidir": str(g["cfg5/bidir_sha"]), "unidir_sha": str(g["cfg5/unidir_sha"])}
+    _full_size_case(gpu, monkeypatch, "cfg5", prefilter, refs)
+
+
+def test_middlebury_pairs_vs_reference_digests(gpu, golden, middlebury):
+    """The reference's own 12 Middlebury pairs through the drop-in class API, `MEMCI(2, **settings)
+    .get_benchmark_frame(frame10, frame11)` (the call src/Benchmark.py:44 makes), against the digests of the
+    unmodified reference's output frames: fs / hbma x unidir / bidir / bidir2, and fs +-16 with median smoothing;
+    plus the block-level full-search fields of both directions."""
+    import ast
+    from interpolatory_b200 import MEMCI
+    from interpolatory_b200.ME.full_search import get_motion_vectors as fs
+    g = golden("middlebury_ref_sha.npz")
+    settings = {k: dict(v) for k, v in ast.literal_eval(str(g["settings"])).items()}
+    assert len(middlebury) == 12 and len(settings) == 7
+    for name, (a, b, _) in middlebury.items():
+        assert sha(np.stack([a, b])) == str(g[f"{name}/frames_sha"])
+        assert np.array_equal(blocks_of(fs(8, 7, a, b), 8), g[f"{name}/fs_fwd"]), name
+        assert np.array_equal(blocks_of(fs(8, 7, b, a), 8), g[f"{name}/fs_bwd"]), name
+        for key, st in settings.items():
+            it = MEMCI(2, **st)
+            out = np.asarray(it.get_benchmark_frame(a, b))
+            it.close()
+            assert sha(out) == str(g[f"{name}/{key}"]), (name, key)
+
+
 @pytest.mark.parametrize("H,W,bs,R", [(2160, 3840, 16, 32), (4320, 7680, 16, 32)])
 def test_full_size_properties_4k_8k(gpu, oracle, H, W, bs, R):
     """Size-independent properties at cfg4 / cfg5 sizes (the oracle would take minutes here):

@@ -191,3 +191,41 @@ def test_harness_helpers():
     from interpolatory_b200.util import sToMMSS, getETA
     assert sToMMSS(0) == '0:00' and sToMMSS(61) == '1:01' and sToMMSS(600) == '10:00'
     assert getETA(10, 0, 5) == '0:00' and getETA(10, 2, 6) == '0:20'
+
+
+def test_frame_slot_lru_never_evicts_the_pair_partner():
+    """Random access through get_interpolated_frame(idx) (the reference's VideoStream supports seeking backwards,
+    src/VideoStream.py:61-96): after frames 5, 6, 7 are resident, asking for the pair (3, 4) must not put both
+    frames into one device slot (round-1 advisor finding: eviction by lowest index did)."""
+    from interpolatory_b200 import MEMCI
+
+    class FakeDev:
+        def __init__(self):
+            self.uploads = []
+
+        def upload_frame(self, slot, frame):
+            self.uploads.append((slot, frame))
+
+        def sync(self):
+            pass
+
+    it = MEMCI(60, me_mode='fs', mci_mode='bidir')
+    it.video_stream = it._resident_stream = object()
+    dev = FakeDev()
+    for k in (5, 6, 7):
+        it._frame_slot(dev, k, k)
+    assert sorted(it._resident) == [5, 6, 7]
+    for back in (3, 1, 6, 0):
+        s = it._frame_slot(dev, back, back)
+        t = it._frame_slot(dev, back + 1, back + 1, keep=(back,))
+        assert s != t, (back, it._resident)
+        assert it._resident[back] == s and it._resident[back + 1] == t
+        # what the slots hold is what was last uploaded into them
+        held = {}
+        for slot, f in dev.uploads:
+            held[slot] = f
+        assert held[s] == back and held[t] == back + 1
+    # a resident frame is not uploaded again and becomes the most recently used
+    n = len(dev.uploads)
+    it._frame_slot(dev, 1, 1)
+    assert len(dev.uploads) == n and list(it._resident)[-1] == 1

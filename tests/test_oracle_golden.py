@@ -351,3 +351,34 @@ def test_oracle_me_vs_reference_hashes_on_random_parameters(oracle, golden):
             assert F.sha(np.asarray(f(), np.float32)) == str(g[key]), (it, name, q)
             n += 1
     assert n >= 300
+
+
+def test_oracle_middlebury_pairs_vs_reference(oracle, golden, middlebury):
+    """All 12 Middlebury pairs of the reference's own benchmark set (640x480, 584x388, 420x380: partial blocks on
+    real image content) through the oracle chain that mirrors `MEMCI(2, **settings).get_benchmark_frame(f10, f11)`
+    (src/Benchmark.py:44, base.py:136-157: dist = 0.5) against the digests of the unmodified reference's outputs
+    for fs / hbma x unidir / bidir / bidir2 and fs +-16 + median smoothing (tests/golden/middlebury_ref_sha.npz)."""
+    g = golden("middlebury_ref_sha.npz")
+    half = np.float32(0.5)
+    assert len(middlebury) == 12
+    for name, (a, b, _) in middlebury.items():
+        H, W, _c = a.shape
+        assert sha(np.stack([a, b])) == str(g[f"{name}/frames_sha"]), "PNG decode differs from the fixture generator's"
+        fwd_b, bwd_b = oracle.fs_blocks(8, 7, a, b), oracle.fs_blocks(8, 7, b, a)
+        assert np.array_equal(fwd_b, g[f"{name}/fs_fwd"]) and np.array_equal(bwd_b, g[f"{name}/fs_bwd"]), name
+        fwd, bwd = oracle.expand_dense(fwd_b, 8, H, W), oracle.expand_dense(bwd_b, 8, H, W)
+        steps = oracle.hbma_auto_steps(H, W)
+        fwh, bwh = oracle.hbma(8, 7, 1, steps, 4, a, b), oracle.hbma(8, 7, 1, steps, 4, b, a)
+        f16 = oracle.smooth('median', oracle.fs(8, 16, a, b), 4)
+        b16 = oracle.smooth('median', oracle.fs(8, 16, b, a), 4)
+        got = {
+            "fs_unidir": oracle.unidir_helper(a, b, fwd, half),
+            "fs_bidir": oracle.bidir_helper(a, b, fwd, bwd, half),
+            "fs_bidir2": oracle.bidir2_frame(a, b, fwd, bwd, 0.5, True),
+            "hbma_unidir": oracle.unidir_helper(a, b, fwh, half),
+            "hbma_bidir": oracle.bidir_helper(a, b, fwh, bwh, half),
+            "hbma_bidir2": oracle.bidir2_frame(a, b, fwh, bwh, 0.5, True),
+            "fs16_bidir_median": oracle.bidir_helper(a, b, f16, b16, half),
+        }
+        for key, out in got.items():
+            assert sha(out) == str(g[f"{name}/{key}"]), (name, key)
