@@ -145,6 +145,7 @@ int memci_ctx_destroy(memci_ctx *ctx)
     if (ctx->d_quality) cudaFree(ctx->d_quality);
     if (ctx->h_fs8_feedback) { cudaFreeHost(ctx->h_fs8_feedback); cudaEventDestroy(ctx->ev_fs8_feedback); }
     if (ctx->d_fs8_list) cudaFree(ctx->d_fs8_list);
+    if (ctx->d_f8_tiles) cudaFree(ctx->d_f8_tiles);
     if (ctx->d_fs8_best) cudaFree(ctx->d_fs8_best);
     for (int i = 0; i < 4; ++i) {
         if (ctx->fs_plan[i].d_tiles) cudaFree(ctx->fs_plan[i].d_tiles);

@@ -229,34 +229,6 @@ struct FsTileTab {
     int pre[FS_NBMAX + 1];
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MBAR_DONE;\n"
-        "bra MBAR_WAIT;\n"
-        "MBAR_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int x, int y, uint64_t *bar)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
-}
-
 // geometry of one tile, computed by warp 0 (lane = block within tile)
 __device__ inline void fs_fill_tab(FsTileTab *tab, const FsTile t, const FsParams &p, int lane, int dir)
 {
@@ -332,11 +304,6 @@ __device__ __forceinline__ void fs_finalize(const unsigned (&acc)[G], int n_vali
         kb = min(kb, key);
         kl = min(kl, lo);
     }
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // Work item = (block b, column offset dx): one thread walks all row-offset groups of its
@@ -619,19 +586,30 @@ static PFN_encodeTiled get_encode_fn()
     return fn;
 }
 
-static int make_tmap(memci_ctx *ctx, CUtensorMap *tm, const int32_t *plane, int H, int W, int Wp, int box_w, int box_h)
+// Tiled tensor map, no swizzle / interleave, zero fill outside `dims`.  rank 2 or 3; strides[i] = bytes between
+// consecutive indices of dimension i + 1 (multiples of 16); box[0] * element size must be a multiple of 16 bytes.
+int memci_tmap_encode(memci_ctx *ctx, CUtensorMap *tm, int dtype_u8, int rank, const void *base,
+                      const unsigned long long *dims, const unsigned long long *strides, const unsigned *box)
 {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return memci_fail(ctx, MEMCI_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};        // true extent: x >= W / y >= H zero-fill
-    cuuint64_t strides[1] = {(cuuint64_t)Wp * 4};
-    cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, (void *)plane, dims, strides, box, estr,
+    cuuint64_t d[3], st[2];
+    cuuint32_t bx[3], estr[3] = {1, 1, 1};
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) st[i] = strides[i];
+    CUresult r = enc(tm, dtype_u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_INT32, (cuuint32_t)rank, const_cast<void *>(base), d, st, bx, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return memci_fail(ctx, MEMCI_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", (int)r);
     return MEMCI_OK;
+}
+
+static int make_tmap(memci_ctx *ctx, CUtensorMap *tm, const int32_t *plane, int H, int W, int Wp, int box_w, int box_h)
+{
+    const unsigned long long dims[2] = {(unsigned long long)W, (unsigned long long)H};        // true extent: x >= W / y >= H zero-fill
+    const unsigned long long strides[1] = {(unsigned long long)Wp * 4};
+    const unsigned box[2] = {(unsigned)box_w, (unsigned)box_h};
+    return memci_tmap_encode(ctx, tm, 0, 2, plane, dims, strides, box);
 }
 
 static int pick_G(int R)

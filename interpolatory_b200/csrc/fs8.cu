@@ -14,8 +14,13 @@
 // depends on the content (textured frames: ~0.5 % of the candidates survive; flat frames: all of them -- those blocks go
 // to the block-level redo pass, and past a limit the exact kernel searches the pair, gated on a device-side flag).
 //
-//   fs8_prefilter_kernel  persistent CTAs over tiles of adjacent blocks of one block row; thread = (block, dx) candidate
-//                         column; survivors appended to per-CTA segments of the list
+//   luma8_kernel          L8 as FOUR planes, plane q shifted left by q bytes (zero border): a thread then reads the 8 window
+//                         bytes of any column offset as two aligned words of plane (offset & 3), and TMA -- whose inner
+//                         coordinate must be 16-byte aligned (probed: any other x raises an illegal instruction) -- can
+//                         stage all four shifts with ONE 3-D tile load
+//   fs8_prefilter_kernel  persistent CTAs, dynamic job queue; job = adjacent blocks of one block row (of two, side by side,
+//                         where the column range is clipped), staged by TMA (cp.async.bulk.tensor.3d + mbarrier, two
+//                         stages); thread = (block, dx) candidate column; survivors appended to per-CTA segments of the list
 //   fs8_refine_kernel     8 lanes per survivor: exact luma-SAD (+ float64 replay of flagged sums), 64-bit atomicMin
 //   fs8_output_kernel     thread per block: key -> (dy, dx, sad); decides the pair-level fallback; re-arms the buffers
 // Blocks that cannot be pruned (flat content, segment overflow, flagged sums of 16 x 16 blocks) go to fs_redo_kernel (fs.cu).
@@ -30,22 +35,34 @@
 
 struct F8Params {
     int H, W, bs, m, R, Rp, nbr, nbc;
-    int nb_tile, tiles_per_row, n_tiles_dir, br0, br1, ndir;
-    int rpt;                     // block rows per tile (2 when the taller window fits: staging and barriers per block halve)
-    int pitch8;                  // bytes per row of the padded L8 planes
-    int win_rows;                // staged window rows incl. slack for the last group
-    int rs;                      // words per window row (per pre-shifted plane)
-    int plane_words;             // words per plane, = 8 (mod 32): the four planes of a row land in different banks
-    int ref_rs;                  // words per row of the staged source blocks
-    int a_stride;                // uint16 per candidate column in the A array (multiple of 4)
+    int n_tiles;
+    const struct F8Tile *tiles;  // the jobs, in queue order (host table, cached per search geometry)
+    int n_stage;                 // shared-memory stages of (window planes + source blocks): 2 = the next tile lands while this one is searched
+    unsigned c_two, c_8k;        // the constants 2 and 8192 (F8Conv), opaque to the compiler
+    int box_x0, box_y0;          // padded-plane coordinates of frame pixel (0, 0)
+    int rs;                      // words per staged window row (= TMA box width / 4)
+    int plane_words;             // words per staged plane, = 8 or 24 (mod 32): the four planes of a row land in different banks
+    int ref_rs, ref_rows;        // words per row / rows of the staged source blocks
+    int a_rows;                  // row offsets per A buffer (groups * F8_G)
+    unsigned tx_bytes;           // bytes one tile's TMA loads deliver
     int T;                       // survivor threshold 2 n + 1
-    const uint8_t *l8_src[2], *l8_tgt[2];   // per direction: pixel (0, 0) inside the zero-padded plane
     unsigned *list; int seg_cap;   // survivor list: one segment of seg_cap entries per CTA
     unsigned *seg_counts;         // [grid] entries written per segment
     unsigned *redo_mark;          // [2][n_blk] 0 = block already on the redo list
     int *redo_list; int redo_cap; // blocks for fs_redo_kernel: flat / overflowing blocks here, flagged sums in the refine pass
     int redo_limit;               // more redo blocks than this: the pair falls back to the exact kernel (fs8_output_kernel decides)
-    int *counters;               // [8] survivor list overflowed, [9] survivors
+    int *counters;               // [8] survivor list overflowed, [9] survivors, [11] redo blocks, [12] tile queue cursor
+};
+
+struct F8Tile { short dir, nv; short by, bx0; short nb, pad; };   // direction, block rows (1 or 2), first block row / column, blocks
+
+struct F8Geo {                   // geometry of one job; written by warp 0 before it arms the job's loads
+    int t;                       // index in the table, < 0: the queue is empty
+    int dir, by, bx0, nb, nv;    // direction, first block row / column, blocks, block rows
+    int n_items, n_pad;          // candidate columns of one block row; two-row jobs: row 1's columns sit at thread n_pad + i
+    int uniform;                 // > 0: every block of the tile has that many column offsets
+    int dwin, dref;              // bytes between the 16-byte aligned TMA origin and the wanted one (window / source blocks)
+    int pre[F8_NBMAX + 1], dx_lo[F8_NBMAX];
 };
 
 struct FsBounds8 { int r0, r1, c0, c1; };
@@ -69,31 +86,41 @@ __device__ __forceinline__ unsigned f8_sad4(unsigned a, unsigned b, unsigned acc
     return r;
 }
 
-__device__ __forceinline__ void f8_cp_async4(void *smem_dst, const void *gsrc)
+// One group of F8_G consecutive row offsets of one candidate column is finished.  The accumulators hold A + 1.  The A
+// values go out as an 8-bit MONOTONE code -- code(v) = bits 19..26 of float(2 v): 4 exponent bits (2 <= 2 v < 2^18) + 4
+// mantissa bits, i.e. 16 steps per octave -- so the survivor test later compares code(A + 1) with code(A_min + 1 + T): a
+// superset of the exact test A <= A_min + T (monotone => nothing is lost; a few extra survivors within one step, 1/16
+// of the value, above the threshold).  Half the shared memory of uint16 -- which is what pays for the second stage of
+// the window planes -- with the full 16-bit range, and nothing on the integer-ALU pipe the SADs are bound by: IMAD
+// (times 2), I2F (XU pipe), IMAD.HI (>> 19), with multipliers that come from the parameter block (a literal power of
+// two would be turned back into ALU shifts).  Layout A[row offset][thread], A_PITCH = threads + 4 bytes per row: the 32
+// stores of a warp fall into 8 consecutive words, and the 32 row offsets a warp later reads of ONE column fall into 32
+// different banks.  The column minimum stays exact.  MASK: the group sticks out of the valid row range (last group only).
+struct F8Conv { unsigned two, c8k; };            // the constants 2 and 8192, opaque to the compiler
+__device__ __forceinline__ unsigned f8_code(unsigned v, const F8Conv cv)   // v in [1, 65535]
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+    unsigned t, x;
+    float f;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(v), "r"(cv.two));
+    asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(t));
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(x) : "r"(__float_as_uint(f)), "r"(cv.c8k));
+    return x;                                                      // the code is the low byte
 }
-__device__ __forceinline__ void f8_cp_async_wait_all()
-{
-    asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
-}
-
-// One group of F8_G consecutive row offsets of one candidate column: 8 x 8 source sub-block in rl / rh, window rows
-// streamed from the lane's pre-shifted plane.  MASK: the group sticks out of the valid row range (last group only).
-template <bool MASK>
-__device__ __forceinline__ void f8_finish_group(unsigned (&acc)[F8_G], int n_valid, unsigned short *cg, unsigned &cmin)
+template <bool MASK, int A_PITCH>
+__device__ __forceinline__ void f8_finish_group(unsigned (&acc)[F8_G], int n_valid, unsigned char *cg, unsigned &cmin, const F8Conv cv)
 {
     if (MASK) {
 #pragma unroll
         for (int gi = 0; gi < F8_G; ++gi) acc[gi] = gi < n_valid ? acc[gi] : 0xffffu;
     }
 #pragma unroll
-    for (int gi = 0; gi < F8_G; ++gi) cg[gi] = (unsigned short)acc[gi];
+    for (int gi = 0; gi < F8_G; ++gi) cg[gi * A_PITCH] = (unsigned char)f8_code(acc[gi], cv);
 #pragma unroll
     for (int gi = 0; gi + 1 < F8_G; gi += 2) cmin = min(cmin, min(acc[gi], acc[gi + 1]));     // VIMNMX3
     if (F8_G & 1) cmin = min(cmin, acc[F8_G - 1]);
 }
 
+// 8 x 8 source sub-block in rl / rh, F8_G + 7 window rows streamed from the lane's pre-shifted plane: 176 VABSDIFF4.
 __device__ __forceinline__ void f8_accumulate(unsigned (&acc)[F8_G], const unsigned (&rl)[8], const unsigned (&rh)[8],
                                               const unsigned *wp, int rs)
 {
@@ -108,237 +135,277 @@ __device__ __forceinline__ void f8_accumulate(unsigned (&acc)[F8_G], const unsig
     }
 }
 
-// Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  While a tile is searched, the raw window
-// and source rows of the CTA's next tile stream into shared memory with cp.async; after the search they are expanded
-// into the four byte-shifted planes (shared -> shared), so no global-memory latency sits between two tiles.
+// Persistent.  A JOB is one tile of the host's table (F8Tile): nb adjacent blocks of one block row -- or, where the
+// reference's H-for-W column bound (full_search.py:37) leaves a block only 17 of its 33 column offsets at 1080p, of TWO
+// block rows searched side by side by the two halves of the CTA -- so every job keeps ~500 of the 512 threads busy and
+// all jobs cost the same.  Jobs come off a queue (one global atomic per job, taken by warp 0); a job's target window --
+// all four byte shifts, one 3-D TMA load -- and source blocks land in one of `n_stage` shared-memory stages and signal
+// bar_full.  Per job j:
+//   search the first row-offset group of the thread's candidate column                          -> A[j & 1]
+//   hand-over of job j - 1: its block minima were completed a third of a search ago, so the wait on bar_min[(j - 1) & 1]
+//     falls through; warp 0 refills the stage job j - 1 vacated (job j + 1 lands while job j is searched); the warp
+//     emits job j - 1's survivors
+//   search the other groups; column minima -> block minima (shared atomicMin, generation-tagged: never reset);
+//   arrive bar_min[j & 1]
+// No warp idles for the slowest one, no __syncthreads() after the prologue.  With one stage (wide searches whose window
+// does not fit twice) the hand-over of job j happens at its own end.
 template <bool M1, int F8_NT>
 __global__ void __launch_bounds__(F8_NT, 1024 / F8_NT)
-fs8_prefilter_kernel(const F8Params p)
+fs8_prefilter_kernel(const __grid_constant__ CUtensorMap tm_win_a, const __grid_constant__ CUtensorMap tm_win_b,
+                     const __grid_constant__ CUtensorMap tm_ref_a, const __grid_constant__ CUtensorMap tm_ref_b,
+                     const F8Params p)
 {
-    extern __shared__ __align__(16) unsigned f8_smem[];
-    __shared__ unsigned bmin_s[2][2][F8_NBMAX];  // [tile parity][block row of the tile]; per tile parity: the next tile's geometry is written while slow warps still emit
-    __shared__ int pre_s[2][F8_NBMAX + 1], dx_lo_ss[2][F8_NBMAX];
-    __shared__ unsigned seg_count;
-    __shared__ int uniform_s[2];                                   // > 0: every block of the tile has that many column offsets
+    constexpr int NW = F8_NT / 32;
+    constexpr int A_PITCH = F8_NT + 4;
+    extern __shared__ __align__(128) unsigned f8_smem[];
+    __shared__ __align__(8) uint64_t bar_full[2], bar_min[2];
+    __shared__ F8Geo geo_s[2];
+    __shared__ unsigned bmin_s[4][2][F8_NBMAX];                     // [job & 3][block row of the tile][block]: (generation << 16) | (A_min + 1)
+    __shared__ unsigned seg_count, seg_valid;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bs = p.bs, R = p.R, raw_rs = p.rs + 1;
-    unsigned *planes = f8_smem;                                    // [4][plane_words]
-    unsigned *raw = planes + 4 * p.plane_words;                    // [win_rows][rs + 1]   next tile's window, unshifted
-    const int ref_rows = p.rpt * bs;
-    unsigned *ref0 = raw + p.win_rows * raw_rs;                    // [2][rpt * bs][ref_rs]  source blocks, current / next tile
-    unsigned short *A = reinterpret_cast<unsigned short *>(ref0 + 2 * ref_rows * p.ref_rs);   // [threads][a_stride]
-    const int n_tiles = p.n_tiles_dir * p.ndir;
-
-    auto tile_of = [&](int t, int &dir, int &by, int &bx0, int &nb) {
-        dir = t >= p.n_tiles_dir ? 1 : 0;
-        const int tt = t - dir * p.n_tiles_dir, trow = tt / p.tiles_per_row;
-        by = p.br0 + trow * p.rpt; bx0 = (tt - trow * p.tiles_per_row) * p.nb_tile;      // first block row of the tile
-        nb = min(p.nb_tile, p.nbc - bx0);
-    };
-    auto issue_loads = [&](int dir, int by, int bx0, int nb, int buf) {
-        const int s_row = by * bs;
-        const uint8_t *g = (dir ? p.l8_tgt[1] : p.l8_tgt[0]) + (ptrdiff_t)(s_row - R) * p.pitch8 + (bx0 * bs - p.Rp);
-        const int n_w = (nb * bs + 2 * p.Rp) / 4 + 2;              // words per row incl. the one the last funnel shift reads
-        for (int r = warp; r < p.win_rows; r += F8_NT / 32) {
-            const unsigned *row = reinterpret_cast<const unsigned *>(g + (ptrdiff_t)r * p.pitch8);
-            for (int j = lane; j < n_w; j += 32) f8_cp_async4(raw + r * raw_rs + j, row + j);
-        }
-        const uint8_t *gs = (dir ? p.l8_src[1] : p.l8_src[0]) + (ptrdiff_t)s_row * p.pitch8 + bx0 * bs;
-        unsigned *ref = ref0 + buf * ref_rows * p.ref_rs;
-        const int n_r = nb * bs / 4;
-        for (int r = warp; r < ref_rows; r += F8_NT / 32)                  // rows past the frame are zero in the padded plane
-            for (int j = lane; j < n_r; j += 32)
-                f8_cp_async4(ref + r * p.ref_rs + j, reinterpret_cast<const unsigned *>(gs + (ptrdiff_t)r * p.pitch8) + j);
-    };
-    // raw -> four byte-shifted planes; tile geometry (warp 0)
-    auto build = [&](int by, int bx0, int nb, int par) {
-        int *pre = pre_s[par], *dx_lo_s = dx_lo_ss[par];
-        const int n_w = (nb * bs + 2 * p.Rp) / 4 + 1;
-        for (int r = warp; r < p.win_rows; r += F8_NT / 32) {
-            const unsigned *src = raw + r * raw_rs;
-            unsigned *dst = planes + r * p.rs;
-            for (int j = lane; j < n_w; j += 32) {
-                const unsigned w0 = src[j], w1 = src[j + 1];
-                dst[j] = w0;
-                dst[p.plane_words + j] = __funnelshift_r(w0, w1, 8);
-                dst[2 * p.plane_words + j] = __funnelshift_r(w0, w1, 16);
-                dst[3 * p.plane_words + j] = __funnelshift_r(w0, w1, 24);
-            }
-        }
-        if (warp == 0) {
-            int n_dx = 0, dxl = 0;
-            if (lane < nb) {
-                const FsBounds8 b = f8_bounds(p.H, p.W, bs, R, by * bs, (bx0 + lane) * bs);
-                n_dx = max(b.c1 - b.c0, 0);
-                dxl = b.c0 - (bx0 + lane) * bs;
-            }
-            int incl = n_dx;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            pre[lane + 1] = incl; dx_lo_s[lane] = dxl; bmin_s[par][0][lane] = 0xffffffffu; bmin_s[par][1][lane] = 0xffffffffu;
-            const int n0 = __shfl_sync(0xffffffffu, n_dx, 0);
-            const bool uni = __all_sync(0xffffffffu, lane >= nb || n_dx == n0);
-            if (lane == 0) { pre[0] = 0; uniform_s[par] = (uni && n0 > 0) ? n0 : 0; }
-        }
-    };
-
+    const int bs = p.bs, R = p.R;
+    const F8Conv cv = {p.c_two, p.c_8k};
+    const int stage_words = 4 * p.plane_words + ((p.ref_rows * p.ref_rs + 31) & ~31);   // planes [4][plane_words], then source rows [ref_rows][ref_rs]
+    unsigned char *A_base = reinterpret_cast<unsigned char *>(f8_smem + p.n_stage * stage_words);   // [2][a_rows][A_PITCH]
+    const int a_bytes = p.a_rows * A_PITCH;
     unsigned *seg = p.list + (size_t)blockIdx.x * p.seg_cap;
-    if (tid == 0) seg_count = 0u;
-    int t = blockIdx.x;
-    if (t >= n_tiles) return;
-    int cur = 0;
-    int dir, by, bx0, nb;                                          // geometry of the tile being searched
-    tile_of(t, dir, by, bx0, nb);
-    issue_loads(dir, by, bx0, nb, 0);
-    f8_cp_async_wait_all();
-    __syncwarp();
-    build(by, bx0, nb, 0);                                        // every warp expands the rows it copied itself
-    __syncthreads();
 
-    for (;;) {
-        const int tn = t + gridDim.x;
-        int dir_n = 0, by_n = 0, bx0_n = 0, nb_n = 0;              // ... and of the CTA's next tile
-        if (tn < n_tiles) {
-            tile_of(tn, dir_n, by_n, bx0_n, nb_n);
-            issue_loads(dir_n, by_n, bx0_n, nb_n, cur ^ 1);        // streams in while this tile is searched
-        }
-
-        const int *pre = pre_s[cur], *dx_lo_s = dx_lo_ss[cur];
-        const int n_items = pre[nb];
-        int b = 0, dxi = 0, dx = 0;                                // the thread's candidate column: the same for every block row of the tile
-        if (tid < n_items) {
-            if (uniform_s[cur] > 0) b = tid / uniform_s[cur];
-            else while (b + 1 < nb && pre[b + 1] <= tid) ++b;
-            dxi = tid - pre[b];
-            dx = dx_lo_s[b] + dxi;
-        }
-        unsigned short *col = A + (size_t)tid * p.a_stride;
-        const int nv = min(p.rpt, p.br1 - by);
-#pragma unroll 1
-        for (int v = 0; v < nv; ++v) {
-            unsigned *bmin = bmin_s[cur][v];
-            const int s_row = (by + v) * bs;
-            const unsigned *ref = ref0 + (cur * ref_rows + v * bs) * p.ref_rs;
-            const FsBounds8 b0 = f8_bounds(p.H, p.W, bs, R, s_row, bx0 * bs);
-            const int n_dy = max(b0.r1 - b0.r0, 0);
-            const int wrow_base = b0.r0 - (by * bs - R);               // window rows count from the tile's first block row
-            const bool active = tid < n_items && n_dy > 0;
-            unsigned cmin = 0xffffffffu;
-            if (active) {
-                unsigned rl[8], rh[8];
-                if (M1) {
-                    const unsigned *rp = ref + ((b * 8) >> 2);
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk) {
-                        const uint2 rv = *reinterpret_cast<const uint2 *>(rp + kk * p.ref_rs);
-                        rl[kk] = rv.x; rh[kk] = rv.y;
-                    }
-                }
-                const int wc0 = b * bs + dx + p.Rp;                    // byte offset inside a window row
-                // full groups first, then (clipped windows only) the one group that sticks out of the valid row range: two
-                // separate copies of the loop body, so that the common one carries no masking selects
-                auto group = [&](int g, auto masked) {
-                    unsigned acc[F8_G];
-#pragma unroll
-                    for (int i = 0; i < F8_G; ++i) acc[i] = 0u;
-                    if (M1) {
-                        f8_accumulate(acc, rl, rh, planes + (wc0 & 3) * p.plane_words + (wrow_base + g * F8_G) * p.rs + (wc0 >> 2), p.rs);
-                    } else {
-                        const int m = p.m;
-#pragma unroll 1
-                        for (int sub = 0; sub < m * m; ++sub) {
-                            const int si = sub / m, sj = sub - si * m;
-                            const unsigned *rp = ref + (si * 8) * p.ref_rs + ((b * bs + sj * 8) >> 2);
-#pragma unroll
-                            for (int kk = 0; kk < 8; ++kk) {
-                                const uint2 rv = *reinterpret_cast<const uint2 *>(rp + kk * p.ref_rs);
-                                rl[kk] = rv.x; rh[kk] = rv.y;
-                            }
-                            const int wc = wc0 + sj * 8;
-                            f8_accumulate(acc, rl, rh, planes + (wc & 3) * p.plane_words + (wrow_base + g * F8_G + si * 8) * p.rs + (wc >> 2), p.rs);
-                        }
-                    }
-                    f8_finish_group<decltype(masked)::value>(acc, n_dy - g * F8_G, col + g * F8_G, cmin);
-                };
-                const int n_full = n_dy / F8_G;
-#pragma unroll 1
-                for (int g = 0; g < n_full; ++g) group(g, std::false_type{});
-                if (n_full * F8_G < n_dy) group(n_full, std::true_type{});
-            }
-            // ---- block minima: segmented warp reduction, one shared-memory atomic per (warp, block) ----
-            {
-                unsigned todo = __ballot_sync(0xffffffffu, active);
-                while (todo) {
-                    const int leader = __ffs(todo) - 1;
-                    const int bb = __shfl_sync(0xffffffffu, b, leader);
-                    const bool mine = active && b == bb;
-                    const unsigned mn = __reduce_min_sync(0xffffffffu, mine ? cmin : 0xffffffffu);
-                    if (lane == leader) atomicMin(&bmin[bb], mn);
-                    todo &= ~__ballot_sync(0xffffffffu, mine);
-                }
-            }
-            __syncthreads();
-            // ---- survivors: the warp visits its flagged columns one at a time, lanes = row offsets.  Each CTA appends to
-            //      its own segment of the list (shared-memory cursor, no global atomics); fs8_refine_kernel gets the
-            //      segment lengths at the end ----
-            {
-                const unsigned thr = active ? bmin[b] + (unsigned)p.T : 0u;
-                const unsigned flagged0 = __ballot_sync(0xffffffffu, active && cmin <= thr);
-                const unsigned head_own = (dir ? 0x80000000u : 0u) | ((unsigned)((by + v) * p.nbc + bx0 + b) << 14) | (unsigned)dxi;
-                const unsigned short *cw = A + (size_t)(tid & ~31) * p.a_stride;
-                for (unsigned f = flagged0; f; f &= f - 1) {
-                    const int src = __ffs(f) - 1;
-                    const unsigned thr_c = __shfl_sync(0xffffffffu, thr, src);
-                    const unsigned head = __shfl_sync(0xffffffffu, head_own, src);
-                    // lane l looks at row offsets 2l and 2l + 1 (one 32-bit load): 64 offsets per pass
-                    const unsigned *cs = reinterpret_cast<const unsigned *>(cw + src * p.a_stride);
-                    int hits = 0;
-                    for (int i0 = 0; i0 < n_dy; i0 += 64) {
-                        const int i = i0 + 2 * lane;
-                        const unsigned pv = i < n_dy ? cs[i >> 1] : 0xffffffffu;
-                        hits += __popc(__ballot_sync(0xffffffffu, i < n_dy && (pv & 0xffffu) <= thr_c)) +
-                                __popc(__ballot_sync(0xffffffffu, i + 1 < n_dy && (pv >> 16) <= thr_c));
-                    }
-                    int pos = 0;
-                    if (lane == 0) {
-                        // A column that survives whole is flat content: nothing to prune in this block.  It, and any block
-                        // whose survivors no longer fit the segment, goes to the exact block-level redo pass instead (once).
-                        pos = hits == n_dy ? -1 : (int)atomicAdd(&seg_count, (unsigned)hits);
-                        if (pos >= 0 && pos + hits > p.seg_cap) { atomicSub(&seg_count, (unsigned)hits); pos = -1; }
-                        if (pos < 0) {
-                            const unsigned slot = (head >> 31) * (unsigned)(p.nbr * p.nbc) + ((head >> 14) & 0x1ffffu);
-                            if (atomicExch(&p.redo_mark[slot], 0u) != 0u) {
-                                const int rp = atomicAdd(&p.counters[11], 1);
-                                if (rp < p.redo_cap) p.redo_list[rp] = (int)((head >> 14) & 0x1ffffu) | ((head >> 31) ? 0x40000000 : 0);   // FS_DIR_BIT
-                            }
-                        }
-                    }
-                    pos = __shfl_sync(0xffffffffu, pos, 0);
-                    if (pos < 0) continue;
-                    for (int i0 = 0; i0 < n_dy; i0 += 64) {
-                        const int i = i0 + 2 * lane;
-                        const unsigned pv = i < n_dy ? cs[i >> 1] : 0xffffffffu;
-                        const bool h0 = i < n_dy && (pv & 0xffffu) <= thr_c, h1 = i + 1 < n_dy && (pv >> 16) <= thr_c;
-                        const unsigned b0m = __ballot_sync(0xffffffffu, h0), b1m = __ballot_sync(0xffffffffu, h1);
-                        const unsigned below = (1u << lane) - 1u;
-                        const int off = __popc(b0m & below) + __popc(b1m & below);      // entries of lower lanes come first (order is irrelevant to the result)
-                        if (h0) seg[pos + off] = head | ((unsigned)i << 7);
-                        if (h1) seg[pos + off + (h0 ? 1 : 0)] = head | ((unsigned)(i + 1) << 7);
-                        pos += __popc(b0m) + __popc(b1m);
-                    }
-                }
-            }
-        }                                                          // block rows of the tile
-        if (tn >= n_tiles) break;
-        f8_cp_async_wait_all();
-        __syncwarp();                                              // the warp's own rows of the next tile landed; planes are free since the barrier above
-        build(by_n, bx0_n, nb_n, cur ^ 1);
-        __syncthreads();
-        t = tn; cur ^= 1;
-        dir = dir_n; by = by_n; bx0 = bx0_n; nb = nb_n;
+    if (tid == 0) {
+        mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1); mbar_init(&bar_min[0], NW); mbar_init(&bar_min[1], NW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        seg_count = 0u; seg_valid = 0xffffffffu;
     }
+    if (tid < 4 * 2 * F8_NBMAX) (&bmin_s[0][0][0])[tid] = 0xffffffffu;
     __syncthreads();
-    if (tid == 0) { p.seg_counts[blockIdx.x] = min(seg_count, (unsigned)p.seg_cap); atomicAdd(&p.counters[9], (int)seg_count); }
+
+    // warp 0: take the next job off the queue, publish its geometry (local job number kk), arm the stage's barrier and
+    // issue the two TMA loads
+    auto issue_next = [&](int kk) {
+        const int sb = p.n_stage == 2 ? (kk & 1) : 0;
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&p.counters[12], 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        F8Geo *g = &geo_s[kk & 1];
+        if (t >= p.n_tiles) {
+            if (lane == 0) { g->t = -1; mbar_arrive(&bar_full[sb]); }
+            return;
+        }
+        const F8Tile tile = p.tiles[t];
+        const int dir = tile.dir, by = tile.by, bx0 = tile.bx0, nb = tile.nb, nv = tile.nv;
+        int n_dx = 0, dxl = 0;
+        if (lane < nb) {                                           // column bounds do not depend on the block row
+            const FsBounds8 b = f8_bounds(p.H, p.W, bs, R, by * bs, (bx0 + lane) * bs);
+            n_dx = max(b.c1 - b.c0, 0);
+            dxl = b.c0 - (bx0 + lane) * bs;
+        }
+        int incl = n_dx;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        g->pre[lane + 1] = incl; g->dx_lo[lane] = dxl;
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int n0 = __shfl_sync(0xffffffffu, n_dx, 0);
+        const bool uni = __all_sync(0xffffffffu, lane >= nb || n_dx == n0);
+        const int xw = p.box_x0 + bx0 * bs - p.Rp, xr = p.box_x0 + bx0 * bs;          // wanted x origins (multiples of 4)
+        if (lane == 0) {
+            g->pre[0] = 0; g->t = t; g->dir = dir; g->by = by; g->bx0 = bx0; g->nb = nb; g->nv = nv;
+            g->n_items = total; g->n_pad = (total + 31) & ~31;
+            g->uniform = (uni && n0 > 0) ? n0 : 0;
+            g->dwin = xw & 15; g->dref = xr & 15;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            unsigned *st = f8_smem + sb * stage_words;
+            mbar_expect_tx(&bar_full[sb], p.tx_bytes);
+            tma_load_3d(st, dir ? &tm_win_a : &tm_win_b, xw & ~15, p.box_y0 + by * bs - R, 0, &bar_full[sb]);
+            tma_load_3d(st + 4 * p.plane_words, dir ? &tm_ref_b : &tm_ref_a, xr & ~15, p.box_y0 + by * bs, 0, &bar_full[sb]);
+        }
+    };
+
+    // ---- survivors of one finished job.  A warp takes its flagged columns (column minimum within T of the block minimum:
+    //      typically 2-3 of 32) four at a time: lane = (column slot, row offset mod 8), so one vote covers eight row offsets
+    //      of all four columns; pass 1 counts the hits per column, the first lane of each slot reserves room, pass 2
+    //      writes.  Each CTA appends to its own segment of the list through a shared-memory cursor that only ever moves
+    //      forward: a reservation that does not fit marks where the valid prefix ends (later ones cannot fit either) and
+    //      its block goes to the redo pass.  fs8_refine_kernel gets the length of the valid prefix ----
+    auto emit = [&](const unsigned char *Abuf, unsigned bmin_word, unsigned head_own, unsigned cmin, bool active, int n_dy) {
+        const unsigned thr = active ? (bmin_word & 0xffffu) + (unsigned)p.T : 1u;       // A_min + 1 + T: the accumulators, and so cmin, carry the same + 1
+        unsigned flagged = __ballot_sync(0xffffffffu, active && cmin <= thr);
+        if (!flagged) return;
+        const unsigned thr_code = f8_code(min(thr, 65535u), cv) & 0xffu;
+        const int slot = lane >> 3, sub = lane & 7;
+        const unsigned my_bits = 0xffu << (slot * 8), below = my_bits & ((1u << lane) - 1u);
+        const unsigned char *cw = Abuf + (tid & ~31);
+        const int n_it = (n_dy + 7) >> 3;                          // n_dy is the same for every lane of a warp
+        while (flagged) {
+            int src = -1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                          // slot k takes the k-th flagged column
+                const int sbit = __ffs(flagged) - 1;               // -1 when none is left
+                if (slot == k) src = sbit;
+                flagged &= flagged - 1;
+            }
+            const bool on = src >= 0;
+            const unsigned thr_c = __shfl_sync(0xffffffffu, thr_code, on ? src : 0);
+            const unsigned head = __shfl_sync(0xffffffffu, head_own, on ? src : 0);
+            const unsigned char *cs = cw + (on ? src : 0) + sub * A_PITCH;
+            int hits = 0;
+            for (int m = 0; m < n_it; ++m) {
+                const bool h = on && m * 8 + sub < n_dy && cs[m * 8 * A_PITCH] <= thr_c;
+                hits += __popc(__ballot_sync(0xffffffffu, h) & my_bits);
+            }
+            int pos = -1;
+            if (on && sub == 0) {
+                // A column that survives whole is flat content: nothing to prune in this block.  It, and any block whose
+                // survivors no longer fit the segment, goes to the exact block-level redo pass instead (once).
+                if (hits != n_dy) {
+                    pos = (int)atomicAdd(&seg_count, (unsigned)hits);
+                    if (pos + hits > p.seg_cap) { atomicMin(&seg_valid, (unsigned)pos); pos = -1; }
+                }
+                if (pos < 0) {
+                    const unsigned bslot = (head >> 31) * (unsigned)(p.nbr * p.nbc) + ((head >> 14) & 0x1ffffu);
+                    if (atomicExch(&p.redo_mark[bslot], 0u) != 0u) {
+                        const int rp = atomicAdd(&p.counters[11], 1);
+                        if (rp < p.redo_cap) p.redo_list[rp] = (int)((head >> 14) & 0x1ffffu) | ((head >> 31) ? 0x40000000 : 0);   // FS_DIR_BIT
+                    }
+                }
+            }
+            pos = __shfl_sync(0xffffffffu, pos, slot * 8);
+            if (__any_sync(0xffffffffu, pos >= 0)) {
+                for (int m = 0; m < n_it; ++m) {
+                    const int i = m * 8 + sub;
+                    const bool h = pos >= 0 && i < n_dy && cs[m * 8 * A_PITCH] <= thr_c;
+                    const unsigned bal = __ballot_sync(0xffffffffu, h);
+                    if (h) seg[pos + __popc(bal & below)] = head | ((unsigned)i << 7);   // order inside a column is irrelevant to the result
+                    pos += __popc(bal & my_bits);
+                }
+            }
+        }
+    };
+
+    if (warp == 0) { issue_next(0); if (p.n_stage == 2) issue_next(1); }
+    int n_issued = p.n_stage;
+
+    // the job whose survivors are still to be emitted
+    bool pv_valid = false, pv_active = false;
+    unsigned pv_head = 0u, pv_cmin = 0u;
+    int pv_ndy = 0, pv_bslot = 0;
+    int j = 0;                                                     // jobs searched so far
+
+    auto flush_prev = [&](bool refill) {                            // hand-over of job j - 1 (see above)
+        const int q = j - 1;
+        mbar_wait_sleep(&bar_min[q & 1], (unsigned)((q >> 1) & 1));
+        if (refill) {                                              // every warp is done with that job's stage
+            if (warp == 0) issue_next(n_issued);
+            ++n_issued;
+        }
+        emit(A_base + (q & 1) * a_bytes, (&bmin_s[0][0][0])[pv_bslot], pv_head, pv_cmin, pv_active, pv_ndy);
+        pv_valid = false;
+    };
+
+#pragma unroll 1
+    for (;; ++j) {
+        const int sb = p.n_stage == 2 ? (j & 1) : 0;
+        mbar_wait_sleep(&bar_full[sb], (unsigned)((p.n_stage == 2 ? (j >> 1) : j) & 1));
+        const F8Geo *g = &geo_s[j & 1];
+        if (g->t < 0) break;
+        const int dir = g->dir, by = g->by, bx0 = g->bx0, nb = g->nb, n_items = g->n_items;
+        const unsigned *planes = f8_smem + sb * stage_words;
+        const unsigned *ref0 = planes + 4 * p.plane_words;
+        // the thread's candidate column (block, dx); in a two-row job the upper half of the CTA takes block row 1
+        int it = tid, v = 0;
+        if (g->nv == 2 && tid >= g->n_pad) { it = tid - g->n_pad; v = 1; }
+        const bool has_item = it < n_items;
+        int b = 0, dxi = 0, dx = 0;
+        if (has_item) {
+            if (g->uniform > 0) b = it / g->uniform;
+            else while (b + 1 < nb && g->pre[b + 1] <= it) ++b;
+            dxi = it - g->pre[b];
+            dx = g->dx_lo[b] + dxi;
+        }
+        const int wq = b * bs + dx + p.Rp + g->dwin;                 // byte offset of the column inside a staged window row
+        const unsigned *pl = planes + (wq & 3) * p.plane_words + (wq >> 2);
+        const int s_row = (by + v) * bs;
+        const unsigned *ref = ref0 + (v * bs) * p.ref_rs + ((b * bs + g->dref) >> 2);
+        const FsBounds8 b0 = f8_bounds(p.H, p.W, bs, R, s_row, bx0 * bs);
+        const int n_dy = max(b0.r1 - b0.r0, 0);
+        const int wrow_base = b0.r0 - (by * bs - R);                   // window rows count from the job's first block row
+        const bool active = has_item && n_dy > 0;
+        unsigned char *col = A_base + (j & 1) * a_bytes + tid;
+        unsigned cmin = 0xffffffffu;
+        // Lanes without a column of their own (the tail of the last warp) search block 0 / dx 0 along with their warp: the
+        // hand-over below contains warp-wide votes and shuffles, so control flow stays warp-uniform; their results are ignored.
+        if (__any_sync(0xffffffffu, active)) {
+            unsigned rl[8], rh[8];
+            if (M1) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint2 rv = *reinterpret_cast<const uint2 *>(ref + kk * p.ref_rs);
+                    rl[kk] = rv.x; rh[kk] = rv.y;
+                }
+            }
+            // full groups first, then (clipped windows only) the one group that sticks out of the valid row range: two
+            // separate copies of the loop body, so that the common one carries no masking selects
+            auto group = [&](int gq, auto masked) {
+                unsigned acc[F8_G];
+#pragma unroll
+                for (int i = 0; i < F8_G; ++i) acc[i] = 1u;                  // A + 1: see f8_finish_group
+                if (M1) {
+                    f8_accumulate(acc, rl, rh, pl + (wrow_base + gq * F8_G) * p.rs, p.rs);
+                } else {
+                    const int m = p.m;
+#pragma unroll 1
+                    for (int sub = 0; sub < m * m; ++sub) {
+                        const int si = sub / m, sj = sub - si * m;
+                        const unsigned *rp = ref + (si * 8) * p.ref_rs + sj * 2;
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk) {
+                            const uint2 rv = *reinterpret_cast<const uint2 *>(rp + kk * p.ref_rs);
+                            rl[kk] = rv.x; rh[kk] = rv.y;
+                        }
+                        f8_accumulate(acc, rl, rh, pl + (wrow_base + gq * F8_G + si * 8) * p.rs + sj * 2, p.rs);
+                    }
+                }
+                f8_finish_group<decltype(masked)::value, A_PITCH>(acc, n_dy - gq * F8_G, col + gq * F8_G * A_PITCH, cmin, cv);
+            };
+            const int n_full = n_dy / F8_G;
+#pragma unroll 1
+            for (int gq = 0; gq < n_full; ++gq) {
+                group(gq, std::false_type{});
+                if (gq == 0 && pv_valid) flush_prev(true);
+            }
+            if (n_full * F8_G < n_dy) group(n_full, std::true_type{});
+        }
+        if (pv_valid) flush_prev(true);                             // warps without a full group (or without work) in this job
+        // block minima: segmented warp reduction, one shared-memory atomic per (warp, block).  The generation tag in the
+        // upper half makes every later job's entries smaller than any earlier job's, so the slots are never reset (a slot
+        // is re-used four jobs later; its last reader finished before the hand-over two jobs earlier).
+        const int bslot = ((j & 3) * 2 + v) * F8_NBMAX;
+        {
+            const unsigned tag = (0xffffu - (unsigned)(j >> 2)) << 16;
+            unsigned todo = __ballot_sync(0xffffffffu, active);
+            while (todo) {
+                const int leader = __ffs(todo) - 1;
+                const int bb = __shfl_sync(0xffffffffu, b, leader);
+                const bool mine = active && b == bb;
+                const unsigned mn = __reduce_min_sync(0xffffffffu, mine ? cmin : 0xffffffffu);
+                if (lane == leader) atomicMin(&(&bmin_s[0][0][0])[bslot + bb], tag | mn);
+                todo &= ~__ballot_sync(0xffffffffu, mine);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_min[j & 1]);
+        // this job becomes the pending one
+        pv_valid = true; pv_active = active; pv_cmin = cmin; pv_ndy = n_dy; pv_bslot = bslot + b;
+        pv_head = (dir ? 0x80000000u : 0u) | ((unsigned)((by + v) * p.nbc + bx0 + b) << 14) | (unsigned)dxi;
+        if (p.n_stage == 1) { ++j; flush_prev(true); --j; }        // one stage: the next job's loads cannot start before this hand-over
+    }
+    if (pv_valid) flush_prev(false);
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned n = seg_valid != 0xffffffffu ? seg_valid : seg_count;     // the prefix every entry of which was written
+        p.seg_counts[blockIdx.x] = n;
+        atomicAdd(&p.counters[9], (int)n);
+    }
 }
 
 __device__ __forceinline__ unsigned long long f8_key(unsigned sad, unsigned d2, unsigned ri, unsigned ci)
@@ -503,18 +570,31 @@ __global__ void fs8_output_kernel(unsigned long long *__restrict__ best, unsigne
     (dir ? out_sad1 : out_sad0)[blk] = sad;
 }
 
-// ---- rounded 8-bit luma plane with a zero border (np.pad of the reference and every out-of-frame read) ----
-__global__ void luma8_kernel(const int32_t *__restrict__ L, int H, int W, int Wp, uint8_t *__restrict__ l8, int pitch8)
+// ---- rounded 8-bit luma, four byte-shifted planes with a zero border (np.pad of the reference and every out-of-frame
+//      read): plane q, padded row y, padded column x holds L8[y][x + q].  One thread per word of a row, plus one word to
+//      the left of the frame (planes 1..3 carry the first q pixels of a row there). ----
+__global__ void luma8_kernel(const int32_t *__restrict__ L, int H, int W, int Wp, uint8_t *__restrict__ l8, int pitch8, size_t plane_bytes)
 {
-    const int quads = Wp >> 2;
+    const int quads = (Wp >> 2) + 1;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= H * quads) return;
-    const int y = idx / quads, x = (idx - y * quads) << 2;
-    const int4 v = *reinterpret_cast<const int4 *>(L + (size_t)y * Wp + x);     // pad columns of L are 0
-    const unsigned w = (unsigned)((v.x + 500) / 1000) | ((unsigned)((v.y + 500) / 1000) << 8) |
-                       ((unsigned)((v.z + 500) / 1000) << 16) | ((unsigned)((v.w + 500) / 1000) << 24);
-    *reinterpret_cast<unsigned *>(l8 + (size_t)y * pitch8 + x) = w;
+    const int y = idx / quads, x = ((idx - y * quads) << 2) - 4;                    // x = -4, 0, 4, ...
+    auto pack = [&](int xx) -> unsigned {
+        if (xx < 0 || xx >= Wp) return 0u;
+        const int4 v = *reinterpret_cast<const int4 *>(L + (size_t)y * Wp + xx);     // pad columns of L are 0
+        return (unsigned)((v.x + 500) / 1000) | ((unsigned)((v.y + 500) / 1000) << 8) |
+               ((unsigned)((v.z + 500) / 1000) << 16) | ((unsigned)((v.w + 500) / 1000) << 24);
+    };
+    const unsigned w0 = pack(x), w1 = pack(x + 4);
+    uint8_t *dst = l8 + (size_t)(MEMCI_L8_PAD + y) * pitch8 + MEMCI_L8_PAD + x;
+    *reinterpret_cast<unsigned *>(dst) = w0;
+    *reinterpret_cast<unsigned *>(dst + plane_bytes) = __funnelshift_r(w0, w1, 8);
+    *reinterpret_cast<unsigned *>(dst + 2 * plane_bytes) = __funnelshift_r(w0, w1, 16);
+    *reinterpret_cast<unsigned *>(dst + 3 * plane_bytes) = __funnelshift_r(w0, w1, 24);
 }
+
+static int f8_pitch8(const memci_ctx *ctx) { return (ctx->Wp + 2 * MEMCI_L8_PAD + 63) & ~63; }
+static size_t f8_plane_bytes(const memci_ctx *ctx) { return ((size_t)(ctx->H + 2 * MEMCI_L8_PAD) * f8_pitch8(ctx) + 255) & ~(size_t)255; }
 
 int memci_ensure_luma8(memci_ctx *ctx, int slot)
 {
@@ -522,75 +602,161 @@ int memci_ensure_luma8(memci_ctx *ctx, int slot)
     int rc = memci_ensure_luma(ctx, slot);
     if (rc) return rc;
     if (f.luma8_ok) return MEMCI_OK;
-    const int pitch8 = ctx->Wp + 2 * MEMCI_L8_PAD;
+    const int pitch8 = f8_pitch8(ctx);
+    const size_t plane_bytes = f8_plane_bytes(ctx);
     if (!f.luma8) {
-        const size_t bytes = (size_t)(ctx->H + 2 * MEMCI_L8_PAD) * pitch8 + 16;
-        CK(ctx, cudaMalloc(&f.luma8, bytes));
-        CK(ctx, cudaMemsetAsync(f.luma8, 0, bytes, ctx->stream));
+        CK(ctx, cudaMalloc(&f.luma8, 4 * plane_bytes));
+        CK(ctx, cudaMemsetAsync(f.luma8, 0, 4 * plane_bytes, ctx->stream));
     }
-    uint8_t *org = f.luma8 + (size_t)MEMCI_L8_PAD * pitch8 + MEMCI_L8_PAD;
-    const int n = ctx->H * (ctx->Wp >> 2);
-    luma8_kernel<<<ceil_div_i(n, 256), 256, 0, ctx->stream>>>(f.luma, ctx->H, ctx->W, ctx->Wp, org, pitch8);
+    const int n = ctx->H * ((ctx->Wp >> 2) + 1);
+    luma8_kernel<<<ceil_div_i(n, 256), 256, 0, ctx->stream>>>(f.luma, ctx->H, ctx->W, ctx->Wp, f.luma8, pitch8, plane_bytes);
     CKL(ctx);
     f.luma8_ok = 1;
     return MEMCI_OK;
 }
 
-// Is the prefilter path applicable?  Block sizes 8k, list entry fields (17-bit block, 7-bit offsets), border of the
-// padded plane, one candidate column per thread, shared memory.
-static int f8_smem_bytes(int nt, int rpt, int bs, int R, int nb_tile, int *rs_out, int *plane_words_out, int *ref_rs_out, int *a_stride_out, int *win_rows_out)
+// ---- launch shape ----------------------------------------------------------------------------------------------
+struct F8Shape {
+    int nt, ctas, rpt, n_stage, nb_tile;
+    int win_rows, box_rows, box_w, rs, plane_words, ref_w, ref_rs, a_rows, smem;
+};
+
+// Shared memory of one CTA and the TMA boxes for (threads, block rows per tile, stages).  Returns false when the
+// shape is impossible (box wider than 256 bytes / taller than 256 rows, no column per thread).
+static bool f8_layout(int nt, int rpt, int n_stage, int bs, int R, int nbc, F8Shape *s)
 {
     const int Rp = (R + 3) & ~3;
     const int n_dy = 2 * R + 1;
     const int n_groups = (n_dy + F8_G - 1) / F8_G;
+    int nb_tile = nt / (2 * R + 1);
+    if (nb_tile > F8_NBMAX) nb_tile = F8_NBMAX;
+    if (nb_tile > nbc) nb_tile = nbc;
     const int win_rows = rpt * bs + 2 * R + (n_groups * F8_G - n_dy) + 1;
-    const int rs = (nb_tile * bs + 2 * Rp) / 4 + 1;
-    int plane_words = win_rows * rs;
-    plane_words += (8 - (plane_words & 31) + 32) & 31;
-    const int ref_rs = nb_tile * bs / 4;
-    const int a_stride = (n_groups * F8_G + 3) & ~3;
-    *rs_out = rs; *plane_words_out = plane_words; *ref_rs_out = ref_rs; *a_stride_out = a_stride; *win_rows_out = win_rows;
-    return (4 * plane_words + win_rows * (rs + 1) + 2 * rpt * bs * ref_rs) * 4 + nt * a_stride * 2;
+    int best_bytes = 0;
+    for (; nb_tile >= 1 && !best_bytes; --nb_tile) {
+        // bytes of a staged row a thread may touch: column offset + 12 bytes of TMA alignment slack + second word of the pair
+        const int need_w = 4 * (((nb_tile * bs + R + Rp + 4) >> 2) + 2);
+        for (int bw = (need_w + 15) & ~15; bw <= 256; bw += 16) {
+            for (int e = 0; e < 8 && win_rows + e <= 256; ++e) {
+                const int pw = (bw / 4) * (win_rows + e);          // words per plane: the four planes must start 8 banks apart
+                if ((pw & 31) != 8 && (pw & 31) != 24) continue;
+                if (!best_bytes || pw * 4 < best_bytes) {
+                    best_bytes = pw * 4;
+                    s->box_w = bw; s->box_rows = win_rows + e; s->rs = bw / 4; s->plane_words = pw; s->nb_tile = nb_tile;
+                }
+                break;
+            }
+        }
+    }
+    if (!best_bytes) return false;
+    s->nt = nt; s->rpt = rpt; s->n_stage = n_stage; s->win_rows = win_rows;
+    s->ref_w = (s->nb_tile * bs + 8 + 15) & ~15;
+    s->ref_rs = s->ref_w / 4;
+    s->a_rows = n_groups * F8_G;
+    const int ref_words = (rpt * bs * s->ref_rs + 31) & ~31;
+    s->smem = n_stage * (4 * s->plane_words + ref_words) * 4 + 2 * s->a_rows * (nt + 4);      // two A buffers (uint8): jobs j and j - 1
+    return true;
 }
 
-// CTA shape: 512 threads (two CTAs per SM, wider tiles: 15 blocks of 33 column offsets fill 97 % of the lanes at +-16)
-// when the shared memory of two such CTAs fits, else 256 threads; two block rows per tile when that still fits.
-// MEMCI_F8_NT / MEMCI_F8_RPT override (tuning).
-static void f8_shape(int bs, int R, int *nt_out, int *rpt_out)
+// Preference: 512 threads x 2 CTAs per SM, two block rows per tile, two stages; fewer stages / one CTA per SM / one block
+// row / 256 threads as shared memory dictates (wide searches: 16 x 16 +-32 runs one 512-thread CTA per SM).
+// MEMCI_F8_NT / MEMCI_F8_RPT / MEMCI_F8_STAGES / MEMCI_F8_CTAS override (tuning).
+static bool f8_shape(int bs, int R, int nbc, F8Shape *out)
 {
-    int a, b, c, d, e2;
-    int nt = 256, rpt = 1;
-    {
-        int nb_tile = 512 / (2 * R + 1);
-        if (nb_tile > F8_NBMAX) nb_tile = F8_NBMAX;
-        if (nb_tile >= 1 && f8_smem_bytes(512, 1, bs, R, nb_tile, &a, &b, &c, &d, &e2) <= 110 * 1024) nt = 512;
+    static const int cand[][4] = {      // threads, CTAs per SM, block rows per tile, stages
+        {512, 2, 2, 2}, {512, 2, 2, 1}, {512, 1, 2, 2}, {512, 1, 2, 1}, {512, 2, 1, 2}, {512, 2, 1, 1}, {256, 2, 2, 2}, {256, 2, 2, 1},
+        {256, 2, 1, 2}, {256, 2, 1, 1}, {512, 1, 1, 2}, {512, 1, 1, 1}, {256, 1, 1, 1}};
+    int f_nt = 0, f_rpt = 0, f_st = 0, f_ctas = 0;
+    if (const char *e = getenv("MEMCI_F8_NT")) f_nt = atoi(e);
+    if (const char *e = getenv("MEMCI_F8_RPT")) f_rpt = atoi(e);
+    if (const char *e = getenv("MEMCI_F8_STAGES")) f_st = atoi(e);
+    if (const char *e = getenv("MEMCI_F8_CTAS")) f_ctas = atoi(e);
+    const bool rpt2_ok = R + 2 * bs + 16 <= MEMCI_L8_PAD;
+    for (const auto &c : cand) {
+        if ((f_nt && c[0] != f_nt) || (f_ctas && c[1] != f_ctas) || (f_rpt && c[2] != f_rpt) || (f_st && c[3] != f_st)) continue;
+        if (c[2] == 2 && !rpt2_ok) continue;
+        F8Shape s;
+        if (!f8_layout(c[0], c[2], c[3], bs, R, nbc, &s)) continue;
+        const int budget = (c[1] == 2 ? 113 : 226) * 1024 - 2560;   // 228 KB per SM, 1 KB reserved per CTA, static shared memory
+        if (s.smem > budget) continue;
+        s.ctas = c[1];
+        *out = s;
+        return true;
     }
-    if (const char *e = getenv("MEMCI_F8_NT")) { const int v = atoi(e); if (v == 256 || v == 512) nt = v; }
-    {
-        int nb_tile = nt / (2 * R + 1);
-        if (nb_tile > F8_NBMAX) nb_tile = F8_NBMAX;
-        if (nb_tile >= 1 && R + 2 * bs + 16 <= MEMCI_L8_PAD && f8_smem_bytes(nt, 2, bs, R, nb_tile, &a, &b, &c, &d, &e2) <= 110 * 1024) rpt = 2;
-    }
-    if (const char *e = getenv("MEMCI_F8_RPT")) { const int v = atoi(e); if (v == 1) rpt = 1; }
-    *nt_out = nt; *rpt_out = rpt;
+    return false;
 }
 
+// Is the prefilter path applicable?  Block sizes 8 / 16 (A fits uint16), list entry fields (17-bit block, 7-bit offsets),
+// border of the padded planes, a launch shape that fits shared memory.
 int memci_fs8_eligible(memci_ctx *ctx, int bs, int R)
 {
-    if ((bs != 8 && bs != 16) || R < 1 || R > 63 || R + bs + 16 > MEMCI_L8_PAD) return 0;      // A fits uint16 up to 16 x 16 blocks
+    if ((bs != 8 && bs != 16) || R < 1 || R > 63 || R + bs + 16 > MEMCI_L8_PAD) return 0;
     const long long n_blk = (long long)ceil_div_i(ctx->H, bs) * ceil_div_i(ctx->W, bs);
     if (n_blk >= (1 << 17)) return 0;
-    int nt, rpt;
-    f8_shape(bs, R, &nt, &rpt);
-    int nb_tile = nt / (2 * R + 1);
-    if (nb_tile < 1) return 0;
-    int a, b, c, d, e;
-    if (nb_tile > F8_NBMAX) nb_tile = F8_NBMAX;
-    return f8_smem_bytes(nt, rpt, bs, R, nb_tile, &a, &b, &c, &d, &e) <= 110 * 1024;
+    F8Shape s;
+    return f8_shape(bs, R, ceil_div_i(ctx->W, bs), &s) ? 1 : 0;
 }
 
-// Enqueue prefilter + refine + output for block rows [br0, br1).  counters[8] is left non-zero when the survivor
-// list overflowed; the caller then runs the exact kernel gated on that flag.
+template <bool M1, int NT>
+static int f8_launch(memci_ctx *ctx, const CUtensorMap *tm, const F8Params &p, int grid, int smem)
+{
+    CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<M1, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    fs8_prefilter_kernel<M1, NT><<<grid, NT, smem, ctx->stream>>>(tm[0], tm[1], tm[2], tm[3], p);
+    return MEMCI_OK;
+}
+
+// The jobs of one search geometry, in queue order (cached per context; rebuilt when the geometry changes): row-major over
+// (direction, block row, tile column).  A tile column whose blocks keep so few column offsets that two block rows fit the
+// CTA side by side becomes ONE two-row job per pair of block rows; every other tile is one job per block row.
+static int f8_job_table(memci_ctx *ctx, const F8Shape &sh, int bs, int R, int br0, int br1, int ndir, const F8Tile **tiles, int *n_tiles)
+{
+    const int H = ctx->H, W = ctx->W, nbc = ceil_div_i(W, bs);
+    const int no_split = getenv("MEMCI_F8_NOSPLIT") ? 1 : 0;
+    const int key[8] = {bs, R, br0, br1, ndir, sh.nb_tile, sh.nt * 4 + sh.rpt * 2 + no_split, 1};
+    if (ctx->d_f8_tiles && memcmp(key, ctx->f8_tiles_key, sizeof(key)) == 0) {
+        *tiles = reinterpret_cast<const F8Tile *>(ctx->d_f8_tiles); *n_tiles = ctx->f8_tiles_n;
+        return MEMCI_OK;
+    }
+    const int n_cols = ceil_div_i(nbc, sh.nb_tile);
+    F8Tile *h = (F8Tile *)malloc(sizeof(F8Tile) * (size_t)ndir * (br1 - br0) * n_cols);
+    if (!h) return memci_fail(ctx, MEMCI_ERR_ARG, "out of host memory");
+    unsigned char *two = (unsigned char *)calloc(n_cols, 1);
+    for (int tc = 0; tc < n_cols; ++tc) {                          // column bounds do not depend on the block row
+        const int bx0 = tc * sh.nb_tile, nb = nbc - bx0 < sh.nb_tile ? nbc - bx0 : sh.nb_tile;
+        int items = 0;
+        for (int b = 0; b < nb; ++b) {
+            const int s_col = (bx0 + b) * bs;
+            const int tmc = (s_col + bs >= H) ? s_col + 1 : W - bs;        // full_search.py:37 (sic: compares against H)
+            const int c0 = s_col - R > 0 ? s_col - R : 0, c1 = tmc < s_col + R + 1 ? tmc : s_col + R + 1;
+            items += c1 > c0 ? c1 - c0 : 0;
+        }
+        two[tc] = sh.rpt == 2 && !no_split && items > 0 && ((items + 31) & ~31) + items <= sh.nt;
+    }
+    int n = 0;
+    for (int dir = 0; dir < ndir; ++dir)
+        for (int by = br0; by < br1; ++by)
+            for (int tc = 0; tc < n_cols; ++tc) {
+                const int bx0 = tc * sh.nb_tile, nb = nbc - bx0 < sh.nb_tile ? nbc - bx0 : sh.nb_tile;
+                if (two[tc] && ((by - br0) & 1)) continue;          // second row of a two-row job
+                F8Tile t;
+                t.dir = (short)dir; t.nv = (short)((two[tc] && by + 1 < br1) ? 2 : 1); t.by = (short)by; t.bx0 = (short)bx0; t.nb = (short)nb; t.pad = 0;
+                h[n++] = t;
+            }
+    free(two);
+    if (ctx->d_f8_tiles) { cudaFree(ctx->d_f8_tiles); ctx->d_f8_tiles = nullptr; }
+    cudaError_t e = cudaMalloc(&ctx->d_f8_tiles, sizeof(F8Tile) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_f8_tiles, h, sizeof(F8Tile) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    free(h);
+    if (e != cudaSuccess) { ctx->sticky = 1; return memci_fail(ctx, MEMCI_ERR_CUDA, "prefilter job table: %s", cudaGetErrorString(e)); }
+    memcpy(ctx->f8_tiles_key, key, sizeof(key));
+    ctx->f8_tiles_n = n;
+    *tiles = reinterpret_cast<const F8Tile *>(ctx->d_f8_tiles); *n_tiles = n;
+    return MEMCI_OK;
+}
+
+// Enqueue prefilter + refine + output for block rows [br0, br1).  counters[8] is left non-zero when the pair has to be
+// searched by the exact kernel; the caller runs that kernel gated on the flag.
 int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out, int br0, int br1, MVField *out2)
 {
     const int H = ctx->H, W = ctx->W;
@@ -598,24 +764,32 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     if ((rc = memci_ensure_luma8(ctx, slot_src))) return rc;
     if ((rc = memci_ensure_luma8(ctx, slot_tgt))) return rc;
     const int nbr = ceil_div_i(H, bs), nbc = ceil_div_i(W, bs), n_blk = nbr * nbc, ndir = out2 ? 2 : 1;
+    F8Shape sh;
+    if (!f8_shape(bs, R, nbc, &sh)) return memci_fail(ctx, MEMCI_ERR_ARG, "two-phase full search: no launch shape for block %d, range %d", bs, R);
     F8Params p;
     memset(&p, 0, sizeof(p));
     p.H = H; p.W = W; p.bs = bs; p.m = bs / 8; p.R = R; p.Rp = (R + 3) & ~3; p.nbr = nbr; p.nbc = nbc;
-    int nt, rpt;
-    f8_shape(bs, R, &nt, &rpt);
-    p.rpt = rpt;
-    p.nb_tile = nt / (2 * R + 1);
-    if (p.nb_tile > F8_NBMAX) p.nb_tile = F8_NBMAX;
-    if (p.nb_tile > nbc) p.nb_tile = nbc;
-    p.tiles_per_row = ceil_div_i(nbc, p.nb_tile);
-    p.n_tiles_dir = p.tiles_per_row * ceil_div_i(br1 - br0, rpt); p.br0 = br0; p.br1 = br1; p.ndir = ndir;
-    p.pitch8 = ctx->Wp + 2 * MEMCI_L8_PAD;
-    const int smem = f8_smem_bytes(nt, rpt, bs, R, p.nb_tile, &p.rs, &p.plane_words, &p.ref_rs, &p.a_stride, &p.win_rows);
+    p.n_stage = sh.n_stage;
+    p.c_two = 2u; p.c_8k = 8192u;
+    if ((rc = f8_job_table(ctx, sh, bs, R, br0, br1, ndir, &p.tiles, &p.n_tiles))) return rc;
+    p.box_x0 = MEMCI_L8_PAD; p.box_y0 = MEMCI_L8_PAD;
+    p.rs = sh.rs; p.plane_words = sh.plane_words; p.ref_rs = sh.ref_rs; p.ref_rows = sh.rpt * bs; p.a_rows = sh.a_rows;
+    p.tx_bytes = (unsigned)(4 * sh.plane_words * 4 + sh.ref_w * sh.rpt * bs);
     p.T = 2 * bs * bs + 1;
     const FrameSlot &fs = ctx->frames[slot_src], &ft = ctx->frames[slot_tgt];
-    const size_t org = (size_t)MEMCI_L8_PAD * p.pitch8 + MEMCI_L8_PAD;
-    p.l8_src[0] = fs.luma8 + org; p.l8_tgt[0] = ft.luma8 + org;
-    p.l8_src[1] = ft.luma8 + org; p.l8_tgt[1] = fs.luma8 + org;
+    // tensor maps: the four planes of a frame as one 3-D tensor {pitch8, H + 2 PAD, 4}; window box = all four planes,
+    // source-block box = plane 0 only
+    CUtensorMap tm[4];
+    {
+        const unsigned long long dims[3] = {(unsigned long long)f8_pitch8(ctx), (unsigned long long)(H + 2 * MEMCI_L8_PAD), 4ull};
+        const unsigned long long strides[2] = {(unsigned long long)f8_pitch8(ctx), (unsigned long long)f8_plane_bytes(ctx)};
+        const unsigned box_win[3] = {(unsigned)sh.box_w, (unsigned)sh.box_rows, 4u};
+        const unsigned box_ref[3] = {(unsigned)sh.ref_w, (unsigned)(sh.rpt * bs), 1u};
+        if ((rc = memci_tmap_encode(ctx, &tm[0], 1, 3, fs.luma8, dims, strides, box_win))) return rc;
+        if ((rc = memci_tmap_encode(ctx, &tm[1], 1, 3, ft.luma8, dims, strides, box_win))) return rc;
+        if ((rc = memci_tmap_encode(ctx, &tm[2], 1, 3, fs.luma8, dims, strides, box_ref))) return rc;
+        if ((rc = memci_tmap_encode(ctx, &tm[3], 1, 3, ft.luma8, dims, strides, box_ref))) return rc;
+    }
     // survivor list: an eighth of the candidates, at most 16 M entries (64 MB).  Textured content needs about 0.5 %, but the
     // list is cut into one segment per prefilter CTA and flat regions load a few segments heavily; a segment that fills
     // up sends its blocks to the redo pass, so the size is a performance knob, not a correctness one.
@@ -624,6 +798,7 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     if (cap > (16u << 20)) cap = 16u << 20;
     size_t have = ctx->fs8_list_cap;
     if ((rc = memci_reserve(ctx, (void **)&ctx->d_fs8_list, &have, (cap + F8_MAXSEG) * 4))) return rc;
+    if (have != ctx->fs8_list_cap) CK(ctx, cudaMemsetAsync(ctx->d_fs8_list, 0, have, ctx->stream));     // new buffer: no stale entries, ever
     ctx->fs8_list_cap = have;
     size_t have_b = ctx->fs8_best_cap;
     if ((rc = memci_reserve(ctx, (void **)&ctx->d_fs8_best, &have_b, (size_t)n_blk * 2 * 12))) return rc;       // keys + redo marks
@@ -632,33 +807,29 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     p.counters = ctx->d_counters;
     p.redo_mark = reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2);
     p.redo_list = ctx->d_redo_list; p.redo_cap = ctx->redo_cap; p.redo_limit = n_blk * ndir / 16 + 64;
-    CK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 4 * sizeof(int), ctx->stream));   // [8] overflow [9] survivors [10] float64 replays [11] redo blocks
-    if (!ctx->fs8_attr_set) {                                      // per context: the attribute belongs to the device
-        CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        CK(ctx, cudaFuncSetAttribute(fs8_prefilter_kernel<false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        ctx->fs8_attr_set = 1;
-    }
-    const int n_tiles = p.n_tiles_dir * ndir;
-    int per_sm = 1024 / nt;
-    if (const char *e = getenv("MEMCI_F8_CTAS")) per_sm = atoi(e);          // tuning: persistent CTAs per SM
-    int grid = n_tiles < per_sm * ctx->num_sms ? n_tiles : per_sm * ctx->num_sms;
+    CK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 5 * sizeof(int), ctx->stream));   // [8] overflow [9] survivors [10] float64 replays [11] redo blocks [12] tile queue
+    const int n_tiles = p.n_tiles;
+    int grid = n_tiles < sh.ctas * ctx->num_sms ? n_tiles : sh.ctas * ctx->num_sms;
     if (grid > F8_MAXSEG) grid = F8_MAXSEG;
     p.seg_counts = ctx->d_fs8_list;                                // [F8_MAXSEG] segment lengths, then the segments
     p.list = ctx->d_fs8_list + F8_MAXSEG;
     p.seg_cap = (int)((have / 4 - F8_MAXSEG) / grid);
     if (const char *e = getenv("MEMCI_F8_SEG_CAP")) { const int v = atoi(e); if (v >= 0 && v < p.seg_cap) p.seg_cap = v; }   // tests: force the overflow fallback
     const int prof = memci_prof_begin(ctx, 0);
-    if (nt == 512) {
-        if (bs == 8) fs8_prefilter_kernel<true, 512><<<grid, 512, smem, ctx->stream>>>(p);
-        else fs8_prefilter_kernel<false, 512><<<grid, 512, smem, ctx->stream>>>(p);
-    } else {
-        if (bs == 8) fs8_prefilter_kernel<true, 256><<<grid, 256, smem, ctx->stream>>>(p);
-        else fs8_prefilter_kernel<false, 256><<<grid, 256, smem, ctx->stream>>>(p);
-    }
+    if (sh.nt == 512) rc = bs == 8 ? f8_launch<true, 512>(ctx, tm, p, grid, sh.smem) : f8_launch<false, 512>(ctx, tm, p, grid, sh.smem);
+    else rc = bs == 8 ? f8_launch<true, 256>(ctx, tm, p, grid, sh.smem) : f8_launch<false, 256>(ctx, tm, p, grid, sh.smem);
+    if (rc) return rc;
     memci_prof_end(ctx, prof);
     CKL(ctx);
+    if (getenv("MEMCI_F8_DEBUG")) {
+        int hc[5]; unsigned hs[8];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(hc, ctx->d_counters + 8, sizeof(hc), cudaMemcpyDeviceToHost);
+        cudaMemcpy(hs, p.seg_counts, sizeof(hs), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "f8 debug: err=%s counters[8..12]=%d %d %d %d %d  n_tiles=%d grid=%d seg_cap=%d segs=%u %u %u %u  shape nt=%d ctas=%d rpt=%d stages=%d nb_tile=%d box=%dx%d smem=%d\n",
+                cudaGetErrorString(cudaGetLastError()), hc[0], hc[1], hc[2], hc[3], hc[4], n_tiles, grid, p.seg_cap, hs[0], hs[1], hs[2], hs[3],
+                sh.nt, sh.ctas, sh.rpt, sh.n_stage, sh.nb_tile, sh.box_w, sh.box_rows, sh.smem);
+    }
     fs8_refine_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, ctx->Wp, bs, R, nbc, n_blk,
                                                                  p.list, p.seg_cap, p.seg_counts, grid, ctx->d_counters, ctx->d_fs8_best,
                                                                  reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2), ctx->d_redo_list, ctx->redo_cap);

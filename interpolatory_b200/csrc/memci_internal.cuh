@@ -26,7 +26,7 @@ struct FrameSlot {
     uint8_t *rgb;                      // [H][W][3]
     int32_t *luma;                     // [H][Wp] luma*1000 = 299R+587G+114B (exact integer)
     int luma_ok;
-    uint8_t *luma8;                    // round(luma) as uint8, [H + 2 PAD][Wp + 2 PAD], zero border (fs8.cu); allocated on first use
+    uint8_t *luma8;                    // round(luma) as uint8: four planes [H + 2 PAD][pitch8], plane q shifted left by q bytes, zero border (fs8.cu); allocated on first use
     int luma8_ok;
     // HBMA pyramid cache (levels 1..pyr_levels), invalidated on upload
     int pyr_levels;
@@ -63,6 +63,7 @@ struct memci_ctx {
     // content feedback for the two-phase path: counters [8..11] of a recent search, copied back asynchronously
     int *h_fs8_feedback; cudaEvent_t ev_fs8_feedback; int fs8_feedback_pending; long long fs8_feedback_cand;
     int fs8_attr_set;                  // dynamic shared-memory attribute of the prefilter kernels set on this context's device
+    void *d_f8_tiles; int f8_tiles_n; int f8_tiles_key[8];   // job table of the prefilter (fs8.cu), cached per search geometry
     int fs8_backoff;                   // > 0: that many searches skip the prefilter (the last feedback said it does not pay on this content)
     // MCI scratch
     short2 *d_disp[2]; size_t disp_cap[2];
@@ -105,6 +106,8 @@ int memci_ensure_luma(memci_ctx *ctx, int slot);
 int memci_ensure_pyramid(memci_ctx *ctx, int slot, int levels);
 int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out, int br0, int br1,
                  MVField *out2 = nullptr);   // block rows [br0, br1); br1 < 0 = all; out2: reverse direction in the same launch
+int memci_tmap_encode(memci_ctx *ctx, CUtensorMap *tm, int dtype_u8, int rank, const void *base,
+                      const unsigned long long *dims, const unsigned long long *strides, const unsigned *box);   // fs.cu
 int memci_fs8_eligible(memci_ctx *ctx, int bs, int R);
 int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out, int br0, int br1, MVField *out2);
 int memci_tss_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int steps, MVField *out);
@@ -192,6 +195,65 @@ __device__ __forceinline__ unsigned long long shfl_min_u64(unsigned long long v)
         v = w < v ? w : v;
     }
     return v;
+}
+
+
+// ---- mbarrier / TMA (cp.async.bulk.tensor) primitives shared by fs.cu and fs8.cu ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// Same, for waits that may take a while: after a failed probe the warp sleeps instead of spinning through the issue slots
+// the working warps need.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBARS_DONE;\n"
+        "MBARS_WAIT:\n"
+        "nanosleep.u32 64;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBARS_DONE;\n"
+        "bra MBARS_WAIT;\n"
+        "MBARS_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int x, int y, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, int x, int y, int z, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
 #endif  // __CUDACC__
