@@ -32,13 +32,16 @@
 #define F8_G 11
 #define F8_NBMAX 32
 #define F8_MAXSEG 1024          // CTAs of the prefilter grid = segments of the survivor list
+#define F8_EMIT_WORDS 9          // votes (eight row offsets each) a warp keeps in registers while it emits survivors
 
 struct F8Params {
     int H, W, bs, m, R, Rp, nbr, nbc;
     int n_tiles;
     const struct F8Tile *tiles;  // the jobs, in queue order (host table, cached per search geometry)
     int n_stage;                 // shared-memory stages of (window planes + source blocks): 2 = the next tile lands while this one is searched
-    unsigned c_two, c_8k;        // the constants 2 and 8192 (F8Conv), opaque to the compiler
+    unsigned c_two, c_8k, c_magic; float c_fmagic;   // the constants of F8Conv, opaque to the compiler
+    int ablate;                  // timing experiments only (MEMCI_F8_ABLATE=1): no survivor emission (nothing survives: wrong results)
+    int flush_at;                // the hand-over of the previous job happens after this many + 1 row-offset groups of the current one
     int box_x0, box_y0;          // padded-plane coordinates of frame pixel (0, 0)
     int rs;                      // words per staged window row (= TMA box width / 4)
     int plane_words;             // words per staged plane, = 8 or 24 (mod 32): the four planes of a row land in different banks
@@ -92,17 +95,18 @@ __device__ __forceinline__ unsigned f8_sad4(unsigned a, unsigned b, unsigned acc
 // superset of the exact test A <= A_min + T (monotone => nothing is lost; a few extra survivors within one step, 1/16
 // of the value, above the threshold).  Half the shared memory of uint16 -- which is what pays for the second stage of
 // the window planes -- with the full 16-bit range, and nothing on the integer-ALU pipe the SADs are bound by: IMAD
-// (times 2), I2F (XU pipe), IMAD.HI (>> 19), with multipliers that come from the parameter block (a literal power of
-// two would be turned back into ALU shifts).  Layout A[row offset][thread], A_PITCH = threads + 4 bytes per row: the 32
-// stores of a warp fall into 8 consecutive words, and the 32 row offsets a warp later reads of ONE column fall into 32
-// different banks.  The column minimum stays exact.  MASK: the group sticks out of the valid row range (last group only).
-struct F8Conv { unsigned two, c8k; };            // the constants 2 and 8192, opaque to the compiler
+// (2 v + 2^23-as-float bits), FADD (- 2^23: the classic int-to-float without I2F), IMAD.HI (>> 19), all three on the FMA
+// pipe, with constants that come from the parameter block (literals would be turned back into ALU shifts / logic ops).
+// Layout A[row offset][thread], A_PITCH = threads + 4 bytes per row: the 32 stores of a warp fall into 8 consecutive
+// words, and eight consecutive row offsets of one column fall into eight different banks.  The column minimum stays
+// exact.  MASK: the group sticks out of the valid row range (last group only).
+struct F8Conv { unsigned two, c8k, magic; float fmagic; };       // 2, 8192, 0x4B000000 and 8388608.0f, opaque to the compiler
 __device__ __forceinline__ unsigned f8_code(unsigned v, const F8Conv cv)   // v in [1, 65535]
 {
     unsigned t, x;
     float f;
-    asm("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(v), "r"(cv.two));
-    asm("cvt.rn.f32.u32 %0, %1;" : "=f"(f) : "r"(t));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(v), "r"(cv.two), "r"(cv.magic));
+    asm("sub.f32 %0, %1, %2;" : "=f"(f) : "f"(__uint_as_float(t)), "f"(cv.fmagic));
     asm("mul.hi.u32 %0, %1, %2;" : "=r"(x) : "r"(__float_as_uint(f)), "r"(cv.c8k));
     return x;                                                      // the code is the low byte
 }
@@ -164,7 +168,7 @@ fs8_prefilter_kernel(const __grid_constant__ CUtensorMap tm_win_a, const __grid_
     __shared__ unsigned seg_count, seg_valid;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int bs = p.bs, R = p.R;
-    const F8Conv cv = {p.c_two, p.c_8k};
+    const F8Conv cv = {p.c_two, p.c_8k, p.c_magic, p.c_fmagic};
     const int stage_words = 4 * p.plane_words + ((p.ref_rows * p.ref_rs + 31) & ~31);   // planes [4][plane_words], then source rows [ref_rows][ref_rs]
     unsigned char *A_base = reinterpret_cast<unsigned char *>(f8_smem + p.n_stage * stage_words);   // [2][a_rows][A_PITCH]
     const int a_bytes = p.a_rows * A_PITCH;
@@ -221,12 +225,13 @@ fs8_prefilter_kernel(const __grid_constant__ CUtensorMap tm_win_a, const __grid_
         }
     };
 
-    // ---- survivors of one finished job.  A warp takes its flagged columns (column minimum within T of the block minimum:
-    //      typically 2-3 of 32) four at a time: lane = (column slot, row offset mod 8), so one vote covers eight row offsets
-    //      of all four columns; pass 1 counts the hits per column, the first lane of each slot reserves room, pass 2
-    //      writes.  Each CTA appends to its own segment of the list through a shared-memory cursor that only ever moves
-    //      forward: a reservation that does not fit marks where the valid prefix ends (later ones cannot fit either) and
-    //      its block goes to the redo pass.  fs8_refine_kernel gets the length of the valid prefix ----
+    // ---- survivors of one finished job.  A warp takes its flagged columns (column minimum within T of the block minimum)
+    //      four at a time: lane = (column slot, row offset mod 8), so one vote covers eight row offsets of all four
+    //      columns; the votes stay in registers, the first lane of each slot counts its column's hits and reserves room,
+    //      then every lane writes the entry of each of its own hits.  Each CTA appends to its own segment of the list
+    //      through a shared-memory cursor that only ever moves forward: a reservation that does not fit marks where the
+    //      valid prefix ends (later ones cannot fit either) and its block goes to the redo pass.  fs8_refine_kernel gets
+    //      the length of the valid prefix ----
     auto emit = [&](const unsigned char *Abuf, unsigned bmin_word, unsigned head_own, unsigned cmin, bool active, int n_dy) {
         const unsigned thr = active ? (bmin_word & 0xffffu) + (unsigned)p.T : 1u;       // A_min + 1 + T: the accumulators, and so cmin, carry the same + 1
         unsigned flagged = __ballot_sync(0xffffffffu, active && cmin <= thr);
@@ -248,8 +253,20 @@ fs8_prefilter_kernel(const __grid_constant__ CUtensorMap tm_win_a, const __grid_
             const unsigned thr_c = __shfl_sync(0xffffffffu, thr_code, on ? src : 0);
             const unsigned head = __shfl_sync(0xffffffffu, head_own, on ? src : 0);
             const unsigned char *cs = cw + (on ? src : 0) + sub * A_PITCH;
+            // one vote per eight row offsets; up to F8_EMIT_WORDS votes stay in registers (n_dy <= 72: every range up to +-35),
+            // longer columns are voted on twice
+            unsigned bal[F8_EMIT_WORDS];
             int hits = 0;
-            for (int m = 0; m < n_it; ++m) {
+#pragma unroll
+            for (int m = 0; m < F8_EMIT_WORDS; ++m) {
+                bal[m] = 0u;
+                if (m < n_it) {
+                    const bool h = on && m * 8 + sub < n_dy && cs[m * 8 * A_PITCH] <= thr_c;
+                    bal[m] = __ballot_sync(0xffffffffu, h);
+                    hits += __popc(bal[m] & my_bits);
+                }
+            }
+            for (int m = F8_EMIT_WORDS; m < n_it; ++m) {
                 const bool h = on && m * 8 + sub < n_dy && cs[m * 8 * A_PITCH] <= thr_c;
                 hits += __popc(__ballot_sync(0xffffffffu, h) & my_bits);
             }
@@ -270,13 +287,22 @@ fs8_prefilter_kernel(const __grid_constant__ CUtensorMap tm_win_a, const __grid_
                 }
             }
             pos = __shfl_sync(0xffffffffu, pos, slot * 8);
-            if (__any_sync(0xffffffffu, pos >= 0)) {
-                for (int m = 0; m < n_it; ++m) {
+            if (pos >= 0) {                                        // order inside a column is irrelevant to the result
+#pragma unroll
+                for (int m = 0; m < F8_EMIT_WORDS; ++m) {
+                    if (m < n_it) {
+                        if ((bal[m] >> lane) & 1u) seg[pos + __popc(bal[m] & below)] = head | ((unsigned)(m * 8 + sub) << 7);
+                        pos += __popc(bal[m] & my_bits);
+                    }
+                }
+            }
+            if (n_it > F8_EMIT_WORDS && __any_sync(0xffffffffu, pos >= 0)) {
+                for (int m = F8_EMIT_WORDS; m < n_it; ++m) {
                     const int i = m * 8 + sub;
                     const bool h = pos >= 0 && i < n_dy && cs[m * 8 * A_PITCH] <= thr_c;
-                    const unsigned bal = __ballot_sync(0xffffffffu, h);
-                    if (h) seg[pos + __popc(bal & below)] = head | ((unsigned)i << 7);   // order inside a column is irrelevant to the result
-                    pos += __popc(bal & my_bits);
+                    const unsigned b2 = __ballot_sync(0xffffffffu, h);
+                    if (h) seg[pos + __popc(b2 & below)] = head | ((unsigned)i << 7);
+                    pos += __popc(b2 & my_bits);
                 }
             }
         }
@@ -291,14 +317,14 @@ fs8_prefilter_kernel(const __grid_constant__ CUtensorMap tm_win_a, const __grid_
     int pv_ndy = 0, pv_bslot = 0;
     int j = 0;                                                     // jobs searched so far
 
-    auto flush_prev = [&](bool refill) {                            // hand-over of job j - 1 (see above)
+    auto flush_prev = [&](bool refill, bool wait) {                 // hand-over of job j - 1 (see above)
         const int q = j - 1;
-        mbar_wait_sleep(&bar_min[q & 1], (unsigned)((q >> 1) & 1));
+        if (wait) mbar_wait_sleep(&bar_min[q & 1], (unsigned)((q >> 1) & 1));
         if (refill) {                                              // every warp is done with that job's stage
             if (warp == 0) issue_next(n_issued);
             ++n_issued;
         }
-        emit(A_base + (q & 1) * a_bytes, (&bmin_s[0][0][0])[pv_bslot], pv_head, pv_cmin, pv_active, pv_ndy);
+        if (!(p.ablate & 1)) emit(A_base + (q & 1) * a_bytes, (&bmin_s[0][0][0])[pv_bslot], pv_head, pv_cmin, pv_active, pv_ndy);
         pv_valid = false;
     };
 
@@ -371,11 +397,16 @@ fs8_prefilter_kernel(const __grid_constant__ CUtensorMap tm_win_a, const __grid_
 #pragma unroll 1
             for (int gq = 0; gq < n_full; ++gq) {
                 group(gq, std::false_type{});
-                if (gq == 0 && pv_valid) flush_prev(true);
+                // hand-over of the previous job as soon as its block minima are complete -- probed, not waited for: a warp that
+                // runs ahead of its CTA keeps searching, so the warps of a CTA do not all emit at the same moment
+                if (pv_valid && gq >= p.flush_at) {
+                    const int q = j - 1;
+                    if (__shfl_sync(0xffffffffu, (int)mbar_test(&bar_min[q & 1], (unsigned)((q >> 1) & 1)), 0)) flush_prev(true, false);
+                }
             }
             if (n_full * F8_G < n_dy) group(n_full, std::true_type{});
         }
-        if (pv_valid) flush_prev(true);                             // warps without a full group (or without work) in this job
+        if (pv_valid) flush_prev(true, true);                       // not complete at any probe (or no full group in this job): wait
         // block minima: segmented warp reduction, one shared-memory atomic per (warp, block).  The generation tag in the
         // upper half makes every later job's entries smaller than any earlier job's, so the slots are never reset (a slot
         // is re-used four jobs later; its last reader finished before the hand-over two jobs earlier).
@@ -397,9 +428,9 @@ fs8_prefilter_kernel(const __grid_constant__ CUtensorMap tm_win_a, const __grid_
         // this job becomes the pending one
         pv_valid = true; pv_active = active; pv_cmin = cmin; pv_ndy = n_dy; pv_bslot = bslot + b;
         pv_head = (dir ? 0x80000000u : 0u) | ((unsigned)((by + v) * p.nbc + bx0 + b) << 14) | (unsigned)dxi;
-        if (p.n_stage == 1) { ++j; flush_prev(true); --j; }        // one stage: the next job's loads cannot start before this hand-over
+        if (p.n_stage == 1) { ++j; flush_prev(true, true); --j; }        // one stage: the next job's loads cannot start before this hand-over
     }
-    if (pv_valid) flush_prev(false);
+    if (pv_valid) flush_prev(false, true);
     __syncthreads();
     if (tid == 0) {
         const unsigned n = seg_valid != 0xffffffffu ? seg_valid : seg_count;     // the prefix every entry of which was written
@@ -654,7 +685,7 @@ static bool f8_layout(int nt, int rpt, int n_stage, int bs, int R, int nbc, F8Sh
     s->ref_rs = s->ref_w / 4;
     s->a_rows = n_groups * F8_G;
     const int ref_words = (rpt * bs * s->ref_rs + 31) & ~31;
-    s->smem = n_stage * (4 * s->plane_words + ref_words) * 4 + 2 * s->a_rows * (nt + 4);      // two A buffers (uint8): jobs j and j - 1
+    s->smem = n_stage * (4 * s->plane_words + ref_words) * 4 + 2 * s->a_rows * (nt + 4);      // two A buffers (uint8 codes): jobs j and j - 1
     return true;
 }
 
@@ -770,7 +801,10 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     memset(&p, 0, sizeof(p));
     p.H = H; p.W = W; p.bs = bs; p.m = bs / 8; p.R = R; p.Rp = (R + 3) & ~3; p.nbr = nbr; p.nbc = nbc;
     p.n_stage = sh.n_stage;
-    p.c_two = 2u; p.c_8k = 8192u;
+    p.c_two = 2u; p.c_8k = 8192u; p.c_magic = 0x4B000000u; p.c_fmagic = 8388608.0f;
+    p.flush_at = 0;
+    if (const char *e = getenv("MEMCI_F8_ABLATE")) p.ablate = atoi(e);
+    if (const char *e = getenv("MEMCI_F8_FLUSH_AT")) p.flush_at = atoi(e);
     if ((rc = f8_job_table(ctx, sh, bs, R, br0, br1, ndir, &p.tiles, &p.n_tiles))) return rc;
     p.box_x0 = MEMCI_L8_PAD; p.box_y0 = MEMCI_L8_PAD;
     p.rs = sh.rs; p.plane_words = sh.plane_words; p.ref_rs = sh.ref_rs; p.ref_rows = sh.rpt * bs; p.a_rows = sh.a_rows;

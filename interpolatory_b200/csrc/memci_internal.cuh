@@ -237,6 +237,18 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, unsigned parity)
         "MBARS_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Non-blocking probe: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int x, int y, uint64_t *bar)
 {
     asm volatile(

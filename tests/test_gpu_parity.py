@@ -925,6 +925,34 @@ def test_fs_prefilter_path_equals_exact_kernel_and_oracle(gpu, oracle, monkeypat
     ctx.close()
 
 
+def test_fs_prefilter_segment_partial_fill(gpu, oracle, monkeypatch):
+    """Segments of the survivor list that fill up PART of the way through a search (round-1 advisor finding: the old
+    cursor rolled reservations back, which could drop entries and hand unwritten ones to the refine pass).  The
+    capacity is set just below, at a third of, and far below what a CTA collects; every warp of the CTA emits
+    concurrently.  Whatever does not fit must reach the redo pass: fields equal to the oracle's, every time."""
+    from interpolatory_b200.device import DeviceContext
+    H, W, bs, R = 270, 483, 8, 16
+    fr = make_sequence(H, W, 2, seed=5)
+    want = [oracle.fs_blocks(bs, R, fr[0], fr[1]), oracle.fs_blocks(bs, R, fr[1], fr[0])]
+    ctx = DeviceContext(H, W)
+    ctx.upload_frame(0, fr[0]); ctx.upload_frame(1, fr[1])
+    monkeypatch.setenv("MEMCI_FS_PREFILTER", "1")
+    ctx.me_fs_pair(0, 1, bs, R, 0, 1)
+    n_surv, overflow = ctx.fs_prefilter_stats()
+    assert n_surv > 0 and not overflow
+    n_ctas = min(2 * 148, 2 * -(-(-(-H // bs)) // 1) * -(-(-(-W // bs)) // 15))        # jobs <= CTAs at this size: about one job per CTA
+    per_cta = max(n_surv // max(n_ctas, 1), 8)
+    for cap in (per_cta - 1, per_cta // 3, 7, 1):
+        monkeypatch.setenv("MEMCI_F8_SEG_CAP", str(cap))
+        for _ in range(3):                                  # the interleaving of the emitting warps differs from run to run
+            ctx.me_fs_pair(0, 1, bs, R, 0, 1)
+            for slot, ref in ((0, want[0]), (1, want[1])):
+                _, vec, _, sad = ctx.download_mv_blocks(slot)
+                assert np.array_equal(vec, ref[:, :, :2]) and np.array_equal(sad, ref[:, :, 2]), (cap, slot)
+    monkeypatch.delenv("MEMCI_F8_SEG_CAP")
+    ctx.close()
+
+
 def test_fs_prefilter_flat_and_tie_frames(gpu, oracle):
     """Content where the prefilter cannot prune: flat frames (every candidate survives, the list overflows), two grey
     levels (every SAD an exact multiple of 1000: all survivors are flagged and go to the float64 redo pass)."""
