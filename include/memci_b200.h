@@ -179,6 +179,10 @@ MEMCI_API int memci_mci_bidir2(memci_ctx *ctx, int slot_src, int slot_tgt, int m
 /* After memci_mci_bidir2: largest |int(dist * mv)| and the number of blocks whose shifted slices leave
  * the padded arrays (the reference's numpy slices would clip and its in-place adds fail; we zero-fill). */
 MEMCI_API int memci_bidir2_stats(memci_ctx *ctx, int *max_shift, int *n_out_of_range);
+/* Blocks shifted outside the padded frame summed over EVERY memci_mci_bidir2 call since the last reset (synchronises
+ * the stream): the throughput path (pipeline.PairPipeline) enqueues many frames before it looks, and must still raise
+ * where the reference's numpy slicing fails (MCI/Bidirectional_2.py:98-106 with vectors beyond pad_size). */
+MEMCI_API int memci_bidir2_out_of_range_total(memci_ctx *ctx, int *n_out_of_range, int reset);
 
 /* ---- frame quality (Middlebury harness) --------------------------------------------------- */
 /* Replaces the two skimage calls of the reference's benchmark harness (src/Benchmark.py:46-47 in benchmark(),
@@ -262,6 +266,22 @@ MEMCI_API int memci_last_kernel_ms(memci_ctx *ctx, float *fs_ms, float *mci_ms);
 MEMCI_API int memci_profile_start(memci_ctx *ctx, int capacity);
 MEMCI_API int memci_profile_collect(memci_ctx *ctx, double *fs_ms_sum, int *fs_launches,
                                     double *mci_ms_sum, int *mci_launches);
+/* The same recording, broken down by kernel family.  Each of the three arrays has MEMCI_PROF_KINDS entries
+ * (any may be NULL): summed device time (ms), launches, and the ALGORITHMIC work of those launches as the
+ * library counts it -- SAD pixel-ops for the search kernels (the reference's own candidate bounds),
+ * bytes for the HBM-side kernels (frames read + written; 9 B/px for an interpolated frame).  These are the
+ * numerators of bench.py's per-workload roofline lines; no reference counterpart (the reference only has
+ * wall-clock prints, src/Interpolators/base.py:84,108). */
+#define MEMCI_PROF_FS        0   /* dominant full-search kernel: fs8_prefilter_kernel, or fs_tiled_kernel when the prefilter is off */
+#define MEMCI_PROF_MCI       1   /* mci_splat_kernel (uni / bidir warp + blend) */
+#define MEMCI_PROF_HBMA      2   /* hbma_fs_kernel + hbma_densify*_kernel (coarse search and every densification) */
+#define MEMCI_PROF_HBM_SMALL 3   /* pyr_down_kernel + luma_kernel of the pyramid levels + smooth_kernel */
+#define MEMCI_PROF_REFINE    4   /* fs8_refine_kernel + fs8_output_kernel + fs_redo_kernel */
+#define MEMCI_PROF_HOLEFILL  5   /* mci_holefill_kernel */
+#define MEMCI_PROF_PREP      6   /* luma_kernel / luma8_kernel of a full-size frame */
+#define MEMCI_PROF_BIDIR2    7   /* b2_blocks_kernel + b2_frame_kernel */
+#define MEMCI_PROF_KINDS     8
+MEMCI_API int memci_profile_collect_kinds(memci_ctx *ctx, double *ms_sum, int *launches, double *work);
 
 /* Issue-rate microbenchmark for the SAD kernel's roofline denominator:
  * mode 0 = integer |a-b|+c (VABSDIFF), 1 = the fp32 two-FADD form, 2/3 = both pipes mixed.

@@ -12,7 +12,7 @@ from ..ME.full_search import get_motion_vectors as fs
 from ..ME.hbma import get_motion_vectors as hbma
 from ..ME.tss import get_motion_vectors as tss
 from ..smoothing import mean_filter, median_filter, weighted_mean_filter, filter_mode_of
-from ..util import hbma_auto_steps
+from ..util import hbma_auto_steps, get_first_frame_idx_and_ratio
 
 # device slot plan of one interpolator instance
 _FRAME_SLOTS = (0, 1, 2)      # resident source frames (LRU)
@@ -65,6 +65,14 @@ class MEMCIBaseInterpolator(BaseInterpolator):
                             "min_block_size": self.min_block_size, "cost_str": "sad",
                             "upscale": self.upscale_MV}
         self.device_index = int(args.get('device', 0))
+        # the throughput path behind interpolate_video(): the same settings strings, optionally several GPUs
+        # (devices='0,1,...': pairs are partitioned by index, multigpu.MultiGpuPipeline) and a window of source frames
+        # per batch (stream_window, default max_cache_size)
+        self._settings = {k: args[k] for k in ('me_mode', 'block_size', 'target_region', 'mci_mode', 'filter_mode', 'filter_size') if k in args}
+        self._devices = [int(d) for d in str(args['devices']).split(',')] if 'devices' in args else [self.device_index]
+        self._stream_window = int(args['stream_window']) if 'stream_window' in args else None
+        self._pipe = None
+        self._pin = None
         self._dev = None
         self._resident = {}
         self._resident_stream = None
@@ -125,6 +133,81 @@ class MEMCIBaseInterpolator(BaseInterpolator):
         if self._dev is not None:
             self._dev.close()
             self._dev = None
+        if self._pipe is not None:
+            self._pipe.close()
+            self._pipe = None
+        if self._pin is not None:
+            for b in self._pin:
+                b.close()
+            self._pin = None
+
+    # ---- interpolate_video(): the drop-in call is the fast path ---------------------------------------------
+    def _output_frames(self, n):
+        """The frames get_interpolated_frame(0 .. n-1) would return, in order and byte for byte, produced in windows of
+        source frames: a window is copied into page-locked memory as the stream delivers it, its frame pairs go through
+        the staged multi-stream pipeline (pipeline.PairPipeline, or multigpu.MultiGpuPipeline when several devices were
+        given: each source frame crosses PCIe once, uploads / kernels / downloads overlap), pass-through frames are
+        copied on the host.  Host and device memory are bounded by the window (max_cache_size source frames, as in the
+        reference's VideoStream; `stream_window` overrides), not by the clip.  Output frames the reference would build
+        from a frame past the end of the stream (its reader wraps around, base.py:52-53) are left to the per-frame call."""
+        import numpy as np
+        from ..device import PinnedBuffer
+        from ..pipeline import PairPipeline
+        from ..multigpu import MultiGpuPipeline
+        vs = self.video_stream
+        n_src = int(vs.nframes)
+        plan = []                                        # (source frame index, dist) exactly as get_interpolated_frame derives them
+        for i in range(n):
+            first, inv = get_first_frame_idx_and_ratio(i, self.rate_ratio)
+            dist = 1. - inv
+            plan.append((first, 0.0 if math.isclose(dist, 0.) else float(dist)))
+        win = max(2, self._stream_window if self._stream_window is not None else int(self.max_cache_size))
+        i = 0
+        while i < n:
+            w0 = plan[i][0]
+            if w0 + 1 >= n_src and plan[i][1] != 0.0:      # needs a frame past the end: whatever the stream does there
+                yield self.get_interpolated_frame(i)
+                i += 1
+                continue
+            w1 = min(w0 + win - 1, n_src - 1)             # source frames w0 .. w1 form this window
+            j = i                                        # outputs i .. j-1 live entirely inside it
+            while j < n and (plan[j][0] + 1 <= w1 if plan[j][1] != 0.0 else plan[j][0] <= w1) and plan[j][0] >= w0:
+                j += 1
+            if j == i:                                   # cannot happen for monotone plans; stay safe
+                yield self.get_interpolated_frame(i)
+                i += 1
+                continue
+            f0 = np.asarray(vs.get_frame(w0))
+            H, W = int(f0.shape[0]), int(f0.shape[1])
+            if self._pipe is None or (self._pipe.H, self._pipe.W) != (H, W):
+                self.close()
+                cls = MultiGpuPipeline if len(self._devices) > 1 else PairPipeline
+                kw = dict(devices=self._devices) if len(self._devices) > 1 else dict(device=self._devices[0])
+                self._pipe = cls(H, W, n_contexts=3, **kw, **self._settings)
+            n_out_max = (win - 1) * (int(math.ceil(self.rate_ratio)) + 1) + 2
+            if self._pin is None or self._pin[0].shape[0] < win or self._pin[1].shape[0] < n_out_max:
+                if self._pin is not None:
+                    for b in self._pin:
+                        b.close()
+                self._pin = (PinnedBuffer((win, H, W, 3)), PinnedBuffer((n_out_max, H, W, 3)))
+            src, out = self._pin[0].array, self._pin[1].array
+            src[0] = f0
+            for k in range(w0 + 1, w1 + 1):
+                src[k - w0] = vs.get_frame(k)
+            per_pair = {}
+            for o in range(i, j):
+                k, d = plan[o]
+                if d != 0.0:
+                    per_pair.setdefault(k - w0, []).append((o - i, d))
+            if isinstance(self._pipe, MultiGpuPipeline):
+                self._pipe._dispatch(src, per_pair, out)
+            else:
+                self._pipe._run_pairs(src, per_pair, out)
+            self._pipe.sync()
+            for o in range(i, j):
+                k, d = plan[o]
+                yield (src[k - w0] if d == 0.0 else out[o - i]).copy()
+            i = j
 
     def _mv_dense(self, slot):
         return self._dev.download_mv_dense(slot)

@@ -57,6 +57,7 @@ _PROTOS = {
     "memci_mci_bidir": ([_P, _I, _I, _I, _I, C.c_float, _I], _I),
     "memci_mci_bidir2": ([_P, _I, _I, _I, _I, C.c_float, C.c_float, _I, _I, _P, _I], _I),
     "memci_bidir2_stats": ([_P, C.POINTER(_I), C.POINTER(_I)], _I),
+    "memci_bidir2_out_of_range_total": ([_P, C.POINTER(_I), _I], _I),
     "memci_quality": ([_P, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)], _I),
     "memci_me_fs_rows": ([_P, _I, _I, _I, _I, _I, _I, _I], _I),
     "memci_mci_rows": ([_P, _I, _I, _I, _I, C.c_float, _I, _I, _I, _I], _I),
@@ -75,6 +76,7 @@ _PROTOS = {
     "memci_last_kernel_ms": ([_P, C.POINTER(C.c_float), C.POINTER(C.c_float)], _I),
     "memci_profile_start": ([_P, _I], _I),
     "memci_profile_collect": ([_P, C.POINTER(C.c_double), C.POINTER(_I), C.POINTER(C.c_double), C.POINTER(_I)], _I),
+    "memci_profile_collect_kinds": ([_P, C.POINTER(C.c_double), C.POINTER(_I), C.POINTER(C.c_double)], _I),
     "memci_microbench": ([_P, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_double)], _I),
 }
 EXPORTS = tuple(sorted(_PROTOS))

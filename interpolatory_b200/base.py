@@ -4,7 +4,8 @@ the output-frame loop, and the two-frame benchmark entry point."""
 import math
 import time
 
-from .VideoStream import ArrayVideoStream, BenchmarkVideoStream
+from .VideoStream import ArrayVideoStream, BenchmarkVideoStream, ReaderVideoStream
+from . import util
 
 
 class BaseInterpolator(object):
@@ -35,10 +36,10 @@ class BaseInterpolator(object):
         except ImportError as e:
             raise Exception('reading video files needs imageio + imageio-ffmpeg; '
                             'use set_video_stream() with decoded frames instead') from e
+        # loop=True: reading one frame past the end wraps around, as in the reference (base.py:52-53).  Frames are decoded
+        # on demand behind a window of max_cache_size frames -- never the whole clip in host memory.
         vid = imageio.get_reader(self.video_in_path, 'ffmpeg', loop=True)
-        meta = vid.get_meta_data()
-        frames = [vid.get_data(i) for i in range(meta['nframes'])]
-        self.set_video_stream(ArrayVideoStream(frames, meta['fps']))
+        self.set_video_stream(ReaderVideoStream(vid, self.max_cache_size))
 
     def set_video_stream(self, stream):
         self.video_stream = stream
@@ -56,19 +57,39 @@ class BaseInterpolator(object):
                                                    macro_block_size=0, quality=6)
 
     def interpolate_video(self, sink=None):
-        """Produce every output frame in order (base.py:78-115).  Frames go to the video writer,
-        or to `sink(frame)` when given (e.g. a list's append)."""
+        """Produce every output frame in order (base.py:78-115), with the reference's progress reporting (:91-101,
+        :110-114: a PROGRESS line once per output second, to the progress file the GUI polls and, when the debug flag is
+        set, to stdout).  Frames go to the video writer, or to `sink(frame)` when given (e.g. a list's append)."""
         if sink is None:
             if self.video_in_path is None or self.video_out_path is None:
                 raise Exception('Cannot interpolate video, no input video path or output video path')
             sink = self.video_out_writer.append_data
-        start = time.time()
-        n = min(self.max_frames_possible, self.max_out_frames)
-        for i in range(int(n)):
-            sink(self.get_interpolated_frame(i))
+        start = int(round(time.time()))
+        target_nframes = int(min(self.max_frames_possible, self.max_out_frames))
+        for i, frame in enumerate(self._output_frames(target_nframes)):
+            if (i % self.target_fps) == 0:
+                pct = str(math.floor(100 * (i + 1) / target_nframes)).rjust(3, ' ')
+                elapsed_seconds = int(int(round(time.time())) - start)
+                progStr = (f'PROGRESS::{pct}%::Frame {i}/{target_nframes} | Time elapsed: {util.sToMMSS(elapsed_seconds)} | '
+                           f'Estimated Time Left: {util.getETA(elapsed_seconds, i, target_nframes)}')
+                util.signal_progress(progStr)
+                if util.debug_flags['debug_progress']:
+                    print(progStr)
+            sink(frame)
         if self.video_out_writer is not None:
             self.video_out_writer.close()
-        return time.time() - start
+        end = int(round(time.time()))
+        progStr = f'PROGRESS::100%::Complete | Time taken: {util.sToMMSS(end - start)}'
+        util.signal_progress(progStr)
+        if util.debug_flags['debug_progress']:
+            print(progStr)
+        return end - start
+
+    def _output_frames(self, n):
+        """Output frames 0 .. n-1 in order.  The base class asks for them one by one; the MEMCI interpolators override this
+        with the staged, batched device path (same frames, byte for byte)."""
+        for i in range(n):
+            yield self.get_interpolated_frame(i)
 
     def get_interpolated_frame(self, idx):
         raise NotImplementedError('To be implemented by derived classes')

@@ -51,11 +51,12 @@ int memci_mv_reserve(memci_ctx *ctx, MVField *f, int mv_cell, int mv_rows, int m
         if ((s) < 0 || (s) >= MEMCI_NUM_MV_SLOTS) return memci_fail(ctx, MEMCI_ERR_ARG, "mv slot %d out of range", (s)); \
         if ((need_valid) && !(ctx)->mvs[s].valid) return memci_fail(ctx, MEMCI_ERR_STATE, "mv slot %d is empty", (s)); } while (0)
 
-int memci_prof_begin(memci_ctx *ctx, int kind)
+int memci_prof_begin(memci_ctx *ctx, int kind, double work)
 {
     if (!ctx->pool || ctx->pool_n >= ctx->pool_cap) return -1;
     int i = ctx->pool_n++;
     ctx->pool_kind[i] = (unsigned char)kind;
+    ctx->pool_work[i] = work;
     cudaEventRecord(ctx->pool[2 * i], ctx->stream);
     return i;
 }
@@ -162,7 +163,7 @@ int memci_ctx_destroy(memci_ctx *ctx)
     if (ctx->d_hole_list) cudaFree(ctx->d_hole_list);
     if (ctx->d_dense) cudaFree(ctx->d_dense);
     for (int i = 0; i < 2 * ctx->pool_cap; ++i) cudaEventDestroy(ctx->pool[i]);
-    free(ctx->pool); free(ctx->pool_kind);
+    free(ctx->pool); free(ctx->pool_kind); free(ctx->pool_work);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
     return MEMCI_OK;
@@ -524,6 +525,17 @@ int memci_bidir2_stats(memci_ctx *ctx, int *max_shift, int *n_out_of_range)
     return MEMCI_OK;
 }
 
+int memci_bidir2_out_of_range_total(memci_ctx *ctx, int *n_out_of_range, int reset)
+{
+    REQ_CTX(ctx);
+    int h = 0;
+    CK(ctx, cudaMemcpyAsync(&h, ctx->d_counters + 13, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) CK(ctx, cudaMemsetAsync(ctx->d_counters + 13, 0, sizeof(int), ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_out_of_range) *n_out_of_range = h;
+    return MEMCI_OK;
+}
+
 int memci_quality(memci_ctx *ctx, int slot_a, int slot_b, double *mse, double *ssim)
 {
     REQ_CTX(ctx); REQ_FRAME(ctx, slot_a, 1); REQ_FRAME(ctx, slot_b, 1);
@@ -625,10 +637,11 @@ int memci_profile_start(memci_ctx *ctx, int capacity)
     if (capacity <= 0) return memci_fail(ctx, MEMCI_ERR_ARG, "profile capacity must be positive");
     if (ctx->pool_cap < capacity) {
         for (int i = 0; i < 2 * ctx->pool_cap; ++i) cudaEventDestroy(ctx->pool[i]);
-        free(ctx->pool); free(ctx->pool_kind);
+        free(ctx->pool); free(ctx->pool_kind); free(ctx->pool_work);
         ctx->pool = (cudaEvent_t *)calloc(2 * (size_t)capacity, sizeof(cudaEvent_t));
         ctx->pool_kind = (unsigned char *)calloc(capacity, 1);
-        if (!ctx->pool || !ctx->pool_kind) return memci_fail(ctx, MEMCI_ERR_NOMEM, "out of host memory");
+        ctx->pool_work = (double *)calloc(capacity, sizeof(double));
+        if (!ctx->pool || !ctx->pool_kind || !ctx->pool_work) return memci_fail(ctx, MEMCI_ERR_NOMEM, "out of host memory");
         for (int i = 0; i < 2 * capacity; ++i) CK(ctx, cudaEventCreate(&ctx->pool[i]));
         ctx->pool_cap = capacity;
     }
@@ -645,12 +658,30 @@ int memci_profile_collect(memci_ctx *ctx, double *fs_ms_sum, int *fs_n, double *
     for (int i = 0; i < ctx->pool_n; ++i) {
         float ms = 0.f;
         CK(ctx, cudaEventElapsedTime(&ms, ctx->pool[2 * i], ctx->pool[2 * i + 1]));
-        s[ctx->pool_kind[i] & 1] += ms; n[ctx->pool_kind[i] & 1]++;
+        if (ctx->pool_kind[i] < 2) { s[ctx->pool_kind[i]] += ms; n[ctx->pool_kind[i]]++; }
     }
     if (fs_ms_sum) *fs_ms_sum = s[0];
     if (fs_n) *fs_n = n[0];
     if (mci_ms_sum) *mci_ms_sum = s[1];
     if (mci_n) *mci_n = n[1];
+    ctx->pool_n = ctx->pool_cap;          // stop recording until the next memci_profile_start
+    return MEMCI_OK;
+}
+
+int memci_profile_collect_kinds(memci_ctx *ctx, double *ms_sum, int *launches, double *work)
+{
+    REQ_CTX(ctx);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < MEMCI_PROF_KINDS; ++k) { if (ms_sum) ms_sum[k] = 0.0; if (launches) launches[k] = 0; if (work) work[k] = 0.0; }
+    for (int i = 0; i < ctx->pool_n; ++i) {
+        float ms = 0.f;
+        CK(ctx, cudaEventElapsedTime(&ms, ctx->pool[2 * i], ctx->pool[2 * i + 1]));
+        const int k = ctx->pool_kind[i];
+        if (k >= MEMCI_PROF_KINDS) continue;
+        if (ms_sum) ms_sum[k] += ms;
+        if (launches) launches[k]++;
+        if (work) work[k] += ctx->pool_work[i];
+    }
     ctx->pool_n = ctx->pool_cap;          // stop recording until the next memci_profile_start
     return MEMCI_OK;
 }

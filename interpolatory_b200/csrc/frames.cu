@@ -113,9 +113,13 @@ int memci_ensure_pyramid(memci_ctx *ctx, int slot, int levels)
                 f.pyr_cap[l] = need_rgb;
             }
             int n = ho * wo;
+            // algorithmic bytes of one level: the finer level read once (3 B/px), the coarser level written as RGB (3 B/px)
+            // and read back + written as luma (3 + 4 B/px)
+            const int prof = memci_prof_begin(ctx, MEMCI_PROF_HBM_SMALL, 3.0 * h * w + 10.0 * ho * wo);
             pyr_down_kernel<<<ceil_div_i(n, 256), 256, 0, ctx->stream>>>(prev, h, w, f.pyr_rgb[l], ho, wo);
             CKL(ctx);
             int rc = memci_luma_plane(ctx, f.pyr_rgb[l], ho, wo, wop, f.pyr_luma[l]);
+            memci_prof_end(ctx, prof);
             if (rc) return rc;
             f.pyr_levels = l;
         }

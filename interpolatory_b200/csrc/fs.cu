@@ -811,7 +811,7 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         const int smem = fs_smem_bytes(bs, pl->box_h, p.n_stages, pl->G);
         if (!use8) {
             if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-            prof = memci_prof_begin(ctx, 0);
+            prof = memci_prof_begin(ctx, MEMCI_PROF_FS, (double)ctx->fs_last_ops);
         }
         switch (pl->G) {
         case 5: rc = fs_launch_tiled<5>(ctx, tm, p, smem); break;

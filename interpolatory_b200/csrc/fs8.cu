@@ -849,7 +849,7 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     p.list = ctx->d_fs8_list + F8_MAXSEG;
     p.seg_cap = (int)((have / 4 - F8_MAXSEG) / grid);
     if (const char *e = getenv("MEMCI_F8_SEG_CAP")) { const int v = atoi(e); if (v >= 0 && v < p.seg_cap) p.seg_cap = v; }   // tests: force the overflow fallback
-    const int prof = memci_prof_begin(ctx, 0);
+    const int prof = memci_prof_begin(ctx, MEMCI_PROF_FS, (double)ctx->fs_last_ops);
     if (sh.nt == 512) rc = bs == 8 ? f8_launch<true, 512>(ctx, tm, p, grid, sh.smem) : f8_launch<false, 512>(ctx, tm, p, grid, sh.smem);
     else rc = bs == 8 ? f8_launch<true, 256>(ctx, tm, p, grid, sh.smem) : f8_launch<false, 256>(ctx, tm, p, grid, sh.smem);
     if (rc) return rc;
@@ -864,6 +864,7 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
                 cudaGetErrorString(cudaGetLastError()), hc[0], hc[1], hc[2], hc[3], hc[4], n_tiles, grid, p.seg_cap, hs[0], hs[1], hs[2], hs[3],
                 sh.nt, sh.ctas, sh.rpt, sh.n_stage, sh.nb_tile, sh.box_w, sh.box_rows, sh.smem);
     }
+    const int prof_rf = memci_prof_begin(ctx, MEMCI_PROF_REFINE, 0.0);
     fs8_refine_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, ctx->Wp, bs, R, nbc, n_blk,
                                                                  p.list, p.seg_cap, p.seg_counts, grid, ctx->d_counters, ctx->d_fs8_best,
                                                                  reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2), ctx->d_redo_list, ctx->redo_cap);
@@ -872,6 +873,7 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     fs8_output_kernel<<<ceil_div_i(n_out, 256), 256, 0, ctx->stream>>>(ctx->d_fs8_best, reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2), ctx->d_counters, p.redo_limit,
                                                                       H, W, bs, R, nbc, n_blk, br0 * nbc, br1 * nbc, ndir,
                                                                       out->vec, out->sad, out2 ? out2->vec : out->vec, out2 ? out2->sad : out->sad);
+    memci_prof_end(ctx, prof_rf);
     CKL(ctx);
     return MEMCI_OK;
 }

@@ -508,6 +508,16 @@ int memci_hbma_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int win, 
     };
     int cur = 0;
     int rows = ceil_div_i(hs[steps], bs), cols = ceil_div_i(ws[steps], bs), pitch = cols;
+    // Algorithmic work of the whole call in cost pixel-ops (one |La - Lb| or (La - Lb)^2 accumulate), NOMINAL counts: the
+    // coarse level searches (2 win + 1)^2 candidates per block, every densification 3 vectors x (2 sub + 1)^2 candidates per
+    // child block (hbma.py:100-140); clipping at the frame border removes about 1 % of them and is not subtracted.
+    double work = (double)rows * cols * (2 * win + 1) * (2 * win + 1) * bs * bs;
+    {
+        int r = rows, c = cols;
+        for (int l = steps - 1; l >= 0; --l) { r = ceil_div_i(hs[l], bs); c = ceil_div_i(ws[l], bs); work += 3.0 * r * c * (2 * sub + 1) * (2 * sub + 1) * bs * bs; }
+        for (int b2 = bs >> 1; b2 >= min_bs && b2 > 0; b2 >>= 1) { r = ceil_div_i(ctx->H, b2); c = ceil_div_i(ctx->W, b2); work += 3.0 * r * c * (2 * sub + 1) * (2 * sub + 1) * b2 * b2; }
+    }
+    const int prof = memci_prof_begin(ctx, MEMCI_PROF_HBMA, work);
     {
         const int smi = sm_ints_for(bs, win);
         hbma_fs_kernel<<<grid, nt, smi * HBMA_WARPS * sizeof(int), ctx->stream>>>(
@@ -548,6 +558,7 @@ int memci_hbma_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int win, 
         b >>= 1;
         if ((rc = densify(0, b, 1))) return rc;
     }
+    memci_prof_end(ctx, prof);
     if ((rc = memci_mv_reserve(ctx, out, b, rows, cols, b, rows, cols))) return rc;
     hbma_compact_kernel<<<ceil_div_i(rows * cols, 256), 256, 0, ctx->stream>>>(ctx->tmp_mv[cur].vec, ctx->tmp_mv[cur].sad,
                                                                                pitch, rows, cols, out->vec, out->sad);

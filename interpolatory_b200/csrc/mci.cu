@@ -798,13 +798,15 @@ int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd
     const int tiles_x = ceil_div_i(W, 32), n_tiles = tiles_x * ceil_div_i(P.y_end - P.y_begin, SW_TH);
     ctx->mci_timed = 0;
     if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    const int prof = memci_prof_begin(ctx, 1);
+    const int prof = memci_prof_begin(ctx, MEMCI_PROF_MCI, 9.0 * (double)(P.y_end - P.y_begin) * W);      // 2 frame reads + 1 write
     if (bidir) mci_splat_kernel<true><<<ceil_div_i(n_tiles, SW_WARPS), SW_WARPS * 32, 0, ctx->stream>>>(P, tiles_x, n_tiles);
     else mci_splat_kernel<false><<<ceil_div_i(n_tiles, SW_WARPS), SW_WARPS * 32, 0, ctx->stream>>>(P, tiles_x, n_tiles);
     memci_prof_end(ctx, prof);
     CKL(ctx);
     if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->mci_timed = 1; }
+    const int prof_hf = memci_prof_begin(ctx, MEMCI_PROF_HOLEFILL, 0.0);
     mci_holefill_kernel<<<ctx->num_sms * 6, HF_WARPS * 32, 0, ctx->stream>>>(P.fill, P.out, P.hole_list, P.counters, H, W);
+    memci_prof_end(ctx, prof_hf);
     CKL(ctx);
     FrameSlot &o = ctx->frames[out_slot];
     o.valid = 1; o.luma_ok = 0; o.luma8_ok = 0; o.pyr_levels = 0;

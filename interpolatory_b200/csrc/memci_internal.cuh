@@ -74,7 +74,7 @@ struct memci_ctx {
     // timing
     int timing; cudaEvent_t ev[4]; int fs_timed, mci_timed;
     // event pool: per-launch device times of the two hot kernels inside a caller's timed region
-    cudaEvent_t *pool; int pool_cap, pool_n; unsigned char *pool_kind;   // pairs (2i, 2i+1); kind 0 = fs, 1 = mci
+    cudaEvent_t *pool; int pool_cap, pool_n; unsigned char *pool_kind; double *pool_work;   // pairs (2i, 2i+1); kinds: MEMCI_PROF_* (memci_b200.h); work = algorithmic px-ops / bytes of the launch
     // asynchronous drain of output frames through a stager's D2H stream: slot may be rewritten only after its copy
     cudaEvent_t ev_out_ready[MEMCI_NUM_FRAME_SLOTS], ev_out_copied[MEMCI_NUM_FRAME_SLOTS];
     unsigned char out_pending[MEMCI_NUM_FRAME_SLOTS];
@@ -121,7 +121,7 @@ int memci_bidir2_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *
 int memci_quality_run(memci_ctx *ctx, int slot_a, int slot_b, double *h_result);   // h_result[0] = sum of squared differences, [1] = sum of SSIM map
 int memci_mv_to_dense(memci_ctx *ctx, const MVField *f, float *d_dense);
 // returns an event pair index (>= 0) after recording the start event, or -1 when profiling is off / full
-int memci_prof_begin(memci_ctx *ctx, int kind);
+int memci_prof_begin(memci_ctx *ctx, int kind, double work = 0.0);
 void memci_prof_end(memci_ctx *ctx, int idx);
 int memci_dense_to_mv(memci_ctx *ctx, const float *d_dense, MVField *f);
 

@@ -60,8 +60,11 @@ int memci_smooth_run(memci_ctx *ctx, const MVField *in, int mode, int fsz, MVFie
     int rows = ceil_div_i(ctx->H, fsz), cols = ceil_div_i(ctx->W, fsz);
     int rc = memci_mv_reserve(ctx, out, fsz, rows, cols, in->sad_cell, in->sad_rows, in->sad_cols);
     if (rc) return rc;
+    // algorithmic bytes: the vector grid read once (8 B per input cell), one filtered vector written per filter cell
+    const int prof = memci_prof_begin(ctx, MEMCI_PROF_HBM_SMALL, 8.0 * in->mv_rows * in->mv_cols + 8.0 * rows * cols);
     smooth_kernel<<<ceil_div_i(rows * cols, 128), 128, 0, ctx->stream>>>(in->vec, in->mv_cell, in->mv_cols, ctx->H, ctx->W,
                                                                          mode, fsz, out->vec, rows, cols);
+    memci_prof_end(ctx, prof);
     CKL(ctx);
     CK(ctx, cudaMemcpyAsync(out->sad, in->sad, sizeof(float) * (size_t)in->sad_rows * in->sad_cols,
                             cudaMemcpyDeviceToDevice, ctx->stream));

@@ -190,6 +190,12 @@ class DeviceContext:
         self._ck(self.L.memci_bidir2_stats(self._ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def bidir2_out_of_range_total(self, reset=True):
+        """Blocks shifted outside the padded frame over every bidir2 call since the last reset (synchronises)."""
+        n = C.c_int()
+        self._ck(self.L.memci_bidir2_out_of_range_total(self._ctx, C.byref(n), 1 if reset else 0))
+        return n.value
+
     # -- frame quality (Middlebury harness)
     def quality(self, slot_a, slot_b):
         """(mean squared error, mean SSIM) of two resident frames; see memci_quality in include/memci_b200.h."""
@@ -237,6 +243,15 @@ class DeviceContext:
         na, nb = C.c_int(), C.c_int()
         self._ck(self.L.memci_profile_collect(self._ctx, C.byref(a), C.byref(na), C.byref(b), C.byref(nb)))
         return a.value, na.value, b.value, nb.value
+
+    PROF_KINDS = ("fs", "mci", "hbma", "hbm_small", "refine", "holefill", "prep", "bidir2")
+
+    def profile_collect_kinds(self):
+        """{kind: (ms_sum, launches, algorithmic work)} since profile_start(); kinds as MEMCI_PROF_* in the header."""
+        n = len(self.PROF_KINDS)
+        ms, cnt, work = (C.c_double * n)(), (C.c_int * n)(), (C.c_double * n)()
+        self._ck(self.L.memci_profile_collect_kinds(self._ctx, ms, cnt, work))
+        return {k: (ms[i], cnt[i], work[i]) for i, k in enumerate(self.PROF_KINDS)}
 
     def microbench(self, mode, iters=4096):
         """(ms, px_ops) of one launch of the issue-rate microbenchmark (roofline denominator)."""

@@ -71,6 +71,7 @@ class PairPipeline:
             self._w = get_weight_kern(2 * self.params.min_block_size)
         self.ctxs = [DeviceContext(H, W, device) for _ in range(max(1, int(n_contexts)))]
         self.stager = None
+        self._ring_cursor = 0
 
     def close(self):
         if self.ctxs:
@@ -90,6 +91,12 @@ class PairPipeline:
             c.sync()
         if self.stager is not None:
             self.stager.sync()
+        if self.bidir2:
+            # like the class API (MCI/Bidirectional_2._check_shifts): the reference's numpy slices fail when a block is shifted
+            # outside the padded frame (vectors beyond pad_size); the frames enqueued since the last sync are then invalid
+            n_bad = sum(c.bidir2_out_of_range_total() for c in self.ctxs)
+            if n_bad:
+                raise Exception(f'bidir2: {n_bad} block(s) shifted outside the padded frame (pad_size too small for these motion vectors)')
 
     def plan_clip(self, n_frames, fps_in, fps_out):
         """Output schedule of a whole clip, exactly as BaseInterpolator.interpolate_video walks it (base.py:78-115):
@@ -138,36 +145,50 @@ class PairPipeline:
         return out
 
     def _run_pairs(self, frames, per_pair, out):
-        """per_pair: {pair index k: [(output index, dist), ...]}; pairs without work are skipped."""
-        n_frames = len(frames)
+        """per_pair: {pair index k: [(output index, dist), ...]}; pairs without work are skipped.  Everything is
+        only enqueued here; sync() waits.  The stager is a RING of 2 C + 4 device buffers: a source frame is uploaded
+        right before the first context that needs it asks for it (in enqueue order), the H2D stream runs ahead as far
+        as ring slots are free, and a slot is rewritten once its previous tenant has been copied out (the stager
+        waits for those copies itself) -- so device memory does not grow with the length of the clip."""
         pairs = sorted(per_pair)
         n_pairs = len(pairs)
-        if self.stager is None or self.stager.n < n_frames:
+        if n_pairs == 0:
+            return
+        C = min(len(self.ctxs), n_pairs)
+        n_ring = 2 * C + 4
+        if self.stager is None or self.stager.n < n_ring:
             if self.stager is not None:
                 self.sync()
                 self.stager.close()
-            self.stager = FrameStager(self.H, self.W, n_frames, self.device)
+            self.stager = FrameStager(self.H, self.W, n_ring, self.device)
         st = self.stager
-        C = min(len(self.ctxs), n_pairs)
+        n_ring = st.n
         bounds = [round(i * n_pairs / C) for i in range(C + 1)]
-        # enqueue order: the runs advance in lock step; uploads are issued in the order that order needs them
+        # enqueue order: the runs advance in lock step
         order = [(c, bounds[c] + r) for r in range(max(bounds[c + 1] - bounds[c] for c in range(C))) for c in range(C)
                  if bounds[c] + r < bounds[c + 1]]
-        staged = set()
-        for c, r in order:
-            k = pairs[r]
-            for f in (k, k + 1):
-                if f not in staged:
-                    st.upload(f, frames[f])              # ring slot = frame index within the batch
-                    staged.add(f)
+        ring_of = {}                                     # frame index -> ring slot of its current upload
+        n_up = self._ring_cursor
+
+        def staged(f):
+            nonlocal n_up
+            if f not in ring_of:
+                slot = n_up % n_ring
+                for g in [g for g, s_ in ring_of.items() if s_ == slot]:
+                    del ring_of[g]                       # that frame's tenancy ends; a later taker uploads it again
+                st.upload(slot, frames[f])
+                ring_of[f] = slot
+                n_up += 1
+            return ring_of[f]
+
         prev = {}                                        # context -> pair it processed last
         for c, r in order:
             k = pairs[r]
             ctx = self.ctxs[c]
             a, b = k % 3, (k + 1) % 3
             if prev.get(c) != k - 1:
-                ctx.frame_from_stager(a, st, k)           # not the successor of this context's last pair: both frames are new to it
-            ctx.frame_from_stager(b, st, k + 1)
+                ctx.frame_from_stager(a, st, staged(k))  # not the successor of this context's last pair: both frames are new to it
+            ctx.frame_from_stager(b, st, staged(k + 1))
             prev[c] = k
             ctx.estimate_pair(self.params, a, b, 0, 1)
             for j, (oi, d) in enumerate(per_pair[k]):
@@ -181,3 +202,4 @@ class PairPipeline:
                 else:
                     ctx.mci_unidir(a, b, 0, d, o)
                 ctx.download_frame_via(o, out[oi], st)
+        self._ring_cursor = n_up % n_ring

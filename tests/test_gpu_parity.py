@@ -2,6 +2,7 @@
 reference interface, against the CPU oracle on seeded inputs and against the committed golden
 fixtures (outputs of the unmodified reference).  Bar: bit-exact (np.array_equal) everywhere."""
 import hashlib
+import math
 
 import numpy as np
 import pytest
@@ -632,6 +633,66 @@ def test_run_clip_24_to_60_equals_class_api(gpu):
     for i in range(len(plan)):
         assert np.array_equal(np.asarray(it.get_interpolated_frame(i)), out[i]), (i, plan[i])
     it.close()
+
+
+@pytest.mark.parametrize("st,fps_in,fps_out", [
+    (dict(me_mode='fs', block_size='8', target_region='7', mci_mode='bidir'), 24, 60),
+    (dict(me_mode='hbma', mci_mode='unidir', filter_mode='median'), 30, 60),
+    (dict(me_mode='hbma', mci_mode='bidir2'), 24, 120),
+    (dict(me_mode='tss', mci_mode='bidir', filter_mode='weighted'), 25, 60),
+])
+def test_interpolate_video_is_the_fast_path_and_equals_frame_by_frame(gpu, st, fps_in, fps_out):
+    """BaseInterpolator.interpolate_video (the call the reference's CLI makes, base.py:78-115) runs the staged,
+    batched pipeline in windows of max_cache_size / stream_window source frames: its frames must equal
+    get_interpolated_frame(i) one by one, whatever the window size, on one device and on a two-way device list."""
+    from interpolatory_b200 import MEMCI, ArrayVideoStream
+    H, W, n_src = 120, 168, 8
+    frames = list(make_sequence(H, W, n_src, seed=31))
+    n_out = int(math.floor((n_src - 1) * fps_out / fps_in)) + 1          # up to and including the last source frame
+    ref_it = MEMCI(fps_out, **st)
+    ref_it.set_video_stream(ArrayVideoStream(frames, fps_in))
+    want = [np.asarray(ref_it.get_interpolated_frame(i)).copy() for i in range(n_out)]
+    ref_it.close()
+    for extra in (dict(max_cache_size=2), dict(max_cache_size=3), dict(stream_window='5'), dict(stream_window='64'),
+                  dict(stream_window='4', devices='0,0')):
+        it = MEMCI(fps_out, max_out_frames=n_out, **extra, **st)
+        it.set_video_stream(ArrayVideoStream(frames, fps_in))
+        got = []
+        it.interpolate_video(sink=got.append)
+        launches = it._pipe.launch_count()
+        it.close()
+        assert len(got) == n_out, extra
+        for i, (g, w) in enumerate(zip(got, want)):
+            assert np.array_equal(g, w), (st, extra, i)
+        assert launches > 0 and it._dev is None            # the pipeline ran; the per-frame context was never created
+
+
+def test_multigpu_pipeline_equals_single_pipeline(gpu):
+    """One clip over N pipelines by pair index (multigpu.MultiGpuPipeline, one host thread each): byte-identical to the
+    single-GPU run_clip.  Runs on two physical GPUs when the box has them, and always on a [0, 0, 0] device list (three
+    pipelines sharing one GPU: the same partitioning, threading and staging code)."""
+    from interpolatory_b200._native import lib
+    from interpolatory_b200.multigpu import MultiGpuPipeline
+    from interpolatory_b200.pipeline import PairPipeline
+    H, W = 136, 200
+    frames = make_sequence(H, W, 10, seed=77)
+    st = dict(me_mode='fs', block_size='8', target_region='16', mci_mode='bidir')
+    single = PairPipeline(H, W, n_contexts=2, **st)
+    plan = single.plan_clip(len(frames), 24, 60)
+    want = np.zeros((len(plan), H, W, 3), np.uint8)
+    single.run_clip(frames, 24, 60, want)
+    single.close()
+    device_lists = [[0, 0, 0]]
+    if lib().memci_device_count() >= 2:
+        device_lists.append([0, 1])
+    for devs in device_lists:
+        mg = MultiGpuPipeline(H, W, devices=devs, n_contexts=2, **st)
+        got = np.zeros_like(want)
+        assert mg.run_clip(frames, 24, 60, got) == plan
+        assert sum(mg.last_shards, []) == sorted({k for k, d in plan if d != 0.0})
+        assert all(len(s_) > 0 for s_ in mg.last_shards)
+        mg.close()
+        assert np.array_equal(got, want), devs
 
 
 @pytest.mark.parametrize("H,W", [(8, 8), (16, 24), (9, 40), (33, 17)])

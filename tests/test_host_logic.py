@@ -229,3 +229,51 @@ def test_frame_slot_lru_never_evicts_the_pair_partner():
     n = len(dev.uploads)
     it._frame_slot(dev, 1, 1)
     assert len(dev.uploads) == n and list(it._resident)[-1] == 1
+
+
+def test_reader_video_stream_window():
+    """ReaderVideoStream (reference: VideoStream, src/VideoStream.py:29-107): bounded forward-moving window, preload,
+    fall-through reads behind the window / after a jump, duration from the metadata, nframes counted when the reader
+    reports inf."""
+    from interpolatory_b200.VideoStream import ReaderVideoStream
+
+    class FakeReader:
+        def __init__(self, n, nframes_meta):
+            self.n, self.meta_n, self.reads = n, nframes_meta, []
+
+        def get_meta_data(self):
+            return {'fps': 24.0, 'size': (64, 48), 'duration': 1.7, 'nframes': self.meta_n}
+
+        def count_frames(self):
+            return self.n
+
+        def get_data(self, i):
+            self.reads.append(i)
+            return ('frame', i % self.n)                 # loop=True readers wrap around
+
+    r = FakeReader(40, float('inf'))
+    vs = ReaderVideoStream(r, 3)
+    assert vs.nframes == 40 and vs.duration == 1.7 and vs.fps == 24.0
+    assert r.reads == [0, 1, 2]                           # preload
+    assert vs.get_frame(1) == ('frame', 1) and r.reads == [0, 1, 2]
+    assert vs.get_frame(3) == ('frame', 3) and r.reads[-1] == 3
+    assert vs.get_frame(0) == ('frame', 0) and r.reads[-1] == 0      # behind the window: straight from the reader
+    assert vs.get_frame(2) == ('frame', 2) and r.reads[-1] == 0      # still cached (window is 1..3)
+    assert vs.get_frame(9) == ('frame', 9) and r.reads[-1] == 9      # a jump: no caching
+    assert vs.get_frame(4) == ('frame', 4) and vs.get_frame(4) == ('frame', 4) and r.reads.count(4) == 1
+    assert len(vs._window) == 3 and vs._first == 2
+    r0 = FakeReader(5, 5)
+    v0 = ReaderVideoStream(r0, 0)
+    assert r0.reads == [] and v0.get_frame(2) == ('frame', 2) and v0.get_frame(2) == ('frame', 2) and r0.reads == [2, 2]
+    import pytest
+    with pytest.raises(Exception):
+        ReaderVideoStream(r0, -1)
+
+
+def test_multigpu_partition_is_contiguous_and_complete():
+    from interpolatory_b200.multigpu import rank_pairs
+    pairs = [0, 1, 2, 5, 6, 9, 10, 11, 12]
+    for world in (1, 2, 3, 4, 8, 16):
+        parts = [rank_pairs(pairs, r, world) for r in range(world)]
+        assert sum(parts, []) == pairs
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
