@@ -134,7 +134,8 @@ class MEMCIBaseInterpolator(BaseInterpolator):
             self._dev.close()
             self._dev = None
         if self._pipe is not None:
-            self._pipe.close()
+            for p_ in self._pipe:
+                p_.close()
             self._pipe = None
         if self._pin is not None:
             for b in self._pin:
@@ -142,72 +143,95 @@ class MEMCIBaseInterpolator(BaseInterpolator):
             self._pin = None
 
     # ---- interpolate_video(): the drop-in call is the fast path ---------------------------------------------
-    def _output_frames(self, n):
+    def _output_frames(self, n, copy=True):
         """The frames get_interpolated_frame(0 .. n-1) would return, in order and byte for byte, produced in windows of
-        source frames: a window is copied into page-locked memory as the stream delivers it, its frame pairs go through
-        the staged multi-stream pipeline (pipeline.PairPipeline, or multigpu.MultiGpuPipeline when several devices were
-        given: each source frame crosses PCIe once, uploads / kernels / downloads overlap), pass-through frames are
-        copied on the host.  Host and device memory are bounded by the window (max_cache_size source frames, as in the
-        reference's VideoStream; `stream_window` overrides), not by the clip.  Output frames the reference would build
-        from a frame past the end of the stream (its reader wraps around, base.py:52-53) are left to the per-frame call."""
+        source frames: a window is copied into page-locked memory as the stream delivers it (or used in place when the
+        stream says its frames are page-locked already), its frame pairs go through the staged multi-stream pipeline
+        (pipeline.PairPipeline, or multigpu.MultiGpuPipeline when several devices were given: each source frame crosses
+        PCIe once, uploads / kernels / downloads overlap), pass-through frames are copied on the host.  Two pipelines
+        alternate, so window w + 1 is decoded, staged and computed while window w's frames are handed to the sink.
+        Host and device memory are bounded by the window (max_cache_size source frames, as in the reference's
+        VideoStream; `stream_window` overrides), not by the clip.  Output frames the reference would build from a frame
+        past the end of the stream (its reader wraps around, base.py:52-53) are left to the per-frame call.
+        copy=False yields views into the staging buffers, valid until the next frame is requested two windows later
+        (what a video writer needs); the default hands out independent arrays."""
         import numpy as np
         from ..device import PinnedBuffer
         from ..pipeline import PairPipeline
         from ..multigpu import MultiGpuPipeline
         vs = self.video_stream
         n_src = int(vs.nframes)
+        in_place = bool(getattr(vs, 'page_locked', False))
         plan = []                                        # (source frame index, dist) exactly as get_interpolated_frame derives them
         for i in range(n):
             first, inv = get_first_frame_idx_and_ratio(i, self.rate_ratio)
             dist = 1. - inv
             plan.append((first, 0.0 if math.isclose(dist, 0.) else float(dist)))
         win = max(2, self._stream_window if self._stream_window is not None else int(self.max_cache_size))
-        i = 0
-        while i < n:
-            w0 = plan[i][0]
-            if w0 + 1 >= n_src and plan[i][1] != 0.0:      # needs a frame past the end: whatever the stream does there
-                yield self.get_interpolated_frame(i)
-                i += 1
-                continue
-            w1 = min(w0 + win - 1, n_src - 1)             # source frames w0 .. w1 form this window
-            j = i                                        # outputs i .. j-1 live entirely inside it
-            while j < n and (plan[j][0] + 1 <= w1 if plan[j][1] != 0.0 else plan[j][0] <= w1) and plan[j][0] >= w0:
-                j += 1
-            if j == i:                                   # cannot happen for monotone plans; stay safe
-                yield self.get_interpolated_frame(i)
-                i += 1
-                continue
-            f0 = np.asarray(vs.get_frame(w0))
-            H, W = int(f0.shape[0]), int(f0.shape[1])
-            if self._pipe is None or (self._pipe.H, self._pipe.W) != (H, W):
+        n_out_max = (win - 1) * (int(math.ceil(self.rate_ratio)) + 1) + 2
+
+        def ensure(H, W):
+            if self._pipe is None or (self._pipe[0].H, self._pipe[0].W) != (H, W):
                 self.close()
                 cls = MultiGpuPipeline if len(self._devices) > 1 else PairPipeline
                 kw = dict(devices=self._devices) if len(self._devices) > 1 else dict(device=self._devices[0])
-                self._pipe = cls(H, W, n_contexts=3, **kw, **self._settings)
-            n_out_max = (win - 1) * (int(math.ceil(self.rate_ratio)) + 1) + 2
+                self._pipe = [cls(H, W, n_contexts=3, **kw, **self._settings) for _ in range(2)]
             if self._pin is None or self._pin[0].shape[0] < win or self._pin[1].shape[0] < n_out_max:
                 if self._pin is not None:
                     for b in self._pin:
                         b.close()
-                self._pin = (PinnedBuffer((win, H, W, 3)), PinnedBuffer((n_out_max, H, W, 3)))
-            src, out = self._pin[0].array, self._pin[1].array
-            src[0] = f0
-            for k in range(w0 + 1, w1 + 1):
-                src[k - w0] = vs.get_frame(k)
+                self._pin = [PinnedBuffer((win, H, W, 3)), PinnedBuffer((n_out_max, H, W, 3)),
+                             PinnedBuffer((win, H, W, 3)), PinnedBuffer((n_out_max, H, W, 3))]
+
+        def enqueue(slot, i, j, w0, w1):
+            """outputs i .. j-1 from source frames w0 .. w1 on pipeline `slot`; returns what drain() needs"""
+            f0 = np.asarray(vs.get_frame(w0))
+            ensure(int(f0.shape[0]), int(f0.shape[1]))
+            out = self._pin[2 * slot + 1].array
+            if in_place:
+                src = [f0] + [np.asarray(vs.get_frame(k)) for k in range(w0 + 1, w1 + 1)]
+            else:
+                src = self._pin[2 * slot].array
+                src[0] = f0
+                for k in range(w0 + 1, w1 + 1):
+                    src[k - w0] = vs.get_frame(k)
             per_pair = {}
             for o in range(i, j):
                 k, d = plan[o]
                 if d != 0.0:
                     per_pair.setdefault(k - w0, []).append((o - i, d))
-            if isinstance(self._pipe, MultiGpuPipeline):
-                self._pipe._dispatch(src, per_pair, out)
+            pipe = self._pipe[slot]
+            if isinstance(pipe, MultiGpuPipeline):
+                pipe._dispatch(src, per_pair, out)
             else:
-                self._pipe._run_pairs(src, per_pair, out)
-            self._pipe.sync()
+                pipe._run_pairs(src, per_pair, out)
+            return slot, i, j, w0, src, out
+
+        def drain(job):
+            slot, i, j, w0, src, out = job
+            self._pipe[slot].sync()
             for o in range(i, j):
                 k, d = plan[o]
-                yield (src[k - w0] if d == 0.0 else out[o - i]).copy()
-            i = j
+                f = src[k - w0] if d == 0.0 else out[o - i]
+                yield f.copy() if copy else f
 
-    def _mv_dense(self, slot):
-        return self._dev.download_mv_dense(slot)
+        pending, slot, i = None, 0, 0
+        while i < n:
+            w0 = plan[i][0]
+            w1 = min(w0 + win - 1, n_src - 1)             # source frames w0 .. w1 form this window
+            j = i                                        # outputs i .. j-1 live entirely inside it
+            while j < n and plan[j][0] >= w0 and (plan[j][0] + 1 <= w1 if plan[j][1] != 0.0 else plan[j][0] <= w1):
+                j += 1
+            if j == i:                                   # needs a frame past the end of the stream: whatever the stream does there
+                if pending is not None:
+                    yield from drain(pending)
+                    pending = None
+                yield self.get_interpolated_frame(i)
+                i += 1
+                continue
+            job = enqueue(slot, i, j, w0, w1)
+            if pending is not None:
+                yield from drain(pending)
+            pending, slot, i = job, slot ^ 1, j
+        if pending is not None:
+            yield from drain(pending)

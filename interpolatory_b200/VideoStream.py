@@ -78,8 +78,9 @@ class BenchmarkVideoStream(BaseVideoStream):
 class ArrayVideoStream(BaseVideoStream):
     """In-memory frames (decoded elsewhere, or synthetic) at a nominal frame rate."""
 
-    def __init__(self, frames, fps):
+    def __init__(self, frames, fps, page_locked=False):
         self.frames = frames
+        self.page_locked = page_locked                    # frames live in page-locked memory (device.PinnedBuffer): staged in place
         self.nframes = len(frames)
         self.fps = fps
         self.duration = self.nframes / fps

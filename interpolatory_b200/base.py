@@ -60,13 +60,15 @@ class BaseInterpolator(object):
         """Produce every output frame in order (base.py:78-115), with the reference's progress reporting (:91-101,
         :110-114: a PROGRESS line once per output second, to the progress file the GUI polls and, when the debug flag is
         set, to stdout).  Frames go to the video writer, or to `sink(frame)` when given (e.g. a list's append)."""
+        copy = True
         if sink is None:
             if self.video_in_path is None or self.video_out_path is None:
                 raise Exception('Cannot interpolate video, no input video path or output video path')
             sink = self.video_out_writer.append_data
+            copy = False                                  # the writer encodes a frame before it returns
         start = int(round(time.time()))
         target_nframes = int(min(self.max_frames_possible, self.max_out_frames))
-        for i, frame in enumerate(self._output_frames(target_nframes)):
+        for i, frame in enumerate(self._output_frames(target_nframes, copy=copy and not getattr(self, 'sink_keeps_no_reference', False))):
             if (i % self.target_fps) == 0:
                 pct = str(math.floor(100 * (i + 1) / target_nframes)).rjust(3, ' ')
                 elapsed_seconds = int(int(round(time.time())) - start)
@@ -85,7 +87,7 @@ class BaseInterpolator(object):
             print(progStr)
         return end - start
 
-    def _output_frames(self, n):
+    def _output_frames(self, n, copy=True):
         """Output frames 0 .. n-1 in order.  The base class asks for them one by one; the MEMCI interpolators override this
         with the staged, batched device path (same frames, byte for byte)."""
         for i in range(n):

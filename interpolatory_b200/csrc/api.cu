@@ -529,8 +529,8 @@ int memci_bidir2_out_of_range_total(memci_ctx *ctx, int *n_out_of_range, int res
 {
     REQ_CTX(ctx);
     int h = 0;
-    CK(ctx, cudaMemcpyAsync(&h, ctx->d_counters + 13, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (reset) CK(ctx, cudaMemsetAsync(ctx->d_counters + 13, 0, sizeof(int), ctx->stream));
+    CK(ctx, cudaMemcpyAsync(&h, ctx->d_counters + 15, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (reset) CK(ctx, cudaMemsetAsync(ctx->d_counters + 15, 0, sizeof(int), ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     if (n_out_of_range) *n_out_of_range = h;
     return MEMCI_OK;

@@ -63,7 +63,7 @@ __global__ void b2_blocks_kernel(const float2 *__restrict__ vec, int mv_cell, in
     const unsigned nbad = __popc(__ballot_sync(0xffffffffu, bad));
     if ((threadIdx.x & 31) == 0) {
         if (tmax > 0) atomicMax(&counters[5], tmax);
-        if (nbad) { atomicAdd(&counters[6], (int)nbad); atomicAdd(&counters[13], (int)nbad); }   // [13]: running total (memci_bidir2_out_of_range_total)
+        if (nbad) { atomicAdd(&counters[6], (int)nbad); atomicAdd(&counters[15], (int)nbad); }   // [15]: running total (memci_bidir2_out_of_range_total)
     }
 }
 

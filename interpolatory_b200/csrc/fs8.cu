@@ -21,7 +21,8 @@
 //   fs8_prefilter_kernel  persistent CTAs, dynamic job queue; job = adjacent blocks of one block row (of two, side by side,
 //                         where the column range is clipped), staged by TMA (cp.async.bulk.tensor.3d + mbarrier, two
 //                         stages); thread = (block, dx) candidate column; survivors appended to per-CTA segments of the list
-//   fs8_refine_kernel     8 lanes per survivor: exact luma-SAD (+ float64 replay of flagged sums), 64-bit atomicMin
+//   fs8_refine_kernel     8 lanes per survivor: exact luma-SAD, 64-bit atomicMin; flagged sums go on a short list
+//   fs8_replay_kernel     float64 replay of the flagged sums in the reference's operation order
 //   fs8_output_kernel     thread per block: key -> (dy, dx, sad); decides the pair-level fallback; re-arms the buffers
 // Blocks that cannot be pruned (flat content, segment overflow, flagged sums of 16 x 16 blocks) go to fs_redo_kernel (fs.cu).
 #include <stdlib.h>
@@ -32,6 +33,7 @@
 #define F8_G 11
 #define F8_NBMAX 32
 #define F8_MAXSEG 1024          // CTAs of the prefilter grid = segments of the survivor list
+#define F8_FLAG_CAP 16384        // flagged survivors (sum a multiple of 1000) replayed in float64 per search
 #define F8_EMIT_WORDS 9          // votes (eight row offsets each) a warp keeps in registers while it emits survivors
 
 struct F8Params {
@@ -444,21 +446,80 @@ __device__ __forceinline__ unsigned long long f8_key(unsigned sad, unsigned d2, 
     return ((unsigned long long)sad << 32) | ((unsigned long long)d2 << 16) | (ri << 8) | ci;    // = fs.cu fs_key
 }
 
-// Eight lanes per survivor: lane l covers row l of each 8 x 8 sub-block -- the source row as two aligned 16-byte
-// vectors, the target row as one 32-byte run -- so a survivor costs a few dozen sectors instead of 128 scattered words.
-// Blocks already on the redo list (dense blocks, earlier flagged sums) are skipped.
-__global__ void __launch_bounds__(256)
+// Exact SAD of one survivor by eight lanes: lane pr covers row pr of each 8 x 8 sub-block -- the source row as two
+// aligned 16-byte vectors, the target row as one 32-byte run; returns the lane's partial sum of |dL1000|.
+// (Measured alternatives, both slower at 8 x 8: a whole warp per survivor with lane = (row, pixel pair), 102 vs 76 us at
+// 1080p -- the per-survivor decode and hand-over then run 32 instead of 8 lanes wide -- and the target row as the three
+// aligned 16-byte vectors that cover it, 83 us: half as many load instructions, 1.5 x the bytes.)
+__device__ __forceinline__ unsigned f8_survivor_sad(const int32_t *__restrict__ Ls, const int32_t *__restrict__ Lt, int H, int W, int Wp,
+                                                    int bs, int m, int s_row, int s_col, int t_row, int t_col, int pr)
+{
+    unsigned S = 0;
+    if (s_row + bs <= H && s_col + bs <= W && t_row + bs <= H && t_col + bs <= W) {      // no padding involved
+        for (int sub = 0; sub < m * m; ++sub) {
+            const int si = sub / m, sj = sub - si * m;
+            const int r = si * 8 + pr, c = sj * 8;
+            const int32_t *ps = Ls + (size_t)(s_row + r) * Wp + s_col + c;
+            const int4 a0 = *reinterpret_cast<const int4 *>(ps), a1 = *reinterpret_cast<const int4 *>(ps + 4);
+            const int32_t *q = Lt + (size_t)(t_row + r) * Wp + t_col + c;
+            S = __sad(a0.x, q[0], S); S = __sad(a0.y, q[1], S); S = __sad(a0.z, q[2], S); S = __sad(a0.w, q[3], S);
+            S = __sad(a1.x, q[4], S); S = __sad(a1.y, q[5], S); S = __sad(a1.z, q[6], S); S = __sad(a1.w, q[7], S);
+        }
+    } else {                                                // zero padding (np.pad) on either side
+        for (int sub = 0; sub < m * m; ++sub) {
+            const int si = sub / m, sj = sub - si * m;
+            const int r1 = s_row + si * 8 + pr, r2 = t_row + si * 8 + pr;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int c1 = s_col + sj * 8 + k, c2 = t_col + sj * 8 + k;
+                const int a = (r1 < H && c1 < W) ? Ls[(size_t)r1 * Wp + c1] : 0;
+                const int v = (r2 < H && c2 < W) ? Lt[(size_t)r2 * Wp + c2] : 0;
+                S = __sad(a, v, S);
+            }
+        }
+    }
+    return S;
+}
+
+struct F8Entry { int dir, blk, dyi, dxi, s_row, s_col, t_row, t_col; };
+__device__ __forceinline__ F8Entry f8_decode(unsigned e, int nbc, float inv_nbc, int bs, int R)
+{
+    F8Entry x;
+    x.dir = e >> 31; x.blk = (int)((e >> 14) & 0x1ffffu); x.dyi = (int)((e >> 7) & 127u); x.dxi = (int)(e & 127u);
+    int br = (int)(((float)x.blk + 0.5f) * inv_nbc);          // blk / nbc (blk < 2^17: the float quotient is off by at most one)
+    br -= (br * nbc > x.blk); br += ((br + 1) * nbc <= x.blk);
+    const int bc = x.blk - br * nbc;
+    x.s_row = br * bs; x.s_col = bc * bs;
+    x.t_row = max(x.s_row - R, 0) + x.dyi; x.t_col = max(x.s_col - R, 0) + x.dxi;      // window origin (r0, c0) of f8_bounds
+    return x;
+}
+
+// Every CTA takes one contiguous range of the survivor list (the concatenation of the per-CTA segments of the
+// prefilter); its 32 eight-lane groups walk that range side by side, so neighbouring groups take neighbouring survivors
+// (same block, same column offset: the same source rows and overlapping target rows -- loads of the same line coalesce)
+// and a group finds its segment by stepping forward, not by searching.  A flagged sum (S a positive multiple of 1000: the
+// reference's float64 accumulation may land just below the integer and truncate to S / 1000 - 1, fs.cu) is NOT decided
+// here: the survivor goes on a short list for fs8_replay_kernel, which keeps this kernel at 32 registers and the SM full.
+// Blocks already on the redo list (dense blocks) still get their keys; the redo pass overwrites them.
+__global__ void __launch_bounds__(256, 8)
 fs8_refine_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
-                  const uint8_t *__restrict__ rgb0, const uint8_t *__restrict__ rgb1,
                   int H, int W, int Wp, int bs, int R, int nbc, int n_blk,
                   const unsigned *__restrict__ list, int seg_cap, const unsigned *__restrict__ seg_counts, int n_seg,
-                  int *__restrict__ counters,
-                  unsigned long long *__restrict__ best, unsigned *__restrict__ redo_mark,
-                  int *__restrict__ redo_list, int redo_cap)
+                  int *__restrict__ counters, unsigned long long *__restrict__ best,
+                  unsigned *__restrict__ flag_list, int flag_cap,
+                  unsigned *__restrict__ redo_mark, int *__restrict__ redo_list, int redo_cap)
 {
     if (counters[8]) return;                                       // overflow: the exact kernel takes the pair
     // exclusive prefix of the segment lengths (n_seg <= F8_MAXSEG, every CTA computes it for itself)
     __shared__ int seg_pre[F8_MAXSEG + 1];
+    __shared__ int lo_s;
+    // Minimum keys are combined per CTA before they touch global memory: a CTA's range is contiguous, i.e. a handful of
+    // blocks, and a block whose content is nearly flat can own a thousand survivors -- a thousand atomics on ONE address
+    // would serialise in L2 and set the duration of the whole kernel.  Direct-mapped, 128 (direction, block) slots; a
+    // survivor whose slot belongs to another block goes to global memory directly.
+    __shared__ unsigned long long ckey[128];
+    __shared__ int cid[128];
+    if (threadIdx.x < 128) { ckey[threadIdx.x] = 0xffffffffffffffffull; cid[threadIdx.x] = -1; }
     {
         __shared__ int wsum[8];
         const int per = (n_seg + 255) / 256;
@@ -477,72 +538,89 @@ fs8_refine_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1
         __syncthreads();
     }
     const int n = seg_pre[n_seg];
+    const int per_cta = (((n + gridDim.x - 1) / gridDim.x) + 31) & ~31;
+    const int cs = blockIdx.x * per_cta, ce = min(n, cs + per_cta);
+    if (cs >= ce) return;
+    if (threadIdx.x == 0) {                                        // segment of the range's first survivor
+        int lo = 0, hi = n_seg;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_pre[mid] <= cs) lo = mid; else hi = mid; }
+        lo_s = lo;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, pr = lane & 7, grp = threadIdx.x >> 3;
+    const int m = bs >> 3;
+    const float inv_nbc = 1.0f / (float)nbc;
+    int lo = lo_s;
+    for (int i0 = cs; i0 < ce; i0 += 32) {                         // warp-uniform trip count (shuffles inside)
+        const int i = i0 + grp;
+        const bool on = i < ce;
+        unsigned e = 0u;
+        if (on) {
+            while (seg_pre[lo + 1] <= i) ++lo;                     // empty segments are stepped over
+            e = list[(size_t)lo * seg_cap + (i - seg_pre[lo])];
+        }
+        const F8Entry x = f8_decode(e, nbc, inv_nbc, bs, R);
+        unsigned S = on ? f8_survivor_sad(x.dir ? L1 : L0, x.dir ? L0 : L1, H, W, Wp, bs, m, x.s_row, x.s_col, x.t_row, x.t_col, pr) : 0u;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+        if (on && pr == 0) {
+            const unsigned sad = S / 1000u;
+            bool decided = true;
+            if (S != 0u && sad * 1000u == S) {                     // flagged: decided by the replay pass
+                const int fp = atomicAdd(&counters[13], 1);
+                if (fp < flag_cap) { flag_list[fp] = e; decided = false; }
+                else if (atomicExch(&redo_mark[(size_t)x.dir * n_blk + x.blk], 0u) != 0u) {      // list full: the block is searched exactly
+                    const int pos = atomicAdd(&counters[11], 1);
+                    if (pos < redo_cap) redo_list[pos] = x.blk | (x.dir ? 0x40000000 : 0);       // FS_DIR_BIT
+                }
+            }
+            if (decided) {
+                const int dr = x.s_row - x.t_row, dc = x.s_col - x.t_col;
+                const unsigned long long key = f8_key(sad, (unsigned)(dr * dr + dc * dc), (unsigned)x.dyi, (unsigned)x.dxi);
+                const int id = x.dir * n_blk + x.blk, h = id & 127;
+                const int owner = atomicCAS(&cid[h], -1, id);
+                if (owner == -1 || owner == id) atomicMin(&ckey[h], key);
+                else atomicMin(&best[id], key);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 128 && cid[threadIdx.x] >= 0) atomicMin(&best[cid[threadIdx.x]], ckey[threadIdx.x]);
+}
+
+// Flagged survivors (a few hundred per 1080p pair): 8 x 8 blocks are replayed in float64 in the reference's operation
+// order -- each lane forms the |dL| terms of its row, then the 64 terms are added row by row, column by column -- larger
+// blocks go to the block-level redo pass (their integer SAD is entered meanwhile; the redo pass overwrites the block).
+__global__ void __launch_bounds__(256)
+fs8_replay_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
+                  const uint8_t *__restrict__ rgb0, const uint8_t *__restrict__ rgb1,
+                  int H, int W, int Wp, int bs, int R, int nbc, int n_blk,
+                  const unsigned *__restrict__ flag_list, int flag_cap, int *__restrict__ counters,
+                  unsigned long long *__restrict__ best, unsigned *__restrict__ redo_mark,
+                  int *__restrict__ redo_list, int redo_cap)
+{
+    if (counters[8]) return;
+    const int n = min(counters[13], flag_cap);
     const int lane = threadIdx.x & 31, pr = lane & 7;
     const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, n_grp = (gridDim.x * blockDim.x) >> 3;
     const int m = bs >> 3;
     const float inv_nbc = 1.0f / (float)nbc;
-    // neighbouring 8-lane groups take neighbouring survivors (same block, same column: shared source rows and target
-    // rows in L1 at the same time)
     for (int i0 = 0; i0 < n; i0 += n_grp) {                        // warp-uniform trip count (shuffles inside)
         const int i = i0 + grp;
         const bool on = i < n;
-        unsigned e = 0u;
-        if (on) {                                                  // global index -> (segment, offset)
-            int lo = 0, hi = n_seg;
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (seg_pre[mid] <= i) lo = mid; else hi = mid; }
-            e = list[(size_t)lo * seg_cap + (i - seg_pre[lo])];
-        }
-        const int dir = e >> 31, blk = (int)((e >> 14) & 0x1ffffu), dyi = (int)((e >> 7) & 127u), dxi = (int)(e & 127u);
-        const int32_t *Ls = dir ? L1 : L0, *Lt = dir ? L0 : L1;
-        int br = (int)(((float)blk + 0.5f) * inv_nbc);             // blk / nbc (blk < 2^17: the float quotient is off by at most one)
-        br -= (br * nbc > blk); br += ((br + 1) * nbc <= blk);
-        const int bc = blk - br * nbc;
-        const int s_row = br * bs, s_col = bc * bs;
-        const int t_row = max(s_row - R, 0) + dyi, t_col = max(s_col - R, 0) + dxi;             // window origin (r0, c0) of f8_bounds
-        unsigned S = 0;
-        if (on) {
-            if (s_row + bs <= H && s_col + bs <= W && t_row + bs <= H && t_col + bs <= W) {      // no padding involved
-                for (int sub = 0; sub < m * m; ++sub) {
-                    const int si = sub / m, sj = sub - si * m;
-                    const int r = si * 8 + pr, c = sj * 8;
-                    const int32_t *ps = Ls + (size_t)(s_row + r) * Wp + s_col + c;
-                    const int4 a0 = *reinterpret_cast<const int4 *>(ps), a1 = *reinterpret_cast<const int4 *>(ps + 4);
-                    const int32_t *q = Lt + (size_t)(t_row + r) * Wp + t_col + c;
-                    S = __sad(a0.x, q[0], S); S = __sad(a0.y, q[1], S); S = __sad(a0.z, q[2], S); S = __sad(a0.w, q[3], S);
-                    S = __sad(a1.x, q[4], S); S = __sad(a1.y, q[5], S); S = __sad(a1.z, q[6], S); S = __sad(a1.w, q[7], S);
-                }
-            } else {                                                // zero padding (np.pad) on either side
-                for (int sub = 0; sub < m * m; ++sub) {
-                    const int si = sub / m, sj = sub - si * m;
-                    const int r1 = s_row + si * 8 + pr, r2 = t_row + si * 8 + pr;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int c1 = s_col + sj * 8 + k, c2 = t_col + sj * 8 + k;
-                        const int a = (r1 < H && c1 < W) ? Ls[(size_t)r1 * Wp + c1] : 0;
-                        const int v = (r2 < H && c2 < W) ? Lt[(size_t)r2 * Wp + c2] : 0;
-                        S = __sad(a, v, S);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
-        // Flagged sum (S a positive multiple of 1000): the reference's float64 accumulation may land just below the
-        // integer and truncate to S / 1000 - 1 (fs.cu).  8 x 8 blocks are replayed here in the reference's operation
-        // order -- each lane forms the |dL| terms of its row, then the 64 terms are added row by row, column by column --
-        // larger blocks go to the block-level redo pass.
-        const bool flagged = on && S != 0u && (S / 1000u) * 1000u == S;
-        unsigned sad = S / 1000u;
-        if (bs == 8 && __any_sync(0xffffffffu, flagged)) {
+        const unsigned e = on ? flag_list[i] : 0u;
+        const F8Entry x = f8_decode(e, nbc, inv_nbc, bs, R);
+        unsigned sad = 0u;
+        if (bs == 8) {
             double tr[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) tr[c] = 0.0;
-            if (flagged) {
-                const uint8_t *rgb_s = dir ? rgb1 : rgb0, *rgb_t = dir ? rgb0 : rgb1;
-                const int r1 = s_row + pr, r2 = t_row + pr;
+            if (on) {
+                const uint8_t *rgb_s = x.dir ? rgb1 : rgb0, *rgb_t = x.dir ? rgb0 : rgb1;
+                const int r1 = x.s_row + pr, r2 = x.t_row + pr;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const int c1 = s_col + c, c2 = t_col + c;
+                    const int c1 = x.s_col + c, c2 = x.t_col + c;
                     double l1 = 0.0, l2 = 0.0;
                     if (r1 < H && c1 < W) { const uint8_t *q = rgb_s + ((size_t)r1 * W + c1) * 3; l1 = luma_f64(q[0], q[1], q[2]); }
                     if (r2 < H && c2 < W) { const uint8_t *q = rgb_t + ((size_t)r2 * W + c2) * 3; l2 = luma_f64(q[0], q[1], q[2]); }
@@ -551,21 +629,25 @@ fs8_refine_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1
             }
             double acc = 0.0;
 #pragma unroll 1
-            for (int i = 0; i < 8; ++i) {
+            for (int r = 0; r < 8; ++r) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, tr[c], i, 8));
+                for (int c = 0; c < 8; ++c) acc = __dadd_rn(acc, __shfl_sync(0xffffffffu, tr[c], r, 8));
             }
-            if (flagged) { sad = (unsigned)acc; if (pr == 0) atomicAdd(&counters[10], 1); }
+            sad = (unsigned)acc;
+            if (on && pr == 0) atomicAdd(&counters[10], 1);
+        } else {
+            unsigned S = on ? f8_survivor_sad(x.dir ? L1 : L0, x.dir ? L0 : L1, H, W, Wp, bs, m, x.s_row, x.s_col, x.t_row, x.t_col, pr) : 0u;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+            sad = S / 1000u;
+            if (on && pr == 0 && atomicExch(&redo_mark[(size_t)x.dir * n_blk + x.blk], 0u) != 0u) {
+                const int pos = atomicAdd(&counters[11], 1);
+                if (pos < redo_cap) redo_list[pos] = x.blk | (x.dir ? 0x40000000 : 0);           // FS_DIR_BIT
+            }
         }
         if (on && pr == 0) {
-            if (flagged && bs != 8) {
-                if (atomicExch(&redo_mark[(size_t)dir * n_blk + blk], 0u) != 0u) {
-                    const int pos = atomicAdd(&counters[11], 1);
-                    if (pos < redo_cap) redo_list[pos] = blk | (dir ? 0x40000000 : 0);           // FS_DIR_BIT
-                }
-            }
-            const int dr = s_row - t_row, dc = s_col - t_col;
-            atomicMin(&best[(size_t)dir * n_blk + blk], f8_key(sad, (unsigned)(dr * dr + dc * dc), (unsigned)dyi, (unsigned)dxi));
+            const int dr = x.s_row - x.t_row, dc = x.s_col - x.t_col;
+            atomicMin(&best[(size_t)x.dir * n_blk + x.blk], f8_key(sad, (unsigned)(dr * dr + dc * dc), (unsigned)x.dyi, (unsigned)x.dxi));
         }
     }
 }
@@ -835,13 +917,13 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     if (have != ctx->fs8_list_cap) CK(ctx, cudaMemsetAsync(ctx->d_fs8_list, 0, have, ctx->stream));     // new buffer: no stale entries, ever
     ctx->fs8_list_cap = have;
     size_t have_b = ctx->fs8_best_cap;
-    if ((rc = memci_reserve(ctx, (void **)&ctx->d_fs8_best, &have_b, (size_t)n_blk * 2 * 12))) return rc;       // keys + redo marks
+    if ((rc = memci_reserve(ctx, (void **)&ctx->d_fs8_best, &have_b, (size_t)n_blk * 2 * 12 + F8_FLAG_CAP * 4))) return rc;       // keys + redo marks + flagged survivors
     if (have_b != ctx->fs8_best_cap) CK(ctx, cudaMemsetAsync(ctx->d_fs8_best, 0xff, have_b, ctx->stream));    // new buffer: armed once, then by fs8_output_kernel
     ctx->fs8_best_cap = have_b;
     p.counters = ctx->d_counters;
     p.redo_mark = reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2);
     p.redo_list = ctx->d_redo_list; p.redo_cap = ctx->redo_cap; p.redo_limit = n_blk * ndir / 16 + 64;
-    CK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 5 * sizeof(int), ctx->stream));   // [8] overflow [9] survivors [10] float64 replays [11] redo blocks [12] tile queue
+    CK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 6 * sizeof(int), ctx->stream));   // [8] overflow [9] survivors [10] float64 replays [11] redo blocks [12] tile queue [13] flagged survivors
     const int n_tiles = p.n_tiles;
     int grid = n_tiles < sh.ctas * ctx->num_sms ? n_tiles : sh.ctas * ctx->num_sms;
     if (grid > F8_MAXSEG) grid = F8_MAXSEG;
@@ -865,9 +947,15 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
                 sh.nt, sh.ctas, sh.rpt, sh.n_stage, sh.nb_tile, sh.box_w, sh.box_rows, sh.smem);
     }
     const int prof_rf = memci_prof_begin(ctx, MEMCI_PROF_REFINE, 0.0);
-    fs8_refine_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, ctx->Wp, bs, R, nbc, n_blk,
+    // the flagged-survivor list lives behind the redo marks (F8_FLAG_CAP entries)
+    unsigned *d_marks = reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2);
+    unsigned *d_flags = d_marks + (size_t)n_blk * 2;
+    fs8_refine_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(fs.luma, ft.luma, H, W, ctx->Wp, bs, R, nbc, n_blk,
                                                                  p.list, p.seg_cap, p.seg_counts, grid, ctx->d_counters, ctx->d_fs8_best,
-                                                                 reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2), ctx->d_redo_list, ctx->redo_cap);
+                                                                 d_flags, F8_FLAG_CAP, d_marks, ctx->d_redo_list, ctx->redo_cap);
+    CKL(ctx);
+    fs8_replay_kernel<<<32, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, ctx->Wp, bs, R, nbc, n_blk, d_flags, F8_FLAG_CAP,
+                                                   ctx->d_counters, ctx->d_fs8_best, d_marks, ctx->d_redo_list, ctx->redo_cap);
     CKL(ctx);
     const int n_out = (br1 - br0) * nbc * ndir;
     fs8_output_kernel<<<ceil_div_i(n_out, 256), 256, 0, ctx->stream>>>(ctx->d_fs8_best, reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2), ctx->d_counters, p.redo_limit,

@@ -199,7 +199,12 @@ __device__ __forceinline__ unsigned mci_key(int eff_r, int eff_c, int dir)
 //      this displacement?" is one shared-memory load and one compare -- and replays the reference's state
 //      machine on a match.
 // Output: the uint8 frame, the packed hole-fill image (P.fill) and the list of hole runs.
+#ifndef SW_TH
 #define SW_TH 8
+#endif
+#ifndef SW_MINB
+#define SW_MINB 4
+#endif
 #define SW_WARPS 4
 #define SW_MAXK 256          // distinct (displacement, direction) keys per tile; more -> dense fallback
 #define SW_STAGE 320         // staged displacement cells per direction
@@ -348,13 +353,16 @@ __device__ __forceinline__ void sw_test_entry(const MciParams &P, const SwShared
 }
 
 template <bool BIDIR>
-__global__ void __launch_bounds__(SW_WARPS * 32, 4)      // 128 registers: any tighter cap spills the 40-register decision state (measured slower)
+__global__ void __launch_bounds__(SW_WARPS * 32, SW_MINB)
 mci_splat_kernel(const __grid_constant__ MciParams P, int tiles_x, int n_tiles)
 {
     __shared__ SwShared sm_all[SW_WARPS];
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
     if (tile >= n_tiles) return;
+#ifdef SW_PHASE_TIMING
+    long long t_ph0 = clock64();
+#endif
     SwShared &sm = sm_all[threadIdx.x >> 5];
     const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
     const int tx0 = txi * 32, ty0 = P.y_begin + tyi * SW_TH;
@@ -463,6 +471,9 @@ mci_splat_kernel(const __grid_constant__ MciParams P, int tiles_x, int n_tiles)
         __syncwarp();
     }
 
+#ifdef SW_PHASE_TIMING
+    long long t_ph1 = clock64();
+#endif
     // ---- 3. phase A: which events fire for the lane's SW_TH pixels (no frame access) ----
     unsigned val[SW_TH];                                       // packed result, bit 24 = hole
     const int sr0_0 = sm.s_r0[0], sc0_0 = sm.s_c0[0], snc_0 = sm.s_nc[0], sr0_1 = sm.s_r0[1], sc0_1 = sm.s_c0[1], snc_1 = sm.s_nc[1];
@@ -542,6 +553,9 @@ mci_splat_kernel(const __grid_constant__ MciParams P, int tiles_x, int n_tiles)
         }
     }
 
+#ifdef SW_PHASE_TIMING
+    long long t_ph2 = clock64();
+#endif
     // ---- 4. outputs: uint8 frame, packed hole-fill image, hole runs (one atomic pair per tile) ----
     // The per-row values go through shared memory (keys[] is dead after the sort) so that this loop can
     // stay rolled: the unrolled form was a quarter of the kernel's code.
@@ -611,6 +625,9 @@ mci_splat_kernel(const __grid_constant__ MciParams P, int tiles_x, int n_tiles)
             pos0 += __popc(sb);
         }
     }
+#ifdef SW_PHASE_TIMING
+    if (lane == 0) { long long t_ph3 = clock64(); unsigned long long *tp = reinterpret_cast<unsigned long long *>(P.hole_list) + 100000; atomicAdd(tp + 0, (unsigned long long)(t_ph1 - t_ph0)); atomicAdd(tp + 1, (unsigned long long)(t_ph2 - t_ph1)); atomicAdd(tp + 2, (unsigned long long)(t_ph3 - t_ph2)); atomicAdd(tp + 3, (unsigned long long)n); atomicAdd(tp + 4, fast ? 1ull : 0ull); atomicAdd(tp + 5, 1ull); }
+#endif
 }
 
 // ---- hole filling: Unidirectional.py:62-80 / Bidirectional.py:55-73 -----------------------------
@@ -798,12 +815,19 @@ int memci_mci_run(memci_ctx *ctx, int slot_src, int slot_tgt, const MVField *fwd
     const int tiles_x = ceil_div_i(W, 32), n_tiles = tiles_x * ceil_div_i(P.y_end - P.y_begin, SW_TH);
     ctx->mci_timed = 0;
     if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+#ifdef SW_PHASE_TIMING
+    cudaMemsetAsync(reinterpret_cast<unsigned long long *>(ctx->d_hole_list) + 100000, 0, 64, ctx->stream);
+#endif
     const int prof = memci_prof_begin(ctx, MEMCI_PROF_MCI, 9.0 * (double)(P.y_end - P.y_begin) * W);      // 2 frame reads + 1 write
     if (bidir) mci_splat_kernel<true><<<ceil_div_i(n_tiles, SW_WARPS), SW_WARPS * 32, 0, ctx->stream>>>(P, tiles_x, n_tiles);
     else mci_splat_kernel<false><<<ceil_div_i(n_tiles, SW_WARPS), SW_WARPS * 32, 0, ctx->stream>>>(P, tiles_x, n_tiles);
     memci_prof_end(ctx, prof);
     CKL(ctx);
     if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[3], ctx->stream)); ctx->mci_timed = 1; }
+#ifdef SW_PHASE_TIMING
+    { unsigned long long h[6]; cudaStreamSynchronize(ctx->stream); cudaMemcpy(h, reinterpret_cast<unsigned long long *>(ctx->d_hole_list) + 100000, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "splat phases (avg cycles per tile-warp): list %.0f, walk+pixels %.0f, output %.0f; entries/tile %.2f, fast tiles %.3f, tiles %llu\n", (double)h[0] / h[5], (double)h[1] / h[5], (double)h[2] / h[5], (double)h[3] / h[5], (double)h[4] / h[5], h[5]); }
+#endif
     const int prof_hf = memci_prof_begin(ctx, MEMCI_PROF_HOLEFILL, 0.0);
     mci_holefill_kernel<<<ctx->num_sms * 6, HF_WARPS * 32, 0, ctx->stream>>>(P.fill, P.out, P.hole_list, P.counters, H, W);
     memci_prof_end(ctx, prof_hf);

@@ -72,6 +72,7 @@ class PairPipeline:
         self.ctxs = [DeviceContext(H, W, device) for _ in range(max(1, int(n_contexts)))]
         self.stager = None
         self._ring_cursor = 0
+        self.uploads = 0                                  # source frames copied host -> device so far
 
     def close(self):
         if self.ctxs:
@@ -179,6 +180,7 @@ class PairPipeline:
                 st.upload(slot, frames[f])
                 ring_of[f] = slot
                 n_up += 1
+                self.uploads += 1
             return ring_of[f]
 
         prev = {}                                        # context -> pair it processed last

@@ -659,7 +659,7 @@ def test_interpolate_video_is_the_fast_path_and_equals_frame_by_frame(gpu, st, f
         it.set_video_stream(ArrayVideoStream(frames, fps_in))
         got = []
         it.interpolate_video(sink=got.append)
-        launches = it._pipe.launch_count()
+        launches = sum(p_.launch_count() for p_ in it._pipe)
         it.close()
         assert len(got) == n_out, extra
         for i, (g, w) in enumerate(zip(got, want)):
