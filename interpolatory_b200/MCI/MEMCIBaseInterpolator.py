@@ -142,6 +142,9 @@ class MEMCIBaseInterpolator(BaseInterpolator):
                 b.close()
             self._pin = None
 
+    def _mv_dense(self, slot):
+        return self._dev.download_mv_dense(slot)
+
     # ---- interpolate_video(): the drop-in call is the fast path ---------------------------------------------
     def _output_frames(self, n, copy=True):
         """The frames get_interpolated_frame(0 .. n-1) would return, in order and byte for byte, produced in windows of

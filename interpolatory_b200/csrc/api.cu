@@ -148,6 +148,7 @@ int memci_ctx_destroy(memci_ctx *ctx)
     if (ctx->d_fs8_list) cudaFree(ctx->d_fs8_list);
     if (ctx->d_f8_tiles) cudaFree(ctx->d_f8_tiles);
     if (ctx->d_fs8_best) cudaFree(ctx->d_fs8_best);
+    if (ctx->d_fs8_codes) cudaFree(ctx->d_fs8_codes);
     for (int i = 0; i < 4; ++i) {
         if (ctx->fs_plan[i].d_tiles) cudaFree(ctx->fs_plan[i].d_tiles);
         free(ctx->fs_plan[i].row_tile_start); free(ctx->fs_plan[i].row_cand);

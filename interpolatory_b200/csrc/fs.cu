@@ -95,13 +95,29 @@ __global__ void fs_generic_kernel(const int32_t *__restrict__ L0, const int32_t 
 }
 
 // =========================================================================================
-// Redo pass: one CTA per listed block (same exact arithmetic as fs_generic_kernel; 8 warps, about four candidates
-// per thread at +-16, eight CTAs per SM so that several hundred listed blocks run in one wave).
+// Redo pass: one CTA per listed block, same exact arithmetic as fs_generic_kernel.  Block and search window are staged
+// in shared memory as luma1000 ints (zero padded like np.pad).  A thread takes (column offset, FS_REDO_G consecutive row
+// offsets): it keeps an 8 x 8 source sub-block in 64 registers and walks the FS_REDO_G + 7 window rows those candidates
+// share, 8 LDS per row, neighbouring threads = neighbouring columns (conflict-free) -- a third of a shared-memory load per
+// pixel pair (the first version read both operands from shared memory for every pair, staged a float64 copy of the
+// whole window for the rare flagged candidate, and spent 20 us on a thousand 8 x 8 blocks, 350 us on as many 16 x 16 +-32
+// blocks).  Flagged candidates (sum a positive multiple of 1000) are marked in a bitmap; only if there are any, the
+// float64 luma of block and window is staged as well and every marked candidate is replayed by one thread in the
+// reference's order.  (Flat grey content flags EVERY candidate of a block -- all sums are multiples of 1000 there -- so the
+// replays must run thread-parallel out of shared memory; textured blocks have about one flagged candidate in a thousand,
+// and up to FS_REDO_FLAGS of them are replayed straight from the RGB bytes, a warp each, without staging anything.)
 // =========================================================================================
 // List entries carry the search direction in bit 30 (pair launches: direction 1 swaps the frames).
 #define FS_DIR_BIT 0x40000000
 #define FS_REDO_NT 256
-__global__ void __launch_bounds__(FS_REDO_NT)
+#define FS_REDO_G 4
+#define FS_REDO_FLAGS 16           // up to this many flagged candidates per block are replayed straight from the RGB bytes, a warp each
+static inline int fs_redo_smem_bytes(int bs, int R)
+{
+    const int ww = bs + 2 * R;
+    return (bs * bs + (ww + FS_REDO_G) * ww) * 4 + 8 + (bs * bs + ww * ww) * 8 + ((ww * ww + 31) / 32) * 4;
+}
+__global__ void __launch_bounds__(FS_REDO_NT, 2)
 fs_redo_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
                const uint8_t *__restrict__ rgb0, const uint8_t *__restrict__ rgb1,
                int H, int W, int Wp, int bs, int R, int nbc,
@@ -109,13 +125,15 @@ fs_redo_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
                float2 *__restrict__ out_vec0, float *__restrict__ out_sad0,
                float2 *__restrict__ out_vec1, float *__restrict__ out_sad1)
 {
-    // Shared staging, zero padded like np.pad: the block and its search window as luma1000 ints
-    // (fast SAD) and as the reference's float64 luma (exact replay of flagged candidates).
-    extern __shared__ double redo_sm[];
+    extern __shared__ __align__(16) int redo_sm[];
     __shared__ unsigned long long wbest[FS_REDO_NT / 32];
-    const int ww = bs + 2 * R;
-    double *dref = redo_sm, *dwin = redo_sm + bs * bs;
-    int *ref = reinterpret_cast<int *>(dwin + ww * ww), *win = ref + bs * bs;
+    __shared__ int n_flag_s;
+    __shared__ unsigned short flag_s[FS_REDO_FLAGS];
+    const int ww = bs + 2 * R, m = bs >> 3;
+    int *ref = redo_sm, *win = ref + bs * bs;
+    double *dref = reinterpret_cast<double *>(redo_sm + (((bs * bs + (ww + FS_REDO_G) * ww) + 1) & ~1)), *dwin = dref + bs * bs;
+    unsigned *bits = reinterpret_cast<unsigned *>(dwin + ww * ww);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int total = *list_count;
     for (int it = blockIdx.x; it < total; it += gridDim.x) {
         const int entry = list[it];
@@ -130,49 +148,127 @@ fs_redo_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1,
         const int nr = b.r1 - b.r0, nc = b.c1 - b.c0;
         for (int i = threadIdx.x; i < bs * bs; i += blockDim.x) {
             const int r = s_row + i / bs, c = s_col + i % bs;
-            int v = 0; double d = 0.0;
-            if (r < H && c < W) {
-                const uint8_t *p = rgb_s + ((size_t)r * W + c) * 3;
-                v = Ls[(size_t)r * Wp + c];
-                d = luma_f64(p[0], p[1], p[2]);
-            }
-            ref[i] = v; dref[i] = d;
+            ref[i] = (r < H && c < W) ? Ls[(size_t)r * Wp + c] : 0;
         }
-        for (int i = threadIdx.x; i < ww * ww; i += blockDim.x) {
+        for (int i = threadIdx.x; i < (ww + FS_REDO_G) * ww; i += blockDim.x) {
             const int r = s_row - R + i / ww, c = s_col - R + i % ww;
-            int v = 0; double d = 0.0;
-            if (r >= 0 && r < H && c >= 0 && c < W) {
-                const uint8_t *p = rgb_t + ((size_t)r * W + c) * 3;
-                v = Lt[(size_t)r * Wp + c];
-                d = luma_f64(p[0], p[1], p[2]);
-            }
-            win[i] = v; dwin[i] = d;
+            win[i] = (r >= 0 && r < H && c >= 0 && c < W) ? Lt[(size_t)r * Wp + c] : 0;
         }
+        const int ncand = nr > 0 && nc > 0 ? nr * nc : 0;
+        for (int i = threadIdx.x; i < (ncand + 31) / 32; i += blockDim.x) bits[i] = 0u;
+        if (threadIdx.x == 0) n_flag_s = 0;
         __syncthreads();
         unsigned long long best = KEY_NONE;
-        const int ncand = nr > 0 && nc > 0 ? nr * nc : 0;
-        for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
-            const int ri = c / nc, ci = c - ri * nc;
-            const int t_row = b.r0 + ri, t_col = b.c0 + ci;
-            const int woff = (t_row - (s_row - R)) * ww + (t_col - (s_col - R));
-            unsigned S = 0;
-            for (int i = 0; i < bs; ++i)
-                for (int j = 0; j < bs; ++j) S = __sad(ref[i * bs + j], win[woff + i * ww + j], S);
-            unsigned sad = S / 1000u;
-            if (S != 0 && sad * 1000u == S) {
-                // flagged: sequential f64 accumulation in the reference's order (full_search.py:17)
+        const int n_grp = (nr + FS_REDO_G - 1) / FS_REDO_G;
+        const int n_items = nr > 0 && nc > 0 ? n_grp * nc : 0;
+        for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
+            const int gi = item / nc, ci = item - gi * nc, ri0 = gi * FS_REDO_G;
+            const int *w0 = win + (b.r0 - (s_row - R) + ri0) * ww + (b.c0 - (s_col - R) + ci);
+            unsigned S[FS_REDO_G];
+#pragma unroll
+            for (int g = 0; g < FS_REDO_G; ++g) S[g] = 0u;
+            for (int sub = 0; sub < m * m; ++sub) {
+                const int si = sub / m, sj = sub - si * m;
+                int rf[64];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int4 a0 = *reinterpret_cast<const int4 *>(ref + (si * 8 + i) * bs + sj * 8);
+                    const int4 a1 = *reinterpret_cast<const int4 *>(ref + (si * 8 + i) * bs + sj * 8 + 4);
+                    rf[i * 8 + 0] = a0.x; rf[i * 8 + 1] = a0.y; rf[i * 8 + 2] = a0.z; rf[i * 8 + 3] = a0.w;
+                    rf[i * 8 + 4] = a1.x; rf[i * 8 + 5] = a1.y; rf[i * 8 + 6] = a1.z; rf[i * 8 + 7] = a1.w;
+                }
+                const int *wp = w0 + (si * 8) * ww + sj * 8;
+#pragma unroll
+                for (int wr = 0; wr < FS_REDO_G + 7; ++wr) {
+                    int wv[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) wv[q] = wp[wr * ww + q];
+#pragma unroll
+                    for (int g = 0; g < FS_REDO_G; ++g) {
+                        const int i = wr - g;
+                        if (i >= 0 && i < 8) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) S[g] = __sad(rf[i * 8 + q], wv[q], S[g]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < FS_REDO_G; ++g) {
+                const int ri = ri0 + g;
+                if (ri >= nr) continue;
+                const int t_row = b.r0 + ri, t_col = b.c0 + ci;
+                unsigned sad = S[g] / 1000u;
+                if (S[g] != 0 && sad * 1000u == S[g]) {
+                    const int c = ri * nc + ci;                      // flagged: decided by the float64 replay below
+                    atomicOr(&bits[c >> 5], 1u << (c & 31));
+                    const int fp = atomicAdd(&n_flag_s, 1);
+                    if (fp < FS_REDO_FLAGS) flag_s[fp] = (unsigned short)((ri << 8) | ci);
+                    continue;
+                }
+                const int dr = s_row - t_row, dc = s_col - t_col;
+                const unsigned long long k = fs_key(sad, (unsigned)(dr * dr + dc * dc), ri, ci);
+                best = k < best ? k : best;
+            }
+        }
+        __syncthreads();
+        const int nf = n_flag_s;                          // CTA-uniform
+        if (nf > 0 && nf <= FS_REDO_FLAGS && (FS_REDO_NT / 32) * bs * bs <= ww * ww) {
+            // a few flagged candidates: a warp each -- lanes form the |dL| terms side by side, lane 0 adds them up in the
+            // reference's order (full_search.py:17); the term buffers live where the float64 window would
+            for (int f = warp; f < nf; f += FS_REDO_NT / 32) {
+                const int ri = flag_s[f] >> 8, ci = flag_s[f] & 255;
+                const int t_row = b.r0 + ri, t_col = b.c0 + ci;
+                double *tb = dwin + (size_t)warp * bs * bs;
+                for (int px = lane; px < bs * bs; px += 32) {
+                    const int i = px / bs, j = px - i * bs;
+                    const int r1 = s_row + i, c1 = s_col + j, r2 = t_row + i, c2 = t_col + j;
+                    double l1 = 0.0, l2 = 0.0;
+                    if (r1 < H && c1 < W) { const uint8_t *q = rgb_s + ((size_t)r1 * W + c1) * 3; l1 = luma_f64(q[0], q[1], q[2]); }
+                    if (r2 < H && c2 < W) { const uint8_t *q = rgb_t + ((size_t)r2 * W + c2) * 3; l2 = luma_f64(q[0], q[1], q[2]); }
+                    tb[px] = fabs(__dsub_rn(l1, l2));
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    double acc = 0.0;
+                    for (int px = 0; px < bs * bs; ++px) acc = __dadd_rn(acc, tb[px]);
+                    const int dr = s_row - t_row, dc = s_col - t_col;
+                    const unsigned long long k = fs_key((unsigned)acc, (unsigned)(dr * dr + dc * dc), ri, ci);
+                    best = k < best ? k : best;
+                }
+                __syncwarp();
+            }
+        } else if (nf > 0) {                              // many (flat content flags every candidate): float64 copy of block and window
+            for (int i = threadIdx.x; i < bs * bs; i += blockDim.x) {
+                const int r = s_row + i / bs, c = s_col + i % bs;
+                double d = 0.0;
+                if (r < H && c < W) { const uint8_t *q = rgb_s + ((size_t)r * W + c) * 3; d = luma_f64(q[0], q[1], q[2]); }
+                dref[i] = d;
+            }
+            for (int i = threadIdx.x; i < ww * ww; i += blockDim.x) {
+                const int r = s_row - R + i / ww, c = s_col - R + i % ww;
+                double d = 0.0;
+                if (r >= 0 && r < H && c >= 0 && c < W) { const uint8_t *q = rgb_t + ((size_t)r * W + c) * 3; d = luma_f64(q[0], q[1], q[2]); }
+                dwin[i] = d;
+            }
+            __syncthreads();
+            for (int c = threadIdx.x; c < ncand; c += blockDim.x) {
+                if (!(bits[c >> 5] & (1u << (c & 31)))) continue;
+                const int ri = c / nc, ci = c - ri * nc;
+                const int t_row = b.r0 + ri, t_col = b.c0 + ci;
+                const int woff = (t_row - (s_row - R)) * ww + (t_col - (s_col - R));
+                // sequential f64 accumulation in the reference's order (full_search.py:17)
                 double acc = 0.0;
                 for (int i = 0; i < bs; ++i)
                     for (int j = 0; j < bs; ++j)
                         acc = __dadd_rn(acc, fabs(__dsub_rn(dref[i * bs + j], dwin[woff + i * ww + j])));
-                sad = (unsigned)acc;
+                const int dr = s_row - t_row, dc = s_col - t_col;
+                const unsigned long long k = fs_key((unsigned)acc, (unsigned)(dr * dr + dc * dc), ri, ci);
+                best = k < best ? k : best;
             }
-            const int dr = s_row - t_row, dc = s_col - t_col;
-            const unsigned long long k = fs_key(sad, (unsigned)(dr * dr + dc * dc), ri, ci);
-            best = k < best ? k : best;
         }
         best = shfl_min_u64(best);
-        if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
+        if (lane == 0) wbest[warp] = best;
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int w = 1; w < FS_REDO_NT / 32; ++w) best = wbest[w] < best ? wbest[w] : best;
@@ -762,13 +858,19 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
     const char *pf_env = getenv("MEMCI_FS_PREFILTER");
     bool use8 = pl->n_tiles > 0 && !(pf_env && atoi(pf_env) == 0) && memci_fs8_eligible(ctx, bs, R);
     // Content feedback: the prefilter only pays where it prunes.  The counters of a recent two-phase search come back
-    // through an asynchronous copy; if they show an overflow, many redo blocks or more than 5 % survivors, the next
-    // 32 searches go straight to the exact kernel (then the prefilter is probed again).  MEMCI_FS_PREFILTER=1 pins it on.
+    // through an asynchronous copy; if they show an overflow, or survivors and redo blocks that cost more than the exact
+    // kernel would have, the next 32 searches go straight to the exact kernel (then the prefilter is probed again).  MEMCI_FS_PREFILTER=1 pins it on.
     if (use8 && !(pf_env && atoi(pf_env) == 1)) {
         if (ctx->fs8_feedback_pending && cudaEventQuery(ctx->ev_fs8_feedback) == cudaSuccess) {
             const int *h = ctx->h_fs8_feedback;
             ctx->fs8_feedback_pending = 0;
-            if (h[0] != 0 || (long long)h[1] * 20 > ctx->fs8_feedback_cand || h[3] > nbr * nbc * ndir / 32) ctx->fs8_backoff = 32;
+            // Estimated GPU time of what that search did against the exact kernel's, from measured rates (1080p 8 x 8 +-16 and
+            // 4K 16 x 16 +-32, profiles/): exact 12.9 T pixel-ops/s, prefilter 36 T, refine 0.15 + 0.001 bs^2 ns per
+            // survivor, redo pass 4 T pixel-ops/s.  An overflow (h[0]) means the exact kernel ran on top of everything.
+            const double ops = (double)ctx->fs8_feedback_cand * bs * bs;
+            const double per_block = ops / ((double)nbr * nbc * ndir);
+            const double est_us = ops / 36e6 + h[1] * (0.15 + 0.001 * bs * bs) * 1e-3 + h[3] * per_block / 4e6;
+            if (h[0] != 0 || est_us > ops / 12.9e6) ctx->fs8_backoff = 32;
         }
         if (ctx->fs8_backoff > 0) { --ctx->fs8_backoff; use8 = false; }
     }
@@ -812,6 +914,8 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         if (!use8) {
             if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
             prof = memci_prof_begin(ctx, MEMCI_PROF_FS, (double)ctx->fs_last_ops);
+        } else {
+            prof = memci_prof_begin(ctx, MEMCI_PROF_REFINE, 0.0);      // the gated exact kernel (normally a no-op) and the redo pass
         }
         switch (pl->G) {
         case 5: rc = fs_launch_tiled<5>(ctx, tm, p, smem); break;
@@ -821,7 +925,7 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         case 33: rc = fs_launch_tiled<33>(ctx, tm, p, smem); break;
         default: rc = fs_launch_tiled<11>(ctx, tm, p, smem); break;
         }
-        if (!use8) memci_prof_end(ctx, prof);
+        if (!use8) { memci_prof_end(ctx, prof); prof = -1; }
         if (p.trace) {                                   // debug dump: one line per (tile, warp)
             unsigned long long *h = (unsigned long long *)malloc(trace_n * 8);
             cudaStreamSynchronize(ctx->stream);
@@ -835,10 +939,10 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         if (rc) return rc;
         if (ctx->timing) { CK(ctx, cudaEventRecord(ctx->ev[1], ctx->stream)); ctx->fs_timed = 1; }
         // exact pass over the (normally few) blocks on the redo list
-        const int redo_smem = (bs * bs + (bs + 2 * R) * (bs + 2 * R)) * 12;
+        const int redo_smem = fs_redo_smem_bytes(bs, R);
         if (redo_smem <= 160 * 1024) {
             CK(ctx, cudaFuncSetAttribute(fs_redo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, redo_smem));
-            fs_redo_kernel<<<ctx->num_sms * 8, FS_REDO_NT, redo_smem, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbc,
+            fs_redo_kernel<<<ctx->num_sms * 4, FS_REDO_NT, redo_smem, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, Wp, bs, R, nbc,
                                                                               ctx->d_redo_list, redo_count, out->vec, out->sad,
                                                                               p.out_vec[1], p.out_sad[1]);
         } else {
@@ -846,6 +950,7 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
                                                                      ctx->d_redo_list, redo_count, out->vec, out->sad,
                                                                      p.out_vec[1], p.out_sad[1]);
         }
+        if (prof >= 0) memci_prof_end(ctx, prof);
         CKL(ctx);
     } else {
         if (ctx->timing) CK(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));

@@ -18,13 +18,20 @@
 //                         bytes of any column offset as two aligned words of plane (offset & 3), and TMA -- whose inner
 //                         coordinate must be 16-byte aligned (probed: any other x raises an illegal instruction) -- can
 //                         stage all four shifts with ONE 3-D tile load
-//   fs8_prefilter_kernel  persistent CTAs, dynamic job queue; job = adjacent blocks of one block row (of two, side by side,
-//                         where the column range is clipped), staged by TMA (cp.async.bulk.tensor.3d + mbarrier, two
-//                         stages); thread = (block, dx) candidate column; survivors appended to per-CTA segments of the list
+//   fs8_prefilter_kernel  pure search: persistent CTAs, dynamic job queue; job = adjacent blocks of one block row (of two,
+//                         side by side, where the column range is clipped), staged by TMA (cp.async.bulk.tensor.3d +
+//                         mbarrier, two or three stages); thread = (block, dx) candidate column.  Out: an 8-bit monotone code
+//                         of every A (global memory, one byte per candidate: L2-resident until the next kernel reads it)
+//                         and the block minima (one global atomicMin per warp and block)
+//                         -- plus the exact minimum of every column and the block minima (one global atomicMin per warp
+//                         and block).  No survivor logic, no CTA-wide hand-over: 0.54 of the VABSDIFF4 issue rate at 1080p
+//   fs8_scan_kernel       thread per candidate column (the prefilter's own mapping, so every load is coalesced): column
+//                         minimum against the block's threshold; the few columns that pass compare their codes and append
+//                         their survivors to the list (one global atomic per warp)
 //   fs8_refine_kernel     8 lanes per survivor: exact luma-SAD, 64-bit atomicMin; flagged sums go on a short list
 //   fs8_replay_kernel     float64 replay of the flagged sums in the reference's operation order
 //   fs8_output_kernel     thread per block: key -> (dy, dx, sad); decides the pair-level fallback; re-arms the buffers
-// Blocks that cannot be pruned (flat content, segment overflow, flagged sums of 16 x 16 blocks) go to fs_redo_kernel (fs.cu).
+// Blocks that cannot be pruned (flat content, flagged sums of 16 x 16 blocks) go to fs_redo_kernel (fs.cu).
 #include <stdlib.h>
 #include <type_traits>
 
@@ -32,34 +39,33 @@
 
 #define F8_G 11
 #define F8_NBMAX 32
-#define F8_MAXSEG 1024          // CTAs of the prefilter grid = segments of the survivor list
+#define F8_COL_HITS 12           // survivors a candidate column may hold; more: the block has nothing to prune, exact block search (redo pass)
+#define F8_NLIST 64             // sub-lists of the survivor list (spreads the scan pass's atomics over as many addresses)
+#define F8_CURSOR_STRIDE 32     // words between the cursors of two sub-lists: one 128-byte line each
 #define F8_FLAG_CAP 16384        // flagged survivors (sum a multiple of 1000) replayed in float64 per search
-#define F8_EMIT_WORDS 9          // votes (eight row offsets each) a warp keeps in registers while it emits survivors
+#define F8_CODE_CAP ((size_t)512 << 20)   // bytes of candidate codes kept at a time; longer searches run in chunks of jobs
+
+struct F8Tile { short dir, nv; short by, bx0; short nb, pad; };   // direction, block rows (1 or 2), first block row / column, blocks
+
+struct F8Conv { unsigned one, two, c8k, magic, c256, c64k, c16m, unbias; float fmagic; };   // 1, 2, 8192, 0x4B000000, 2^8, 2^16, 2^24, -0x08080800, 8388608.0f: opaque to the compiler
 
 struct F8Params {
-    int H, W, bs, m, R, Rp, nbr, nbc;
-    int n_tiles;
-    const struct F8Tile *tiles;  // the jobs, in queue order (host table, cached per search geometry)
-    int n_stage;                 // shared-memory stages of (window planes + source blocks): 2 = the next tile lands while this one is searched
-    unsigned c_two, c_8k, c_magic; float c_fmagic;   // the constants of F8Conv, opaque to the compiler
-    int ablate;                  // timing experiments only (MEMCI_F8_ABLATE=1): no survivor emission (nothing survives: wrong results)
-    int flush_at;                // the hand-over of the previous job happens after this many + 1 row-offset groups of the current one
+    int H, W, bs, m, R, Rp, nbr, nbc, n_blk;
+    int t0, n_tiles;             // jobs [t0, t0 + n_tiles) of the table
+    const F8Tile *tiles;         // the jobs, in queue order (host table, cached per search geometry)
+    int n_stage;                 // shared-memory stages of (window planes + source blocks): the next jobs land while this one is searched
+    F8Conv cv;                   // conversion / packing constants, opaque to the compiler
     int box_x0, box_y0;          // padded-plane coordinates of frame pixel (0, 0)
     int rs;                      // words per staged window row (= TMA box width / 4)
     int plane_words;             // words per staged plane, = 8 or 24 (mod 32): the four planes of a row land in different banks
     int ref_rs, ref_rows;        // words per row / rows of the staged source blocks
-    int a_rows;                  // row offsets per A buffer (groups * F8_G)
-    unsigned tx_bytes;           // bytes one tile's TMA loads deliver
-    int T;                       // survivor threshold 2 n + 1
-    unsigned *list; int seg_cap;   // survivor list: one segment of seg_cap entries per CTA
-    unsigned *seg_counts;         // [grid] entries written per segment
-    unsigned *redo_mark;          // [2][n_blk] 0 = block already on the redo list
-    int *redo_list; int redo_cap; // blocks for fs_redo_kernel: flat / overflowing blocks here, flagged sums in the refine pass
-    int redo_limit;               // more redo blocks than this: the pair falls back to the exact kernel (fs8_output_kernel decides)
-    int *counters;               // [8] survivor list overflowed, [9] survivors, [11] redo blocks, [12] tile queue cursor
+    int n_groups;                // groups of F8_G row offsets per candidate column = 16-byte words per column in the code array
+    unsigned tx_bytes;           // bytes one job's TMA loads deliver
+    uint4 *codes;                // [n_tiles][threads][n_groups]: codes of A + 1 of (job, candidate column), eleven row offsets per word
+    unsigned *colinfo;           // [n_tiles][threads]: min(A) + 1 of the candidate column (exact) | slot << 16 | column offset << 22; 0xffffffff: no column
+    unsigned *bmin;              // [n_tiles][64] A_min + 1 per (job, slot = block row of the job * 32 + block); 0xffffffff between searches
+    int *counters;               // [8] pair falls back to the exact kernel, [9] survivors, [10] float64 replays, [11] redo blocks, [12] job queue cursor, [13] flagged survivors
 };
-
-struct F8Tile { short dir, nv; short by, bx0; short nb, pad; };   // direction, block rows (1 or 2), first block row / column, blocks
 
 struct F8Geo {                   // geometry of one job; written by warp 0 before it arms the job's loads
     int t;                       // index in the table, < 0: the queue is empty
@@ -69,6 +75,7 @@ struct F8Geo {                   // geometry of one job; written by warp 0 befor
     int dwin, dref;              // bytes between the 16-byte aligned TMA origin and the wanted one (window / source blocks)
     int pre[F8_NBMAX + 1], dx_lo[F8_NBMAX];
 };
+
 
 struct FsBounds8 { int r0, r1, c0, c1; };
 // candidate window of one block: full_search.py:33-43 incl. the H-for-W comparison at :37 (same as fs.cu fs_bounds)
@@ -91,19 +98,20 @@ __device__ __forceinline__ unsigned f8_sad4(unsigned a, unsigned b, unsigned acc
     return r;
 }
 
+
 // One group of F8_G consecutive row offsets of one candidate column is finished.  The accumulators hold A + 1.  The A
 // values go out as an 8-bit MONOTONE code -- code(v) = bits 19..26 of float(2 v): 4 exponent bits (2 <= 2 v < 2^18) + 4
 // mantissa bits, i.e. 16 steps per octave -- so the survivor test later compares code(A + 1) with code(A_min + 1 + T): a
 // superset of the exact test A <= A_min + T (monotone => nothing is lost; a few extra survivors within one step, 1/16
-// of the value, above the threshold).  Half the shared memory of uint16 -- which is what pays for the second stage of
-// the window planes -- with the full 16-bit range, and nothing on the integer-ALU pipe the SADs are bound by: IMAD
-// (2 v + 2^23-as-float bits), FADD (- 2^23: the classic int-to-float without I2F), IMAD.HI (>> 19), all three on the FMA
-// pipe, with constants that come from the parameter block (literals would be turned back into ALU shifts / logic ops).
-// Layout A[row offset][thread], A_PITCH = threads + 4 bytes per row: the 32 stores of a warp fall into 8 consecutive
-// words, and eight consecutive row offsets of one column fall into eight different banks.  The column minimum stays
-// exact.  MASK: the group sticks out of the valid row range (last group only).
-struct F8Conv { unsigned two, c8k, magic; float fmagic; };       // 2, 8192, 0x4B000000 and 8388608.0f, opaque to the compiler
-__device__ __forceinline__ unsigned f8_code(unsigned v, const F8Conv cv)   // v in [1, 65535]
+// of the value, above the threshold).  Nothing of the conversion touches the integer-ALU pipe the SADs are bound by:
+// IMAD (2 v + 2^23-as-float bits), FADD (- 2^23: the classic int-to-float without I2F), IMAD.HI (>> 19; leaves code + 2048),
+// then the eleven codes of the group are packed into three words by IMADs (x * 256^k + w; the 2048s come off with one
+// more IMAD per word) -- all on the FMA pipe, with constants that come from the parameter block (literals would be
+// turned back into ALU shifts / logic ops) -- and leave as ONE 16-byte store.  Layout [job][thread][group]: the codes of
+// a candidate column are contiguous (48 bytes at 1080p), which is what the scan pass wants -- it reads only the ~15 % of the
+// columns whose minimum is near their block's, and a column stored down a [row][thread] array would cost it 33 sectors
+// instead of 2.  The column minimum stays exact.  MASK: the group sticks out of the valid row range (last group only).
+__device__ __forceinline__ unsigned f8_code(unsigned v, const F8Conv cv)   // v in [1, 65535]; returns code + 2048
 {
     unsigned t, x;
     float f;
@@ -112,19 +120,34 @@ __device__ __forceinline__ unsigned f8_code(unsigned v, const F8Conv cv)   // v 
     asm("mul.hi.u32 %0, %1, %2;" : "=r"(x) : "r"(__float_as_uint(f)), "r"(cv.c8k));
     return x;                                                      // the code is the low byte
 }
-template <bool MASK, int A_PITCH>
-__device__ __forceinline__ void f8_finish_group(unsigned (&acc)[F8_G], int n_valid, unsigned char *cg, unsigned &cmin, const F8Conv cv)
+__device__ __forceinline__ unsigned f8_mad(unsigned a, unsigned b, unsigned c)
 {
+    unsigned r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+template <bool MASK>
+__device__ __forceinline__ void f8_finish_group(unsigned (&acc)[F8_G], int n_valid, uint4 *cg, unsigned &cmin, const F8Conv cv)
+{
+    static_assert(F8_G == 11, "three words of packed codes per group");
     if (MASK) {
 #pragma unroll
         for (int gi = 0; gi < F8_G; ++gi) acc[gi] = gi < n_valid ? acc[gi] : 0xffffu;
     }
+    unsigned x[F8_G];
 #pragma unroll
-    for (int gi = 0; gi < F8_G; ++gi) cg[gi * A_PITCH] = (unsigned char)f8_code(acc[gi], cv);
+    for (int gi = 0; gi < F8_G; ++gi) x[gi] = f8_code(acc[gi], cv);
+    uint4 w;
+    w.x = f8_mad(f8_mad(x[3], cv.c16m, f8_mad(x[2], cv.c64k, f8_mad(x[1], cv.c256, x[0]))), cv.one, cv.unbias);
+    w.y = f8_mad(f8_mad(x[7], cv.c16m, f8_mad(x[6], cv.c64k, f8_mad(x[5], cv.c256, x[4]))), cv.one, cv.unbias);
+    w.z = f8_mad(f8_mad(x[10], cv.c64k, f8_mad(x[9], cv.c256, x[8])), cv.one, cv.unbias);
+    w.w = 0u;
+    *cg = w;
 #pragma unroll
     for (int gi = 0; gi + 1 < F8_G; gi += 2) cmin = min(cmin, min(acc[gi], acc[gi + 1]));     // VIMNMX3
     if (F8_G & 1) cmin = min(cmin, acc[F8_G - 1]);
 }
+
 
 // 8 x 8 source sub-block in rl / rh, F8_G + 7 window rows streamed from the lane's pre-shifted plane: 176 VABSDIFF4.
 __device__ __forceinline__ void f8_accumulate(unsigned (&acc)[F8_G], const unsigned (&rl)[8], const unsigned (&rh)[8],
@@ -141,20 +164,17 @@ __device__ __forceinline__ void f8_accumulate(unsigned (&acc)[F8_G], const unsig
     }
 }
 
+
 // Persistent.  A JOB is one tile of the host's table (F8Tile): nb adjacent blocks of one block row -- or, where the
 // reference's H-for-W column bound (full_search.py:37) leaves a block only 17 of its 33 column offsets at 1080p, of TWO
 // block rows searched side by side by the two halves of the CTA -- so every job keeps ~500 of the 512 threads busy and
 // all jobs cost the same.  Jobs come off a queue (one global atomic per job, taken by warp 0); a job's target window --
 // all four byte shifts, one 3-D TMA load -- and source blocks land in one of `n_stage` shared-memory stages and signal
-// bar_full.  Per job j:
-//   search the first row-offset group of the thread's candidate column                          -> A[j & 1]
-//   hand-over of job j - 1: its block minima were completed a third of a search ago, so the wait on bar_min[(j - 1) & 1]
-//     falls through; warp 0 refills the stage job j - 1 vacated (job j + 1 lands while job j is searched); the warp
-//     emits job j - 1's survivors
-//   search the other groups; column minima -> block minima (shared atomicMin, generation-tagged: never reset);
-//   arrive bar_min[j & 1]
-// No warp idles for the slowest one, no __syncthreads() after the prologue.  With one stage (wide searches whose window
-// does not fit twice) the hand-over of job j happens at its own end.
+// bar_full[stage].  A warp searches its 32 candidate columns, stores the codes, says "done with the stage"
+// (bar_empty[stage]) and folds its column minima into the block minima in global memory (segmented warp reduction, one
+// atomicMin per warp and block; a block belongs to one job, so the minima are kept per job and slot); warp 0 refills a stage as soon as all sixteen warps are done with it, probing at its
+// row-group boundaries.  Nothing here waits for another warp: no __syncthreads() after the prologue, no survivor logic --
+// that is fs8_scan_kernel's, which runs when all block minima are final.
 template <bool M1, int F8_NT>
 __global__ void __launch_bounds__(F8_NT, 1024 / F8_NT)
 fs8_prefilter_kernel(const __grid_constant__ CUtensorMap tm_win_a, const __grid_constant__ CUtensorMap tm_win_b,
@@ -162,40 +182,32 @@ fs8_prefilter_kernel(const __grid_constant__ CUtensorMap tm_win_a, const __grid_
                      const F8Params p)
 {
     constexpr int NW = F8_NT / 32;
-    constexpr int A_PITCH = F8_NT + 4;
     extern __shared__ __align__(128) unsigned f8_smem[];
-    __shared__ __align__(8) uint64_t bar_full[2], bar_min[2];
-    __shared__ F8Geo geo_s[2];
-    __shared__ unsigned bmin_s[4][2][F8_NBMAX];                     // [job & 3][block row of the tile][block]: (generation << 16) | (A_min + 1)
-    __shared__ unsigned seg_count, seg_valid;
+    __shared__ __align__(8) uint64_t bar_full[3], bar_empty[3];
+    __shared__ F8Geo geo_s[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bs = p.bs, R = p.R;
-    const F8Conv cv = {p.c_two, p.c_8k, p.c_magic, p.c_fmagic};
+    const int bs = p.bs, R = p.R, n_stage = p.n_stage;
+    const F8Conv cv = p.cv;
     const int stage_words = 4 * p.plane_words + ((p.ref_rows * p.ref_rs + 31) & ~31);   // planes [4][plane_words], then source rows [ref_rows][ref_rs]
-    unsigned char *A_base = reinterpret_cast<unsigned char *>(f8_smem + p.n_stage * stage_words);   // [2][a_rows][A_PITCH]
-    const int a_bytes = p.a_rows * A_PITCH;
-    unsigned *seg = p.list + (size_t)blockIdx.x * p.seg_cap;
 
     if (tid == 0) {
-        mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1); mbar_init(&bar_min[0], NW); mbar_init(&bar_min[1], NW);
+        for (int i = 0; i < 3; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        seg_count = 0u; seg_valid = 0xffffffffu;
     }
-    if (tid < 4 * 2 * F8_NBMAX) (&bmin_s[0][0][0])[tid] = 0xffffffffu;
     __syncthreads();
 
-    // warp 0: take the next job off the queue, publish its geometry (local job number kk), arm the stage's barrier and
-    // issue the two TMA loads
-    auto issue_next = [&](int kk) {
-        const int sb = p.n_stage == 2 ? (kk & 1) : 0;
+    // warp 0: take the next job off the queue, publish its geometry (local job number kk, stage sb), arm the stage's
+    // barrier and issue the two TMA loads.  Returns false when the queue is empty (an end marker is published instead).
+    auto issue_next = [&](int kk, int sb) -> bool {
         int t = 0;
         if (lane == 0) t = atomicAdd(&p.counters[12], 1);
         t = __shfl_sync(0xffffffffu, t, 0);
-        F8Geo *g = &geo_s[kk & 1];
+        F8Geo *g = &geo_s[kk & 3];
         if (t >= p.n_tiles) {
             if (lane == 0) { g->t = -1; mbar_arrive(&bar_full[sb]); }
-            return;
+            return false;
         }
+        t += p.t0;
         const F8Tile tile = p.tiles[t];
         const int dir = tile.dir, by = tile.by, bx0 = tile.bx0, nb = tile.nb, nv = tile.nv;
         int n_dx = 0, dxl = 0;
@@ -225,116 +237,35 @@ fs8_prefilter_kernel(const __grid_constant__ CUtensorMap tm_win_a, const __grid_
             tma_load_3d(st, dir ? &tm_win_a : &tm_win_b, xw & ~15, p.box_y0 + by * bs - R, 0, &bar_full[sb]);
             tma_load_3d(st + 4 * p.plane_words, dir ? &tm_ref_b : &tm_ref_a, xr & ~15, p.box_y0 + by * bs, 0, &bar_full[sb]);
         }
+        return true;
     };
 
-    // ---- survivors of one finished job.  A warp takes its flagged columns (column minimum within T of the block minimum)
-    //      four at a time: lane = (column slot, row offset mod 8), so one vote covers eight row offsets of all four
-    //      columns; the votes stay in registers, the first lane of each slot counts its column's hits and reserves room,
-    //      then every lane writes the entry of each of its own hits.  Each CTA appends to its own segment of the list
-    //      through a shared-memory cursor that only ever moves forward: a reservation that does not fit marks where the
-    //      valid prefix ends (later ones cannot fit either) and its block goes to the redo pass.  fs8_refine_kernel gets
-    //      the length of the valid prefix ----
-    auto emit = [&](const unsigned char *Abuf, unsigned bmin_word, unsigned head_own, unsigned cmin, bool active, int n_dy) {
-        const unsigned thr = active ? (bmin_word & 0xffffu) + (unsigned)p.T : 1u;       // A_min + 1 + T: the accumulators, and so cmin, carry the same + 1
-        unsigned flagged = __ballot_sync(0xffffffffu, active && cmin <= thr);
-        if (!flagged) return;
-        const unsigned thr_code = f8_code(min(thr, 65535u), cv) & 0xffu;
-        const int slot = lane >> 3, sub = lane & 7;
-        const unsigned my_bits = 0xffu << (slot * 8), below = my_bits & ((1u << lane) - 1u);
-        const unsigned char *cw = Abuf + (tid & ~31);
-        const int n_it = (n_dy + 7) >> 3;                          // n_dy is the same for every lane of a warp
-        while (flagged) {
-            int src = -1;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {                          // slot k takes the k-th flagged column
-                const int sbit = __ffs(flagged) - 1;               // -1 when none is left
-                if (slot == k) src = sbit;
-                flagged &= flagged - 1;
+    // warp 0's bookkeeping: jobs issued so far, and the oldest job whose stage has not been refilled yet
+    int n_issued = 0, rf_stage = 0, rf_round = 0;
+    bool queue_open = true;
+    if (warp == 0) {
+        for (; n_issued < n_stage && queue_open; ++n_issued) queue_open = issue_next(n_issued, n_issued);
+    }
+    // refill every stage whose job all warps are done with; block (sleeping) only while local job `need` is not issued yet
+    auto refill = [&](int need) {
+        while (queue_open) {
+            bool free_ = mbar_test(&bar_empty[rf_stage], (unsigned)(rf_round & 1));
+            free_ = __shfl_sync(0xffffffffu, (int)free_, 0) != 0;
+            if (!free_) {
+                if (n_issued > need) break;
+                mbar_wait_sleep(&bar_empty[rf_stage], (unsigned)(rf_round & 1));
             }
-            const bool on = src >= 0;
-            const unsigned thr_c = __shfl_sync(0xffffffffu, thr_code, on ? src : 0);
-            const unsigned head = __shfl_sync(0xffffffffu, head_own, on ? src : 0);
-            const unsigned char *cs = cw + (on ? src : 0) + sub * A_PITCH;
-            // one vote per eight row offsets; up to F8_EMIT_WORDS votes stay in registers (n_dy <= 72: every range up to +-35),
-            // longer columns are voted on twice
-            unsigned bal[F8_EMIT_WORDS];
-            int hits = 0;
-#pragma unroll
-            for (int m = 0; m < F8_EMIT_WORDS; ++m) {
-                bal[m] = 0u;
-                if (m < n_it) {
-                    const bool h = on && m * 8 + sub < n_dy && cs[m * 8 * A_PITCH] <= thr_c;
-                    bal[m] = __ballot_sync(0xffffffffu, h);
-                    hits += __popc(bal[m] & my_bits);
-                }
-            }
-            for (int m = F8_EMIT_WORDS; m < n_it; ++m) {
-                const bool h = on && m * 8 + sub < n_dy && cs[m * 8 * A_PITCH] <= thr_c;
-                hits += __popc(__ballot_sync(0xffffffffu, h) & my_bits);
-            }
-            int pos = -1;
-            if (on && sub == 0) {
-                // A column that survives whole is flat content: nothing to prune in this block.  It, and any block whose
-                // survivors no longer fit the segment, goes to the exact block-level redo pass instead (once).
-                if (hits != n_dy) {
-                    pos = (int)atomicAdd(&seg_count, (unsigned)hits);
-                    if (pos + hits > p.seg_cap) { atomicMin(&seg_valid, (unsigned)pos); pos = -1; }
-                }
-                if (pos < 0) {
-                    const unsigned bslot = (head >> 31) * (unsigned)(p.nbr * p.nbc) + ((head >> 14) & 0x1ffffu);
-                    if (atomicExch(&p.redo_mark[bslot], 0u) != 0u) {
-                        const int rp = atomicAdd(&p.counters[11], 1);
-                        if (rp < p.redo_cap) p.redo_list[rp] = (int)((head >> 14) & 0x1ffffu) | ((head >> 31) ? 0x40000000 : 0);   // FS_DIR_BIT
-                    }
-                }
-            }
-            pos = __shfl_sync(0xffffffffu, pos, slot * 8);
-            if (pos >= 0) {                                        // order inside a column is irrelevant to the result
-#pragma unroll
-                for (int m = 0; m < F8_EMIT_WORDS; ++m) {
-                    if (m < n_it) {
-                        if ((bal[m] >> lane) & 1u) seg[pos + __popc(bal[m] & below)] = head | ((unsigned)(m * 8 + sub) << 7);
-                        pos += __popc(bal[m] & my_bits);
-                    }
-                }
-            }
-            if (n_it > F8_EMIT_WORDS && __any_sync(0xffffffffu, pos >= 0)) {
-                for (int m = F8_EMIT_WORDS; m < n_it; ++m) {
-                    const int i = m * 8 + sub;
-                    const bool h = pos >= 0 && i < n_dy && cs[m * 8 * A_PITCH] <= thr_c;
-                    const unsigned b2 = __ballot_sync(0xffffffffu, h);
-                    if (h) seg[pos + __popc(b2 & below)] = head | ((unsigned)i << 7);
-                    pos += __popc(b2 & my_bits);
-                }
-            }
-        }
-    };
-
-    if (warp == 0) { issue_next(0); if (p.n_stage == 2) issue_next(1); }
-    int n_issued = p.n_stage;
-
-    // the job whose survivors are still to be emitted
-    bool pv_valid = false, pv_active = false;
-    unsigned pv_head = 0u, pv_cmin = 0u;
-    int pv_ndy = 0, pv_bslot = 0;
-    int j = 0;                                                     // jobs searched so far
-
-    auto flush_prev = [&](bool refill, bool wait) {                 // hand-over of job j - 1 (see above)
-        const int q = j - 1;
-        if (wait) mbar_wait_sleep(&bar_min[q & 1], (unsigned)((q >> 1) & 1));
-        if (refill) {                                              // every warp is done with that job's stage
-            if (warp == 0) issue_next(n_issued);
+            queue_open = issue_next(n_issued, rf_stage);
             ++n_issued;
+            if (++rf_stage == n_stage) { rf_stage = 0; ++rf_round; }
         }
-        if (!(p.ablate & 1)) emit(A_base + (q & 1) * a_bytes, (&bmin_s[0][0][0])[pv_bslot], pv_head, pv_cmin, pv_active, pv_ndy);
-        pv_valid = false;
     };
 
+    int sb = 0, round = 0;
 #pragma unroll 1
-    for (;; ++j) {
-        const int sb = p.n_stage == 2 ? (j & 1) : 0;
-        mbar_wait_sleep(&bar_full[sb], (unsigned)((p.n_stage == 2 ? (j >> 1) : j) & 1));
-        const F8Geo *g = &geo_s[j & 1];
+    for (int j = 0;; ++j) {
+        mbar_wait_sleep(&bar_full[sb], (unsigned)(round & 1));
+        const F8Geo *g = &geo_s[j & 3];
         if (g->t < 0) break;
         const int dir = g->dir, by = g->by, bx0 = g->bx0, nb = g->nb, n_items = g->n_items;
         const unsigned *planes = f8_smem + sb * stage_words;
@@ -358,10 +289,10 @@ fs8_prefilter_kernel(const __grid_constant__ CUtensorMap tm_win_a, const __grid_
         const int n_dy = max(b0.r1 - b0.r0, 0);
         const int wrow_base = b0.r0 - (by * bs - R);                   // window rows count from the job's first block row
         const bool active = has_item && n_dy > 0;
-        unsigned char *col = A_base + (j & 1) * a_bytes + tid;
+        uint4 *col = p.codes + ((size_t)(g->t - p.t0) * F8_NT + tid) * p.n_groups;
         unsigned cmin = 0xffffffffu;
-        // Lanes without a column of their own (the tail of the last warp) search block 0 / dx 0 along with their warp: the
-        // hand-over below contains warp-wide votes and shuffles, so control flow stays warp-uniform; their results are ignored.
+        // Lanes without a column of their own (the tail of the last warp) search block 0 / dx 0 along with their warp, so
+        // that control flow stays warp-uniform; their results are ignored.
         if (__any_sync(0xffffffffu, active)) {
             unsigned rl[8], rh[8];
             if (M1) {
@@ -393,51 +324,177 @@ fs8_prefilter_kernel(const __grid_constant__ CUtensorMap tm_win_a, const __grid_
                         f8_accumulate(acc, rl, rh, pl + (wrow_base + gq * F8_G + si * 8) * p.rs + sj * 2, p.rs);
                     }
                 }
-                f8_finish_group<decltype(masked)::value, A_PITCH>(acc, n_dy - gq * F8_G, col + gq * F8_G * A_PITCH, cmin, cv);
+                f8_finish_group<decltype(masked)::value>(acc, n_dy - gq * F8_G, col + gq, cmin, cv);
             };
             const int n_full = n_dy / F8_G;
 #pragma unroll 1
             for (int gq = 0; gq < n_full; ++gq) {
                 group(gq, std::false_type{});
-                // hand-over of the previous job as soon as its block minima are complete -- probed, not waited for: a warp that
-                // runs ahead of its CTA keeps searching, so the warps of a CTA do not all emit at the same moment
-                if (pv_valid && gq >= p.flush_at) {
-                    const int q = j - 1;
-                    if (__shfl_sync(0xffffffffu, (int)mbar_test(&bar_min[q & 1], (unsigned)((q >> 1) & 1)), 0)) flush_prev(true, false);
-                }
+                if (warp == 0) refill(-1);                          // a probe, never a wait
             }
             if (n_full * F8_G < n_dy) group(n_full, std::true_type{});
         }
-        if (pv_valid) flush_prev(true, true);                       // not complete at any probe (or no full group in this job): wait
-        // block minima: segmented warp reduction, one shared-memory atomic per (warp, block).  The generation tag in the
-        // upper half makes every later job's entries smaller than any earlier job's, so the slots are never reset (a slot
-        // is re-used four jobs later; its last reader finished before the hand-over two jobs earlier).
-        const int bslot = ((j & 3) * 2 + v) * F8_NBMAX;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[sb]);                 // this warp is done with the stage
+        p.colinfo[(size_t)(g->t - p.t0) * F8_NT + tid] = active ? (min(cmin, 65535u) | ((unsigned)(v * 32 + b) << 16) | ((unsigned)dxi << 22)) : 0xffffffffu;
+        // block minima: segmented warp reduction, one global atomicMin per (warp, block)
         {
-            const unsigned tag = (0xffffu - (unsigned)(j >> 2)) << 16;
+            unsigned *bmin = p.bmin + (size_t)(g->t - p.t0) * 64 + v * 32;
             unsigned todo = __ballot_sync(0xffffffffu, active);
             while (todo) {
                 const int leader = __ffs(todo) - 1;
                 const int bb = __shfl_sync(0xffffffffu, b, leader);
                 const bool mine = active && b == bb;
                 const unsigned mn = __reduce_min_sync(0xffffffffu, mine ? cmin : 0xffffffffu);
-                if (lane == leader) atomicMin(&(&bmin_s[0][0][0])[bslot + bb], tag | mn);
+                if (lane == leader) atomicMin(&bmin[bb], mn);
                 todo &= ~__ballot_sync(0xffffffffu, mine);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_min[j & 1]);
-        // this job becomes the pending one
-        pv_valid = true; pv_active = active; pv_cmin = cmin; pv_ndy = n_dy; pv_bslot = bslot + b;
-        pv_head = (dir ? 0x80000000u : 0u) | ((unsigned)((by + v) * p.nbc + bx0 + b) << 14) | (unsigned)dxi;
-        if (p.n_stage == 1) { ++j; flush_prev(true, true); --j; }        // one stage: the next job's loads cannot start before this hand-over
+        if (warp == 0) refill(j + 1);                               // the next job must be on its way before we wait for it
+        if (++sb == n_stage) { sb = 0; ++round; }
     }
-    if (pv_valid) flush_prev(false, true);
+}
+
+
+// CTA per job, a quarter of the prefilter's threads.  Phase 1, four candidate columns per thread (one 16-byte load): a
+// column can only hold survivors if its minimum is within T of its block's minimum; the ones that pass (15 - 30 % on
+// texture) are compacted, in order, into a shared-memory list.  Phase 2, thread per listed column: its codes --
+// contiguous, two or three 16-byte loads -- against the code of the threshold, four at a time; the hits of a warp are
+// added up by a shuffle scan, reserved with one global atomic and appended to the survivor list.  Everything phase 1
+// reads is indexed by (job, thread) -- the prefilter leaves slot and column offset next to the column minimum, and the
+// block minima per job -- so no load waits for another one: the CTA's life is four L2 round trips (column info, codes,
+// atomic, list), and small CTAs keep enough of them resident to go through all jobs in under two waves.
+// The list is F8_NLIST sub-lists (CTA and warp pick one): same-address atomics retire one every ~4 ns -- 3382 of them,
+// one per job, were 14 of the first version's 39 us.
+// A column that survives whole is flat content -- nothing to prune in this block: the block goes to the exact
+// block-level redo pass instead (once).  A sub-list that would overflow hands the whole pair to the exact kernel.
+template <int NT>
+__global__ void __launch_bounds__(NT / 4)
+fs8_scan_kernel(int H, int W, int bs, int R, int nbc, int n_blk, int n_groups, int T, int t0, const F8Tile *__restrict__ tiles,
+                const uint4 *__restrict__ codes, const uint4 *__restrict__ colinfo, unsigned *__restrict__ bmin,
+                const F8Conv cv, unsigned *__restrict__ list, unsigned seg_cap, unsigned *__restrict__ cursors,
+                unsigned *__restrict__ redo_mark, int *__restrict__ redo_list, int redo_cap, int *__restrict__ counters, int col_hits)
+{
+    constexpr int NS = NT / 4, NW = NS / 32;
+    __shared__ unsigned thr_s[64];                      // min(A_min + 1 + T, 65535) of the slot; 0: no candidates
+    __shared__ unsigned flist[NT];                      // listed columns: thread of the prefilter | slot << 9 | column offset << 15
+    __shared__ int wcount[NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint4 info4 = colinfo[(size_t)blockIdx.x * NS + tid];
+    const F8Tile tile = tiles[t0 + blockIdx.x];
+    if (tid < 64) {
+        unsigned *bp = bmin + (size_t)blockIdx.x * 64 + tid;
+        const unsigned bm = *bp;
+        thr_s[tid] = bm == 0xffffffffu ? 0u : min(bm + (unsigned)T, 65535u);
+        if (bm != 0xffffffffu) *bp = 0xffffffffu;                  // re-armed for the next search
+    }
     __syncthreads();
-    if (tid == 0) {
-        const unsigned n = seg_valid != 0xffffffffu ? seg_valid : seg_count;     // the prefix every entry of which was written
-        p.seg_counts[blockIdx.x] = n;
-        atomicAdd(&p.counters[9], (int)n);
+    const unsigned info[4] = {info4.x, info4.y, info4.z, info4.w};
+    unsigned fl = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fl |= (info[q] != 0xffffffffu && (info[q] & 0xffffu) <= thr_s[(info[q] >> 16) & 63u]) ? 1u << q : 0u;
+    const int mine = __popc(fl);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wcount[warp] = incl;
+    __syncthreads();
+    int base = 0, n_flag = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { const int c = wcount[w]; base += w < warp ? c : 0; n_flag += c; }
+    {
+        int pos = base + incl - mine;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (fl & (1u << q)) flist[pos++] = (unsigned)(tid * 4 + q) | ((info[q] >> 16) << 9);
+    }
+    __syncthreads();
+    // ---- phase 2: thread per listed column ----
+    const int dir = tile.dir;
+    for (int k0 = warp * 32; k0 < n_flag; k0 += NS) {              // warp-uniform trip count (shuffles inside)
+        const bool on = k0 + lane < n_flag;
+        unsigned long long hm_lo = 0ull, hm_hi = 0ull;
+        int hits = 0, blk = 0, dxi = 0;
+        bool redo = false;
+        if (on) {
+            const unsigned e = flist[k0 + lane];
+            const int col_t = (int)(e & 511u), slot = (int)((e >> 9) & 63u);
+            dxi = (int)(e >> 15);
+            const int row = tile.by + (slot >> 5);
+            blk = row * nbc + tile.bx0 + (slot & 31);
+            const FsBounds8 b0 = f8_bounds(H, W, bs, R, row * bs, tile.bx0 * bs);
+            const int n_dy = max(b0.r1 - b0.r0, 0);
+            // four codes per step: byte-wise code <= threshold, SWAR.  With xl = x & 0x7f.., T1 = (t & 0x7f..) | 0x80..: bit 7
+            // of each byte of T1 - xl says low7(t) >= low7(x) (no borrow crosses a byte), and
+            //     x <= t  <=>  (x7 < t7) or (x7 == t7 and low7(x) <= low7(t)).
+            // Hits are rare (one or two per column), so only words with a hit are taken apart -- and a column with more than
+            // F8_COL_HITS of them belongs to a block with nothing to prune (flat content; a whole job of such columns kept
+            // one CTA busy for 45 k cycles, three times the rest of the kernel): the block goes to the redo pass instead.
+            const unsigned t4 = (f8_code(thr_s[slot], cv) & 0xffu) * 0x01010101u;
+            const unsigned T1 = (t4 & 0x7f7f7f7fu) | 0x80808080u;
+            const uint4 *col = codes + ((size_t)blockIdx.x * NT + col_t) * n_groups;
+            for (int g0 = 0; g0 * F8_G < n_dy && !redo; g0 += 3) {   // three groups (33 row offsets) at a time: the loads go out together
+                uint4 w[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) w[q] = (g0 + q) * F8_G < n_dy ? col[g0 + q] : make_uint4(~0u, ~0u, ~0u, ~0u);
+                unsigned le[9];
+                int cnt = 0;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const unsigned ww[3] = {w[q].x, w[q].y, w[q].z};
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const unsigned x = ww[k];
+                        const unsigned d = T1 - (x & 0x7f7f7f7fu);
+                        const int rem = n_dy - ((g0 + q) * F8_G + k * 4);                 // row offsets left in the window from this word on
+                        unsigned valid = k == 2 ? 0x00808080u : 0x80808080u;              // a group is eleven codes: the twelfth byte is padding
+                        if (rem < 4) valid = rem <= 0 ? 0u : valid & (0x00808080u >> (8 * (3 - rem)));
+                        le[q * 3 + k] = ((~x & t4) | (~(x ^ t4) & d)) & valid;
+                        cnt += __popc(le[q * 3 + k]);
+                    }
+                }
+                hits += cnt;
+                if (hits > col_hits) { redo = true; break; }
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        unsigned m = le[q * 3 + k];
+                        while (m) {
+                            const int bit = __ffs((int)m) - 1;
+                            m &= m - 1u;
+                            const int idx = (g0 + q) * F8_G + k * 4 + (bit >> 3);
+                            if (idx < 64) hm_lo |= 1ull << idx; else hm_hi |= 1ull << (idx - 64);
+                        }
+                    }
+                }
+            }
+            if (redo) hits = 0;
+        }
+        int inc2 = hits;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += t; }
+        const int total = __shfl_sync(0xffffffffu, inc2, 31);
+        const unsigned seg = (blockIdx.x + (unsigned)(k0 >> 5)) & (F8_NLIST - 1);
+        unsigned pos0 = 0u;
+        if (total > 0) {                                           // room for the warp's survivors: one global atomic
+            if (lane == 0) {
+                pos0 = atomicAdd(&cursors[seg * F8_CURSOR_STRIDE], (unsigned)total);
+                if (pos0 + (unsigned)total > seg_cap) { counters[8] = 1; pos0 = 0xffffffffu; }     // overflow: the exact kernel takes the pair
+            }
+            pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+        }
+        if (hits > 0 && pos0 != 0xffffffffu) {
+            unsigned *dst = list + (size_t)seg * seg_cap + pos0 + (unsigned)(inc2 - hits);
+            const unsigned head = (dir ? 0x80000000u : 0u) | ((unsigned)blk << 14) | (unsigned)dxi;
+            for (unsigned long long mk = hm_lo; mk; mk &= mk - 1) *dst++ = head | ((unsigned)(__ffsll((long long)mk) - 1) << 7);
+            for (unsigned long long mk = hm_hi; mk; mk &= mk - 1) *dst++ = head | ((unsigned)(63 + __ffsll((long long)mk)) << 7);
+        }
+        if (redo) {
+            if (atomicExch(&redo_mark[(size_t)dir * n_blk + blk], 0u) != 0u) {
+                const int rp = atomicAdd(&counters[11], 1);
+                if (rp < redo_cap) redo_list[rp] = blk | (dir ? 0x40000000 : 0);                   // FS_DIR_BIT
+            }
+        }
     }
 }
 
@@ -446,11 +503,12 @@ __device__ __forceinline__ unsigned long long f8_key(unsigned sad, unsigned d2, 
     return ((unsigned long long)sad << 32) | ((unsigned long long)d2 << 16) | (ri << 8) | ci;    // = fs.cu fs_key
 }
 
-// Exact SAD of one survivor by eight lanes: lane pr covers row pr of each 8 x 8 sub-block -- the source row as two
-// aligned 16-byte vectors, the target row as one 32-byte run; returns the lane's partial sum of |dL1000|.
-// (Measured alternatives, both slower at 8 x 8: a whole warp per survivor with lane = (row, pixel pair), 102 vs 76 us at
-// 1080p -- the per-survivor decode and hand-over then run 32 instead of 8 lanes wide -- and the target row as the three
-// aligned 16-byte vectors that cover it, 83 us: half as many load instructions, 1.5 x the bytes.)
+// Exact SAD of one survivor by eight lanes: lane pr covers COLUMN pr of each 8 x 8 sub-block, row by row -- the eight
+// lanes of a group read one 32-byte run per row (one or two sectors of one line), so a warp-wide load touches the lines of
+// four survivors' rows, not 32 different ones (lane = row, the first version, kept the L1 tag stage busy five times as
+// long: 76 us at 1080p).  Returns the lane's partial sum of |dL1000|.
+// (Also measured, both slower than lane = row: a whole warp per survivor with lane = (row, pixel pair), 102 us, and the
+// target row as the three aligned 16-byte vectors that cover it, 83 us.)
 __device__ __forceinline__ unsigned f8_survivor_sad(const int32_t *__restrict__ Ls, const int32_t *__restrict__ Lt, int H, int W, int Wp,
                                                     int bs, int m, int s_row, int s_col, int t_row, int t_col, int pr)
 {
@@ -458,20 +516,21 @@ __device__ __forceinline__ unsigned f8_survivor_sad(const int32_t *__restrict__ 
     if (s_row + bs <= H && s_col + bs <= W && t_row + bs <= H && t_col + bs <= W) {      // no padding involved
         for (int sub = 0; sub < m * m; ++sub) {
             const int si = sub / m, sj = sub - si * m;
-            const int r = si * 8 + pr, c = sj * 8;
-            const int32_t *ps = Ls + (size_t)(s_row + r) * Wp + s_col + c;
-            const int4 a0 = *reinterpret_cast<const int4 *>(ps), a1 = *reinterpret_cast<const int4 *>(ps + 4);
-            const int32_t *q = Lt + (size_t)(t_row + r) * Wp + t_col + c;
-            S = __sad(a0.x, q[0], S); S = __sad(a0.y, q[1], S); S = __sad(a0.z, q[2], S); S = __sad(a0.w, q[3], S);
-            S = __sad(a1.x, q[4], S); S = __sad(a1.y, q[5], S); S = __sad(a1.z, q[6], S); S = __sad(a1.w, q[7], S);
+            const int32_t *ps = Ls + (size_t)(s_row + si * 8) * Wp + s_col + sj * 8 + pr;
+            const int32_t *pt = Lt + (size_t)(t_row + si * 8) * Wp + t_col + sj * 8 + pr;
+            int a[8], b[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { a[r] = ps[(size_t)r * Wp]; b[r] = pt[(size_t)r * Wp]; }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) S = __sad(a[r], b[r], S);
         }
     } else {                                                // zero padding (np.pad) on either side
         for (int sub = 0; sub < m * m; ++sub) {
             const int si = sub / m, sj = sub - si * m;
-            const int r1 = s_row + si * 8 + pr, r2 = t_row + si * 8 + pr;
+            const int c1 = s_col + sj * 8 + pr, c2 = t_col + sj * 8 + pr;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int c1 = s_col + sj * 8 + k, c2 = t_col + sj * 8 + k;
+            for (int r = 0; r < 8; ++r) {
+                const int r1 = s_row + si * 8 + r, r2 = t_row + si * 8 + r;
                 const int a = (r1 < H && c1 < W) ? Ls[(size_t)r1 * Wp + c1] : 0;
                 const int v = (r2 < H && c2 < W) ? Lt[(size_t)r2 * Wp + c2] : 0;
                 S = __sad(a, v, S);
@@ -494,8 +553,7 @@ __device__ __forceinline__ F8Entry f8_decode(unsigned e, int nbc, float inv_nbc,
     return x;
 }
 
-// Every CTA takes one contiguous range of the survivor list (the concatenation of the per-CTA segments of the
-// prefilter); its 32 eight-lane groups walk that range side by side, so neighbouring groups take neighbouring survivors
+// Every CTA takes one contiguous range of the survivor list (the concatenation of the scan pass's sub-lists); its 32 eight-lane groups walk that range side by side, so neighbouring groups take neighbouring survivors
 // (same block, same column offset: the same source rows and overlapping target rows -- loads of the same line coalesce)
 // and a group finds its segment by stepping forward, not by searching.  A flagged sum (S a positive multiple of 1000: the
 // reference's float64 accumulation may land just below the integer and truncate to S / 1000 - 1, fs.cu) is NOT decided
@@ -510,8 +568,8 @@ fs8_refine_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1
                   unsigned *__restrict__ redo_mark, int *__restrict__ redo_list, int redo_cap)
 {
     if (counters[8]) return;                                       // overflow: the exact kernel takes the pair
-    // exclusive prefix of the segment lengths (n_seg <= F8_MAXSEG, every CTA computes it for itself)
-    __shared__ int seg_pre[F8_MAXSEG + 1];
+    // exclusive prefix of the sub-list lengths (n_seg <= F8_NLIST, every CTA computes it for itself)
+    __shared__ int seg_pre[F8_NLIST + 1];
     __shared__ int lo_s;
     // Minimum keys are combined per CTA before they touch global memory: a CTA's range is contiguous, i.e. a handful of
     // blocks, and a block whose content is nearly flat can own a thousand survivors -- a thousand atomics on ONE address
@@ -524,7 +582,7 @@ fs8_refine_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1
         __shared__ int wsum[8];
         const int per = (n_seg + 255) / 256;
         int loc = 0;
-        for (int k = 0; k < per; ++k) { const int si = threadIdx.x * per + k; if (si < n_seg) loc += (int)seg_counts[si]; }
+        for (int k = 0; k < per; ++k) { const int si = threadIdx.x * per + k; if (si < n_seg) loc += (int)seg_counts[si * F8_CURSOR_STRIDE]; }
         int incl = loc;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += v; }
@@ -533,11 +591,12 @@ fs8_refine_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1
         int wbase = 0;
         for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += wsum[w];
         int run = wbase + incl - loc;
-        for (int k = 0; k < per; ++k) { const int si = threadIdx.x * per + k; if (si < n_seg) { seg_pre[si] = run; run += (int)seg_counts[si]; } }
+        for (int k = 0; k < per; ++k) { const int si = threadIdx.x * per + k; if (si < n_seg) { seg_pre[si] = run; run += (int)seg_counts[si * F8_CURSOR_STRIDE]; } }
         if (threadIdx.x == 255) seg_pre[n_seg] = run;
         __syncthreads();
     }
     const int n = seg_pre[n_seg];
+    if (blockIdx.x == 0 && threadIdx.x == 0) counters[9] = n;      // statistics
     const int per_cta = (((n + gridDim.x - 1) / gridDim.x) + 31) & ~31;
     const int cs = blockIdx.x * per_cta, ce = min(n, cs + per_cta);
     if (cs >= ce) return;
@@ -652,14 +711,15 @@ fs8_replay_kernel(const int32_t *__restrict__ L0, const int32_t *__restrict__ L1
     }
 }
 
-// Also re-arms the key / redo-mark buffers for the next search (no memset per call).
-__global__ void fs8_output_kernel(unsigned long long *__restrict__ best, unsigned *__restrict__ redo_mark, int *__restrict__ counters, int redo_limit,
+// Also re-arms the key / redo-mark buffers and the sub-list cursors for the next search (no memset per call).
+__global__ void fs8_output_kernel(unsigned long long *__restrict__ best, unsigned *__restrict__ redo_mark, unsigned *__restrict__ cursors, int *__restrict__ counters, int redo_limit,
                                   int H, int W, int bs, int R, int nbc, int n_blk, int blk_begin, int blk_end, int ndir,
                                   float2 *__restrict__ out_vec0, float *__restrict__ out_sad0,
                                   float2 *__restrict__ out_vec1, float *__restrict__ out_sad1)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int per = blk_end - blk_begin;
+    if (i < F8_NLIST) cursors[i * F8_CURSOR_STRIDE] = 0u;
     if (i >= per * ndir) return;
     // too many blocks for the block-level redo pass (mostly flat content): the exact kernel takes the whole pair
     const bool fallback = counters[8] != 0 || counters[11] > redo_limit;
@@ -682,6 +742,7 @@ __global__ void fs8_output_kernel(unsigned long long *__restrict__ best, unsigne
     (dir ? out_vec1 : out_vec0)[blk] = make_float2(dy, dx);
     (dir ? out_sad1 : out_sad0)[blk] = sad;
 }
+
 
 // ---- rounded 8-bit luma, four byte-shifted planes with a zero border (np.pad of the reference and every out-of-frame
 //      read): plane q, padded row y, padded column x holds L8[y][x + q].  One thread per word of a row, plus one word to
@@ -728,13 +789,14 @@ int memci_ensure_luma8(memci_ctx *ctx, int slot)
     return MEMCI_OK;
 }
 
+
 // ---- launch shape ----------------------------------------------------------------------------------------------
 struct F8Shape {
     int nt, ctas, rpt, n_stage, nb_tile;
     int win_rows, box_rows, box_w, rs, plane_words, ref_w, ref_rs, a_rows, smem;
 };
 
-// Shared memory of one CTA and the TMA boxes for (threads, block rows per tile, stages).  Returns false when the
+// Shared memory of one CTA and the TMA boxes for (threads, block rows per job, stages).  Returns false when the
 // shape is impossible (box wider than 256 bytes / taller than 256 rows, no column per thread).
 static bool f8_layout(int nt, int rpt, int n_stage, int bs, int R, int nbc, F8Shape *s)
 {
@@ -767,18 +829,18 @@ static bool f8_layout(int nt, int rpt, int n_stage, int bs, int R, int nbc, F8Sh
     s->ref_rs = s->ref_w / 4;
     s->a_rows = n_groups * F8_G;
     const int ref_words = (rpt * bs * s->ref_rs + 31) & ~31;
-    s->smem = n_stage * (4 * s->plane_words + ref_words) * 4 + 2 * s->a_rows * (nt + 4);      // two A buffers (uint8 codes): jobs j and j - 1
+    s->smem = n_stage * (4 * s->plane_words + ref_words) * 4;
     return true;
 }
 
-// Preference: 512 threads x 2 CTAs per SM, two block rows per tile, two stages; fewer stages / one CTA per SM / one block
-// row / 256 threads as shared memory dictates (wide searches: 16 x 16 +-32 runs one 512-thread CTA per SM).
+// Preference: 512 threads x 2 CTAs per SM, two-row jobs where columns are clipped, as many stages as fit (3, 2, 1); one
+// CTA per SM / no two-row jobs / 256 threads as shared memory dictates (wide searches).
 // MEMCI_F8_NT / MEMCI_F8_RPT / MEMCI_F8_STAGES / MEMCI_F8_CTAS override (tuning).
 static bool f8_shape(int bs, int R, int nbc, F8Shape *out)
 {
-    static const int cand[][4] = {      // threads, CTAs per SM, block rows per tile, stages
-        {512, 2, 2, 2}, {512, 2, 2, 1}, {512, 1, 2, 2}, {512, 1, 2, 1}, {512, 2, 1, 2}, {512, 2, 1, 1}, {256, 2, 2, 2}, {256, 2, 2, 1},
-        {256, 2, 1, 2}, {256, 2, 1, 1}, {512, 1, 1, 2}, {512, 1, 1, 1}, {256, 1, 1, 1}};
+    static const int cand[][4] = {      // threads, CTAs per SM, block rows per job (max), stages
+        {512, 2, 2, 3}, {512, 2, 2, 2}, {512, 1, 2, 3}, {512, 1, 2, 2}, {512, 2, 2, 1}, {512, 2, 1, 2}, {256, 2, 2, 2}, {512, 1, 2, 1},
+        {512, 2, 1, 1}, {256, 2, 2, 1}, {256, 2, 1, 2}, {256, 2, 1, 1}, {512, 1, 1, 2}, {512, 1, 1, 1}, {256, 1, 1, 1}};
     int f_nt = 0, f_rpt = 0, f_st = 0, f_ctas = 0;
     if (const char *e = getenv("MEMCI_F8_NT")) f_nt = atoi(e);
     if (const char *e = getenv("MEMCI_F8_RPT")) f_rpt = atoi(e);
@@ -799,13 +861,12 @@ static bool f8_shape(int bs, int R, int nbc, F8Shape *out)
     return false;
 }
 
-// Is the prefilter path applicable?  Block sizes 8 / 16 (A fits uint16), list entry fields (17-bit block, 7-bit offsets),
-// border of the padded planes, a launch shape that fits shared memory.
+// Is the prefilter path applicable?  Block sizes 8 / 16 (A fits 16 bits), 7-bit window offsets, border of the padded
+// planes, a launch shape that fits shared memory.
 int memci_fs8_eligible(memci_ctx *ctx, int bs, int R)
 {
     if ((bs != 8 && bs != 16) || R < 1 || R > 63 || R + bs + 16 > MEMCI_L8_PAD) return 0;
-    const long long n_blk = (long long)ceil_div_i(ctx->H, bs) * ceil_div_i(ctx->W, bs);
-    if (n_blk >= (1 << 17)) return 0;
+    if (ceil_div_i(ctx->H, bs) > 32767 || ceil_div_i(ctx->W, bs) > 32767) return 0;
     F8Shape s;
     return f8_shape(bs, R, ceil_div_i(ctx->W, bs), &s) ? 1 : 0;
 }
@@ -821,55 +882,56 @@ static int f8_launch(memci_ctx *ctx, const CUtensorMap *tm, const F8Params &p, i
 // The jobs of one search geometry, in queue order (cached per context; rebuilt when the geometry changes): row-major over
 // (direction, block row, tile column).  A tile column whose blocks keep so few column offsets that two block rows fit the
 // CTA side by side becomes ONE two-row job per pair of block rows; every other tile is one job per block row.
-static int f8_job_table(memci_ctx *ctx, const F8Shape &sh, int bs, int R, int br0, int br1, int ndir, const F8Tile **tiles, int *n_tiles)
+static int f8_job_table(memci_ctx *ctx, const F8Shape &sh, int bs, int R, int br0, int br1, int ndir,
+                        const F8Tile **tiles, int *n_tiles)
 {
     const int H = ctx->H, W = ctx->W, nbc = ceil_div_i(W, bs);
     const int no_split = getenv("MEMCI_F8_NOSPLIT") ? 1 : 0;
-    const int key[8] = {bs, R, br0, br1, ndir, sh.nb_tile, sh.nt * 4 + sh.rpt * 2 + no_split, 1};
-    if (ctx->d_f8_tiles && memcmp(key, ctx->f8_tiles_key, sizeof(key)) == 0) {
-        *tiles = reinterpret_cast<const F8Tile *>(ctx->d_f8_tiles); *n_tiles = ctx->f8_tiles_n;
-        return MEMCI_OK;
-    }
-    const int n_cols = ceil_div_i(nbc, sh.nb_tile);
-    F8Tile *h = (F8Tile *)malloc(sizeof(F8Tile) * (size_t)ndir * (br1 - br0) * n_cols);
-    if (!h) return memci_fail(ctx, MEMCI_ERR_ARG, "out of host memory");
-    unsigned char *two = (unsigned char *)calloc(n_cols, 1);
-    for (int tc = 0; tc < n_cols; ++tc) {                          // column bounds do not depend on the block row
-        const int bx0 = tc * sh.nb_tile, nb = nbc - bx0 < sh.nb_tile ? nbc - bx0 : sh.nb_tile;
-        int items = 0;
-        for (int b = 0; b < nb; ++b) {
-            const int s_col = (bx0 + b) * bs;
+    const int key[8] = {bs, R, br0, br1, ndir, sh.nb_tile, sh.nt * 4 + sh.rpt * 2 + no_split, 2};
+    if (!(ctx->d_f8_tiles && memcmp(key, ctx->f8_tiles_key, sizeof(key)) == 0)) {
+        const int n_cols = ceil_div_i(nbc, sh.nb_tile);
+        F8Tile *h = (F8Tile *)malloc(sizeof(F8Tile) * (size_t)ndir * (br1 - br0) * n_cols);
+        unsigned char *two = (unsigned char *)calloc(n_cols, 1);
+        int *items = (int *)calloc(n_cols, sizeof(int));
+        int *n_dx = (int *)calloc(nbc, sizeof(int));
+        if (!h || !two || !items || !n_dx) { free(h); free(two); free(items); free(n_dx); return memci_fail(ctx, MEMCI_ERR_NOMEM, "out of host memory"); }
+        for (int bc = 0; bc < nbc; ++bc) {                         // column bounds do not depend on the block row
+            const int s_col = bc * bs;
             const int tmc = (s_col + bs >= H) ? s_col + 1 : W - bs;        // full_search.py:37 (sic: compares against H)
             const int c0 = s_col - R > 0 ? s_col - R : 0, c1 = tmc < s_col + R + 1 ? tmc : s_col + R + 1;
-            items += c1 > c0 ? c1 - c0 : 0;
+            n_dx[bc] = c1 > c0 ? c1 - c0 : 0;
+            items[bc / sh.nb_tile] += n_dx[bc];
         }
-        two[tc] = sh.rpt == 2 && !no_split && items > 0 && ((items + 31) & ~31) + items <= sh.nt;
+        for (int tc = 0; tc < n_cols; ++tc)
+            two[tc] = sh.rpt == 2 && !no_split && items[tc] > 0 && ((items[tc] + 31) & ~31) + items[tc] <= sh.nt;
+        int n = 0;
+        for (int dir = 0; dir < ndir; ++dir)
+            for (int by = br0; by < br1; ++by)
+                for (int tc = 0; tc < n_cols; ++tc) {
+                    const int bx0 = tc * sh.nb_tile, nb = nbc - bx0 < sh.nb_tile ? nbc - bx0 : sh.nb_tile;
+                    if (two[tc] && ((by - br0) & 1)) continue;      // second row of a two-row job
+                    F8Tile t;
+                    t.dir = (short)dir; t.nv = (short)((two[tc] && by + 1 < br1) ? 2 : 1); t.by = (short)by; t.bx0 = (short)bx0; t.nb = (short)nb; t.pad = 0;
+                    h[n++] = t;
+                }
+        free(two); free(items); free(n_dx);
+        if (ctx->d_f8_tiles) { cudaFree(ctx->d_f8_tiles); ctx->d_f8_tiles = nullptr; }
+        cudaError_t e = cudaMalloc(&ctx->d_f8_tiles, sizeof(F8Tile) * (size_t)(n > 0 ? n : 1));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_f8_tiles, h, sizeof(F8Tile) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        free(h);
+        if (e != cudaSuccess) { ctx->sticky = 1; return memci_fail(ctx, MEMCI_ERR_CUDA, "prefilter job table: %s", cudaGetErrorString(e)); }
+        memcpy(ctx->f8_tiles_key, key, sizeof(key));
+        ctx->f8_tiles_n = n;
     }
-    int n = 0;
-    for (int dir = 0; dir < ndir; ++dir)
-        for (int by = br0; by < br1; ++by)
-            for (int tc = 0; tc < n_cols; ++tc) {
-                const int bx0 = tc * sh.nb_tile, nb = nbc - bx0 < sh.nb_tile ? nbc - bx0 : sh.nb_tile;
-                if (two[tc] && ((by - br0) & 1)) continue;          // second row of a two-row job
-                F8Tile t;
-                t.dir = (short)dir; t.nv = (short)((two[tc] && by + 1 < br1) ? 2 : 1); t.by = (short)by; t.bx0 = (short)bx0; t.nb = (short)nb; t.pad = 0;
-                h[n++] = t;
-            }
-    free(two);
-    if (ctx->d_f8_tiles) { cudaFree(ctx->d_f8_tiles); ctx->d_f8_tiles = nullptr; }
-    cudaError_t e = cudaMalloc(&ctx->d_f8_tiles, sizeof(F8Tile) * (size_t)n);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_f8_tiles, h, sizeof(F8Tile) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    free(h);
-    if (e != cudaSuccess) { ctx->sticky = 1; return memci_fail(ctx, MEMCI_ERR_CUDA, "prefilter job table: %s", cudaGetErrorString(e)); }
-    memcpy(ctx->f8_tiles_key, key, sizeof(key));
-    ctx->f8_tiles_n = n;
-    *tiles = reinterpret_cast<const F8Tile *>(ctx->d_f8_tiles); *n_tiles = n;
+    *tiles = reinterpret_cast<const F8Tile *>(ctx->d_f8_tiles); *n_tiles = ctx->f8_tiles_n;
     return MEMCI_OK;
 }
 
-// Enqueue prefilter + refine + output for block rows [br0, br1).  counters[8] is left non-zero when the pair has to be
-// searched by the exact kernel; the caller runs that kernel gated on the flag.
+
+// Enqueue prefilter + scan (per chunk of jobs), refine, replay and output for block rows [br0, br1).  counters[8] is left
+// non-zero when the pair has to be searched by the exact kernel; the caller runs that kernel gated on the flag, and
+// fs_redo_kernel on the blocks listed here.
 int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVField *out, int br0, int br1, MVField *out2)
 {
     const int H = ctx->H, W = ctx->W;
@@ -881,17 +943,16 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
     if (!f8_shape(bs, R, nbc, &sh)) return memci_fail(ctx, MEMCI_ERR_ARG, "two-phase full search: no launch shape for block %d, range %d", bs, R);
     F8Params p;
     memset(&p, 0, sizeof(p));
-    p.H = H; p.W = W; p.bs = bs; p.m = bs / 8; p.R = R; p.Rp = (R + 3) & ~3; p.nbr = nbr; p.nbc = nbc;
+    p.H = H; p.W = W; p.bs = bs; p.m = bs / 8; p.R = R; p.Rp = (R + 3) & ~3; p.nbr = nbr; p.nbc = nbc; p.n_blk = n_blk;
     p.n_stage = sh.n_stage;
-    p.c_two = 2u; p.c_8k = 8192u; p.c_magic = 0x4B000000u; p.c_fmagic = 8388608.0f;
-    p.flush_at = 0;
-    if (const char *e = getenv("MEMCI_F8_ABLATE")) p.ablate = atoi(e);
-    if (const char *e = getenv("MEMCI_F8_FLUSH_AT")) p.flush_at = atoi(e);
-    if ((rc = f8_job_table(ctx, sh, bs, R, br0, br1, ndir, &p.tiles, &p.n_tiles))) return rc;
+    p.cv.one = 1u; p.cv.two = 2u; p.cv.c8k = 8192u; p.cv.magic = 0x4B000000u; p.cv.c256 = 256u; p.cv.c64k = 65536u; p.cv.c16m = 1u << 24;
+    p.cv.unbias = 0u - 0x08080800u; p.cv.fmagic = 8388608.0f;
+    int n_jobs = 0;
+    if ((rc = f8_job_table(ctx, sh, bs, R, br0, br1, ndir, &p.tiles, &n_jobs))) return rc;
     p.box_x0 = MEMCI_L8_PAD; p.box_y0 = MEMCI_L8_PAD;
-    p.rs = sh.rs; p.plane_words = sh.plane_words; p.ref_rs = sh.ref_rs; p.ref_rows = sh.rpt * bs; p.a_rows = sh.a_rows;
+    p.rs = sh.rs; p.plane_words = sh.plane_words; p.ref_rs = sh.ref_rs; p.ref_rows = sh.rpt * bs; p.n_groups = sh.a_rows / F8_G;
     p.tx_bytes = (unsigned)(4 * sh.plane_words * 4 + sh.ref_w * sh.rpt * bs);
-    p.T = 2 * bs * bs + 1;
+    const int T = 2 * bs * bs + 1;
     const FrameSlot &fs = ctx->frames[slot_src], &ft = ctx->frames[slot_tgt];
     // tensor maps: the four planes of a frame as one 3-D tensor {pitch8, H + 2 PAD, 4}; window box = all four planes,
     // source-block box = plane 0 only
@@ -906,59 +967,89 @@ int memci_fs8_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVF
         if ((rc = memci_tmap_encode(ctx, &tm[2], 1, 3, fs.luma8, dims, strides, box_ref))) return rc;
         if ((rc = memci_tmap_encode(ctx, &tm[3], 1, 3, ft.luma8, dims, strides, box_ref))) return rc;
     }
-    // survivor list: an eighth of the candidates, at most 16 M entries (64 MB).  Textured content needs about 0.5 %, but the
-    // list is cut into one segment per prefilter CTA and flat regions load a few segments heavily; a segment that fills
-    // up sends its blocks to the redo pass, so the size is a performance knob, not a correctness one.
+    // code array: 16 bytes per (job, thread, group of eleven row offsets), at most F8_CODE_CAP bytes at a time -- longer job lists (8K
+    // frames) are searched in chunks of whole jobs, scan pass after each; behind it the column minima of the chunk and
+    // the block minima of the search
+    const size_t job_bytes = (size_t)(sh.a_rows / F8_G) * 16 * sh.nt;
+    size_t chunk_jobs = F8_CODE_CAP / job_bytes;
+    if (chunk_jobs < 1) chunk_jobs = 1;
+    if (chunk_jobs > (size_t)n_jobs) chunk_jobs = (size_t)n_jobs;
+    if (const char *e = getenv("MEMCI_F8_CHUNK_JOBS")) { const int v = atoi(e); if (v >= 1 && (size_t)v < chunk_jobs) chunk_jobs = (size_t)v; }   // tests: force chunking
+    const size_t off_colmin = (chunk_jobs * job_bytes + 255) & ~(size_t)255;
+    const size_t off_bmin = (off_colmin + chunk_jobs * sh.nt * 4 + 255) & ~(size_t)255;
+    size_t have_c = ctx->fs8_codes_cap;
+    if ((rc = memci_reserve(ctx, (void **)&ctx->d_fs8_codes, &have_c, off_bmin + chunk_jobs * 64 * 4))) return rc;
+    const bool new_codes = have_c != ctx->fs8_codes_cap || off_bmin != ctx->fs8_bmin_off;
+    ctx->fs8_codes_cap = have_c; ctx->fs8_bmin_off = off_bmin;
+    p.codes = reinterpret_cast<uint4 *>(ctx->d_fs8_codes);
+    p.colinfo = reinterpret_cast<unsigned *>(ctx->d_fs8_codes + off_colmin);
+    p.bmin = reinterpret_cast<unsigned *>(ctx->d_fs8_codes + off_bmin);
+    if (new_codes) CK(ctx, cudaMemsetAsync(p.bmin, 0xff, chunk_jobs * 64 * 4, ctx->stream));          // armed once, then by fs8_scan_kernel
+    // survivor list: an eighth of the candidates, at most 16 M entries (64 MB), as F8_NLIST sub-lists behind their cursors.
+    // Textured content needs about 0.5 %; a sub-list that fills up hands the pair to the exact kernel, so the size is a
+    // performance knob, not a correctness one.
     const size_t cand_max = (size_t)n_blk * (2 * R + 1) * (2 * R + 1) * 2;
     size_t cap = cand_max / 8 < (1u << 20) ? (1u << 20) : cand_max / 8;
     if (cap > (16u << 20)) cap = 16u << 20;
+    const size_t cursor_words = (size_t)F8_NLIST * F8_CURSOR_STRIDE;
     size_t have = ctx->fs8_list_cap;
-    if ((rc = memci_reserve(ctx, (void **)&ctx->d_fs8_list, &have, (cap + F8_MAXSEG) * 4))) return rc;
-    if (have != ctx->fs8_list_cap) CK(ctx, cudaMemsetAsync(ctx->d_fs8_list, 0, have, ctx->stream));     // new buffer: no stale entries, ever
+    if ((rc = memci_reserve(ctx, (void **)&ctx->d_fs8_list, &have, (cap + cursor_words) * 4))) return rc;
+    if (have != ctx->fs8_list_cap) CK(ctx, cudaMemsetAsync(ctx->d_fs8_list, 0, cursor_words * 4, ctx->stream));   // new buffer: cursors zeroed once, then by fs8_output_kernel
     ctx->fs8_list_cap = have;
+    unsigned *d_cursors = ctx->d_fs8_list, *d_list = ctx->d_fs8_list + cursor_words;
+    unsigned seg_cap = (unsigned)((have / 4 - cursor_words) / F8_NLIST);
+    if (const char *e = getenv("MEMCI_F8_SEG_CAP")) { const int v = atoi(e); if (v >= 0 && (unsigned)v < seg_cap) seg_cap = (unsigned)v; }   // tests: force the overflow fallback
     size_t have_b = ctx->fs8_best_cap;
     if ((rc = memci_reserve(ctx, (void **)&ctx->d_fs8_best, &have_b, (size_t)n_blk * 2 * 12 + F8_FLAG_CAP * 4))) return rc;       // keys + redo marks + flagged survivors
     if (have_b != ctx->fs8_best_cap) CK(ctx, cudaMemsetAsync(ctx->d_fs8_best, 0xff, have_b, ctx->stream));    // new buffer: armed once, then by fs8_output_kernel
     ctx->fs8_best_cap = have_b;
+    unsigned *d_marks = reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2);
+    unsigned *d_flags = d_marks + (size_t)n_blk * 2;               // the flagged-survivor list lives behind the redo marks
     p.counters = ctx->d_counters;
-    p.redo_mark = reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2);
-    p.redo_list = ctx->d_redo_list; p.redo_cap = ctx->redo_cap; p.redo_limit = n_blk * ndir / 16 + 64;
-    CK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 6 * sizeof(int), ctx->stream));   // [8] overflow [9] survivors [10] float64 replays [11] redo blocks [12] tile queue [13] flagged survivors
-    const int n_tiles = p.n_tiles;
-    int grid = n_tiles < sh.ctas * ctx->num_sms ? n_tiles : sh.ctas * ctx->num_sms;
-    if (grid > F8_MAXSEG) grid = F8_MAXSEG;
-    p.seg_counts = ctx->d_fs8_list;                                // [F8_MAXSEG] segment lengths, then the segments
-    p.list = ctx->d_fs8_list + F8_MAXSEG;
-    p.seg_cap = (int)((have / 4 - F8_MAXSEG) / grid);
-    if (const char *e = getenv("MEMCI_F8_SEG_CAP")) { const int v = atoi(e); if (v >= 0 && v < p.seg_cap) p.seg_cap = v; }   // tests: force the overflow fallback
-    const int prof = memci_prof_begin(ctx, MEMCI_PROF_FS, (double)ctx->fs_last_ops);
-    if (sh.nt == 512) rc = bs == 8 ? f8_launch<true, 512>(ctx, tm, p, grid, sh.smem) : f8_launch<false, 512>(ctx, tm, p, grid, sh.smem);
-    else rc = bs == 8 ? f8_launch<true, 256>(ctx, tm, p, grid, sh.smem) : f8_launch<false, 256>(ctx, tm, p, grid, sh.smem);
-    if (rc) return rc;
-    memci_prof_end(ctx, prof);
-    CKL(ctx);
+    int redo_div = 4, col_hits = F8_COL_HITS;       // redo pass: ~4 T pixel-ops/s against the exact kernel's 12.9 -- past a quarter of the blocks the exact kernel is cheaper
+    if (const char *e = getenv("MEMCI_F8_REDO_DIV")) { const int v = atoi(e); if (v >= 1) redo_div = v; }      // tuning
+    if (const char *e = getenv("MEMCI_F8_COL_HITS")) { const int v = atoi(e); if (v >= 1) col_hits = v; }
+    const int redo_limit = n_blk * ndir / redo_div + 64;
+    CK(ctx, cudaMemsetAsync(ctx->d_counters + 8, 0, 6 * sizeof(int), ctx->stream));   // [8] overflow [9] survivors [10] float64 replays [11] redo blocks [12] job queue [13] flagged survivors
+    const F8Conv cv = p.cv;
+    for (int t0 = 0; t0 < n_jobs; t0 += (int)chunk_jobs) {
+        p.t0 = t0; p.n_tiles = n_jobs - t0 < (int)chunk_jobs ? n_jobs - t0 : (int)chunk_jobs;
+        if (t0 > 0) CK(ctx, cudaMemsetAsync(ctx->d_counters + 12, 0, sizeof(int), ctx->stream));
+        int grid = p.n_tiles < sh.ctas * ctx->num_sms ? p.n_tiles : sh.ctas * ctx->num_sms;
+        const int prof = memci_prof_begin(ctx, MEMCI_PROF_FS, (double)ctx->fs_last_ops * p.n_tiles / n_jobs);
+        if (sh.nt == 512) rc = bs == 8 ? f8_launch<true, 512>(ctx, tm, p, grid, sh.smem) : f8_launch<false, 512>(ctx, tm, p, grid, sh.smem);
+        else rc = bs == 8 ? f8_launch<true, 256>(ctx, tm, p, grid, sh.smem) : f8_launch<false, 256>(ctx, tm, p, grid, sh.smem);
+        if (rc) return rc;
+        memci_prof_end(ctx, prof);
+        CKL(ctx);
+        const int prof_sc = memci_prof_begin(ctx, getenv("MEMCI_F8_SCANKIND") ? MEMCI_PROF_HBM_SMALL : MEMCI_PROF_REFINE, 0.0);
+        if (sh.nt == 512)
+            fs8_scan_kernel<512><<<p.n_tiles, 128, 0, ctx->stream>>>(H, W, bs, R, nbc, n_blk, p.n_groups, T, t0, p.tiles, p.codes, reinterpret_cast<const uint4 *>(p.colinfo), p.bmin, cv,
+                                                                     d_list, seg_cap, d_cursors, d_marks, ctx->d_redo_list, ctx->redo_cap, ctx->d_counters, col_hits);
+        else
+            fs8_scan_kernel<256><<<p.n_tiles, 64, 0, ctx->stream>>>(H, W, bs, R, nbc, n_blk, p.n_groups, T, t0, p.tiles, p.codes, reinterpret_cast<const uint4 *>(p.colinfo), p.bmin, cv,
+                                                                    d_list, seg_cap, d_cursors, d_marks, ctx->d_redo_list, ctx->redo_cap, ctx->d_counters, col_hits);
+        memci_prof_end(ctx, prof_sc);
+        CKL(ctx);
+    }
     if (getenv("MEMCI_F8_DEBUG")) {
-        int hc[5]; unsigned hs[8];
+        int hc[6];
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpy(hc, ctx->d_counters + 8, sizeof(hc), cudaMemcpyDeviceToHost);
-        cudaMemcpy(hs, p.seg_counts, sizeof(hs), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "f8 debug: err=%s counters[8..12]=%d %d %d %d %d  n_tiles=%d grid=%d seg_cap=%d segs=%u %u %u %u  shape nt=%d ctas=%d rpt=%d stages=%d nb_tile=%d box=%dx%d smem=%d\n",
-                cudaGetErrorString(cudaGetLastError()), hc[0], hc[1], hc[2], hc[3], hc[4], n_tiles, grid, p.seg_cap, hs[0], hs[1], hs[2], hs[3],
+        fprintf(stderr, "f8 debug: err=%s counters[8..13]=%d %d %d %d %d %d  n_jobs=%d chunk=%d seg_cap=%u  shape nt=%d ctas=%d rpt=%d stages=%d nb_tile=%d box=%dx%d smem=%d\n",
+                cudaGetErrorString(cudaGetLastError()), hc[0], hc[1], hc[2], hc[3], hc[4], hc[5], n_jobs, (int)chunk_jobs, seg_cap,
                 sh.nt, sh.ctas, sh.rpt, sh.n_stage, sh.nb_tile, sh.box_w, sh.box_rows, sh.smem);
     }
     const int prof_rf = memci_prof_begin(ctx, MEMCI_PROF_REFINE, 0.0);
-    // the flagged-survivor list lives behind the redo marks (F8_FLAG_CAP entries)
-    unsigned *d_marks = reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2);
-    unsigned *d_flags = d_marks + (size_t)n_blk * 2;
     fs8_refine_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(fs.luma, ft.luma, H, W, ctx->Wp, bs, R, nbc, n_blk,
-                                                                 p.list, p.seg_cap, p.seg_counts, grid, ctx->d_counters, ctx->d_fs8_best,
+                                                                 d_list, (int)seg_cap, d_cursors, F8_NLIST, ctx->d_counters, ctx->d_fs8_best,
                                                                  d_flags, F8_FLAG_CAP, d_marks, ctx->d_redo_list, ctx->redo_cap);
     CKL(ctx);
     fs8_replay_kernel<<<32, 256, 0, ctx->stream>>>(fs.luma, ft.luma, fs.rgb, ft.rgb, H, W, ctx->Wp, bs, R, nbc, n_blk, d_flags, F8_FLAG_CAP,
                                                    ctx->d_counters, ctx->d_fs8_best, d_marks, ctx->d_redo_list, ctx->redo_cap);
     CKL(ctx);
     const int n_out = (br1 - br0) * nbc * ndir;
-    fs8_output_kernel<<<ceil_div_i(n_out, 256), 256, 0, ctx->stream>>>(ctx->d_fs8_best, reinterpret_cast<unsigned *>(ctx->d_fs8_best + (size_t)n_blk * 2), ctx->d_counters, p.redo_limit,
+    fs8_output_kernel<<<ceil_div_i(n_out, 256), 256, 0, ctx->stream>>>(ctx->d_fs8_best, d_marks, d_cursors, ctx->d_counters, redo_limit,
                                                                       H, W, bs, R, nbc, n_blk, br0 * nbc, br1 * nbc, ndir,
                                                                       out->vec, out->sad, out2 ? out2->vec : out->vec, out2 ? out2->sad : out->sad);
     memci_prof_end(ctx, prof_rf);

@@ -58,6 +58,7 @@ struct memci_ctx {
     FsPlan fs_plan[4];
     unsigned *d_fs8_list; size_t fs8_list_cap;          // prefilter survivors (bytes)
     unsigned long long *d_fs8_best; size_t fs8_best_cap; // per (direction, block) minimum key of the refine pass (bytes)
+    unsigned char *d_fs8_codes; size_t fs8_codes_cap, fs8_bmin_off;   // prefilter: candidate codes, column minima, block minima (bytes)
     long long fs_last_cand, fs_last_ops;
     int fs_used_prefilter;             // the last full search took the two-phase path (fs8.cu)
     // content feedback for the two-phase path: counters [8..11] of a recent search, copied back asynchronously

@@ -1030,11 +1030,11 @@ def test_fs_prefilter_flat_and_tie_frames(gpu, oracle):
 
 
 def test_fs_prefilter_backs_off_on_flat_content(gpu, oracle, monkeypatch):
-    """Content feedback: a search whose prefilter could not prune (flat frames: the survivor list overflows and the exact
-    kernel redoes the pair) makes the next searches skip the prefilter; textured content keeps it on."""
+    """Content feedback: a search whose prefilter could not prune (flat frames: every block goes to the redo list, past
+    its limit the exact kernel redoes the pair) makes the next searches skip the prefilter; textured content keeps it on."""
     from interpolatory_b200.device import DeviceContext
     monkeypatch.delenv("MEMCI_FS_PREFILTER", raising=False)
-    H, W = 96, 160
+    H, W = 270, 480            # (on frames of a few dozen blocks the border blocks dominate and the cost estimate rightly prefers the exact kernel)
     flat = np.empty((2, H, W, 3), np.uint8); flat[0] = 77; flat[1] = 80
     tex = make_sequence(H, W, 2, seed=9)
     for frames, expect_on in ((tex, True), (flat, False)):
