@@ -564,8 +564,8 @@ def main():
 
     for _ in range(max(args.warmup, 1)):
         pass_resident(ctxs)
-    t_pass = agree_max(timed_resident(2) / 2) * 1e-3
-    passes = args.passes or max(1, int(math.ceil(MIN_TIMED_S / (args.steps * t_pass))))
+    t_pass = agree_max(timed_resident(8) / 8) * 1e-3          # (short runs pay the pipeline fill: margin below)
+    passes = args.passes or max(1, int(math.ceil(1.2 * MIN_TIMED_S / (args.steps * t_pass))))
     passes = int(agree_max(passes))
     for _ in range(args.warmup):                           # W untimed warm-up steps of the real size
         for _ in range(passes):
@@ -606,11 +606,11 @@ def main():
         pipe.run(pin_in.array, dists, pin_out.array)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(2):
+    for _ in range(6):
         pipe.run(pin_in.array, dists, pin_out.array, sync=False)
     pipe.sync(); barrier()
-    t_pass_e = agree_max((time.perf_counter() - t0) / 2)
-    passes_e = args.passes or int(agree_max(max(1, int(math.ceil(MIN_TIMED_S / (args.steps * t_pass_e))))))
+    t_pass_e = agree_max((time.perf_counter() - t0) / 6)
+    passes_e = args.passes or int(agree_max(max(1, int(math.ceil(1.2 * MIN_TIMED_S / (args.steps * t_pass_e))))))
     for _ in range(min(args.warmup, 2) * passes_e):
         pipe.run(pin_in.array, dists, pin_out.array, sync=False)
     pipe.sync(); barrier()

@@ -987,10 +987,11 @@ def test_fs_prefilter_path_equals_exact_kernel_and_oracle(gpu, oracle, monkeypat
 
 
 def test_fs_prefilter_segment_partial_fill(gpu, oracle, monkeypatch):
-    """Segments of the survivor list that fill up PART of the way through a search (round-1 advisor finding: the old
-    cursor rolled reservations back, which could drop entries and hand unwritten ones to the refine pass).  The
-    capacity is set just below, at a third of, and far below what a CTA collects; every warp of the CTA emits
-    concurrently.  Whatever does not fit must reach the redo pass: fields equal to the oracle's, every time."""
+    """Sub-lists of the survivor list that fill up PART of the way through a search (round-1 advisor finding: the old
+    cursor rolled reservations back, which could drop entries and hand unwritten ones to the refine pass; the scan pass
+    now only ever moves a cursor forward and raises the pair-level fallback flag when a reservation does not fit).  The
+    capacity is set just below, at a third of, and far below what a sub-list collects; the warps of many CTAs reserve
+    concurrently.  Whatever happens, the exact kernel must then redo the pair: fields equal to the oracle's, every time."""
     from interpolatory_b200.device import DeviceContext
     H, W, bs, R = 270, 483, 8, 16
     fr = make_sequence(H, W, 2, seed=5)
@@ -1001,9 +1002,8 @@ def test_fs_prefilter_segment_partial_fill(gpu, oracle, monkeypatch):
     ctx.me_fs_pair(0, 1, bs, R, 0, 1)
     n_surv, overflow = ctx.fs_prefilter_stats()
     assert n_surv > 0 and not overflow
-    n_ctas = min(2 * 148, 2 * -(-(-(-H // bs)) // 1) * -(-(-(-W // bs)) // 15))        # jobs <= CTAs at this size: about one job per CTA
-    per_cta = max(n_surv // max(n_ctas, 1), 8)
-    for cap in (per_cta - 1, per_cta // 3, 7, 1):
+    per_list = max(n_surv // 64, 8)                       # 64 sub-lists (F8_NLIST), filled round-robin by the scan CTAs
+    for cap in (per_list - 1, per_list // 3, 7, 1):
         monkeypatch.setenv("MEMCI_F8_SEG_CAP", str(cap))
         for _ in range(3):                                  # the interleaving of the emitting warps differs from run to run
             ctx.me_fs_pair(0, 1, bs, R, 0, 1)
@@ -1012,6 +1012,39 @@ def test_fs_prefilter_segment_partial_fill(gpu, oracle, monkeypatch):
                 assert np.array_equal(vec, ref[:, :, :2]) and np.array_equal(sad, ref[:, :, 2]), (cap, slot)
     monkeypatch.delenv("MEMCI_F8_SEG_CAP")
     ctx.close()
+
+
+def test_fs_prefilter_shapes_and_chunks(gpu, oracle, monkeypatch):
+    """The two-phase path under every launch shape and list geometry it can take: 256-thread jobs, no two-row jobs,
+    one / two stages, the code array cut into chunks of a few jobs (8K frames do that for real), every per-column
+    survivor cap from 1 (nearly everything goes to the redo pass) to 127 (nothing does), and search ranges whose
+    row offsets need the second half of the hit mask (2R + 1 > 64) and several batches of code words per column."""
+    from interpolatory_b200.device import DeviceContext
+    monkeypatch.setenv("MEMCI_FS_PREFILTER", "1")
+    cases = (((270, 483, 8, 16), ({}, {"MEMCI_F8_NT": "256"}, {"MEMCI_F8_NOSPLIT": "1"}, {"MEMCI_F8_STAGES": "1"}, {"MEMCI_F8_STAGES": "2"},
+                                  {"MEMCI_F8_CHUNK_JOBS": "5"}, {"MEMCI_F8_CHUNK_JOBS": "1", "MEMCI_F8_NT": "256"}, {"MEMCI_F8_CTAS": "1"},
+                                  {"MEMCI_F8_COL_HITS": "1"}, {"MEMCI_F8_COL_HITS": "3"}, {"MEMCI_F8_COL_HITS": "127"}, {"MEMCI_F8_REDO_DIV": "1000"})),
+             ((200, 328, 8, 40), ({}, {"MEMCI_F8_CHUNK_JOBS": "3"}, {"MEMCI_F8_COL_HITS": "127"})),
+             ((131, 250, 16, 32), ({}, {"MEMCI_F8_COL_HITS": "127"}, {"MEMCI_F8_CHUNK_JOBS": "2"})),
+             ((96, 160, 16, 5), ({}, {"MEMCI_F8_NT": "256"})))
+    knobs = ("MEMCI_F8_NT", "MEMCI_F8_NOSPLIT", "MEMCI_F8_STAGES", "MEMCI_F8_CHUNK_JOBS", "MEMCI_F8_CTAS", "MEMCI_F8_COL_HITS", "MEMCI_F8_REDO_DIV")
+    for (H, W, bs, R), envs in cases:
+        fr = make_sequence(H, W, 2, seed=H + R)
+        want = [oracle.fs_blocks(bs, R, fr[0], fr[1]), oracle.fs_blocks(bs, R, fr[1], fr[0])]
+        for env in envs:
+            for k in knobs:
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            ctx = DeviceContext(H, W)
+            ctx.upload_frame(0, fr[0]); ctx.upload_frame(1, fr[1])
+            for rep in range(2):                            # the second search runs on re-armed buffers
+                ctx.me_fs_pair(0, 1, bs, R, 0, 1)
+                for slot, ref in ((0, want[0]), (1, want[1])):
+                    _, vec, _, sad = ctx.download_mv_blocks(slot)
+                    assert np.array_equal(vec, ref[:, :, :2]) and np.array_equal(sad, ref[:, :, 2]), (H, W, bs, R, env, rep, slot)
+            assert ctx.fs_prefilter_stats() != (0, 0), (H, W, bs, R, env)       # the two-phase path did run
+            ctx.close()
 
 
 def test_fs_prefilter_flat_and_tie_frames(gpu, oracle):
