@@ -276,7 +276,8 @@ MEMCI_API int memci_profile_collect(memci_ctx *ctx, double *fs_ms_sum, int *fs_l
 #define MEMCI_PROF_MCI       1   /* mci_splat_kernel (uni / bidir warp + blend) */
 #define MEMCI_PROF_HBMA      2   /* hbma_fs_kernel + hbma_densify*_kernel (coarse search and every densification) */
 #define MEMCI_PROF_HBM_SMALL 3   /* pyr_down_kernel + luma_kernel of the pyramid levels + smooth_kernel */
-#define MEMCI_PROF_REFINE    4   /* fs8_refine_kernel + fs8_output_kernel + fs_redo_kernel */
+#define MEMCI_PROF_REFINE    4   /* two-phase search after the prefilter: fs8_scan_kernel, fs8_refine_kernel + fs8_replay_kernel + fs8_output_kernel,
+                                    the gated fs_tiled_kernel launch + fs_redo_kernel (one entry each); prefilter off: fs_redo_kernel */
 #define MEMCI_PROF_HOLEFILL  5   /* mci_holefill_kernel */
 #define MEMCI_PROF_PREP      6   /* luma_kernel / luma8_kernel of a full-size frame */
 #define MEMCI_PROF_BIDIR2    7   /* b2_blocks_kernel + b2_frame_kernel */

@@ -925,7 +925,7 @@ int memci_fs_run(memci_ctx *ctx, int slot_src, int slot_tgt, int bs, int R, MVFi
         case 33: rc = fs_launch_tiled<33>(ctx, tm, p, smem); break;
         default: rc = fs_launch_tiled<11>(ctx, tm, p, smem); break;
         }
-        if (!use8) { memci_prof_end(ctx, prof); prof = -1; }
+        if (!use8) { memci_prof_end(ctx, prof); prof = memci_prof_begin(ctx, MEMCI_PROF_REFINE, 0.0); }   // the redo pass counts as refinement either way
         if (p.trace) {                                   // debug dump: one line per (tile, warp)
             unsigned long long *h = (unsigned long long *)malloc(trace_n * 8);
             cudaStreamSynchronize(ctx->stream);

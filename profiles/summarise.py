@@ -7,7 +7,7 @@ def w(s=""):
     out.write(s + "\n")
 w(f"# ncu summaries, {tag}")
 w()
-w("Command profiled: `python bench.py --steps 1 --warmup 1 --pairs 4 --no-cpu-baseline` (cfg2: 1080p, fs 8x8 +-16, bidir),")
+w("Command profiled: `python bench.py --steps 1 --warmup 1 --pairs 4 --passes 1 --no-cpu-baseline --no-extras` (cfg2: 1080p, fs 8x8 +-16, bidir),")
 w("each ncu pass run only after the same command exited 0 without ncu (profiles/capture.sh).")
 w()
 w("## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`) -- cold-cache, serialised: compare SHARES")
@@ -28,10 +28,31 @@ w("|---|---:|---:|---:|---:|")
 for k, v in sorted(step.items(), key=lambda kv: -kv[1][1]):
     w(f"| {k} | {v[0]} | {v[1]/1e3:.1f} | {v[1]/v[0]/1e3:.1f} | {v[1]/tot:.3f} |")
 w()
-w("Note: the profiled command also runs bench.py's exact-kernel pass (`roofline_fs_exact`: one warm-up + one timed step with")
-w("MEMCI_FS_PREFILTER=0), so `fs_tiled_kernel` appears with 8 real launches (~270 us each) on top of the 28 gated launches of")
-w("the two-phase path, which return at once (~3 us: the kernel only runs when the survivor list overflowed).  Shares of the")
-w("two-phase step proper: take `fs_tiled_kernel` as 28 x 3 us.")
+w("Note: the profiled command also runs bench.py's exact-kernel pass (`roofline_fs_exact` / `value_prefilter_off`: the same pairs with")
+w("MEMCI_FS_PREFILTER=0), so `fs_tiled_kernel` appears with real launches (~270 us each) on top of the gated launches of")
+w("the two-phase path, which return at once (~3 us: the kernel only runs when the survivor list overflowed), and `fs_redo_kernel`")
+w("with the exact path's redo passes.  Split by duration below.")
+w()
+tiled = [float(r['Metric Value'].replace(',', '')) * {'ns': 1e-3, 'us': 1, 'ms': 1e3}.get(r['Metric Unit'], 1e-3)
+         for r in csv.DictReader(lines) if 'fs_tiled_kernel' in r['Kernel Name']]
+gated = [t for t in tiled if t < 30]
+real = [t for t in tiled if t >= 30]
+if tiled:
+    w(f"`fs_tiled_kernel`: {len(gated)} gated launches, avg {sum(gated) / max(len(gated), 1):.1f} us; {len(real)} real launches, avg {sum(real) / max(len(real), 1):.1f} us.")
+    n_pf = step.get([k for k in step if k.startswith('fs8_prefilter_kernel')][0], [0, 0])[0] if any(k.startswith('fs8_prefilter_kernel') for k in step) else 0
+    two_phase = {k: v for k, v in step.items() if not k.startswith('fs_tiled_kernel')}
+    tot2 = sum(v[1] / v[0] * min(v[0], n_pf) if k.startswith(('fs_redo', 'luma', 'mci')) else v[1] for k, v in two_phase.items()) / 1e3 + sum(gated)
+    w()
+    w(f"Two-phase step proper (per pair: one launch of each fs8_* kernel, the gated launch, one redo pass, one splat / hole fill):")
+    w()
+    w("| kernel | avg us | share of the two-phase pair |")
+    w("|---|---:|---:|")
+    per_pair = {k: v[1] / v[0] / 1e3 for k, v in two_phase.items()}
+    per_pair['fs_tiled_kernel (gated)'] = sum(gated) / max(len(gated), 1)
+    tp = sum(per_pair.values())
+    for k, v in sorted(per_pair.items(), key=lambda kv: -kv[1]):
+        w(f"| {k} | {v:.1f} | {v / tp:.3f} |")
+    w(f"| sum | {tp:.1f} | 1 |")
 w()
 for k, v in agg.items():
     if k.startswith('ub_kernel'):
@@ -52,8 +73,13 @@ want = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__grid_
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
-        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_sector_hit_rate.pct']
-for rep, title in (("prof_fs8", "fs8_prefilter_kernel (dominant kernel: 8-bit prefilter of the two-phase full search)"), ("prof_fs", "fs_tiled_kernel (the exact kernel, MEMCI_FS_PREFILTER=0)"), ("prof_mci", "mci_splat_kernel"), ("prof_hf", "mci_holefill_kernel")):
+        'smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'lts__t_sector_hit_rate.pct']
+for rep, title in (("prof_fs8", "fs8_prefilter_kernel (dominant kernel: 8-bit prefilter of the two-phase full search)"),
+                   ("prof_scan", "fs8_scan_kernel (column minima against block thresholds, survivor list)"),
+                   ("prof_refine", "fs8_refine_kernel (exact luma-SAD of the survivors)"),
+                   ("prof_redo", "fs_redo_kernel (exact block search of the listed blocks)"),
+                   ("prof_fs", "fs_tiled_kernel (the exact kernel, MEMCI_FS_PREFILTER=0)"), ("prof_mci", "mci_splat_kernel"), ("prof_hf", "mci_holefill_kernel")):
     path = f"gpurun_out/{rep}.ncu-rep"
     if not os.path.exists(path):
         continue
@@ -71,7 +97,8 @@ for rep, title in (("prof_fs8", "fs8_prefilter_kernel (dominant kernel: 8-bit pr
     w()
 import json
 traffic = {}
-for rep, kname in (("prof_fs8", "fs8_prefilter_kernel"), ("prof_fs", "fs_tiled_kernel"), ("prof_mci", "mci_splat_kernel")):
+for rep, kname in (("prof_fs8", "fs8_prefilter_kernel"), ("prof_scan", "fs8_scan_kernel"), ("prof_refine", "fs8_refine_kernel"), ("prof_fs", "fs_tiled_kernel"),
+                   ("prof_mci", "mci_splat_kernel"), ("prof_hf", "mci_holefill_kernel")):
     path = f"gpurun_out/{rep}.ncu-rep"
     if not os.path.exists(path):
         continue
