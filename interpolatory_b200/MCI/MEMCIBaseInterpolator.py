@@ -12,7 +12,7 @@ from ..ME.full_search import get_motion_vectors as fs
 from ..ME.hbma import get_motion_vectors as hbma
 from ..ME.tss import get_motion_vectors as tss
 from ..smoothing import mean_filter, median_filter, weighted_mean_filter, filter_mode_of
-from ..util import hbma_auto_steps, get_first_frame_idx_and_ratio
+from ..util import hbma_auto_steps, get_first_frame_idx_and_ratio, warn_if_hbma_reference_undefined
 
 # device slot plan of one interpolator instance
 _FRAME_SLOTS = (0, 1, 2)      # resident source frames (LRU)
@@ -119,6 +119,7 @@ class MEMCIBaseInterpolator(BaseInterpolator):
         p.sub_region = self.sub_region
         if self.me_mode is hbma:
             self.steps = hbma_auto_steps(shape)                  # Unidirectional.py:116-121 / Bidirectional.py:144-149
+            warn_if_hbma_reference_undefined(shape[0], shape[1], self.block_size, self.steps, self.min_block_size)
         p.steps = self.steps
         p.min_block_size = self.min_block_size
         p.filter_mode = FILTER_MODES[filter_mode_of(self.filter_mode)]

@@ -4,6 +4,7 @@ cost_str='sad', upscale=True)."""
 import numpy as np
 
 from ..device import get_context
+from ..util import warn_if_hbma_reference_undefined
 
 cost_key_map = {'sad': 0, 'ssd': 1}
 
@@ -15,6 +16,7 @@ def get_motion_vectors(block_size, win_size, sub_win_size, steps, min_block_size
     cost_key = cost_key_map[cost_str]
     im1 = np.asarray(im1)
     H, W, _ = im1.shape
+    warn_if_hbma_reference_undefined(H, W, block_size, steps, min_block_size)
     ctx = get_context(H, W, device)
     a = ctx.upload_frame(0, im1)
     b = ctx.upload_frame(1, im2)

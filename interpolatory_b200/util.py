@@ -92,3 +92,36 @@ def hbma_auto_steps(shape):
         min_side /= 2
         steps += 1
     return steps
+
+
+def hbma_reference_undefined(H, W, block_size, steps, min_block_size):
+    """True where the reference's HBMA reads outside its motion field: `increase_vec_density_jit` takes
+    `mvs[row + 1]` / `mvs[row, col + 1]` as the neighbour of the first block row / column (ME/hbma.py:108-115), which does
+    not exist when a coarser field has a single block row or column, and numba does not bounds-check.  This
+    implementation clamps the neighbour index there; its result is well defined, the reference's is not."""
+    sizes = [(H, W)]
+    for _ in range(steps):
+        h, w = sizes[-1]
+        sizes.append(((h + 1) // 2, (w + 1) // 2))
+    rows, cols = -(-sizes[-1][0] // block_size), -(-sizes[-1][1] // block_size)
+    for (h, w) in sizes[-2::-1]:                       # densification through the pyramid at constant block size
+        if rows == 1 or cols == 1:
+            return True
+        rows, cols = -(-h // block_size), -(-w // block_size)
+    bs = block_size
+    while bs > min_block_size:                         # then the block size is halved at full resolution
+        if rows == 1 or cols == 1:
+            return True
+        bs >>= 1
+        rows, cols = -(-H // bs), -(-W // bs)
+    return False
+
+
+def warn_if_hbma_reference_undefined(H, W, block_size, steps, min_block_size):
+    """One warning per geometry (Python's default filter): the caller is comparing against a reference whose own output
+    depends on whatever lies behind its array here."""
+    if hbma_reference_undefined(H, W, block_size, steps, min_block_size):
+        import warnings
+        warnings.warn(f"HBMA on a {H}x{W} frame with block_size {block_size}, {steps} pyramid steps, min_block_size {min_block_size}: "
+                      "a motion field of the pyramid has a single block row or column, where the reference reads out of bounds "
+                      "(ME/hbma.py:108-115); the neighbour index is clamped here", RuntimeWarning, stacklevel=3)

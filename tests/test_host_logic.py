@@ -277,3 +277,26 @@ def test_multigpu_partition_is_contiguous_and_complete():
         parts = [rank_pairs(pairs, r, world) for r in range(world)]
         assert sum(parts, []) == pairs
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_hbma_reference_undefined_regime_is_named(oracle):
+    """The geometry where the reference's HBMA reads out of bounds (single block row / column at some level,
+    ME/hbma.py:108-115): the product's predicate equals the oracle's on random geometry, and the class path warns."""
+    import warnings
+    from interpolatory_b200.util import hbma_reference_undefined, warn_if_hbma_reference_undefined
+    rng = np.random.default_rng(7)
+    hits = 0
+    for _ in range(2000):
+        H, W = int(rng.integers(4, 400)), int(rng.integers(4, 400))
+        bs = int(rng.choice([4, 8, 16, 32])); steps = int(rng.integers(0, 5)); mbs = int(rng.choice([2, 4, 8]))
+        got = hbma_reference_undefined(H, W, bs, steps, mbs)
+        assert got == oracle.hbma_undefined_in_reference(H, W, bs, steps, mbs), (H, W, bs, steps, mbs)
+        hits += got
+    assert 0 < hits < 2000
+    assert not hbma_reference_undefined(1080, 1920, 8, 4, 4) and not hbma_reference_undefined(360, 640, 8, 2, 4)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        warn_if_hbma_reference_undefined(1080, 1920, 8, 4, 4)
+        assert not w
+        warn_if_hbma_reference_undefined(24, 200, 8, 2, 4)
+        assert len(w) == 1 and issubclass(w[0].category, RuntimeWarning) and "hbma.py:108-115" in str(w[0].message)
