@@ -1047,6 +1047,38 @@ def test_fs_prefilter_shapes_and_chunks(gpu, oracle, monkeypatch):
             ctx.close()
 
 
+def test_fs_prefilter_not_applicable_beyond_its_entry_format(gpu, monkeypatch):
+    """A survivor entry carries a 17-bit block index: a frame with 2^17 blocks or more (8K at 8 x 8) must take the exact
+    kernel even with the prefilter pinned on -- same field as with it pinned off, and the statistics say it did not run."""
+    from interpolatory_b200.device import DeviceContext
+    H = W = 2904                                            # 363 x 363 = 131 769 blocks of 8 x 8
+    fr = make_sequence(H, W, 2, seed=17)
+    got = {}
+    for pf in ("1", "0"):
+        monkeypatch.setenv("MEMCI_FS_PREFILTER", pf)
+        ctx = DeviceContext(H, W)
+        ctx.upload_frame(0, fr[0]); ctx.upload_frame(1, fr[1])
+        ctx.me_fs_pair(0, 1, 8, 4, 0, 1)
+        got[pf] = [ctx.download_mv_blocks(s) for s in (0, 1)]
+        assert ctx.fs_prefilter_stats() == (0, 0)
+        ctx.close()
+    for a, b in zip(got["1"], got["0"]):
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
+    # one block row fewer is inside the format: the two-phase path runs and agrees with the exact kernel
+    H2 = 2896 - 8 * 2                                       # 360 x 363 = 130 680 blocks
+    fr2 = fr[:, :H2]
+    for pf in ("1", "0"):
+        monkeypatch.setenv("MEMCI_FS_PREFILTER", pf)
+        ctx = DeviceContext(H2, W)
+        ctx.upload_frame(0, np.ascontiguousarray(fr2[0])); ctx.upload_frame(1, np.ascontiguousarray(fr2[1]))
+        ctx.me_fs_pair(0, 1, 8, 4, 0, 1)
+        got[pf] = [ctx.download_mv_blocks(s) for s in (0, 1)]
+        assert (ctx.fs_prefilter_stats() != (0, 0)) == (pf == "1")
+        ctx.close()
+    for a, b in zip(got["1"], got["0"]):
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[3], b[3])
+
+
 def test_fs_prefilter_flat_and_tie_frames(gpu, oracle):
     """Content where the prefilter cannot prune: flat frames (every candidate survives, the list overflows), two grey
     levels (every SAD an exact multiple of 1000: all survivors are flagged and go to the float64 redo pass)."""
