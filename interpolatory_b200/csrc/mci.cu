@@ -324,6 +324,29 @@ __device__ __forceinline__ void sw_walk_entry(const MciParams &P, const SwShared
     const int lc = (col_ok ? cell_of(p_c, P.cmul[D]) : sc0) - sc0;
     const int p_r0 = ty0 - eff_r;
     const unsigned want = col_ok ? ent.y : 0x80008000u;          // (-32768, -32768) is never a displacement: mci_disp_kernel clamps to +-32767
+    if (P.cell[D] >= SW_TH) {                                     // warp-uniform
+        // MV cells at least as tall as the tile: the tile's source rows lie in at most two cell rows, so the lane tests two
+        // staged cells instead of SW_TH, and an entry no lane matches is dropped after one vote
+        const int j_lo = max(0, -p_r0), j_hi = min(SW_TH, min(H - p_r0, P.y_end - ty0));      // rows [j_lo, j_hi) have a source row
+        if (j_lo >= j_hi) return;
+        const int cA = cell_of(p_r0 + j_lo, P.cmul[D]);
+        const int j_split = (cA + 1) * P.cell[D] - p_r0;          // first tile row whose source row is in the next cell row
+        const int siA = (cA - sr0) * snc + lc;
+        const bool hitA = sm.stage[D][siA] == want;
+        const float sadA = sm.stage_sad[D][siA];
+        bool hitB = false;
+        float sadB = 0.f;
+        if (j_split < j_hi) { hitB = sm.stage[D][siA + snc] == want; sadB = sm.stage_sad[D][siA + snc]; }
+        if (!__any_sync(0xffffffffu, hitA || hitB)) return;
+#pragma unroll
+        for (int j = 0; j < SW_TH; ++j) {
+            if (j < j_lo || j >= j_hi) continue;                  // warp-uniform
+            const bool in_b = j >= j_split;
+            if (in_b ? hitB : hitA)
+                sw_fire<D, BIDIR>(P, sadi[j], base[j], bp[j], bs[j], bi[j], (p_r0 + j) * W + p_c, in_b ? sadB : sadA, false);
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < SW_TH; ++j) {
         const int p_r = p_r0 + j;

@@ -228,15 +228,14 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, unsigned parity)
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra MBARS_DONE;\n"
         "MBARS_WAIT:\n"
-        "nanosleep.u32 64;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra MBARS_DONE;\n"
         "bra MBARS_WAIT;\n"
         "MBARS_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");      // the thread is suspended for up to ~20 us per try
 }
 // Non-blocking probe: has the phase with this parity completed?
 __device__ __forceinline__ bool mbar_test(uint64_t *bar, unsigned parity)
