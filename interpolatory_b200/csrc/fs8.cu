@@ -11,7 +11,7 @@
 //     survivors = { c : A(c) <= A_min + 2n + 1 }.
 // The reference's winner is always among them; every survivor is then evaluated exactly (same arithmetic, same
 // total order as fs.cu) and the minimum key taken.  The result is bit-identical; only the amount of exact work
-// depends on the content (textured frames: ~0.5 % of the candidates survive; flat frames: all of them -- those blocks go
+// depends on the content (textured frames: ~0.3 % of the candidates survive; flat frames: all of them -- those blocks go
 // to the block-level redo pass, and past a limit the exact kernel searches the pair, gated on a device-side flag).
 //
 //   luma8_kernel          L8 as FOUR planes, plane q shifted left by q bytes (zero border): a thread then reads the 8 window
@@ -21,14 +21,14 @@
 //   fs8_prefilter_kernel  pure search: persistent CTAs, dynamic job queue; job = adjacent blocks of one block row (of two,
 //                         side by side, where the column range is clipped), staged by TMA (cp.async.bulk.tensor.3d +
 //                         mbarrier, two or three stages); thread = (block, dx) candidate column.  Out: an 8-bit monotone code
-//                         of every A (global memory, one byte per candidate: L2-resident until the next kernel reads it)
-//                         and the block minima (one global atomicMin per warp and block)
-//                         -- plus the exact minimum of every column and the block minima (one global atomicMin per warp
-//                         and block).  No survivor logic, no CTA-wide hand-over: 0.54 of the VABSDIFF4 issue rate at 1080p
-//   fs8_scan_kernel       thread per candidate column (the prefilter's own mapping, so every load is coalesced): column
-//                         minimum against the block's threshold; the few columns that pass compare their codes and append
-//                         their survivors to the list (one global atomic per warp)
-//   fs8_refine_kernel     8 lanes per survivor: exact luma-SAD, 64-bit atomicMin; flagged sums go on a short list
+//                         of every A, eleven to a 16-byte store, column-major (L2-resident until the scan pass reads it),
+//                         the exact minimum of every column, and the block minima (one global atomicMin per warp and
+//                         block).  No survivor logic, no CTA-wide hand-over: 0.55 of the VABSDIFF4 issue rate at 1080p
+//   fs8_scan_kernel       CTA per job: column minima against the block's threshold, the columns that pass (15 - 30 %) are
+//                         compacted; thread per listed column compares its codes four at a time and appends its
+//                         survivors to one of 64 sub-lists (one global atomic per warp); flat columns -> redo list
+//   fs8_refine_kernel     8 lanes per survivor (lane = column of the block): exact luma-SAD, keys combined per CTA, 64-bit
+//                         atomicMin; flagged sums go on a short list
 //   fs8_replay_kernel     float64 replay of the flagged sums in the reference's operation order
 //   fs8_output_kernel     thread per block: key -> (dy, dx, sad); decides the pair-level fallback; re-arms the buffers
 // Blocks that cannot be pruned (flat content, flagged sums of 16 x 16 blocks) go to fs_redo_kernel (fs.cu).
